@@ -1,0 +1,105 @@
+"""Known-answer and shape checks of the VQT oracle (oracle/vqt_oracle.py).
+
+The reference ships no vectors for generate_XQT and librosa/resampy are absent (parity unpinned,
+see the oracle header), so the pins are the shape literals the reference relies on
+(/root/reference/zeroNoteSamba/pretext.py:255-256,285; fma_loader.py:37,67-76), closed-form
+answers of the published algorithm, and the float64 variant of the same mathematics.
+"""
+import numpy as np
+import pytest
+
+from oracle import vqt_oracle as vo
+from zeronotesamba_b200 import synth
+
+
+@pytest.mark.parametrize("n,frames", [(160000, 626), (480000, 1876), (80001, 313), (4096, 17), (4097, 17)])
+def test_frame_counts(n, frames):
+    out = vo.vqt_ref_f32(np.zeros(n, np.float32))
+    assert out.shape == (96, frames) and out.dtype == np.float32
+    assert out.shape[1] == 1 + n // 256
+
+
+def test_silence_is_log_eps():
+    out = vo.vqt_ref_f32(np.zeros(16000, np.float32))
+    assert np.all(out == np.float32(np.log(np.float32(1e-9))))
+    assert abs(float(out[0, 0]) - (-20.7233)) < 1e-3
+
+
+def test_mode_error_matches_reference():
+    with pytest.raises(Exception, match="Mode can only be vqt or cqt!"):
+        vo.vqt_ref_f32(np.zeros(4096, np.float32), 16000, "stft")
+
+
+def test_decimator_taps():
+    h = vo.decimator_taps()
+    assert h.shape == (33,)
+    assert abs(h[0] - 0.425) < 1e-15
+    dc = h[0] + 2 * h[1:32].sum()
+    assert abs(dc - 1.0000281273908893) < 1e-12
+    known = [0.425, 0.3083022, 0.07112822, -0.07787547, -0.06044671]
+    assert np.allclose(h[:5], known, atol=5e-8)
+
+
+def test_octave_table():
+    n_ffts = [128, 128, 128, 128, 64, 32, 32, 16]
+    for i, n_fft in enumerate(n_ffts):
+        fb, nf, lengths = vo.octave_fft_basis(i, 16000.0, vo.default_gamma())
+        assert nf == n_fft and fb.shape == (12, n_fft // 2 + 1) and fb.dtype == np.complex64
+    assert abs(vo.default_gamma() - 13.59942991365365) < 1e-9
+    L = vo.constant_q_lengths(16000.0, vo.FMIN_C0, 96, vo.default_gamma())
+    assert abs(L[0] - 1098.015) < 1e-2 and abs(L[95] - 64.375) < 1e-2
+
+
+@pytest.mark.parametrize("k", [0, 17, 40, 66, 95])
+def test_bin_centred_tone(k):
+    """A steady tone of amplitude A at bin centre k gives |V[k]| ~ A sqrt(L_k) / 2 in every octave."""
+    sr, n = 16000, 160000
+    f = vo.FMIN_C0 * 2 ** (k / 12)
+    y = (0.5 * np.cos(2 * np.pi * f * np.arange(n) / sr)).astype(np.float32)
+    v = np.exp(vo.vqt_ref_f32(y).astype(np.float64))
+    L = vo.constant_q_lengths(16000.0, vo.FMIN_C0, 96, vo.default_gamma())
+    mid = v[:, 200:400]
+    assert np.argmax(mid.mean(axis=1)) == k
+    assert np.allclose(mid[k], 0.5 * np.sqrt(L[k]) / 2, rtol=2e-2)
+
+
+def test_cqt_is_gamma_zero():
+    y = synth.stem_pair(3, 2.0)[1]
+    a = vo.vqt_ref_f32(y, 16000, "cqt")
+    b = vo.vqt_ref_f32(y, 16000, "vqt")
+    assert a.shape == b.shape and not np.allclose(a, b)
+    # top octave filters are nearly identical (gamma matters at low frequency)
+    assert np.abs(a[90:] - b[90:]).mean() < np.abs(a[:12] - b[:12]).mean()
+
+
+def test_time_domain_kernels_equal_frequency_domain():
+    """C = basis . rfft(frame) == sum_n g[k,n] frame[n]: the identity the device plan relies on."""
+    rng = np.random.default_rng(0)
+    for i in (0, 4, 7):
+        fb, n_fft, _ = vo.octave_fft_basis(i, 16000.0, vo.default_gamma())
+        g, n2 = vo.octave_time_kernels(i, 16000.0, vo.default_gamma())
+        fr = rng.standard_normal(n_fft)
+        a = fb.astype(np.complex128) @ np.fft.rfft(fr)
+        b = g @ fr
+        assert n2 == n_fft and np.allclose(a, b, rtol=1e-10, atol=1e-12)
+
+
+def test_f32_follows_f64_truth():
+    """fp32-faithful variant vs float64 truth: <= 1e-4 relative above 1e-2 max, 1e-6 max below."""
+    for stem in synth.stem_pair(0, 4.0):
+        v32 = np.abs(vo.xqt_complex(stem, 16000, "vqt", True)).astype(np.float64)
+        v64 = np.abs(vo.xqt_complex(stem, 16000, "vqt", False))
+        mx = v64.max()
+        big = v64 >= 1e-2 * mx
+        assert (np.abs(v32 - v64)[big] / v64[big]).max() < 1e-4
+        assert np.abs(v32 - v64).max() < 1e-6 * mx
+
+
+def test_resampler_f32_vs_f64():
+    y = synth.stem_pair(1, 1.0)[0]
+    a = vo.resample_2to1_f32(y).astype(np.float64)
+    b = vo.resample_2to1_f64(y)
+    assert a.shape == b.shape == (8000,)
+    assert np.abs(a - b).max() < 5e-7
+    odd = vo.resample_2to1_f32(y[:1001])
+    assert odd.shape == (501,) and odd[-1] == 0.0  # fix_length zero-fills the last sample
