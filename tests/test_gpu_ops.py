@@ -1,0 +1,456 @@
+"""GPU parity tests of every C-ABI entry point against the oracle / fp32 torch references.
+All calls go through libzns_sm100.so (zeronotesamba_b200._lib)."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from zeronotesamba_b200 import _lib as L
+from zeronotesamba_b200 import synth
+from helpers import bf16_round, from_act, pack_wd, pack_wf, rel_err, to_act, vqt_check
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    L.check(L.lib().zns_device_check())
+    yield
+
+
+def st():
+    return L.current_stream()
+
+
+# --------------------------------------------------------------------------------------------
+# tcgen05 descriptor probe
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,k", [(64, 64), (128, 128), (256, 64), (128, 256), (64, 192)])
+def test_umma_probe(variant, n, k):
+    g = torch.Generator(device="cpu").manual_seed(100 + n + k)
+    if variant == 0:
+        a = torch.randn(128, k, generator=g).to(torch.bfloat16)
+        b = torch.randn(n, k, generator=g).to(torch.bfloat16)
+        ref = a.float() @ b.float().t()
+    else:
+        a = torch.randn(k, 128, generator=g).to(torch.bfloat16)
+        b = torch.randn(k, n, generator=g).to(torch.bfloat16)
+        ref = a.float().t() @ b.float()
+    a, b = a.to(DEV), b.to(DEV)
+    d = torch.full((128, n), float("nan"), device=DEV)
+    L.check(L.lib().zns_dbg_umma_probe(variant, L.ptr(a), L.ptr(b), L.ptr(d), n, k, st()))
+    torch.cuda.synchronize()
+    err = rel_err(d.cpu(), ref)
+    assert err < 1e-5, f"probe variant {variant} n={n} k={k}: rel err {err}"
+
+
+# --------------------------------------------------------------------------------------------
+# VQT
+# --------------------------------------------------------------------------------------------
+def _plan(max_batch, max_samples, gamma=-1.0):
+    h = C.c_void_p()
+    fmin = 440.0 * 2.0 ** ((12 - 69) / 12.0)
+    L.check(L.lib().zns_vqt_plan_create(16000, 256, 96, 12, fmin, gamma, max_batch, max_samples, C.byref(h)))
+    return h
+
+
+@pytest.mark.parametrize("mode,gamma", [("vqt", -1.0), ("cqt", 0.0)])
+def test_vqt_vs_oracle(mode, gamma):
+    from oracle import vqt_oracle as vo
+    n = 160000
+    d, o = synth.stem_batch(0, 2, 10.0)
+    y = np.concatenate([d, o], axis=0)  # [4, n]
+    plan = _plan(4, n, gamma)
+    yd = torch.from_numpy(y).to(DEV)
+    out = torch.empty(4, 96, 626, device=DEV)
+    L.check(L.lib().zns_vqt_forward(plan, L.ptr(yd), 4, n, L.ptr(out), st()))
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for i in range(4):
+        ref = vo.vqt_ref_f32(y[i], 16000, mode)
+        assert ref.shape == (96, 626)
+        rel, ab = vqt_check(out[i], ref)
+        assert rel < 1e-4 and ab < 1e-6, f"clip {i}: rel {rel} abs/max {ab}"
+    L.check(L.lib().zns_vqt_plan_destroy(plan))
+
+
+@pytest.mark.parametrize("n", [80001, 4096, 20479, 480000])
+def test_vqt_ragged_lengths_host_path(n):
+    from oracle import vqt_oracle as vo
+    y = synth.stem_pair(5, n_samples=n)[1]
+    plan = _plan(1, n)
+    frames = L.lib().zns_vqt_num_frames(n, 256)
+    assert frames == 1 + n // 256
+    out = np.empty((96, frames), np.float32)
+    L.check(L.lib().zns_vqt_forward_host(plan, y.ctypes.data, 1, n, out.ctypes.data, st()))
+    ref = vo.vqt_ref_f32(y)
+    rel, ab = vqt_check(out, ref)
+    assert rel < 1e-4 and ab < 1e-6, f"n={n}: rel {rel} abs/max {ab}"
+    L.check(L.lib().zns_vqt_plan_destroy(plan))
+
+
+def test_vqt_silence_and_tone():
+    n = 160000
+    plan = _plan(2, n)
+    y = np.zeros((2, n), np.float32)
+    k = 40
+    f = 440.0 * 2.0 ** ((12 - 69) / 12.0) * 2 ** (k / 12)
+    y[1] = 0.5 * np.cos(2 * np.pi * f * np.arange(n) / 16000)
+    out = np.empty((2, 96, 626), np.float32)
+    L.check(L.lib().zns_vqt_forward_host(plan, y.ctypes.data, 2, n, out.ctypes.data, st()))
+    assert np.allclose(out[0], np.log(np.float32(1e-9)), atol=1e-5)
+    assert int(np.argmax(out[1][:, 300])) == k
+    L.check(L.lib().zns_vqt_plan_destroy(plan))
+
+
+def test_crop_gather():
+    vq = torch.randn(2, 96, 626, device=DEV)
+    starts = torch.tensor([0, 312, 17, 100, 250], dtype=torch.int32, device=DEV)
+    out = torch.empty(5, 2, 96, 313, device=DEV)
+    L.check(L.lib().zns_crop_gather(L.ptr(vq), 2, 96, 626, L.ptr(starts), 5, 313, L.ptr(out), st()))
+    torch.cuda.synchronize()
+    for i, s in enumerate(starts.tolist()):
+        assert torch.equal(out[i], vq[:, :, s:s + 313])
+
+
+# --------------------------------------------------------------------------------------------
+# bandwidth-bound encoder pieces
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W", [(8, 96, 48), (5, 12, 37), (16, 96, 313)])
+def test_conv1_fwd_wgrad(B, H, W):
+    g = torch.Generator().manual_seed(1)
+    x2 = (torch.randn(B, 2, H, W, generator=g) * 3 - 4).to(DEV)
+    w = (torch.randn(64, 1, 3, 11, generator=g) * 0.2).to(DEV)
+    b = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    G = (B + 7) // 8
+    for ch in (0, 1):
+        x = x2[:, ch]
+        out = torch.empty(G, H, W, 8, 64, dtype=torch.bfloat16, device=DEV)
+        L.check(L.lib().zns_conv1_fwd(L.ptr(x2) + ch * H * W * 4, 2 * H * W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.0,
+                                      0, None, 0, st()))
+        ref = F.relu(F.conv2d(x.unsqueeze(1), w, b, padding=(1, 5)))
+        got = from_act(out, B)
+        assert rel_err(got, ref) < 4e-3
+        if B % 8:
+            assert float(out.view(G, H, W, 8, 64)[-1, :, :, B % 8:, :].float().abs().max()) == 0.0
+        # weight gradient against autograd on the same (bf16-rounded) dy
+        dy = torch.randn(B, 64, H, W, generator=g).to(DEV)
+        dy_act = to_act(dy)
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(b)
+        L.check(L.lib().zns_conv1_wgrad(L.ptr(dy_act), L.ptr(x2) + ch * H * W * 4, 2 * H * W, L.ptr(dw), L.ptr(db), B, H, W,
+                                        st()))
+        wr = w.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        F.conv2d(x.unsqueeze(1), wr, br, padding=(1, 5)).backward(bf16_round(dy))
+        assert rel_err(dw, wr.grad) < 1e-4
+        assert rel_err(db, br.grad) < 1e-4
+
+
+def test_conv1_dropout_statistics():
+    B, H, W = 8, 96, 64
+    x = torch.rand(B, H, W, device=DEV) + 1.0
+    w = torch.full((64, 1, 3, 11), 0.05, device=DEV)
+    b = torch.ones(64, device=DEV)
+    out = torch.empty(1, H, W, 8, 64, dtype=torch.bfloat16, device=DEV)
+    ref = torch.empty_like(out)
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, L.ptr(w), L.ptr(b), L.ptr(ref), B, H, W, 0.0, 7, None, 3, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.1, 7, None, 3, st()))
+    kept = out.float() != 0
+    rate = float(kept.float().mean())
+    assert abs(rate - 0.9) < 3e-3, rate
+    ratio = (out.float()[kept] / ref.float()[kept])
+    assert float((ratio - 1 / 0.9).abs().max()) < 1e-2
+    out2 = torch.empty_like(out)
+    ctr = torch.tensor([5], dtype=torch.int32, device=DEV)
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, L.ptr(w), L.ptr(b), L.ptr(out2), B, H, W, 0.1, 7, L.ptr(ctr), 3, st()))
+    assert float(((out2.float() != 0) != kept).float().mean()) > 0.1  # a different mask with a device seed word
+
+
+@pytest.mark.parametrize("B,H,W,Cc,pool", [(8, 96, 20, 64, 3), (16, 32, 33, 128, 4), (3, 8, 50, 256, 8)])
+def test_pool_fwd_bwd(B, H, W, Cc, pool):
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(B, Cc, H, W, generator=g).to(DEV)
+    ya = to_act(y)
+    G = (B + 7) // 8
+    out = torch.empty(G, H // pool, W, 8, Cc, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().zns_pool_fwd(L.ptr(ya), L.ptr(out), B, H, W, Cc, pool, 0.0, 0, None, 0, st()))
+    yr = bf16_round(y).requires_grad_(True)
+    ref = F.relu(F.max_pool2d(yr, (pool, 1)))
+    assert torch.equal(from_act(out, B), ref.detach())
+    dp = torch.randn(B, Cc, H // pool, W, generator=g).to(DEV)
+    # the dgrad epilogue has already applied the ReLU mask to dp in the product path
+    dp_masked = bf16_round(dp) * (ref.detach() > 0)
+    dy = torch.empty_like(ya)
+    L.check(L.lib().zns_pool_bwd(L.ptr(ya), L.ptr(to_act(dp_masked)), L.ptr(dy), B, H, W, Cc, pool, st()))
+    ref.backward(bf16_round(dp))
+    assert torch.equal(from_act(dy, B), yr.grad)
+
+
+@pytest.mark.parametrize("B,T", [(16, 313), (5, 40), (1, 1876)])
+def test_head_fwd_bwd(B, T):
+    g = torch.Generator().manual_seed(3)
+    x = F.relu(torch.randn(B, 128, 1, T, generator=g)).to(DEV)
+    w = (torch.randn(1, 128, 1, generator=g) * 0.1).to(DEV)
+    b = torch.tensor([0.05], device=DEV)
+    xa = to_act(x)
+    emb = torch.empty(B, T, device=DEV)
+    L.check(L.lib().zns_head_fwd(L.ptr(xa), L.ptr(w), L.ptr(b), L.ptr(emb), B, T, st()))
+    xr = bf16_round(x).squeeze(2).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = torch.sigmoid(F.conv1d(xr, wr, br)).reshape(B, T)
+    assert torch.allclose(emb, ref.detach(), rtol=1e-5, atol=1e-6)
+    de = torch.randn(B, T, generator=g).to(DEV)
+    ref.backward(de)
+    dw = torch.zeros_like(w)
+    db = torch.zeros_like(b)
+    G = (B + 7) // 8
+    dy = torch.empty(G, 1, T, 8, 128, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().zns_head_bwd(L.ptr(xa), L.ptr(emb), L.ptr(de), L.ptr(w), L.ptr(dw), L.ptr(db), L.ptr(dy), B, T, 1.0,
+                                 st()))
+    assert rel_err(dw, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    want = (xr.grad * (xr.detach() > 0)).unsqueeze(2)
+    assert rel_err(from_act(dy, B), want) < 4e-3
+
+
+def test_merge_and_layout():
+    a = torch.rand(3, 1876, device=DEV)
+    b = torch.rand(3, 1876, device=DEV)
+    o = torch.empty_like(a)
+    L.check(L.lib().zns_merge(L.ptr(a), L.ptr(b), L.ptr(o), a.numel(), 0, st()))
+    assert torch.equal(o, torch.maximum(a, b))
+    L.check(L.lib().zns_merge(L.ptr(a), L.ptr(b), L.ptr(o), a.numel(), 1, st()))
+    assert torch.allclose(o, (a + b) / 2)
+    x = torch.randn(5, 64, 7, 9, device=DEV)
+    act = torch.empty(1, 7, 9, 8, 64, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().zns_act_from_nchw(L.ptr(x), L.ptr(act), 5, 64, 7, 9, st()))
+    assert torch.equal(act, to_act(x))
+    back = torch.empty_like(x)
+    L.check(L.lib().zns_act_to_nchw(L.ptr(act), L.ptr(back), 5, 64, 7, 9, st()))
+    assert torch.equal(back, bf16_round(x))
+
+
+@pytest.mark.parametrize("co,ci,kh,kw", [(64, 64, 7, 13), (128, 128, 9, 17), (256, 128, 3, 19), (128, 256, 1, 23)])
+def test_pack_unpack(co, ci, kh, kw):
+    w = torch.randn(co, ci, kh, kw, device=DEV)
+    wf = torch.empty(kh * kw, co, ci, dtype=torch.bfloat16, device=DEV)
+    wd = torch.empty(kh * kw, ci, co, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(wf), L.ptr(wd), st()))
+    assert torch.equal(wf, pack_wf(w)) and torch.equal(wd, pack_wd(w))
+    gp = torch.randn(kh * kw, co, ci, device=DEV)
+    gout = torch.ones(co, ci, kh, kw, device=DEV)
+    L.check(L.lib().zns_unpack_grads(L.ptr(gp), co, ci, kh, kw, 0.5, 0, L.ptr(gout), st()))
+    want = 0.5 * gp.view(kh, kw, co, ci).permute(2, 3, 0, 1)
+    assert torch.allclose(gout, want)
+    L.check(L.lib().zns_unpack_grads(L.ptr(gp), co, ci, kh, kw, 0.5, 1, L.ptr(gout), st()))
+    assert torch.allclose(gout, 2 * want)
+
+
+@pytest.mark.parametrize("C_", [64, 128, 256])
+def test_bias_grad(C_):
+    dy = torch.randn(16, C_, 8, 33, device=DEV)
+    a = to_act(dy)
+    db = torch.zeros(C_, device=DEV)
+    L.check(L.lib().zns_bias_grad(L.ptr(a), 16, 8, 33, C_, L.ptr(db), st()))
+    assert rel_err(db, bf16_round(dy).sum(dim=(0, 2, 3))) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------
+# NT-Xent and Adam
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,D,bl,tau", [(16, 313, 16, 0.25), (5, 313, 16, 0.25), (8, 48, 8, 0.5), (64, 100, 64, 0.1)])
+def test_ntxent(n, D, bl, tau):
+    from oracle import encoder_oracle as eo
+    g = torch.Generator().manual_seed(4)
+    a = torch.rand(n, D, generator=g)
+    p = torch.rand(n, D, generator=g)
+    ar, pr = a.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    loss, cp, cn = eo.ntxent(ar, pr, bl, tau)
+    loss.backward()
+    ad, pd = a.to(DEV), p.to(DEV)
+    res = torch.empty(3, device=DEV)
+    da, dp = torch.empty_like(ad), torch.empty_like(pd)
+    L.check(L.lib().zns_ntxent_fwd_bwd(L.ptr(ad), L.ptr(pd), n, D, bl, tau, L.ptr(res), L.ptr(da), L.ptr(dp), st()))
+    r = res.cpu().numpy()
+    assert np.allclose(r, [float(loss), cp, cn], rtol=2e-5, atol=1e-6), (r, float(loss), cp, cn)
+    assert rel_err(da.cpu(), ar.grad) < 1e-4 and rel_err(dp.cpu(), pr.grad) < 1e-4
+
+
+def test_ntxent_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "encoder_golden.npz"))
+    a, p = torch.from_numpy(gold["nt_a"]).to(DEV), torch.from_numpy(gold["nt_p"]).to(DEV)
+    res = torch.empty(3, device=DEV)
+    L.check(L.lib().zns_ntxent_fwd_bwd(L.ptr(a), L.ptr(p), 16, 313, 16, 0.25, L.ptr(res), None, None, st()))
+    assert np.allclose(res.cpu().numpy(), gold["nt_full"], rtol=1e-5)
+    a5, p5 = a[:5].contiguous(), p[:5].contiguous()
+    L.check(L.lib().zns_ntxent_fwd_bwd(L.ptr(a5), L.ptr(p5), 5, 313, 16, 0.25, L.ptr(res), None, None, st()))
+    assert np.allclose(res.cpu().numpy(), gold["nt_short"], rtol=1e-5)
+
+
+def test_adam_matches_torch():
+    n = 1_000_003
+    g = torch.Generator().manual_seed(6)
+    p0 = torch.randn(n + 1, generator=g)[:n].to(DEV)
+    p = p0.clone()
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pt], lr=1e-6)
+    ctr = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for step in range(1, 4):
+        grad = (torch.randn(n, generator=g) * 1e-3).to(DEV)
+        pt.grad = grad.clone()
+        opt.step()
+        L.check(L.lib().zns_counter_add(L.ptr(ctr), 1, st()))
+        L.check(L.lib().zns_adam_flat(L.ptr(p), L.ptr(grad), L.ptr(m), L.ptr(v), n, 1e-6, 0.9, 0.999, 1e-8, 0, L.ptr(ctr), 1.0,
+                                      st()))
+        d_ref = (pt.detach() - p0).double()
+        d_got = (p - p0).double()
+        assert float((d_got - d_ref).norm() / d_ref.norm()) < 1e-3  # fp32 subtraction noise on 1e-6 steps
+    assert int(ctr.item()) == 3
+
+
+# --------------------------------------------------------------------------------------------
+# tcgen05 convolutions
+# --------------------------------------------------------------------------------------------
+SMALL = [  # B, H, W, ci, co, kh, kw
+    (8, 4, 16, 64, 64, 1, 1),
+    (8, 4, 16, 64, 64, 1, 3),
+    (8, 8, 40, 64, 64, 3, 5),
+    (8, 8, 40, 64, 128, 3, 5),
+    (8, 8, 40, 128, 256, 3, 5),
+    (16, 12, 37, 64, 64, 7, 13),
+    (16, 9, 50, 128, 128, 9, 17),
+    (16, 8, 45, 256, 256, 5, 21),
+    (5, 1, 70, 256, 128, 1, 23),
+    (16, 1, 313, 128, 128, 1, 25),
+]
+
+
+def _conv_case(B, H, W, ci, co, kh, kw, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, ci, H, W, generator=g).to(DEV)
+    w = (torch.randn(co, ci, kh, kw, generator=g) / math.sqrt(ci * kh * kw)).to(DEV)
+    b = (torch.randn(co, generator=g) * 0.1).to(DEV)
+    return x, w, b
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,kh,kw", SMALL)
+def test_conv_fwd_umma(B, H, W, ci, co, kh, kw):
+    x, w, b = _conv_case(B, H, W, ci, co, kh, kw)
+    xa, wf = to_act(x), pack_wf(w)
+    G = (B + 7) // 8
+    out = torch.full((G, H, W, 8, co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=1)
+    L.check(L.lib().zns_conv_fwd(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([wf]), L.ptr_array([b]), None,
+                                 L.ptr_array([out]), st()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(bf16_round(x), bf16_round(w), b, padding=(kh // 2, kw // 2)))
+    got = from_act(out, B)
+    assert not torch.isnan(got).any()
+    err = rel_err(got, ref)
+    simt = torch.empty_like(out)
+    L.check(L.lib().zns_dbg_conv_fwd_simt(C.byref(d), L.ptr(xa), L.ptr(wf), L.ptr(b), None, L.ptr(simt), st()))
+    err_simt = rel_err(from_act(simt, B), ref)
+    assert err_simt < 4e-3, f"SIMT reference itself off: {err_simt}"
+    assert err < 4e-3, f"umma fwd rel err {err} (simt {err_simt})"
+
+
+def test_conv_fwd_two_branches_mask_scale():
+    B, H, W, ci, co, kh, kw = 16, 8, 40, 128, 64, 3, 7
+    xs, ws, outs, masks, refs = [], [], [], [], []
+    for br in range(2):
+        x, w, _ = _conv_case(B, H, W, ci, co, kh, kw, seed=10 + br)
+        m = torch.randn(B, co, H, W, device=DEV)
+        xs.append(to_act(x)); ws.append(pack_wf(w)); masks.append(to_act(m))
+        outs.append(torch.empty(2, H, W, 8, co, dtype=torch.bfloat16, device=DEV))
+        ref = F.conv2d(bf16_round(x), bf16_round(w), None, padding=(kh // 2, kw // 2))
+        refs.append(ref * (bf16_round(m) > 0) * 1.25)
+    d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=0, out_scale=1.25)
+    L.check(L.lib().zns_conv_fwd(C.byref(d), 2, L.ptr_array(xs), L.ptr_array(ws), None, L.ptr_array(masks),
+                                 L.ptr_array(outs), st()))
+    for br in range(2):
+        assert rel_err(from_act(outs[br], B), refs[br]) < 4e-3
+
+
+def test_conv_dgrad_via_flipped_pack():
+    B, H, W, ci, co, kh, kw = 8, 8, 40, 64, 128, 5, 15
+    x, w, _ = _conv_case(B, H, W, ci, co, kh, kw, seed=3)
+    dy = torch.randn(B, co, H, W, device=DEV)
+    xr = bf16_round(x).requires_grad_(True)
+    F.conv2d(xr, bf16_round(w), None, padding=(kh // 2, kw // 2)).backward(bf16_round(dy))
+    wd = torch.empty(kh * kw, ci, co, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, None, L.ptr(wd), st()))
+    dx = torch.empty(1, H, W, 8, ci, dtype=torch.bfloat16, device=DEV)
+    d = L.conv_desc(B, H, W, co, ci, kh, kw)
+    L.check(L.lib().zns_conv_fwd(C.byref(d), 1, L.ptr_array([to_act(dy)]), L.ptr_array([wd]), None, None,
+                                 L.ptr_array([dx]), st()))
+    assert rel_err(from_act(dx, B), xr.grad) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,kh,kw", SMALL)
+def test_conv_wgrad_umma(B, H, W, ci, co, kh, kw):
+    x, w, _ = _conv_case(B, H, W, ci, co, kh, kw, seed=5)
+    dy = torch.randn(B, co, H, W, device=DEV)
+    xa, dya = to_act(x), to_act(dy)
+    d = L.conv_desc(B, H, W, ci, co, kh, kw)
+    gp = torch.zeros(kh * kw, co, ci, device=DEV)
+    L.check(L.lib().zns_conv_wgrad(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([dya]), L.ptr_array([gp]), st()))
+    torch.cuda.synchronize()
+    wr = bf16_round(w).requires_grad_(True)
+    F.conv2d(bf16_round(x), wr, None, padding=(kh // 2, kw // 2)).backward(bf16_round(dy))
+    want = wr.grad.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+    gs = torch.zeros_like(gp)
+    L.check(L.lib().zns_dbg_conv_wgrad_simt(C.byref(d), L.ptr(xa), L.ptr(dya), L.ptr(gs), st()))
+    err_simt = rel_err(gs, want)
+    assert err_simt < 1e-4, f"SIMT wgrad reference off: {err_simt}"
+    err = rel_err(gp, want)
+    assert err < 1e-4, f"umma wgrad rel err {err}"
+    # accumulation (+=) semantics
+    L.check(L.lib().zns_conv_wgrad(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([dya]), L.ptr_array([gp]), st()))
+    assert rel_err(gp, 2 * want) < 1e-4
+
+
+FULL = [  # the reference's layers at B=16, T=313
+    (16, 96, 313, 64, 64, 7, 13),
+    (16, 32, 313, 64, 128, 5, 15),
+    (16, 32, 313, 128, 128, 9, 17),
+    (16, 8, 313, 128, 256, 3, 19),
+    (16, 8, 313, 256, 256, 5, 21),
+    (16, 1, 313, 256, 128, 1, 23),
+    (16, 1, 313, 128, 128, 1, 25),
+]
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,kh,kw", FULL)
+def test_conv_full_size_layers(B, H, W, ci, co, kh, kw):
+    x, w, b = _conv_case(B, H, W, ci, co, kh, kw, seed=9)
+    dy = torch.randn(B, co, H, W, device=DEV)
+    xa, wf, dya = to_act(x), pack_wf(w), to_act(dy)
+    out = torch.empty(2, H, W, 8, co, dtype=torch.bfloat16, device=DEV)
+    d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=0)
+    L.check(L.lib().zns_conv_fwd(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([wf]), L.ptr_array([b]), None,
+                                 L.ptr_array([out]), st()))
+    wr = bf16_round(w).requires_grad_(True)
+    xr = bf16_round(x).requires_grad_(True)
+    ref = F.conv2d(xr, wr, b, padding=(kh // 2, kw // 2))
+    assert rel_err(from_act(out, B), ref.detach()) < 4e-3
+    ref.backward(bf16_round(dy))
+    gp = torch.zeros(kh * kw, co, ci, device=DEV)
+    L.check(L.lib().zns_conv_wgrad(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([dya]), L.ptr_array([gp]), st()))
+    assert rel_err(gp, wr.grad.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)) < 2e-4
+    wd = pack_wd(w)
+    dx = torch.empty(2, H, W, 8, ci, dtype=torch.bfloat16, device=DEV)
+    dd = L.conv_desc(B, H, W, co, ci, kh, kw)
+    L.check(L.lib().zns_conv_fwd(C.byref(dd), 1, L.ptr_array([dya]), L.ptr_array([wd]), None, None, L.ptr_array([dx]), st()))
+    assert rel_err(from_act(dx, B), xr.grad) < 4e-3

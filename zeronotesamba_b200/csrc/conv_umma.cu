@@ -1,0 +1,702 @@
+// cv2..cv8 of the encoders as implicit GEMMs on tcgen05 / TMEM with TMA-staged operands.
+//
+// Reference semantics: nn.Conv2d "same" convolutions of _CNN
+// (/root/reference/zeroNoteSamba/models/models.py:17-23,41-70), their data gradient (the same
+// kernel on flipped/transposed packed weights) and their weight gradient.
+//
+// Layout trick (see common.cuh): activations are bf16 [G][H][W][8][C].  A TMA box
+// (64 ch, 8 clips, w-span, 1, 1) lands in shared memory as one 1024-byte, 128B-swizzled atom per
+// time frame w (8 clip rows x 64 channels).  Consequences:
+//   * forward / dgrad: M = 128 output positions = 16 frames x 8 clips of one frequency row.  The
+//     A operand of filter tap (r, s) is the SAME shared-memory row buffer offset by s atoms, so
+//     one halo row (16 + kw - 1 atoms) is loaded once per 64-channel chunk and reused by all kw
+//     taps and by up to HT output rows (HT accumulators in TMEM share every weight tile).
+//     Zero "same" padding along W is TMA out-of-bounds fill; padding rows along H are skipped.
+//   * wgrad: the reduction runs over positions; both operands are MN-major views of the same
+//     kind of tile (x halo row shifted by the tap, dy tile), accumulators are per-tap
+//     [c_in x c_out] blocks in TMEM, reduced across position slices with fp32 atomics.
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return ZNS_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  ZNS_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return zns_set_error(ZNS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = (PFN_encodeTiled)fn;
+  return ZNS_OK;
+}
+
+// act bf16 [G][H][W][8][C] -> 5-D map (C, 8, W, H, G), box (64, 8, wbox, 1, 1), 128B swizzle
+static int make_act_map(CUtensorMap* m, const void* base, int G, int H, int W, int C, int wbox) {
+  int rc = get_encode();
+  if (rc) return rc;
+  cuuint64_t dims[5] = {(cuuint64_t)C, 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)G};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 16, (cuuint64_t)W * C * 16, (cuuint64_t)H * W * C * 16};
+  cuuint32_t box[5] = {64, 8, (cuuint32_t)wbox, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return zns_set_error(ZNS_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+  return ZNS_OK;
+}
+
+// packed weights bf16 [taps][rows][K] -> 3-D map (K, rows, taps), box (64, nrows, 1)
+static int make_w_map(CUtensorMap* m, const void* base, int taps, int rows, int K, int nrows) {
+  int rc = get_encode();
+  if (rc) return rc;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * K * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)nrows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return zns_set_error(ZNS_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return ZNS_OK;
+}
+
+#define ZNS_SMEM_LIMIT 232448  // 227 KB opt-in maximum per CTA
+#define WT 16                  // frames per M tile (x 8 clips = 128 rows)
+#define MAX_RING 8
+
+// ---------------------------------------------------------------------------------------------
+// forward / data-gradient kernel
+// ---------------------------------------------------------------------------------------------
+struct FwdParams {
+  int G, H, W, batch;
+  int kh, kw, ph, pw;
+  int n_chunks;             // input channels / 64
+  int n_wtiles, n_htiles;
+  int n_slots, n_bstages;   // A row ring, B tile ring
+  uint32_t slot_bytes;      // (WT + kw - 1) * 1024
+  int relu;
+  float drop_p, scale;
+  uint32_t seed, stream_id;
+  const uint32_t* seed_dev;
+  const float* bias[2];
+  const bf16* mask[2];
+  bf16* out[2];
+};
+
+struct FwdBarriers {
+  uint64_t a_full[MAX_RING], a_empty[MAX_RING], b_full[MAX_RING], b_empty[MAX_RING], acc_full;
+  uint32_t tmem_base;
+};
+
+template <int N, int HT>
+__global__ void __launch_bounds__(192, 1)
+conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+                     const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                     const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + p.n_slots * p.slot_bytes;
+  constexpr uint32_t kBTile = N * 128;
+  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem_raw + (b_base + p.n_bstages * kBTile - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int br = blockIdx.z;
+  const CUtensorMap* tm_in = br ? &tm_in1 : &tm_in0;
+  const CUtensorMap* tm_w = br ? &tm_w1 : &tm_w0;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int wt = t % p.n_wtiles; t /= p.n_wtiles;
+  const int htile = t % p.n_htiles; t /= p.n_htiles;
+  const int g = t;
+  const int w0 = wt * WT, h0 = htile * HT;
+  const int ht_eff = min(HT, p.H - h0);
+  // input rows rr (relative): hh = h0 - ph + rr, valid when 0 <= hh < H
+  const int rr_lo = max(0, p.ph - h0);
+  const int rr_hi = min(ht_eff + p.kh - 1, p.H + p.ph - h0);
+  const int n_valid = rr_hi - rr_lo;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < p.n_bstages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tm_in);
+    tma_prefetch_desc(tm_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int a_cnt = 0, b_cnt = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo;
+        for (int r = 0; r < p.kh; ++r) {
+          const int need_hi = min(r + ht_eff, rr_hi);
+          while (next_row < need_hi) {
+            const int slot = a_cnt % p.n_slots;
+            mbar_wait(smem_u32(&bars->a_empty[slot]), ((a_cnt / p.n_slots) & 1) ^ 1);
+            mbar_expect_tx(smem_u32(&bars->a_full[slot]), p.slot_bytes);
+            tma_load_5d(a_base + slot * p.slot_bytes, tm_in, smem_u32(&bars->a_full[slot]), c * 64, 0, w0 - p.pw,
+                        h0 - p.ph + next_row, g);
+            ++a_cnt;
+            ++next_row;
+          }
+          if (max(r, rr_lo) >= min(r + ht_eff, rr_hi)) continue;  // tap row touches no valid input row
+          for (int s = 0; s < p.kw; ++s) {
+            const int st = b_cnt % p.n_bstages;
+            mbar_wait(smem_u32(&bars->b_empty[st]), ((b_cnt / p.n_bstages) & 1) ^ 1);
+            mbar_expect_tx(smem_u32(&bars->b_full[st]), kBTile);
+            tma_load_3d(b_base + st * kBTile, tm_w, smem_u32(&bars->b_full[st]), c * 64, 0, r * p.kw + s);
+            ++b_cnt;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+      int a_wait = 0, b_cnt = 0;
+      uint32_t started = 0;  // bit h: accumulator h holds data
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const int row_base = c * n_valid - rr_lo;  // sequence number of relative row rr is row_base + rr
+        int next_row = rr_lo, rel_row = rr_lo;
+        for (int r = 0; r < p.kh; ++r) {
+          const int need_hi = min(r + ht_eff, rr_hi);
+          while (next_row < need_hi) {
+            const int slot = a_wait % p.n_slots;
+            mbar_wait(smem_u32(&bars->a_full[slot]), (a_wait / p.n_slots) & 1);
+            ++a_wait;
+            ++next_row;
+          }
+          const int lo = max(r, rr_lo), hi = min(r + ht_eff, rr_hi);
+          if (lo < hi) {
+            for (int s = 0; s < p.kw; ++s) {
+              const int st = b_cnt % p.n_bstages;
+              mbar_wait(smem_u32(&bars->b_full[st]), (b_cnt / p.n_bstages) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = b_base + st * kBTile;
+              for (int rr = lo; rr < hi; ++rr) {
+                const int h = rr - r;
+                const uint32_t a_addr = a_base + ((row_base + rr) % p.n_slots) * p.slot_bytes + s * 1024;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(tmem + h * N, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                            umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, ((started >> h) & 1) | (k > 0));
+                }
+                started |= 1u << h;
+              }
+              umma_commit(smem_u32(&bars->b_empty[st]));
+              ++b_cnt;
+            }
+          }
+          while (rel_row <= r && rel_row < rr_hi) {
+            umma_commit(smem_u32(&bars->a_empty[(row_base + rel_row) % p.n_slots]));
+            ++rel_row;
+          }
+        }
+        while (rel_row < rr_hi) {
+          umma_commit(smem_u32(&bars->a_empty[(row_base + rel_row) % p.n_slots]));
+          ++rel_row;
+        }
+      }
+      umma_commit(smem_u32(&bars->acc_full));
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias / ReLU / dropout / mask -> bf16 act =====
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int w = w0 + (m >> 3), b8 = m & 7;
+    const bool valid = (w < p.W);
+    const float* bias = p.bias[br];
+    const bf16* mask = p.mask[br];
+    bf16* out = p.out[br];
+    uint32_t seed = p.seed;
+    if (p.seed_dev) seed ^= __ldg(p.seed_dev) * 0x9E3779B9u;
+    const bool do_drop = p.drop_p > 0.f;
+    const double thr_d = (double)p.drop_p * 4294967296.0;
+    const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
+    const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int h = 0; h < ht_eff; ++h) {
+      const size_t e0 = zns_act_index(g, h0 + h, valid ? w : 0, b8, 0, p.H, p.W, N);
+#pragma unroll 1
+      for (int nb = 0; nb < N / 32; ++nb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + h * N + nb * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (bias) x += __ldg(bias + nb * 32 + j);
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (do_drop) x = (zns_hash32(e0 + nb * 32 + j, seed, p.stream_id) >= thr) ? x * keep : 0.f;
+            f[j] = x;
+          }
+          if (mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(mask + e0 + nb * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 mv = __ldg(mp + q);
+              const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 mf = __bfloat1622float2(m2[j]);
+                if (!(mf.x > 0.f)) f[q * 8 + 2 * j] = 0.f;
+                if (!(mf.y > 0.f)) f[q * 8 + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + e0 + nb * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_bf16x2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale),
+                                pack_bf16x2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale),
+                                pack_bf16x2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale),
+                                pack_bf16x2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int N, int HT>
+static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
+                      const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st) {
+  const int G = zns_groups(d->batch);
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.G = G; p.H = d->H; p.W = d->W; p.batch = d->batch;
+  p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
+  p.n_chunks = d->c_in / 64;
+  p.n_wtiles = (d->W + WT - 1) / WT;
+  p.n_htiles = (d->H + HT - 1) / HT;
+  p.slot_bytes = (uint32_t)(WT + d->kw - 1) * 1024u;
+  p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
+  const int ht_max = std::min(HT, d->H);
+  const uint32_t btile = N * 128;
+  const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdBarriers) - 64;
+  int slots = ht_max + 1, bst = 2;
+  ZNS_REQUIRE((uint64_t)slots * p.slot_bytes + (uint64_t)bst * btile <= budget,
+              "conv tile does not fit shared memory (kw %d, c_out %d)", d->kw, N);
+  while (bst < 4 && (uint64_t)slots * p.slot_bytes + (uint64_t)(bst + 1) * btile <= budget) ++bst;
+  if (slots < MAX_RING && slots < ht_max + d->kh - 1 &&
+      (uint64_t)(slots + 1) * p.slot_bytes + (uint64_t)bst * btile <= budget)
+    ++slots;
+  while (bst < MAX_RING && (uint64_t)slots * p.slot_bytes + (uint64_t)(bst + 1) * btile <= budget) ++bst;
+  p.n_slots = slots; p.n_bstages = bst;
+  const size_t smem = 1024 + (size_t)slots * p.slot_bytes + (size_t)bst * btile + sizeof(FwdBarriers) + 64;
+
+  CUtensorMap tm_in[2], tm_w[2];
+  for (int b = 0; b < 2; ++b) {
+    const int s = b < n_br ? b : 0;
+    int rc = make_act_map(&tm_in[b], in[s], G, d->H, d->W, d->c_in, WT + d->kw - 1);
+    if (rc) return rc;
+    rc = make_w_map(&tm_w[b], wpk[s], d->kh * d->kw, d->c_out, d->c_in, N);
+    if (rc) return rc;
+    p.bias[b] = bias ? bias[s] : nullptr;
+    p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
+    p.out[b] = (bf16*)out[s];
+  }
+  auto kern = conv_fwd_umma_kernel<N, HT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    attr_set = true;
+  }
+  dim3 grid(p.n_wtiles * p.n_htiles * G, 1, n_br);
+  kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
+                            const float* const* bias, const void* const* mask, void* const* out, void* stream) {
+  ZNS_REQUIRE(d && in && wpk && out, "NULL argument");
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  ZNS_REQUIRE(d->c_in % 64 == 0 && d->c_in >= 64, "c_in must be a multiple of 64 (got %d)", d->c_in);
+  ZNS_REQUIRE((d->kh & 1) && (d->kw & 1) && d->kw <= 41 && d->kh <= 15, "filter %dx%d not supported", d->kh, d->kw);
+  ZNS_REQUIRE(d->batch > 0 && d->H > 0 && d->W > 0, "bad geometry");
+  ZNS_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout_p out of range");
+  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->c_out) {
+    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);
+    case 128: return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st);
+    case 256: return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st);
+    default: return zns_set_error(ZNS_ERR_INVALID, "c_out must be 64, 128 or 256 (got %d)", d->c_out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient kernel
+//   D_tap[cin][cout] = sum_p x[p + tap][cin] * dy[p][cout]
+//   A (M side) = x halo row, MN-major; M = 128 = two 64-channel chunks (LBO = chunk stride) or, for
+//   c_in == 64, two adjacent taps (LBO = one atom).  B (N side) = dy tile, MN-major, N = NB.
+// ---------------------------------------------------------------------------------------------
+struct WgParams {
+  int G, H, W;
+  int Cin, Cout;
+  int kh, kw, ph, pw;
+  int n_wtiles;
+  int fold;                 // 1: c_in == 64, M = 2 taps x 64 channels
+  int n_acc;                // accumulators (TMEM) per CTA
+  int taps_per_cta;         // n_acc * (fold ? 2 : 1)
+  int n_sgroups;            // ceil(kw / taps_per_cta)
+  int n_cin_blocks;         // fold ? 1 : Cin / 128
+  int n_cout_blocks;        // Cout / NB
+  int n_slices;             // position slices
+  int n_stages;
+  uint32_t x_chunk_bytes;   // (WT + taps_per_cta - 1) * 1024
+  uint32_t stage_bytes;
+  float* dw[2];
+};
+
+struct WgBarriers {
+  uint64_t full[MAX_RING], empty[MAX_RING], acc_full;
+  uint32_t tmem_base;
+  uint32_t any_step;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                       const __grid_constant__ CUtensorMap tm_dy0, const __grid_constant__ CUtensorMap tm_dy1,
+                       const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  WgBarriers* bars = reinterpret_cast<WgBarriers*>(smem_raw + (smem_base + p.n_stages * p.stage_bytes - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int br = blockIdx.z;
+  const CUtensorMap* tm_x = br ? &tm_x1 : &tm_x0;
+  const CUtensorMap* tm_dy = br ? &tm_dy1 : &tm_dy0;
+
+  // work item: (tap row r, s-group, cin block, cout block) x position slice
+  int t = blockIdx.x;
+  const int slice = t % p.n_slices; t /= p.n_slices;
+  const int cob = t % p.n_cout_blocks; t /= p.n_cout_blocks;
+  const int cib = t % p.n_cin_blocks; t /= p.n_cin_blocks;
+  const int sg = t % p.n_sgroups; t /= p.n_sgroups;
+  const int r = t;
+  const int s0 = sg * p.taps_per_cta;
+  const int n_xchunks = p.fold ? 1 : 2;
+  const int n_steps_total = p.G * p.H * p.n_wtiles;
+  const int q0 = (int)((long long)n_steps_total * slice / p.n_slices);
+  const int q1 = (int)((long long)n_steps_total * (slice + 1) / p.n_slices);
+  const int n_acc_eff = min(p.n_acc, (p.kw - s0 + (p.fold ? 1 : 0)) / (p.fold ? 2 : 1));
+  constexpr uint32_t kDyChunk = WT * 1024;  // 128 positions x 64 channels
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    bars->any_step = 0;
+    mbar_fence_init();
+    tma_prefetch_desc(tm_x);
+    tma_prefetch_desc(tm_dy);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t dy_off = n_xchunks * p.x_chunk_bytes;  // dy tiles follow the x chunks inside a stage
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int cnt = 0;
+      for (int q = q0; q < q1; ++q) {
+        const int wt = q % p.n_wtiles;
+        const int gh = q / p.n_wtiles;
+        const int h = gh % p.H, g = gh / p.H;
+        const int hh = h + r - p.ph;
+        if (hh < 0 || hh >= p.H) continue;
+        const int st = cnt % p.n_stages;
+        mbar_wait(smem_u32(&bars->empty[st]), ((cnt / p.n_stages) & 1) ^ 1);
+        const uint32_t base = smem_base + st * p.stage_bytes;
+        mbar_expect_tx(smem_u32(&bars->full[st]), p.stage_bytes);
+        for (int xc = 0; xc < n_xchunks; ++xc)
+          tma_load_5d(base + xc * p.x_chunk_bytes, tm_x, smem_u32(&bars->full[st]), (cib * n_xchunks + xc) * 64, 0,
+                      wt * WT - p.pw + s0, hh, g);
+        for (int j = 0; j < NB / 64; ++j)
+          tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, smem_u32(&bars->full[st]), cob * NB + j * 64, 0, wt * WT, h, g);
+        ++cnt;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, NB, 1, 1);
+      const uint32_t a_lbo = p.fold ? 1024u : p.x_chunk_bytes;
+      int cnt = 0;
+      for (int q = q0; q < q1; ++q) {
+        const int gh = q / p.n_wtiles;
+        const int h = gh % p.H;
+        const int hh = h + r - p.ph;
+        if (hh < 0 || hh >= p.H) continue;
+        const int st = cnt % p.n_stages;
+        mbar_wait(smem_u32(&bars->full[st]), (cnt / p.n_stages) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_base + st * p.stage_bytes;
+        for (int a = 0; a < n_acc_eff; ++a) {
+          const uint32_t xa = base + (uint32_t)(p.fold ? 2 * a : a) * 1024u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16(tmem + a * NB, umma_desc_sw128(xa + k * 2048, a_lbo, 1024),
+                      umma_desc_sw128(base + dy_off + k * 2048, kDyChunk, 1024), idesc, (cnt > 0) | (k > 0));
+          }
+        }
+        umma_commit(smem_u32(&bars->empty[st]));
+        ++cnt;
+      }
+      if (cnt > 0) {
+        *reinterpret_cast<volatile uint32_t*>(&bars->any_step) = 1;
+        umma_commit(smem_u32(&bars->acc_full));
+      } else {
+        mbar_arrive(smem_u32(&bars->acc_full));
+      }
+    }
+  } else {
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    tc_fence_after();
+    const bool any = *reinterpret_cast<volatile uint32_t*>(&bars->any_step) != 0;
+    if (any) {
+      const int quad = warp & 3;
+      const int m = quad * 32 + lane;
+      float* dw = p.dw[br];
+      for (int a = 0; a < n_acc_eff; ++a) {
+        int tap_s, cin;
+        if (p.fold) { tap_s = s0 + 2 * a + (m >> 6); cin = m & 63; }
+        else        { tap_s = s0 + a; cin = cib * 128 + m; }
+        const bool valid = tap_s < p.kw;
+        const size_t o0 = ((size_t)(r * p.kw + (valid ? tap_s : 0)) * p.Cout + cob * NB) * p.Cin + cin;
+#pragma unroll 1
+        for (int nb = 0; nb < NB / 32; ++nb) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + a * NB + nb * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dw + o0 + (size_t)(nb * 32 + j) * p.Cin, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int NB>
+static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy, float* const* dwpk,
+                        cudaStream_t st) {
+  const int G = zns_groups(d->batch);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.G = G; p.H = d->H; p.W = d->W; p.Cin = d->c_in; p.Cout = d->c_out;
+  p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
+  p.n_wtiles = (d->W + WT - 1) / WT;
+  p.fold = d->c_in == 64;
+  p.n_acc = 512 / NB;
+  if (p.fold) p.n_acc = std::min(p.n_acc, (d->kw + 1) / 2);
+  else p.n_acc = std::min(p.n_acc, d->kw);
+  // balance the taps over the s-groups (e.g. 17 taps, 4 accumulators -> 5 groups of 4,4,3,3,3 become 5 x <=4)
+  {
+    const int tpc = p.n_acc * (p.fold ? 2 : 1);
+    const int groups = (d->kw + tpc - 1) / tpc;
+    int per = (d->kw + groups - 1) / groups;
+    if (p.fold) per = (per + 1) & ~1;
+    p.n_acc = p.fold ? per / 2 : per;
+    p.taps_per_cta = p.n_acc * (p.fold ? 2 : 1);
+    p.n_sgroups = (d->kw + p.taps_per_cta - 1) / p.taps_per_cta;
+  }
+  p.n_cin_blocks = p.fold ? 1 : d->c_in / 128;
+  p.n_cout_blocks = d->c_out / NB;
+  p.x_chunk_bytes = (uint32_t)(WT + p.taps_per_cta - 1) * 1024u;
+  p.stage_bytes = (p.fold ? 1 : 2) * p.x_chunk_bytes + (NB / 64) * WT * 1024u;
+  const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(WgBarriers) - 64;
+  p.n_stages = std::min<int>(MAX_RING, budget / p.stage_bytes);
+  ZNS_REQUIRE(p.n_stages >= 2, "wgrad stage does not fit shared memory twice");
+  const int items = d->kh * p.n_sgroups * p.n_cin_blocks * p.n_cout_blocks;
+  const int n_steps_total = G * d->H * p.n_wtiles;
+  // position slices: fill the 148 SMs a whole number of times while keeping >= 24 steps per CTA
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 64; ++s) {
+    if (n_steps_total / s < 24 && s > 1) break;
+    const long long ctas = (long long)items * n_br * s;
+    const double waves = (double)ctas / 148.0;
+    const double eff = waves / ceil(waves);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  p.n_slices = best;
+  const size_t smem = 1024 + (size_t)p.n_stages * p.stage_bytes + sizeof(WgBarriers) + 64;
+
+  CUtensorMap tm_x[2], tm_dy[2];
+  for (int b = 0; b < 2; ++b) {
+    const int s = b < n_br ? b : 0;
+    int rc = make_act_map(&tm_x[b], x[s], G, d->H, d->W, d->c_in, WT + p.taps_per_cta - 1);
+    if (rc) return rc;
+    rc = make_act_map(&tm_dy[b], dy[s], G, d->H, d->W, d->c_out, WT);
+    if (rc) return rc;
+    p.dw[b] = dwpk[s];
+  }
+  auto kern = conv_wgrad_umma_kernel<NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    attr_set = true;
+  }
+  dim3 grid(items * p.n_slices, 1, n_br);
+  kern<<<grid, 192, smem, st>>>(tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy,
+                              float* const* dwpk, void* stream) {
+  ZNS_REQUIRE(d && x && dy && dwpk, "NULL argument");
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  ZNS_REQUIRE(d->c_in == 64 || d->c_in % 128 == 0, "wgrad needs c_in == 64 or a multiple of 128 (got %d)", d->c_in);
+  ZNS_REQUIRE(d->c_out % 64 == 0, "c_out must be a multiple of 64");
+  ZNS_REQUIRE((d->kh & 1) && (d->kw & 1) && d->kw <= 41 && d->kh <= 15, "filter %dx%d not supported", d->kh, d->kw);
+  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(x[b] && dy[b] && dwpk[b], "NULL tensor for branch %d", b);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->c_out == 64) return launch_wgrad<64>(d, n_br, x, dy, dwpk, st);
+  return launch_wgrad<128>(d, n_br, x, dy, dwpk, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// descriptor probe: one CTA, one accumulator, operands written to shared memory by plain stores
+// with the 128B swizzle applied by hand, so that the UMMA descriptor conventions are tested
+// independently of TMA.   variant 0: A, B K-major ([128][k], [n][k]);  variant 1: A, B MN-major
+// ([k][128], [k][n]).  D fp32 [128][n].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(int variant, const bf16* __restrict__ A, const bf16* __restrict__ B, float* __restrict__ D, int n, int k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int kblocks = k / 64;
+  const uint32_t a_bytes = variant == 0 ? (uint32_t)kblocks * 128 * 128 : (uint32_t)2 * k * 128;
+  uint8_t* sa = sm;
+  uint8_t* sb = sm + a_bytes;
+  if (variant == 0) {
+    // K-major: tile per 64-wide k block: [rows][128 B], atoms of 8 rows
+    for (int i = threadIdx.x; i < 128 * k; i += 128) {
+      const int row = i / k, kk = i % k;
+      const int kb = kk / 64, kl = kk % 64;
+      const uint32_t off = kb * (128 * 128) + (row / 8) * 1024 + (row % 8) * 128 + (((kl / 8) ^ (row % 8)) * 16) + (kl % 8) * 2;
+      *reinterpret_cast<bf16*>(sa + off) = A[i];
+    }
+    for (int i = threadIdx.x; i < n * k; i += 128) {
+      const int row = i / k, kk = i % k;
+      const int kb = kk / 64, kl = kk % 64;
+      const uint32_t off = kb * (n * 128) + (row / 8) * 1024 + (row % 8) * 128 + (((kl / 8) ^ (row % 8)) * 16) + (kl % 8) * 2;
+      *reinterpret_cast<bf16*>(sb + off) = B[i];
+    }
+  } else {
+    // MN-major: per 64-wide mn group: [k rows][128 B]; atoms of 8 k rows; groups at LBO = k*128
+    for (int i = threadIdx.x; i < 128 * k; i += 128) {
+      const int kk = i / 128, mm = i % 128;
+      const int mg = mm / 64, ml = mm % 64;
+      const uint32_t off = mg * (k * 128) + (kk / 8) * 1024 + (kk % 8) * 128 + (((ml / 8) ^ (kk % 8)) * 16) + (ml % 8) * 2;
+      *reinterpret_cast<bf16*>(sa + off) = A[i];
+    }
+    for (int i = threadIdx.x; i < n * k; i += 128) {
+      const int kk = i / n, nn = i % n;
+      const int ng = nn / 64, nl = nn % 64;
+      const uint32_t off = ng * (k * 128) + (kk / 8) * 1024 + (kk % 8) * 128 + (((nl / 8) ^ (kk % 8)) * 16) + (nl % 8) * 2;
+      *reinterpret_cast<bf16*>(sb + off) = B[i];
+    }
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tmem_slot), 256); tmem_relinquish(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA) reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, n, variant, variant);
+    const uint32_t sa_u = base, sb_u = base + a_bytes;
+    for (int ks = 0; ks < k / 16; ++ks) {
+      uint64_t da, db;
+      if (variant == 0) {
+        const int kb = ks / 4, kq = ks % 4;
+        da = umma_desc_sw128(sa_u + kb * (128 * 128) + kq * 32, 16, 1024);
+        db = umma_desc_sw128(sb_u + kb * (n * 128) + kq * 32, 16, 1024);
+      } else {
+        da = umma_desc_sw128(sa_u + ks * 2048, (uint32_t)k * 128, 1024);
+        db = umma_desc_sw128(sb_u + ks * 2048, (uint32_t)k * 128, 1024);
+      }
+      umma_bf16(tmem, da, db, idesc, ks > 0);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int nb = 0; nb < n / 32; ++nb) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + nb * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) D[(size_t)(warp * 32 + lane) * n + nb * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+extern "C" int zns_dbg_umma_probe(int variant, const void* a, const void* b, float* d, int n, int k, void* stream) {
+  ZNS_REQUIRE(a && b && d, "NULL argument");
+  ZNS_REQUIRE((variant == 0 || variant == 1) && n % 64 == 0 && n >= 64 && n <= 256 && k % 64 == 0 && k >= 64 && k <= 256,
+              "probe supports n,k in multiples of 64 up to 256");
+  const size_t smem = 1024 + (size_t)(128 + n) * k * 2 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    attr_set = true;
+  }
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const bf16*)a, (const bf16*)b, d, n, k);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}

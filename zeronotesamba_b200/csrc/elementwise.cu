@@ -1,0 +1,582 @@
+// Bandwidth-bound pieces of the encoder path on the act layout (bf16 [G][H][W][8][C]):
+// cv1 (C_in = 1) forward / weight gradient, frequency max-pool + ReLU + dropout and its backward,
+// the fc1 + sigmoid head and its backward, layout converters, weight packing, bias gradients,
+// Down_CNN merge and the flat Adam update.
+// Reference semantics: /root/reference/zeroNoteSamba/models/models.py:16-74,85-103,139-150 and
+// torch.optim.Adam as constructed at /root/reference/zeroNoteSamba/pretext.py:202.
+#include <algorithm>
+
+#include "common.cuh"
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  // keep iff hash >= threshold  (P[drop] = p)
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv1 forward: x fp32 [B][H][W] -> act [G][H][W][8][64], 3x11 taps, pad (1,5), ReLU, dropout
+// ---------------------------------------------------------------------------------------------
+#define C1_KH 3
+#define C1_KW 11
+#define C1_TAPS 33
+#define C1_CO 64
+
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, long long clip_stride,
+                                                        const float* __restrict__ weight,
+                                                        const float* __restrict__ bias, bf16* __restrict__ out,
+                                                        int B, int H, int W, float drop_p, uint32_t seed,
+                                                        const uint32_t* __restrict__ seed_dev, uint32_t stream_id) {
+  __shared__ __align__(16) float ws[C1_TAPS][C1_CO];
+  if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
+  __shared__ float bs[C1_CO];
+  for (int i = threadIdx.x; i < C1_TAPS * C1_CO; i += 256) {
+    int c = i / C1_TAPS, t = i - c * C1_TAPS;  // weight is [64][1][3][11]
+    ws[t][c] = weight[i];
+  }
+  if (threadIdx.x < C1_CO) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int b8 = threadIdx.x & 7, wl = threadIdx.x >> 3;
+  const int g = blockIdx.z, h = blockIdx.y, w = blockIdx.x * 32 + wl;
+  if (w >= W) return;
+  const int b = g * 8 + b8;
+  uint4* dst = reinterpret_cast<uint4*>(out + zns_act_index(g, h, w, b8, 0, H, W, C1_CO));
+  if (b >= B) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float xin[C1_TAPS];
+  const float* xb = x + (size_t)b * clip_stride;
+#pragma unroll
+  for (int r = 0; r < C1_KH; ++r)
+#pragma unroll
+    for (int s = 0; s < C1_KW; ++s) {
+      int hh = h + r - 1, ww = w + s - 5;
+      xin[r * C1_KW + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * W + ww) : 0.f;
+    }
+  const uint32_t thr = dropout_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const size_t e0 = zns_act_index(g, h, w, b8, 0, H, W, C1_CO);
+#pragma unroll
+  for (int cb = 0; cb < C1_CO; cb += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bs[cb + i];
+#pragma unroll
+    for (int t = 0; t < C1_TAPS; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[t][cb]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[t][cb + 4]);
+      const float v = xin[t];
+      acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
+      acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+      acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
+      acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaxf(acc[i], 0.f);
+      if (drop_p > 0.f) v = (zns_hash32(e0 + cb + i, seed, stream_id) >= thr) ? v * keep_scale : 0.f;
+      acc[i] = v;
+    }
+    dst[cb / 8] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                             pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, const float* weight, const float* bias,
+                             void* out_act, int batch, int H, int W, float drop_p, uint32_t seed,
+                             const uint32_t* seed_dev, uint32_t rng_stream, void* stream) {
+  ZNS_REQUIRE(x && weight && bias && out_act, "NULL argument");
+  ZNS_REQUIRE(batch > 0 && H > 0 && W > 0 && drop_p >= 0.f && drop_p < 1.f, "bad conv1 geometry");
+  dim3 grid((W + 31) / 32, H, zns_groups(batch));
+  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, clip_stride, weight, bias, (bf16*)out_act, batch, H, W,
+                                                           drop_p, seed, seed_dev, rng_stream);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv1 weight / bias gradient
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+                                                          long long clip_stride, float* __restrict__ dw,
+                                                          float* __restrict__ db, int B, int H, int W) {
+  __shared__ float xs[C1_KH][8][32 + C1_KW - 1];
+  const int g = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < C1_KH * 8 * 42; i += 256) {
+    int r = i / (8 * 42), rem = i - r * 8 * 42;
+    int b8 = rem / 42, j = rem - b8 * 42;
+    int hh = h + r - 1, ww = w0 + j - 5, b = g * 8 + b8;
+    xs[r][b8][j] = (b < B && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (size_t)b * clip_stride + (size_t)hh * W + ww)
+                                                                    : 0.f;
+  }
+  __syncthreads();
+  const int n = threadIdx.x & 63, q = threadIdx.x >> 6;
+  float acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+  float accb = 0.f;
+  const int wmax = min(32, W - w0);
+  for (int wl = 0; wl < wmax; ++wl) {
+#pragma unroll
+    for (int b8 = 0; b8 < 8; ++b8) {
+      const float d = __bfloat162float(dy[zns_act_index(g, h, w0 + wl, b8, n, H, W, C1_CO)]);
+      accb += d;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int t = q + 4 * j;
+        if (t < C1_TAPS) {
+          const int r = t / C1_KW, s = t - r * C1_KW;
+          acc[j] = fmaf(d, xs[r][b8][wl + s], acc[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int t = q + 4 * j;
+    if (t < C1_TAPS) atomicAdd(dw + n * C1_TAPS + t, acc[j]);
+  }
+  if (q == 0) atomicAdd(db + n, accb);
+}
+
+extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long clip_stride, float* dw, float* db, int batch,
+                               int H, int W, void* stream) {
+  ZNS_REQUIRE(dy_act && x && dw && db, "NULL argument");
+  dim3 grid((W + 31) / 32, H, zns_groups(batch));
+  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, x, clip_stride, dw, db, batch, H, W);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d((pool,1)) -> ReLU -> Dropout, and its backward (first arg-max routing)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 v = __bfloat1622float2(p[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+__global__ void pool_fwd_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, size_t n_vec, size_t row_vec,
+                                int Hp, int pool, float drop_p, uint32_t seed, const uint32_t* __restrict__ seed_dev,
+                                uint32_t stream_id) {
+  if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
+  // vec index = ((g*Hp + hp) * row_vec + r), row_vec = W*8*C/8
+  const uint32_t thr = dropout_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t ghp = i / row_vec, r = i - ghp * row_vec;
+    const size_t g = ghp / Hp, hp = ghp - g * Hp;
+    const uint4* src = y + ((g * Hp + hp) * pool) * row_vec + r;
+    float m[8], v[8];
+    unpack8(__ldg(src), m);
+    for (int k = 1; k < pool; ++k) {
+      unpack8(__ldg(src + (size_t)k * row_vec), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaxf(m[j], 0.f);
+      if (drop_p > 0.f) t = (zns_hash32(i * 8 + j, seed, stream_id) >= thr) ? t * keep_scale : 0.f;
+      m[j] = t;
+    }
+    out[i] = pack8(m);
+  }
+}
+
+extern "C" int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, int W, int C, int pool, float drop_p,
+                            uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, void* stream) {
+  ZNS_REQUIRE(y_act && out_act, "NULL argument");
+  ZNS_REQUIRE(pool >= 1 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
+  const int G = zns_groups(batch), Hp = H / pool;
+  const size_t row_vec = (size_t)W * 8 * C / 8;
+  const size_t n_vec = (size_t)G * Hp * row_vec;
+  const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+  pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_act, (uint4*)out_act, n_vec, row_vec, Hp,
+                                                            pool, drop_p, seed, seed_dev, rng_stream);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+__global__ void pool_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dp, uint4* __restrict__ dy,
+                                size_t n_vec, size_t row_vec, int Hp, int pool) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t ghp = i / row_vec, r = i - ghp * row_vec;
+    const size_t g = ghp / Hp, hp = ghp - g * Hp;
+    const size_t base = ((g * Hp + hp) * pool) * row_vec + r;
+    float m[8], v[8], d[8];
+    int arg[8];
+    unpack8(__ldg(y + base), m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) arg[j] = 0;
+    for (int k = 1; k < pool; ++k) {
+      unpack8(__ldg(y + base + (size_t)k * row_vec), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > m[j]) { m[j] = v[j]; arg[j] = k; }
+    }
+    unpack8(__ldg(dp + i), d);
+    for (int k = 0; k < pool; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (arg[j] == k) ? d[j] : 0.f;
+      dy[base + (size_t)k * row_vec] = pack8(v);
+    }
+  }
+}
+
+extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_act, int batch, int H, int W, int C,
+                            int pool, void* stream) {
+  ZNS_REQUIRE(y_act && dpool_act && dy_act, "NULL argument");
+  ZNS_REQUIRE(pool >= 1 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
+  const int G = zns_groups(batch), Hp = H / pool;
+  const size_t row_vec = (size_t)W * 8 * C / 8;
+  const size_t n_vec = (size_t)G * Hp * row_vec;
+  const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+  pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_act, (const uint4*)dpool_act, (uint4*)dy_act,
+                                                            n_vec, row_vec, Hp, pool);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// head: Conv1d(128, 1, k=1) + Sigmoid + flatten, forward and backward
+// block = 256 threads = 32 positions x 8 lanes; a lane owns 16 channels
+// ---------------------------------------------------------------------------------------------
+#define HD_C 128
+
+__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ emb, int B,
+                                                       int T, int n_pos) {
+  const int part = threadIdx.x & 7;
+  const int pos = blockIdx.x * 32 + (threadIdx.x >> 3);
+  float acc = 0.f;
+  if (pos < n_pos) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)pos * HD_C + part * 16);
+    float v[8];
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      unpack8(__ldg(src + hlf), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(v[j], __ldg(w + part * 16 + hlf * 8 + j), acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (part == 0 && pos < n_pos) {
+    // pos = (g*T + t)*8 + b8
+    const int b8 = pos & 7, gt = pos >> 3;
+    const int g = gt / T, t = gt - g * T;
+    const int b = g * 8 + b8;
+    if (b < B) emb[(size_t)b * T + t] = 1.f / (1.f + expf(-(acc + __ldg(bias))));
+  }
+}
+
+extern "C" int zns_head_fwd(const void* x_act, const float* w128, const float* bias1, float* emb, int batch, int T,
+                            void* stream) {
+  ZNS_REQUIRE(x_act && w128 && bias1 && emb, "NULL argument");
+  const int n_pos = zns_groups(batch) * T * 8;
+  head_fwd_kernel<<<(n_pos + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_act, w128, bias1, emb, batch, T,
+                                                                        n_pos);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ emb,
+                                                       const float* __restrict__ d_emb, const float* __restrict__ w,
+                                                       float* __restrict__ dw, float* __restrict__ dbias,
+                                                       bf16* __restrict__ dy, int B, int T, int n_pos, float out_scale) {
+  __shared__ float sdw[HD_C];
+  __shared__ float sdb;
+  if (threadIdx.x < HD_C) sdw[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) sdb = 0.f;
+  __syncthreads();
+  const int part = threadIdx.x & 7;
+  const int pos = blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (pos < n_pos) {
+    const int b8 = pos & 7, gt = pos >> 3;
+    const int g = gt / T, t = gt - g * T;
+    const int b = g * 8 + b8;
+    float dz = 0.f;
+    if (b < B) {
+      const float e = emb[(size_t)b * T + t];
+      dz = d_emb[(size_t)b * T + t] * e * (1.f - e);
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)pos * HD_C + part * 16);
+    uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)pos * HD_C + part * 16);
+    float v[8], o[8];
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      unpack8(__ldg(src + hlf), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = part * 16 + hlf * 8 + j;
+        o[j] = v[j] > 0.f ? dz * __ldg(w + c) * out_scale : 0.f;
+        if (dz != 0.f) atomicAdd(&sdw[c], dz * v[j]);
+      }
+      dst[hlf] = pack8(o);
+    }
+    if (part == 0 && dz != 0.f) atomicAdd(&sdb, dz);
+  }
+  __syncthreads();
+  if (threadIdx.x < HD_C) atomicAdd(dw + threadIdx.x, sdw[threadIdx.x]);
+  if (threadIdx.x == 0) atomicAdd(dbias, sdb);
+}
+
+extern "C" int zns_head_bwd(const void* x_act, const float* emb, const float* d_emb, const float* w128, float* dw128,
+                            float* dbias1, void* dy_act, int batch, int T, float out_scale, void* stream) {
+  ZNS_REQUIRE(x_act && emb && d_emb && w128 && dw128 && dbias1 && dy_act, "NULL argument");
+  const int n_pos = zns_groups(batch) * T * 8;
+  head_bwd_kernel<<<(n_pos + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_act, emb, d_emb, w128, dw128,
+                                                                        dbias1, (bf16*)dy_act, batch, T, n_pos, out_scale);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Down_CNN merge
+// ---------------------------------------------------------------------------------------------
+__global__ void merge_kernel(const float* a, const float* b, float* out, long long n, int mode) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = mode == 0 ? fmaxf(a[i], b[i]) : (a[i] + b[i]) / 2.f;
+}
+
+extern "C" int zns_merge(const float* a, const float* b, float* out, long long n, int mode, void* stream) {
+  ZNS_REQUIRE(a && b && out && n >= 0, "NULL argument");
+  ZNS_REQUIRE(mode == 0 || mode == 1, "merge mode must be 0 (max) or 1 (mean)");
+  if (n == 0) return ZNS_OK;
+  merge_kernel<<<(int)std::min<long long>((n + 255) / 256, 1184), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, mode);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout converters
+// ---------------------------------------------------------------------------------------------
+__global__ void act_from_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ act, int B, int C, int H, int W,
+                                     size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int c = (int)(r % C); r /= C;
+    const int b8 = (int)(r % 8); r /= 8;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int b = (int)r * 8 + b8;
+    act[i] = __float2bfloat16(b < B ? x[(((size_t)b * C + c) * H + h) * W + w] : 0.f);
+  }
+}
+__global__ void act_to_nchw_kernel(const bf16* __restrict__ act, float* __restrict__ x, int B, int C, int H, int W,
+                                   size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C); r /= C;
+    const int b = (int)r;
+    x[i] = __bfloat162float(act[zns_act_index(b / 8, h, w, b % 8, c, H, W, C)]);
+  }
+}
+
+extern "C" int zns_act_from_nchw(const float* x, void* act, int batch, int C, int H, int W, void* stream) {
+  ZNS_REQUIRE(x && act, "NULL argument");
+  const size_t total = (size_t)zns_groups(batch) * H * W * 8 * C;
+  act_from_nchw_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      x, (bf16*)act, batch, C, H, W, total);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+extern "C" int zns_act_to_nchw(const void* act, float* x, int batch, int C, int H, int W, void* stream) {
+  ZNS_REQUIRE(x && act, "NULL argument");
+  const size_t total = (size_t)batch * C * H * W;
+  act_to_nchw_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)act, x, batch, C, H, W, total);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 [co][ci][tap] -> bf16 wf [tap][co][ci] and wd [ntaps-1-tap][ci][co]
+// (each through a shared-memory tile so that both sides stay coalesced)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_wf_kernel(const float* __restrict__ w, bf16* __restrict__ wf, int c_out,
+                                                      int c_in, int ntaps) {
+  extern __shared__ float tile[];  // [64 ci][ntaps]
+  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  const float* src = w + ((size_t)co * c_in + ci0) * ntaps;
+  const int n = 64 * ntaps;
+  for (int i = threadIdx.x; i < n; i += 256) tile[i] = __ldg(src + i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int t = i / 64, ci = i - t * 64;
+    wf[((size_t)t * c_out + co) * c_in + ci0 + ci] = __float2bfloat16(tile[ci * ntaps + t]);
+  }
+}
+__global__ void __launch_bounds__(256) pack_wd_kernel(const float* __restrict__ w, bf16* __restrict__ wd, int c_out,
+                                                      int c_in, int ntaps) {
+  extern __shared__ float tile[];  // [64 co][ntaps]
+  const int ci = blockIdx.y, co0 = blockIdx.x * 64;
+  const int n = 64 * ntaps;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int co = i / ntaps, t = i - co * ntaps;
+    tile[i] = __ldg(w + ((size_t)(co0 + co) * c_in + ci) * ntaps + t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int t = i / 64, co = i - t * 64;
+    wd[((size_t)(ntaps - 1 - t) * c_in + ci) * c_out + co0 + co] = __float2bfloat16(tile[co * ntaps + t]);
+  }
+}
+
+extern "C" int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, void* stream) {
+  ZNS_REQUIRE(w, "NULL weight");
+  ZNS_REQUIRE(c_out % 64 == 0 && c_in % 64 == 0, "channels must be multiples of 64 (got %d, %d)", c_out, c_in);
+  const int ntaps = kh * kw;
+  const size_t smem = (size_t)64 * ntaps * sizeof(float);
+  ZNS_REQUIRE(smem <= 48 * 1024, "filter with %d taps not supported", ntaps);
+  if (wf) {
+    pack_wf_kernel<<<dim3(c_in / 64, c_out), 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wf, c_out, c_in, ntaps);
+    ZNS_CHECK_LAUNCH();
+  }
+  if (wd) {
+    pack_wd_kernel<<<dim3(c_out / 64, c_in), 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wd, c_out, c_in, ntaps);
+    ZNS_CHECK_LAUNCH();
+  }
+  return ZNS_OK;
+}
+
+__global__ void __launch_bounds__(256) unpack_grads_kernel(const float* __restrict__ gpk, float* __restrict__ g,
+                                                           int c_out, int c_in, int ntaps, float scale, int accumulate) {
+  extern __shared__ float tile[];  // [64 ci][ntaps]
+  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  const int n = 64 * ntaps;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int t = i / 64, ci = i - t * 64;
+    tile[ci * ntaps + t] = __ldg(gpk + ((size_t)t * c_out + co) * c_in + ci0 + ci);
+  }
+  __syncthreads();
+  float* dst = g + ((size_t)co * c_in + ci0) * ntaps;
+  for (int i = threadIdx.x; i < n; i += 256) dst[i] = (accumulate ? dst[i] : 0.f) + scale * tile[i];
+}
+
+extern "C" int zns_unpack_grads(const float* gpk, int c_out, int c_in, int kh, int kw, float scale, int accumulate,
+                                float* g, void* stream) {
+  ZNS_REQUIRE(gpk && g, "NULL argument");
+  ZNS_REQUIRE(c_out >= 1 && c_in % 64 == 0, "c_in must be a multiple of 64");
+  const int ntaps = kh * kw;
+  const size_t smem = (size_t)64 * ntaps * sizeof(float);
+  ZNS_REQUIRE(smem <= 48 * 1024, "filter with %d taps not supported", ntaps);
+  unpack_grads_kernel<<<dim3(c_in / 64, c_out), 256, smem, (cudaStream_t)stream>>>(gpk, g, c_out, c_in, ntaps, scale,
+                                                                                   accumulate);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias gradient: db[c] += sum_p dy[p][c]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dy, size_t n_pos, int C,
+                                                        float* __restrict__ db) {
+  __shared__ float red[256];
+  const int c = threadIdx.x % C;            // C in {64,128,256}
+  const int lane_row = threadIdx.x / C;
+  const int rows_per_it = 256 / C;
+  float acc = 0.f;
+  for (size_t p = (size_t)blockIdx.x * rows_per_it + lane_row; p < n_pos; p += (size_t)gridDim.x * rows_per_it)
+    acc += __bfloat162float(dy[p * C + c]);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int r = 0; r < rows_per_it; ++r) s += red[r * C + threadIdx.x];
+    atomicAdd(db + threadIdx.x, s);
+  }
+}
+
+extern "C" int zns_bias_grad(const void* dy_act, int batch, int H, int W, int C, float* db, void* stream) {
+  ZNS_REQUIRE(dy_act && db, "NULL argument");
+  ZNS_REQUIRE(C == 64 || C == 128 || C == 256, "bias_grad supports C in {64,128,256}");
+  const size_t n_pos = (size_t)zns_groups(batch) * H * W * 8;
+  const int blocks = (int)std::min<size_t>((n_pos * C + 65535) / 65536, 148 * 4);
+  bias_grad_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, n_pos, C, db);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), flat fp32 buffers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                   float b1, float b2, float eps, float inv_bc1, float inv_sqrt_bc2,
+                                                   const uint32_t* __restrict__ step_dev, float gscale) {
+  if (step_dev) {
+    const double st = (double)__ldg(step_dev);
+    inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, st)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, st)));
+  }
+  const long long n4 = n / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define ZNS_ADAM1(f)                                                        \
+  {                                                                         \
+    const float gr = gg.f * gscale;                                         \
+    mm.f = b1 * mm.f + (1.f - b1) * gr;                                     \
+    vv.f = b2 * vv.f + (1.f - b2) * gr * gr;                                \
+    const float denom = sqrtf(vv.f) * inv_sqrt_bc2 + eps;                   \
+    pp.f -= (lr * inv_bc1) * (mm.f / denom);                                \
+  }
+    ZNS_ADAM1(x) ZNS_ADAM1(y) ZNS_ADAM1(z) ZNS_ADAM1(w)
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gr = g[i] * gscale;
+    const float mm = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mm;
+    v[i] = vv;
+    p[i] -= (lr * inv_bc1) * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+  }
+}
+
+extern "C" int zns_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                             float beta2, float eps, int step, const uint32_t* step_dev, float grad_scale, void* stream) {
+  ZNS_REQUIRE(p && g && m && v, "NULL argument");
+  ZNS_REQUIRE((step >= 1 || step_dev) && n >= 0, "Adam step counts from 1");
+  if (step < 1) step = 1;
+  ZNS_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "Adam buffers must be 16-byte aligned");
+  if (n == 0) return ZNS_OK;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, 148 * 8);
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)(1.0 / bc1),
+                                                        (float)(1.0 / sqrt(bc2)), step_dev, grad_scale);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+__global__ void counter_add_kernel(uint32_t* ctr, uint32_t inc) { *ctr += inc; }
+
+extern "C" int zns_counter_add(uint32_t* ctr, uint32_t inc, void* stream) {
+  ZNS_REQUIRE(ctr, "NULL counter");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, inc);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}

@@ -1,0 +1,517 @@
+// VQT / CQT front-end: host-side basis construction, stride-2 decimation chain and the
+// per-octave framed filterbank with the |.|, 1/sqrt(len), log(. + 1e-9) epilogue fused.
+//
+// Replaces librosa.vqt / librosa.cqt (0.8.1) + resampy 0.4.2 as the reference calls them at
+// /root/reference/zeroNoteSamba/processing/input_rep.py:27-34,42-49 and the log-magnitude of
+// input_rep.py:36-37,51-52.  The frequency-domain sparse basis librosa builds per call is turned
+// once, on the host in float64, into per-octave time-domain kernels g_i[k][n]; on the device the
+// response is C_i[k,t] = sum_n g_i[k,n] * ypad_i[t*hop_i + n] (reflect padding by n_fft_i/2 at
+// the octave's own rate), which is the same contraction as basis_i . rfft(frame).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <complex>
+#include <vector>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (shared by every translation unit)
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_zns_err[512] = "";
+
+int zns_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_zns_err, sizeof(g_zns_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+extern "C" const char* zns_last_error(void) { return g_zns_err; }
+extern "C" int zns_version(void) { return ZNS_VERSION; }
+
+extern "C" int zns_device_check(void) {
+  int dev = 0;
+  ZNS_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  ZNS_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return zns_set_error(ZNS_ERR_CUDA, "device %s is sm_%d%d; libzns_sm100 needs sm_100a (B200)", prop.name, prop.major,
+                         prop.minor);
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: resampy "kaiser_fast" taps and the librosa constant-Q basis
+// ---------------------------------------------------------------------------------------------
+static double bessel_i0(double x) {
+  // power series, converges quickly for |x| < 20
+  double sum = 1.0, term = 1.0, q = x * x / 4.0;
+  for (int k = 1; k < 200; ++k) {
+    term *= q / ((double)k * (double)k);
+    sum += term;
+    if (term < 1e-18 * sum) break;
+  }
+  return sum;
+}
+
+static const double kKaiserFastBeta = 8.555504641634386;
+static const double kRolloff = 0.85;
+static const double kPi = 3.14159265358979323846;
+
+extern "C" int zns_vqt_decimator_taps_host(double* taps32) {
+  // interp_win[j*256] of sinc_window(num_zeros=16, precision=9, rolloff=0.85, kaiser(beta)), times
+  // sample_ratio 0.5.  Table position j*256 of 8193 (512 entries per zero crossing) <-> x = j/2
+  // zero crossings, taper argument j/32 of the half Kaiser window of length 2*8192+1.
+  ZNS_REQUIRE(taps32 != nullptr, "taps32 is NULL");
+  const double i0b = bessel_i0(kKaiserFastBeta);
+  for (int j = 0; j < 32; ++j) {
+    double x = (double)j / 2.0;
+    double s = (j == 0) ? 1.0 : sin(kPi * kRolloff * x) / (kPi * kRolloff * x);
+    double r = (double)j / 32.0;
+    double taper = bessel_i0(kKaiserFastBeta * sqrt(1.0 - r * r)) / i0b;
+    taps32[j] = 0.5 * kRolloff * s * taper;
+  }
+  return ZNS_OK;
+}
+
+static double vqt_gamma(double gamma, int bpo) {
+  double alpha = pow(2.0, 1.0 / bpo) - 1.0;
+  return gamma < 0 ? 24.7 * alpha / 0.108 : gamma;
+}
+
+// librosa.filters.constant_q_lengths at rate `sr` for `n` bins starting at fmin
+static void cq_lengths(double sr, double fmin, int n, int bpo, double gamma, std::vector<double>& out) {
+  double alpha = pow(2.0, 1.0 / bpo) - 1.0;
+  double q = 1.0 / alpha;
+  out.resize(n);
+  for (int k = 0; k < n; ++k) {
+    double freq = fmin * pow(2.0, (double)k / bpo);
+    out[k] = q * sr / (freq + gamma / alpha);
+  }
+}
+
+extern "C" int zns_vqt_basis_host(int sr, int n_bins, int bpo, double fmin, double gamma_in, int octave, float* re,
+                                  float* im, int* n_fft_out) {
+  ZNS_REQUIRE(re && im && n_fft_out, "NULL output");
+  ZNS_REQUIRE(bpo > 0 && n_bins > 0 && n_bins % bpo == 0, "n_bins must be a multiple of bins_per_octave");
+  const int n_oct = n_bins / bpo;
+  ZNS_REQUIRE(octave >= 0 && octave < n_oct, "octave out of range");
+  const double gamma = vqt_gamma(gamma_in, bpo);
+  const double alpha = pow(2.0, 1.0 / bpo) - 1.0;
+  const double fmin_t = fmin * pow(2.0, (double)(n_bins - bpo) / bpo);
+  const double my_sr = (double)sr / pow(2.0, octave);
+  const double fmin_i = fmin_t * pow(2.0, -(double)octave);
+  std::vector<double> lengths;
+  cq_lengths(my_sr, fmin_i, bpo, bpo, gamma, lengths);
+  double max_len = *std::max_element(lengths.begin(), lengths.end());
+  const int n_fft = (int)pow(2.0, ceil(log2(max_len)));
+  ZNS_REQUIRE(n_fft >= 2 && n_fft <= 1024, "n_fft %d out of supported range", n_fft);
+  *n_fft_out = n_fft;
+  const int n_bins_f = n_fft / 2 + 1;
+  (void)alpha;
+
+  std::vector<std::complex<double>> spec(n_bins_f);
+  std::vector<double> mags(n_bins_f), sorted(n_bins_f);
+  for (int k = 0; k < bpo; ++k) {
+    const double ilen = lengths[k];
+    const double freq = fmin_i * pow(2.0, (double)k / bpo);
+    const long start = (long)floor(-ilen / 2.0);
+    const long stop = (long)floor(ilen / 2.0);
+    const int L = (int)(stop - start);
+    std::vector<std::complex<double>> sig(L);
+    double l1 = 0.0;
+    for (int j = 0; j < L; ++j) {
+      double n = (double)(start + j);
+      double phase = n * 2.0 * kPi * freq / my_sr;
+      double win = 0.5 - 0.5 * cos(2.0 * kPi * (double)j / (double)L);  // periodic hann
+      sig[j] = std::complex<double>(cos(phase) * win, sin(phase) * win);
+      l1 += std::abs(sig[j]);
+    }
+    // pad_center into n_fft, cast to complex64, then *= len/n_fft (product in double, stored float)
+    std::vector<std::complex<double>> padded(n_fft, std::complex<double>(0.0, 0.0));
+    const int lpad = (n_fft - L) / 2;
+    const double scale = ilen / (double)n_fft;
+    for (int j = 0; j < L; ++j) {
+      std::complex<double> v = sig[j] / l1;
+      float fr = (float)v.real(), fi = (float)v.imag();
+      float gr = (float)((double)fr * scale), gi = (float)((double)fi * scale);
+      padded[lpad + j] = std::complex<double>((double)gr, (double)gi);
+    }
+    // DFT (double), bins 0..n_fft/2
+    double norm = 0.0;
+    for (int b = 0; b < n_bins_f; ++b) {
+      std::complex<double> acc(0.0, 0.0);
+      for (int n = 0; n < n_fft; ++n) {
+        int idx = (int)(((long)b * n) % n_fft);
+        double ang = -2.0 * kPi * (double)idx / (double)n_fft;
+        acc += padded[n] * std::complex<double>(cos(ang), sin(ang));
+      }
+      spec[b] = acc;
+      mags[b] = std::abs(acc);
+      norm += mags[b];
+    }
+    // sparsify_rows(quantile = 0.01)
+    sorted = mags;
+    std::sort(sorted.begin(), sorted.end());
+    double cum = 0.0, thr = sorted[0];
+    for (int b = 0; b < n_bins_f; ++b) {
+      cum += sorted[b] / norm;
+      if (!(cum < 0.01)) {
+        thr = sorted[b];
+        break;
+      }
+    }
+    const float oct_scale = (float)sqrt(pow(2.0, octave));
+    std::vector<std::complex<double>> kept(n_bins_f);
+    for (int b = 0; b < n_bins_f; ++b) {
+      if (mags[b] >= thr) {
+        float fr = (float)spec[b].real(), fi = (float)spec[b].imag();  // complex64 storage
+        kept[b] = std::complex<double>((double)(fr * oct_scale), (double)(fi * oct_scale));
+      } else {
+        kept[b] = std::complex<double>(0.0, 0.0);
+      }
+    }
+    // back to the time domain: g[n] = sum_b kept[b] e^{-2 pi i b n / n_fft}
+    for (int n = 0; n < n_fft; ++n) {
+      std::complex<double> acc(0.0, 0.0);
+      for (int b = 0; b < n_bins_f; ++b) {
+        int idx = (int)(((long)b * n) % n_fft);
+        double ang = -2.0 * kPi * (double)idx / (double)n_fft;
+        acc += kept[b] * std::complex<double>(cos(ang), sin(ang));
+      }
+      re[k * n_fft + n] = (float)acc.real();
+      im[k * n_fft + n] = (float)acc.imag();
+    }
+  }
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+#define ZNS_VQT_MAX_OCT 10
+
+struct zns_vqt_plan {
+  int sr, hop, n_bins, bpo, n_oct;
+  int max_batch, max_samples;
+  int n_fft[ZNS_VQT_MAX_OCT];
+  float* d_coef[ZNS_VQT_MAX_OCT];  // [n_fft][2][bpo/2][2] interleaved (see filterbank kernel)
+  float* d_inv_sqrt_len;           // [n_bins]
+  float* d_scratch[ZNS_VQT_MAX_OCT];  // decimated signals, octave >= 1
+  float* d_stage_in;               // for *_host: [max_batch][max_samples]
+  float* d_stage_out;              // [max_batch][n_bins][frames]
+};
+
+__constant__ float c_dec_taps[32];
+static bool g_taps_uploaded = false;
+
+extern "C" int zns_vqt_num_frames(int n_samples, int hop) { return 1 + n_samples / hop; }
+
+extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double fmin, double gamma_in, int max_batch,
+                                   int max_samples, zns_vqt_plan** out) {
+  ZNS_REQUIRE(out != nullptr, "plan out pointer is NULL");
+  ZNS_REQUIRE(bpo > 0 && bpo % 2 == 0 && n_bins % bpo == 0, "n_bins %% bins_per_octave != 0 or odd bins_per_octave");
+  const int n_oct = n_bins / bpo;
+  ZNS_REQUIRE(n_oct >= 1 && n_oct <= ZNS_VQT_MAX_OCT, "unsupported octave count %d", n_oct);
+  ZNS_REQUIRE(max_batch > 0 && max_samples > 0, "max_batch/max_samples must be positive");
+  int twos = 0;
+  for (int h = hop; h > 0 && (h & 1) == 0; h >>= 1) ++twos;
+  ZNS_REQUIRE(twos >= n_oct - 1, "hop_length must be a positive integer multiple of 2^%d for %d-octave CQT/VQT",
+              n_oct - 1, n_oct);
+  // resampler choice / early downsampling exactly as librosa decides them: only the
+  // kaiser_fast, no-early-downsample configuration (the reference's 16 kHz call) is built.
+  const double gamma = vqt_gamma(gamma_in, bpo);
+  const double alpha = pow(2.0, 1.0 / bpo) - 1.0;
+  const double q = 1.0 / alpha;
+  const double fmax_t = fmin * pow(2.0, (double)(n_bins - 1) / bpo);
+  const double cutoff = fmax_t * (1 + 0.5 * 1.50018310546875 / q) + 0.5 * gamma;
+  const double nyq = sr / 2.0;
+  ZNS_REQUIRE(cutoff < 0.85 * nyq, "filter cutoff %.1f Hz needs kaiser_best resampling: not supported", cutoff);
+  int c1 = std::max(0, (int)ceil(log2(0.85 * nyq / cutoff)) - 1 - 1);
+  int c2 = std::max(0, twos - n_oct + 1);
+  ZNS_REQUIRE(std::min(c1, c2) == 0, "configuration needs early downsampling: not supported");
+  ZNS_REQUIRE(fmax_t * (1 + 0.5 * 1.50018310546875 / q) <= nyq, "filter pass-band lies beyond Nyquist");
+
+  int rc = zns_device_check();
+  if (rc) return rc;
+
+  zns_vqt_plan* p = (zns_vqt_plan*)calloc(1, sizeof(zns_vqt_plan));
+  if (!p) return zns_set_error(ZNS_ERR_ALLOC, "out of host memory");
+  p->sr = sr; p->hop = hop; p->n_bins = n_bins; p->bpo = bpo; p->n_oct = n_oct;
+  p->max_batch = max_batch; p->max_samples = max_samples;
+
+  if (!g_taps_uploaded) {
+    double t64[32];
+    float t32[32];
+    zns_vqt_decimator_taps_host(t64);
+    for (int i = 0; i < 32; ++i) t32[i] = (float)t64[i];
+    ZNS_CHECK_CUDA(cudaMemcpyToSymbol(c_dec_taps, t32, sizeof(t32)));
+    g_taps_uploaded = true;
+  }
+
+  std::vector<float> re(bpo * 1024), im(bpo * 1024), coef;
+  for (int i = 0; i < n_oct; ++i) {
+    int nf = 0;
+    rc = zns_vqt_basis_host(sr, n_bins, bpo, fmin, gamma_in, i, re.data(), im.data(), &nf);
+    if (rc) { free(p); return rc; }
+    p->n_fft[i] = nf;
+    // device layout: coef[n][half][kk][2], kk < bpo/2, filter k = half*(bpo/2) + kk
+    const int hb = bpo / 2;
+    coef.assign((size_t)nf * bpo * 2, 0.f);
+    for (int n = 0; n < nf; ++n)
+      for (int k = 0; k < bpo; ++k) {
+        size_t o = (((size_t)n * 2 + k / hb) * hb + k % hb) * 2;
+        coef[o] = re[k * nf + n];
+        coef[o + 1] = im[k * nf + n];
+      }
+    ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef[i], coef.size() * sizeof(float)));
+    ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef[i], coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  std::vector<double> lens;
+  cq_lengths((double)sr, fmin, n_bins, bpo, gamma, lens);
+  std::vector<float> inv(n_bins);
+  for (int k = 0; k < n_bins; ++k) inv[k] = (float)(1.0 / sqrt(lens[k]));
+  ZNS_CHECK_CUDA(cudaMalloc(&p->d_inv_sqrt_len, n_bins * sizeof(float)));
+  ZNS_CHECK_CUDA(cudaMemcpy(p->d_inv_sqrt_len, inv.data(), n_bins * sizeof(float), cudaMemcpyHostToDevice));
+
+  size_t n = (size_t)max_samples;
+  for (int i = 1; i < n_oct; ++i) {
+    n = (n + 1) / 2;
+    ZNS_CHECK_CUDA(cudaMalloc(&p->d_scratch[i], (size_t)max_batch * n * sizeof(float)));
+  }
+  *out = p;
+  return ZNS_OK;
+}
+
+extern "C" int zns_vqt_plan_destroy(zns_vqt_plan* p) {
+  if (!p) return ZNS_OK;
+  for (int i = 0; i < ZNS_VQT_MAX_OCT; ++i) {
+    if (p->d_coef[i]) cudaFree(p->d_coef[i]);
+    if (p->d_scratch[i]) cudaFree(p->d_scratch[i]);
+  }
+  if (p->d_inv_sqrt_len) cudaFree(p->d_inv_sqrt_len);
+  if (p->d_stage_in) cudaFree(p->d_stage_in);
+  if (p->d_stage_out) cudaFree(p->d_stage_out);
+  free(p);
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: stride-2 decimation  y[t] = (sum_{|j|<=31} h[|j|] x[2t+j]) / sqrt(0.5), zero extended
+// (resampy._resample_loop at ratio 1/2 + librosa fix_length + scale)
+// ---------------------------------------------------------------------------------------------
+#define DEC_TILE 1024  // outputs per block
+#define DEC_THREADS 256
+
+__global__ void __launch_bounds__(DEC_THREADS) vqt_decimate_kernel(const float* __restrict__ x, int n_in,
+                                                                   float* __restrict__ y, int n_out_valid, int n_out) {
+  // even / odd phases in separate arrays so that lanes read consecutive words
+  __shared__ float xe[DEC_TILE + 32];
+  __shared__ float xo[DEC_TILE + 32];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * DEC_TILE;
+  const float* xb = x + (size_t)b * n_in;
+  // sample index range needed: 2*t0 - 31 .. 2*(t0+DEC_TILE-1) + 31  ->  pairs m = t0-16 .. t0+DEC_TILE+15
+  for (int i = threadIdx.x; i < DEC_TILE + 32; i += DEC_THREADS) {
+    int m = t0 - 16 + i;
+    long s0 = 2L * m, s1 = 2L * m + 1;
+    xe[i] = (s0 >= 0 && s0 < n_in) ? __ldg(xb + s0) : 0.f;
+    xo[i] = (s1 >= 0 && s1 < n_in) ? __ldg(xb + s1) : 0.f;
+  }
+  __syncthreads();
+  float* yb = y + (size_t)b * n_out;
+#pragma unroll
+  for (int r = 0; r < DEC_TILE / DEC_THREADS; ++r) {
+    int tl = threadIdx.x + r * DEC_THREADS;
+    int t = t0 + tl;
+    if (t >= n_out) continue;
+    float acc = 0.f;
+    if (t < n_out_valid) {
+      // x[2t + j]: j even -> xe[tl + 16 + j/2]; j odd -> xo[tl + 16 + (j-1)/2]
+      // left wing first (j = 0, -1, ..., -31), then right wing (j = 1..31), as the reference sums
+      const int c = tl + 16;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = (i & 1) ? xo[c - (i + 1) / 2] : xe[c - i / 2];
+        acc = fmaf(c_dec_taps[i], v, acc);
+      }
+#pragma unroll
+      for (int k = 1; k < 32; ++k) {
+        float v = (k & 1) ? xo[c + (k - 1) / 2] : xe[c + k / 2];
+        acc = fmaf(c_dec_taps[k], v, acc);
+      }
+      acc = acc / 0.70710678118654752f;
+    }
+    yb[t] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: framed filterbank of one octave + log-magnitude epilogue
+// block = 128 frames x 2 filter halves; thread (t, half) accumulates bpo/2 complex responses.
+// ---------------------------------------------------------------------------------------------
+#define FB_FRAMES 128
+#define FB_THREADS 256
+
+__device__ __forceinline__ int reflect_index(long q, int n) {
+  // numpy.pad(mode="reflect"): ... x2 x1 | x0 x1 ... x(n-1) | x(n-2) ...
+  if (n == 1) return 0;
+  const long period = 2L * (n - 1);
+  q %= period;
+  if (q < 0) q += period;
+  return (int)(q < n ? q : period - q);
+}
+
+template <int HB>  // filters per thread (bins_per_octave / 2)
+__global__ void __launch_bounds__(FB_THREADS)
+vqt_filterbank_kernel(const float* __restrict__ y, int n_sig, long long sig_stride, const float* __restrict__ coef,
+                      int n_fft, int hop, const float* __restrict__ inv_sqrt_len, int bin0, int n_bins, int n_frames,
+                      float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int ld = n_fft + 1;
+  float* frames = smem;                     // [FB_FRAMES][n_fft + 1]
+  float* cf = smem + FB_FRAMES * ld;        // [n_fft][2][HB][2]
+  const int b = blockIdx.z;
+  const int f0 = blockIdx.x * FB_FRAMES;
+  const float* yb = y + (size_t)b * sig_stride;
+
+  for (int i = threadIdx.x; i < n_fft * HB * 4; i += FB_THREADS) cf[i] = __ldg(coef + i);
+  const int half_fft = n_fft / 2;
+  for (int i = threadIdx.x; i < FB_FRAMES * n_fft; i += FB_THREADS) {
+    int t = i / n_fft, n = i - t * n_fft;
+    int f = f0 + t;
+    float v = 0.f;
+    if (f < n_frames) {
+      long q = (long)f * hop + n - half_fft;
+      v = __ldg(yb + reflect_index(q, n_sig));
+    }
+    frames[t * ld + n] = v;
+  }
+  __syncthreads();
+
+  const int t = threadIdx.x % FB_FRAMES;
+  const int half = threadIdx.x / FB_FRAMES;
+  float acc[HB * 2];
+#pragma unroll
+  for (int i = 0; i < HB * 2; ++i) acc[i] = 0.f;
+  const float* fr = frames + t * ld;
+  const float* c0 = cf + half * HB * 2;
+#pragma unroll 4
+  for (int n = 0; n < n_fft; ++n) {
+    const float s = fr[n];
+    const float* cn = c0 + n * HB * 4;
+#pragma unroll
+    for (int i = 0; i < HB * 2; ++i) acc[i] = fmaf(cn[i], s, acc[i]);
+  }
+  const int f = f0 + t;
+  if (f < n_frames) {
+#pragma unroll
+    for (int kk = 0; kk < HB; ++kk) {
+      const int bin = bin0 + half * HB + kk;
+      float re = acc[2 * kk], im = acc[2 * kk + 1];
+      float mag = sqrtf(re * re + im * im) * __ldg(inv_sqrt_len + bin);
+      out[((size_t)b * n_bins + bin) * n_frames + f] = logf(mag + 1e-9f);
+    }
+  }
+}
+
+static int fb_launch(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
+                     int n_frames, float* out, cudaStream_t st) {
+  const int nf = p->n_fft[oct];
+  const int hb = p->bpo / 2;
+  size_t smem = ((size_t)FB_FRAMES * (nf + 1) + (size_t)nf * hb * 4) * sizeof(float);
+  dim3 grid((n_frames + FB_FRAMES - 1) / FB_FRAMES, 1, batch);
+  const int bin0 = p->n_bins - p->bpo * (oct + 1);
+  if (hb == 6) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_filterbank_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+      attr_set = true;
+    }
+    ZNS_REQUIRE(smem <= 200 * 1024, "filterbank tile does not fit shared memory (n_fft %d)", nf);
+    vqt_filterbank_kernel<6><<<grid, FB_THREADS, smem, st>>>(sig, n_sig, stride, p->d_coef[oct], nf, hop_i,
+                                                              p->d_inv_sqrt_len, bin0, p->n_bins, n_frames, out);
+  } else {
+    return zns_set_error(ZNS_ERR_INVALID, "bins_per_octave %d not built (only 12)", p->bpo);
+  }
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+extern "C" int zns_vqt_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, float* out, void* stream) {
+  ZNS_REQUIRE(p && y && out, "NULL argument");
+  ZNS_REQUIRE(batch >= 1 && batch <= p->max_batch, "batch %d exceeds plan max_batch %d", batch, p->max_batch);
+  ZNS_REQUIRE(n_samples <= p->max_samples, "n_samples %d exceeds plan max_samples %d", n_samples, p->max_samples);
+  ZNS_REQUIRE((n_samples >> (p->n_oct - 1)) >= 2, "signal too short: %d samples for %d octaves", n_samples, p->n_oct);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_frames = zns_vqt_num_frames(n_samples, p->hop);
+  const float* cur = y;
+  int n_cur = n_samples;
+  int hop_i = p->hop;
+  for (int i = 0; i < p->n_oct; ++i) {
+    if (i > 0) {
+      const int n_valid = n_cur / 2;        // resampy output length
+      const int n_next = (n_cur + 1) / 2;   // librosa fix_length
+      dim3 grid((n_next + DEC_TILE - 1) / DEC_TILE, batch);
+      vqt_decimate_kernel<<<grid, DEC_THREADS, 0, st>>>(cur, n_cur, p->d_scratch[i], n_valid, n_next);
+      ZNS_CHECK_LAUNCH();
+      cur = p->d_scratch[i];
+      n_cur = n_next;
+      hop_i >>= 1;
+    }
+    int rc = fb_launch(p, i, cur, n_cur, (long long)n_cur, hop_i, batch, n_frames, out, st);
+    if (rc) return rc;
+  }
+  return ZNS_OK;
+}
+
+extern "C" int zns_vqt_forward_host(zns_vqt_plan* p, const float* y_host, int batch, int n_samples, float* out_host,
+                                    void* stream) {
+  ZNS_REQUIRE(p && y_host && out_host, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p->d_stage_in) {
+    ZNS_CHECK_CUDA(cudaMalloc(&p->d_stage_in, (size_t)p->max_batch * p->max_samples * sizeof(float)));
+    size_t fr = (size_t)zns_vqt_num_frames(p->max_samples, p->hop);
+    ZNS_CHECK_CUDA(cudaMalloc(&p->d_stage_out, (size_t)p->max_batch * p->n_bins * fr * sizeof(float)));
+  }
+  ZNS_REQUIRE(batch >= 1 && batch <= p->max_batch && n_samples <= p->max_samples, "batch/n_samples exceed plan");
+  const size_t in_bytes = (size_t)batch * n_samples * sizeof(float);
+  const size_t out_bytes = (size_t)batch * p->n_bins * zns_vqt_num_frames(n_samples, p->hop) * sizeof(float);
+  ZNS_CHECK_CUDA(cudaMemcpyAsync(p->d_stage_in, y_host, in_bytes, cudaMemcpyHostToDevice, st));
+  int rc = zns_vqt_forward(p, p->d_stage_in, batch, n_samples, p->d_stage_out, stream);
+  if (rc) return rc;
+  ZNS_CHECK_CUDA(cudaMemcpyAsync(out_host, p->d_stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  ZNS_CHECK_CUDA(cudaStreamSynchronize(st));
+  return ZNS_OK;
+}
+
+// Crop sampler (pretext.py:308-318): out[i][c][k][t] = vqt[c][k][starts[i] + t]
+__global__ void crop_gather_kernel(const float* __restrict__ vqt, int rows, int frames, const int32_t* __restrict__ starts,
+                                   int T, float* __restrict__ out) {
+  const int i = blockIdx.y;
+  int s = starts[i];
+  s = max(0, min(s, frames - T));  // the reference samples starts in [0, frames - T) (pretext.py:312)
+  const size_t total = (size_t)rows * T;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(e / T), t = (int)(e - (size_t)r * T);
+    out[(size_t)i * total + e] = __ldg(vqt + (size_t)r * frames + s + t);
+  }
+}
+
+extern "C" int zns_crop_gather(const float* vqt, int channels, int bins, int frames, const int32_t* starts, int n_crops,
+                               int T, float* out, void* stream) {
+  ZNS_REQUIRE(vqt && starts && out, "NULL argument");
+  ZNS_REQUIRE(T >= 1 && T <= frames && n_crops >= 1, "bad crop geometry");
+  const int rows = channels * bins;
+  dim3 grid((unsigned)std::min<size_t>(((size_t)rows * T + 255) / 256, 1024), n_crops);
+  crop_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(vqt, rows, frames, starts, T, out);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
