@@ -254,7 +254,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
             float x = __uint_as_float(v[j]);
             if (bias) x += __ldg(bias + nb * 32 + j);
             if (p.relu) x = fmaxf(x, 0.f);
-            if (do_drop) x = (zns_hash32(e0 + nb * 32 + j, seed, p.stream_id) >= thr) ? x * keep : 0.f;
+            if (do_drop) x = (zns_hash32(e0 + nb * 32 + j, seed, p.stream_id + br) >= thr) ? x * keep : 0.f;
             f[j] = x;
           }
           if (mask) {
@@ -693,7 +693,7 @@ extern "C" int zns_dbg_umma_probe(int variant, const void* a, const void* b, flo
   const size_t smem = 1024 + (size_t)(128 + n) * k * 2 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const bf16*)a, (const bf16*)b, d, n, k);

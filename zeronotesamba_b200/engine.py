@@ -1,0 +1,211 @@
+"""Encoder engine: owns the act-layout workspaces of up to two DS_CNN branches and sequences the
+libzns_sm100 kernels for forward and backward.
+
+Mirrors ``_CNN.forward`` + ``DS_CNN.forward`` (/root/reference/zeroNoteSamba/models/models.py:32-74,
+93-103) layer by layer; both branches of ``Pretext_CNN`` (models.py:114-124) go through every
+tensor-core launch together (``n_br = 2``).  Host code only issues launches on the current CUDA
+stream: no synchronisation, no allocation after construction, so a whole step can be captured in a
+CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+# (name, c_out, c_in, kh, kw, pool)  -- models.py:16-28
+CONV_SPECS = (
+    ("cv1", 64, 1, 3, 11, 1),
+    ("cv2", 64, 64, 7, 13, 3),
+    ("cv3", 128, 64, 5, 15, 1),
+    ("cv4", 128, 128, 9, 17, 4),
+    ("cv5", 256, 128, 3, 19, 1),
+    ("cv6", 256, 256, 5, 21, 8),
+    ("cv7", 128, 256, 1, 23, 1),
+    ("cv8", 128, 128, 1, 25, 1),
+)
+N_BINS = 96
+
+
+def branch_param_names() -> List[str]:
+    """Parameter names of one DS_CNN in registration (= state_dict) order."""
+    names = []
+    for name, *_ in CONV_SPECS:
+        names += [f"pretrained.{name}.weight", f"pretrained.{name}.bias"]
+    return names + ["fc1.weight", "fc1.bias"]
+
+
+class EncoderEngine:
+    """Workspaces + launch sequences for ``n_br`` encoders on a fixed (batch, T) geometry."""
+
+    def __init__(self, batch: int, T: int, n_br: int, device: torch.device, seed: int = 0):
+        assert n_br in (1, 2)
+        L.check(L.lib().zns_device_check())
+        self.B, self.T, self.n_br, self.device = batch, T, n_br, device
+        self.G = (batch + 7) // 8
+        self.seed = seed
+        bf = torch.bfloat16
+        G = self.G
+
+        def act(H, Cc):
+            return [torch.zeros(G, H, T, 8, Cc, dtype=bf, device=device) for _ in range(n_br)]
+
+        # forward activations (kept for backward)
+        self.x1 = act(96, 64)      # dropout(relu(cv1))
+        self.y2 = act(96, 64)      # cv2 pre-pool
+        self.p2 = act(32, 64)      # dropout(relu(pool3(y2)))
+        self.x3 = act(32, 128)
+        self.y4 = act(32, 128)
+        self.p4 = act(8, 128)
+        self.x5 = act(8, 256)
+        self.y6 = act(8, 256)
+        self.p6 = act(1, 256)
+        self.x7 = act(1, 128)
+        self.x8 = act(1, 128)
+        self.emb = [torch.zeros(batch, T, device=device) for _ in range(n_br)]
+        # packed weights / gradients for cv2..cv8
+        self.wf: Dict[str, List[torch.Tensor]] = {}
+        self.wd: Dict[str, List[torch.Tensor]] = {}
+        self.gp: Dict[str, List[torch.Tensor]] = {}
+        for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
+            self.wf[name] = [torch.zeros(kh * kw, co, ci, dtype=bf, device=device) for _ in range(n_br)]
+            self.wd[name] = [torch.zeros(kh * kw, ci, co, dtype=bf, device=device) for _ in range(n_br)]
+        self._grad_ws_ready = False
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=device)  # dropout seed word / Adam step
+        self._x_in: List[Optional[torch.Tensor]] = [None] * n_br
+        self._x_stride = 0
+        self._train = False
+        self._p = 0.0
+
+    # -- workspaces needed only for backward -------------------------------------------------------
+    def _ensure_grad_ws(self):
+        if self._grad_ws_ready:
+            return
+        bf, dev, G, T = torch.bfloat16, self.device, self.G, self.T
+        n = G * 96 * T * 8 * 64
+        self.ga = [torch.zeros(n, dtype=bf, device=dev) for _ in range(self.n_br)]
+        self.gb = [torch.zeros(n, dtype=bf, device=dev) for _ in range(self.n_br)]
+        total = sum(co * ci * kh * kw for _, co, ci, kh, kw, _ in CONV_SPECS[1:])
+        self.gp_flat = [torch.zeros(total, device=dev) for _ in range(self.n_br)]
+        for br in range(self.n_br):
+            off = 0
+            for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
+                self.gp.setdefault(name, []).append(self.gp_flat[br][off:off + co * ci * kh * kw])
+                off += co * ci * kh * kw
+        self._grad_ws_ready = True
+
+    # -- weights -----------------------------------------------------------------------------------
+    def pack_weights(self, params: Sequence[Dict[str, torch.Tensor]], need_dgrad: bool):
+        """fp32 state_dict-layout weights -> bf16 packs (forward, and flipped/transposed for dgrad)."""
+        lib, st = L.lib(), L.current_stream()
+        for br in range(self.n_br):
+            for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
+                w = params[br][f"pretrained.{name}.weight"]
+                L.check(lib.zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(self.wf[name][br]),
+                                             L.ptr(self.wd[name][br]) if (need_dgrad and name != "cv1") else None, st))
+
+    # -- forward -----------------------------------------------------------------------------------
+    def _conv(self, name, H, ins, outs, params, relu, drop, layer_id):
+        _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
+        d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw, relu=relu, dropout_p=self._p if drop else 0.0,
+                        seed=self.seed, rng_stream=layer_id * 2, seed_dev=self.step_ctr if drop and self._p > 0 else None)
+        bias = [params[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]
+        L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(ins), L.ptr_array(self.wf[name]),
+                                     L.ptr_array(bias), None, L.ptr_array(outs), L.current_stream()))
+
+    def _pool(self, H, Cc, pool, ys, outs, layer_id):
+        lib, st = L.lib(), L.current_stream()
+        for br in range(self.n_br):
+            L.check(lib.zns_pool_fwd(L.ptr(ys[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, self._p, self.seed,
+                                     L.ptr(self.step_ctr) if self._p > 0 else None, layer_id * 2 + br, st))
+
+    def forward(self, xs: Sequence[torch.Tensor], x_clip_stride: int, params: Sequence[Dict[str, torch.Tensor]],
+                train: bool, dropout_p: float = 0.1) -> List[torch.Tensor]:
+        """xs[br]: fp32 CUDA tensor whose clip b starts ``b * x_clip_stride`` elements after its
+        data pointer and holds a contiguous (96, T) VQT.  Returns [emb (B, T)] per branch."""
+        lib, st = L.lib(), L.current_stream()
+        self._train, self._p = train, (dropout_p if train else 0.0)
+        self._x_in, self._x_stride = list(xs), x_clip_stride
+        for br in range(self.n_br):
+            p = params[br]
+            L.check(lib.zns_conv1_fwd(L.ptr(xs[br]), x_clip_stride, L.ptr(p["pretrained.cv1.weight"]),
+                                      L.ptr(p["pretrained.cv1.bias"]), L.ptr(self.x1[br]), self.B, N_BINS, self.T,
+                                      self._p, self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, 100 + br, st))
+        self._conv("cv2", 96, self.x1, self.y2, params, relu=0, drop=False, layer_id=2)
+        self._pool(96, 64, 3, self.y2, self.p2, 2)
+        self._conv("cv3", 32, self.p2, self.x3, params, relu=1, drop=True, layer_id=3)
+        self._conv("cv4", 32, self.x3, self.y4, params, relu=0, drop=False, layer_id=4)
+        self._pool(32, 128, 4, self.y4, self.p4, 4)
+        self._conv("cv5", 8, self.p4, self.x5, params, relu=1, drop=True, layer_id=5)
+        self._conv("cv6", 8, self.x5, self.y6, params, relu=0, drop=False, layer_id=6)
+        self._pool(8, 256, 8, self.y6, self.p6, 6)
+        self._conv("cv7", 1, self.p6, self.x7, params, relu=1, drop=True, layer_id=7)
+        self._conv("cv8", 1, self.x7, self.x8, params, relu=1, drop=True, layer_id=8)
+        for br in range(self.n_br):
+            p = params[br]
+            L.check(lib.zns_head_fwd(L.ptr(self.x8[br]), L.ptr(p["fc1.weight"]), L.ptr(p["fc1.bias"]), L.ptr(self.emb[br]),
+                                     self.B, self.T, st))
+        return self.emb
+
+    # -- backward ----------------------------------------------------------------------------------
+    def _wgrad(self, name, H, xs, dys, grads):
+        _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
+        lib, st = L.lib(), L.current_stream()
+        d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw)
+        L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xs), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
+        for br in range(self.n_br):
+            L.check(lib.zns_bias_grad(L.ptr(dys[br]), self.B, H, self.T, co, L.ptr(grads[br][f"pretrained.{name}.bias"]), st))
+
+    def _dgrad(self, name, H, dys, masks, outs):
+        _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
+        scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
+        d = L.conv_desc(self.B, H, self.T, co, ci, kh, kw, relu=0, out_scale=scale)
+        L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(dys), L.ptr_array(self.wd[name]), None,
+                                     L.ptr_array(masks), L.ptr_array(outs), L.current_stream()))
+
+    def _unpool(self, H, Cc, pool, ys, dps, outs):
+        lib, st = L.lib(), L.current_stream()
+        for br in range(self.n_br):
+            L.check(lib.zns_pool_bwd(L.ptr(ys[br]), L.ptr(dps[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, st))
+
+    def backward(self, d_embs: Sequence[torch.Tensor], params: Sequence[Dict[str, torch.Tensor]],
+                 grads: Sequence[Dict[str, torch.Tensor]]) -> None:
+        """Accumulate (+=) parameter gradients into ``grads[br][name]`` (fp32, state_dict layout;
+        they must be zeroed by the caller).  ``d_embs[br]``: (B, T) fp32 gradient of the loss."""
+        self._ensure_grad_ws()
+        lib, st = L.lib(), L.current_stream()
+        scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
+        ga, gb = self.ga, self.gb
+        for br in range(self.n_br):
+            self.gp_flat[br].zero_()
+            p, g = params[br], grads[br]
+            L.check(lib.zns_head_bwd(L.ptr(self.x8[br]), L.ptr(self.emb[br]), L.ptr(d_embs[br]), L.ptr(p["fc1.weight"]),
+                                     L.ptr(g["fc1.weight"]), L.ptr(g["fc1.bias"]), L.ptr(ga[br]), self.B, self.T, scale, st))
+        self._wgrad("cv8", 1, self.x7, ga, grads)
+        self._dgrad("cv8", 1, ga, self.x7, gb)          # dy7
+        self._wgrad("cv7", 1, self.p6, gb, grads)
+        self._dgrad("cv7", 1, gb, self.p6, ga)          # dp6 (masked)
+        self._unpool(8, 256, 8, self.y6, ga, gb)        # dy6
+        self._wgrad("cv6", 8, self.x5, gb, grads)
+        self._dgrad("cv6", 8, gb, self.x5, ga)          # dy5
+        self._wgrad("cv5", 8, self.p4, ga, grads)
+        self._dgrad("cv5", 8, ga, self.p4, gb)          # dp4
+        self._unpool(32, 128, 4, self.y4, gb, ga)       # dy4
+        self._wgrad("cv4", 32, self.x3, ga, grads)
+        self._dgrad("cv4", 32, ga, self.x3, gb)         # dy3
+        self._wgrad("cv3", 32, self.p2, gb, grads)
+        self._dgrad("cv3", 32, gb, self.p2, ga)         # dp2
+        self._unpool(96, 64, 3, self.y2, ga, gb)        # dy2
+        self._wgrad("cv2", 96, self.x1, gb, grads)
+        self._dgrad("cv2", 96, gb, self.x1, ga)         # dy1
+        for br in range(self.n_br):
+            g = grads[br]
+            L.check(lib.zns_conv1_wgrad(L.ptr(ga[br]), L.ptr(self._x_in[br]), self._x_stride,
+                                        L.ptr(g["pretrained.cv1.weight"]), L.ptr(g["pretrained.cv1.bias"]), self.B, N_BINS,
+                                        self.T, st))
+            for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
+                L.check(lib.zns_unpack_grads(L.ptr(self.gp[name][br]), co, ci, kh, kw, 1.0, 1,
+                                             L.ptr(g[f"pretrained.{name}.weight"]), st))
