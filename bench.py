@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- the ZeroNS hot path on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W              # this repo (libzns_sm100 kernels)
+  torchrun ... bench.py --gpus N --steps K --warmup W        # one rank per GPU, NCCL
+  python bench.py --impl reference --steps K --warmup W      # the reference's CPU path (oracle port)
+
+One "step" = the in-loop pretext path of one source clip per GPU: two synthetic 10 s, 16 kHz stems
+(anchor = other, positive = drums) -> VQT (2, 96, 626) -> 16 crops of 313 frames at distinct random
+starts -> two-branch Down_CNN encoders forward + backward -> NT-Xent (tau 0.25) -> gradient
+all-reduce (N > 1) -> Adam (lr 1e-6).  A "clip" is one anchor/positive crop pair.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pretext_clips_per_sec"
+UNIT = "clips/s"
+BATCH = 16
+T_CROP = 313
+CLIP_SECONDS = 10.0
+N_SAMPLES = 160000
+FWD_GFLOP_PER_SAMPLE_BRANCH = 129.59  # SURVEY.md appendix B (cv1..cv8 + fc1, zero-padding MACs included)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port; the Python reference
+# and librosa cannot travel to the GPU box), all host threads, bounded sample per step
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(sd, crops: int, clip_idx: int):
+    """VQT (oracle restatement of librosa 0.8.1) of one stem pair + `crops` crops through the fp32
+    torch-CPU restatement of Pretext_CNN / NTXent / Adam.  Returns seconds."""
+    import torch
+    from oracle import encoder_oracle as eo
+    from oracle import vqt_oracle as vo
+    from zeronotesamba_b200 import synth
+    t0 = time.perf_counter()
+    drums, other = synth.stem_pair(clip_idx, CLIP_SECONDS)
+    pair = np.stack([vo.vqt_ref_f32(other), vo.vqt_ref_f32(drums)])
+    t_vqt = time.perf_counter() - t0
+    starts = random.Random(clip_idx).sample(range(0, 313), crops)
+    batch = torch.from_numpy(np.stack([pair[:, :, s:s + T_CROP] for s in starts]))
+    eo.pretext_step(sd, batch, batch_len=crops, temperature=0.25, lr=1e-6)
+    return time.perf_counter() - t0, t_vqt
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import encoder_oracle as eo
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd = eo.he_normal_state_dict(7)
+    # size the per-step sample so that the whole run stays within ~3 minutes
+    t_probe, _ = cpu_reference_step(sd, 2, 0)
+    per_crop = max(t_probe / 2.0, 1e-3)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    crops = int(max(2, min(BATCH, budget // per_crop)))
+    for i in range(args.warmup):
+        cpu_reference_step(sd, crops, 100 + i)
+    t0 = time.perf_counter()
+    t_vqt = 0.0
+    for i in range(args.steps):
+        _, tv = cpu_reference_step(sd, crops, 200 + i)
+        t_vqt += tv
+    dt = time.perf_counter() - t0
+    value = crops * args.steps / dt
+    sample = (f"{crops} of {BATCH} crops per step (T={T_CROP}) through oracle/encoder_oracle.pretext_step (fp32 torch CPU, "
+              f"dropout 0) + oracle/vqt_oracle.vqt_ref_f32 of one 10 s stem pair per step; {args.steps} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg4 at N=1: end-to-end pretext step (VQT of one 10 s stem pair + crops + two-branch "
+                               "encoders fwd/bwd + NT-Xent + Adam)", "global_batch": crops, "crop_frames": T_CROP,
+                   "note": "reference = oracle port of the reference's CPU path (Python reference + librosa cannot travel)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "vqt_audio_sec_per_sec": 2 * CLIP_SECONDS * args.steps / max(t_vqt, 1e-9)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from zeronotesamba_b200 import _lib as L
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.models.checkpoint import he_normal_state_dict
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import PretextTrainer
+    from zeronotesamba_b200.processing.input_rep import VQTPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.check(L.lib().zns_device_check())
+    peaks = _peaks()
+
+    model = Pretext_CNN().to(dev)
+    model.load_state_dict(he_normal_state_dict(7))
+    model.train()
+    tr = PretextTrainer(model, batch_len=BATCH, temperature=0.25, lr=1e-6, crop_frames=T_CROP, use_graph=True,
+                        seed=1000 + rank)
+
+    # synthetic inputs: a pool of distinct source clips per rank (seed offset = rank)
+    pool = 8
+    host_audio = []
+    for i in range(pool):
+        drums, other = synth.stem_pair(10_000 * rank + i, CLIP_SECONDS)
+        host_audio.append((torch.from_numpy(other).pin_memory(), torch.from_numpy(drums).pin_memory()))
+    dev_audio = [(a.to(dev), p.to(dev)) for a, p in host_audio]
+    rng = random.Random(rank)
+    starts_host = [torch.tensor(rng.sample(range(0, 313), BATCH), dtype=torch.int32).pin_memory() for _ in range(pool)]
+    starts_dev = [s.to(dev) for s in starts_host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        tr.step_from_audio(dev_audio[i % pool][0], dev_audio[i % pool][1], starts_dev[i % pool])
+    barrier()
+    counts0 = dict(L.CALL_COUNTS)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        res = tr.step_from_audio(dev_audio[i % pool][0], dev_audio[i % pool][1], starts_dev[i % pool])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    final = res.cpu().numpy().tolist()
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = BATCH * world * args.steps / (ms * 1e-3)
+
+    # kernels per step: the graphs replay what one eager pass launches
+    graph_calls = dict(tr_calls_per_step(tr, L))
+    launches_per_step = L.kernel_launches(graph_calls)
+
+    # ---- end to end: pinned host audio in, loss out, every step -----------------------------------
+    res_host = torch.zeros(3).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        a, p = host_audio[i % pool]
+        r = tr.step_from_audio(a, p, starts_host[i % pool])
+        res_host.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tmax.item())
+    e2e_value = BATCH * world * args.steps / (ms_e2e * 1e-3)
+    h2d = 2 * N_SAMPLES * 4 + BATCH * 4
+    d2h = 3 * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cfg4 (cfg3 + in-loop VQT at N=1): end-to-end pretext step per GPU = VQT of one 10 s 16 kHz "
+                               "stem pair -> 16 crops x 313 frames -> two-branch Down_CNN encoders fwd+bwd -> NT-Xent "
+                               "(tau 0.25) -> grad all-reduce -> Adam (lr 1e-6), dropout 0.1",
+                   "global_batch": BATCH * world, "crop_frames": T_CROP, "parallelism": f"dp{world}",
+                   "checkpoint": "synthetic He-normal (seed 7), reference state_dict layout",
+                   "l2": "per-step working set (activations + gradients + weights) ~1.5 GB per GPU >> 126 MB L2; "
+                         "8 distinct source clips rotate"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "audio_sec_per_sec": 2 * CLIP_SECONDS * world * args.steps / (ms * 1e-3),
+        "source_clips_per_sec": value / BATCH,
+        "loss_last_step": final,
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        if not args.no_extras:
+            # ---- roofline of the tensor-core kernels: CUDA events around every launch, eager mode -
+            line.update(kernel_roofline(tr, dev_audio, starts_dev, peaks, args, ms / args.steps))
+            # ---- cfg2: batched VQT of 256 x 30 s clips --------------------------------------------
+            line.update(vqt_cfg2(dev, peaks))
+        # ---- CPU baseline on this box's host cores (bounded sample) -------------------------------
+        if world == 1 and not args.no_cpu_baseline and not args.no_extras:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def tr_calls_per_step(tr, L):
+    """C-ABI calls one training step issues (counted on one eager pass; the CUDA graphs replay them)."""
+    import torch
+    snap = (tr.flat_p.clone(), tr.flat_m.clone(), tr.flat_v.clone(), tr.engine.step_ctr.clone())
+    before = dict(L.CALL_COUNTS)
+    tr._front()
+    tr._forward_backward()
+    tr._optimizer()
+    torch.cuda.synchronize()
+    after = dict(L.CALL_COUNTS)
+    tr.flat_p.copy_(snap[0]); tr.flat_m.copy_(snap[1]); tr.flat_v.copy_(snap[2]); tr.engine.step_ctr.copy_(snap[3])
+    return {k: after[k] - before.get(k, 0) for k in after if after[k] != before.get(k, 0)}
+
+
+def kernel_roofline(tr, dev_audio, starts_dev, peaks, args, ms_step):
+    import torch
+    eng = tr.engine
+    snap = (tr.flat_p.clone(), tr.flat_m.clone(), tr.flat_v.clone(), tr.engine.step_ctr.clone())
+    tr._front()
+    for _ in range(2):
+        tr._forward_backward()
+    torch.cuda.synchronize()
+    eng.timers = []
+    n_rep = max(3, min(args.steps, 10))
+    for i in range(n_rep):
+        tr._audio_buf[0].copy_(dev_audio[i % len(dev_audio)][0]); tr._audio_buf[1].copy_(dev_audio[i % len(dev_audio)][1])
+        tr._starts_buf.copy_(starts_dev[i % len(starts_dev)])
+        tr._front()
+        tr._forward_backward()
+    torch.cuda.synchronize()
+    fam = {}
+    for tag, flops, a, b in eng.timers:
+        f = fam.setdefault(tag, [0.0, 0.0, 0])
+        f[0] += flops; f[1] += a.elapsed_time(b) * 1e-3; f[2] += 1
+    eng.timers = None
+    tr.flat_p.copy_(snap[0]); tr.flat_m.copy_(snap[1]); tr.flat_v.copy_(snap[2]); tr.engine.step_ctr.copy_(snap[3])
+    peak = peaks["bf16_tflops_sustained"]
+    kernels = {}
+    tot_f = tot_t = 0.0
+    for tag, (fl, t, n) in fam.items():
+        kernels[tag] = {"tflops": fl / t / 1e12, "frac": fl / t / 1e12 / peak, "launches_per_step": n / n_rep,
+                        "ms_per_step": 1e3 * t / n_rep, "share_of_step": (1e3 * t / n_rep) / ms_step}
+        tot_f += fl; tot_t += t
+    dom = max(fam.items(), key=lambda kv: kv[1][1])[0]
+    return {
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": kernels[dom]["frac"], "traffic": None,
+                     "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
+                     "algorithmic": "2*M*N*K per conv launch (M=B*H*T, N=C_out, K=C_in*kh*kw, both branches), "
+                                    "CUDA events around each launch on the launching stream, eager (non-graph) pass"},
+        "roofline_kernels": kernels,
+        "roofline_all_conv": {"achieved": tot_f / tot_t / 1e12, "frac": tot_f / tot_t / 1e12 / peak, "unit": "TFLOP/s",
+                              "ms_per_step": 1e3 * tot_t / n_rep,
+                              "step_model_tflops": 6 * BATCH * FWD_GFLOP_PER_SAMPLE_BRANCH / 1e3 / (ms_step * 1e-3)},
+    }
+
+
+def vqt_cfg2(dev, peaks):
+    """BASELINE.json configs[1]: batched VQT of 256 synthetic 30 s clips; HBM roofline of the front-end."""
+    import torch
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.processing.input_rep import VQTPlan
+    B, N = 256, 480000
+    base = np.stack([synth.stem_pair(i, 30.0)[i % 2] for i in range(8)])
+    y = torch.from_numpy(base).to(dev).repeat(B // 8, 1)
+    y += 1e-4 * torch.randn_like(y)   # 256 distinct clips
+    plan = VQTPlan(16000, "vqt", B, N)
+    out = torch.empty(B, 96, 1876, device=dev)
+    for _ in range(3):
+        plan.forward(y, out=out)
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        plan.forward(y, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg_bytes = B * (4 * N + 4 * 96 * 1876)
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    return {"vqt_cfg2": {"workload": "256 x 30 s 16 kHz clips -> (256, 96, 1876)", "ms": ms,
+                         "audio_sec_per_sec": B * 30.0 / (ms * 1e-3), "clips_per_sec": B / (ms * 1e-3),
+                         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                                      "algorithmic_bytes": alg_bytes, "kernels": "7 decimation + 8 filterbank launches",
+                                      "note": "input 491 MB + output 184 MB > 126 MB L2"}}}
+
+
+def cpu_baseline():
+    import torch
+    from oracle import encoder_oracle as eo
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd = eo.he_normal_state_dict(7)
+    crops = 4
+    cpu_reference_step(sd, 2, 0)  # warm the thread pool / allocator
+    dt, t_vqt = cpu_reference_step(sd, crops, 1)
+    return {"value": crops / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 step of {crops} (of {BATCH}) crops, T={T_CROP}: oracle VQT of one 10 s stem pair + fp32 torch-CPU "
+                      f"restatement of Pretext_CNN/NTXent/Adam (dropout 0); {dt:.1f} s",
+            "vqt_audio_sec_per_sec": 2 * CLIP_SECONDS / t_vqt, "vqt_cores": 1}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / cfg2 / cpu baseline legs (profiler runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+"""GPU parity of the reference-facing modules (generate_XQT, Down_CNN / Pretext_CNN, NTXent,
+train_epoch / val_epoch, PretextTrainer) against golden vectors produced by the reference's own code
+(tests/golden/encoder_golden.npz, tools/make_golden.py) and against the oracle.
+
+Tolerances (BASELINE.json north_star): embeddings and loss 1e-2 relative (bf16 operands, fp32
+accumulation), one-step weight updates rtol 1e-3."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "encoder_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def sd(gold):
+    from zeronotesamba_b200.models.checkpoint import he_normal_state_dict
+    from oracle import encoder_oracle as eo
+    sd = he_normal_state_dict(int(gold["ckpt_seed"]))
+    ref = eo.he_normal_state_dict(int(gold["ckpt_seed"]))
+    assert list(sd.keys()) == list(ref.keys()) and all(torch.equal(sd[k], ref[k]) for k in sd)
+    return sd
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def test_state_dict_layout_and_load(gold, sd):
+    from zeronotesamba_b200.models.models import Down_CNN, Pretext_CNN
+    m = Pretext_CNN()
+    assert list(m.state_dict().keys()) == [str(k) for k in gold["layout_keys"]]
+    assert [v.numel() for v in m.state_dict().values()] == list(gold["layout_numel"])
+    d = Down_CNN()
+    assert list(d.state_dict().keys()) == ["pretext." + str(k) for k in gold["layout_keys"]]
+    d.pretext.load_state_dict(sd)      # sample_script.py:41-42
+    for k, v in sd.items():
+        assert torch.equal(d.state_dict()["pretext." + k], v)
+
+
+def test_generate_xqt_contract():
+    import zeronotesamba_b200.processing.input_rep as IR
+    from oracle import vqt_oracle as vo
+    from zeronotesamba_b200 import synth
+    from helpers import vqt_check
+    y = synth.stem_pair(2, 10.0)[0]
+    out = IR.generate_XQT(y, 16000, "vqt")
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (96, 626)
+    rel, ab = vqt_check(out, vo.vqt_ref_f32(y))
+    assert rel < 1e-4 and ab < 1e-6
+    out_c = IR.generate_XQT(y, 16000, "cqt")
+    rel, ab = vqt_check(out_c, vo.vqt_ref_f32(y, 16000, "cqt"))
+    assert rel < 1e-4 and ab < 1e-6
+    with pytest.raises(Exception, match="Mode can only be vqt or cqt!"):
+        IR.generate_XQT(y, 16000, "stft")
+    yb = torch.from_numpy(np.stack(synth.stem_pair(2, 10.0))).to(DEV)
+    ob = IR.xqt_batch(yb)
+    assert ob.shape == (2, 96, 626) and np.array_equal(ob[0].cpu().numpy(), out)
+
+
+def test_down_cnn_forward_golden(gold, sd):
+    from zeronotesamba_b200.models.models import Down_CNN
+    x = torch.from_numpy(gold["down_in"]).to(DEV)
+    model = Down_CNN().to(DEV)
+    model.pretext.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        pos = model.pretext.postve(x[:, 1:2])
+        anc = model.pretext.anchor(x[:, 0:1])
+        both = model(x[:, 0:1], x[:, 1:2])
+        mean_model = Down_CNN("mean").to(DEV)
+        mean_model.pretext.load_state_dict(sd)
+        mean = mean_model.eval()(x[:, 0:1], x[:, 1:2])
+    assert anc.shape == (2, 40)
+    assert _rel(anc, gold["down_anchor"]) < 1e-2
+    assert _rel(pos, gold["down_postve"]) < 1e-2
+    assert _rel(both, gold["down_max"]) < 1e-2
+    assert _rel(mean, gold["down_mean"]) < 1e-2
+    assert torch.equal(both, torch.maximum(anc, pos))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.pretext.anchor(x[:, 0:1].cpu())
+
+
+def _check_step(gold, sd, model, res):
+    assert abs(res[0] - gold["train_loss_cos"][0]) <= 1e-2 * abs(gold["train_loss_cos"][0])
+    assert abs(res[1] - gold["train_loss_cos"][1]) <= 1e-2 and abs(res[2] - gold["train_loss_cos"][2]) <= 1e-2
+    keys = [str(k) for k in gold["layout_keys"]]
+    off = gold["sample_off"]
+    new_sd = model.state_dict()
+    for i, k in enumerate(keys):
+        idx = gold["sample_idx"][off[i]:off[i + 1]]
+        got_delta = (new_sd[k].reshape(-1)[idx].double().cpu() - sd[k].reshape(-1)[idx].double()).numpy()
+        want = sd[k].reshape(-1)[idx].double().numpy() + gold["delta_samples"][off[i]:off[i + 1]]
+        got = sd[k].reshape(-1)[idx].double().numpy() + got_delta
+        assert np.allclose(got, want, rtol=1e-3, atol=1e-5), k
+
+
+def test_trainer_step_golden(gold, sd):
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import PretextTrainer
+    batch = torch.from_numpy(gold["step_batch"]).to(DEV)
+    B, _, _, T = batch.shape
+    for use_graph in (False, True):
+        model = Pretext_CNN().to(DEV)
+        model.load_state_dict(sd)
+        tr = PretextTrainer(model, batch_len=B, temperature=0.25, lr=1e-6, crop_frames=T, dropout_p=0.0, use_graph=use_graph)
+        res = tr.step(batch).cpu().numpy()
+        assert _rel(tr.engine.emb[0], gold["step_anc_emb"]) < 1e-2
+        assert _rel(tr.engine.emb[1], gold["step_pos_emb"]) < 1e-2
+        # gradients (state_dict layout views of the flat buffer)
+        keys = [str(k) for k in gold["layout_keys"]]
+        named = dict(model.named_parameters())
+        cosines = []
+        off = gold["sample_off"]
+        for i, k in enumerate(keys):
+            g = named[k].grad
+            assert abs(float(g.double().norm()) - gold["grad_l2"][i]) <= 3e-2 * gold["grad_l2"][i] + 1e-9, k
+            idx = gold["sample_idx"][off[i]:off[i + 1]]
+            gs = g.reshape(-1)[idx].double().cpu().numpy()
+            ref = gold["grad_samples"][off[i]:off[i + 1]]
+            cosines.append(float(gs @ ref / (np.linalg.norm(gs) * np.linalg.norm(ref) + 1e-30)))
+        assert min(cosines) > 0.995, cosines
+        _check_step(gold, sd, model, res)
+
+
+def test_train_epoch_and_val_epoch_reference_signatures(gold, sd):
+    from zeronotesamba_b200.models.loss_functions import NTXent
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import FusedAdam, train_epoch, val_epoch
+    batch = torch.from_numpy(gold["step_batch"])
+    B = batch.shape[0]
+    loader = [[batch]]
+    for opt_kind in ("torch", "fused"):
+        model = Pretext_CNN().to(DEV)
+        model.load_state_dict(sd)
+        for br in (model.anchor, model.postve):
+            br.pretrained.dp.p = 0.0
+        crit = NTXent(batch_len=B, temperature=0.25)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-6) if opt_kind == "torch" else FusedAdam(model.parameters(), lr=1e-6)
+        vl = val_epoch(model, loader, crit, opt)
+        assert np.allclose(vl, gold["val_loss_cos"], rtol=1e-2, atol=1e-2)
+        m2, tl, tp, tn = train_epoch(model, loader, crit, opt)
+        assert m2 is model
+        _check_step(gold, sd, model, (tl, tp, tn))
+
+
+def test_dropout_train_mode_statistics(sd):
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    model = Pretext_CNN().to(DEV)
+    model.load_state_dict(sd)
+    x = (torch.rand(8, 2, 96, 48, device=DEV) * 10 - 9)
+    model.train()
+    with torch.no_grad():
+        a1, _ = model(x[:, 0:1], x[:, 1:2])
+        eng = next(iter(model._cache._engines.values()))
+        x3 = eng.x3[0].float()
+        zero_frac_train = float((x3 == 0).float().mean())
+        model.eval()
+        a2, _ = model(x[:, 0:1], x[:, 1:2])
+        zero_frac_eval = float((eng.x3[0].float() == 0).float().mean())
+    assert not torch.equal(a1, a2)
+    # dropout removes ~10 % of the surviving activations
+    assert 0.05 < (zero_frac_train - zero_frac_eval) / (1 - zero_frac_eval) < 0.15
+
+
+def test_step_from_audio_matches_separate_calls(sd):
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import PretextTrainer, crop_batch, sample_crop_starts
+    from zeronotesamba_b200.processing import input_rep as IR
+    drums, other = synth.stem_pair(11, 10.0)
+    starts = sample_crop_starts(16, random.Random(0))
+    assert len(set(starts)) == 16 and min(starts) >= 0 and max(starts) < 313
+    st = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    results = []
+    for fused_front in (True, False):
+        model = Pretext_CNN().to(DEV)
+        model.load_state_dict(sd)
+        tr = PretextTrainer(model, batch_len=16, dropout_p=0.0, use_graph=fused_front)
+        if fused_front:
+            r = tr.step_from_audio(torch.from_numpy(other).to(DEV), torch.from_numpy(drums).to(DEV), st)
+        else:
+            pair = torch.from_numpy(np.stack([IR.generate_XQT(other, 16000, "vqt"), IR.generate_XQT(drums, 16000, "vqt")])).to(DEV)
+            r = tr.step(crop_batch(pair, st))
+        results.append(r.cpu().numpy().copy())
+    assert np.allclose(results[0], results[1], rtol=1e-4, atol=1e-5), results
+
+
+def test_smoke_entry():
+    from zeronotesamba_b200 import smoke
+    out = smoke.run(verbose=False)
+    assert out["vqt_max_rel"] < 1e-4

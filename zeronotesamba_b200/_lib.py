@@ -68,10 +68,47 @@ _PROTOS = {
 
 EXPORTS = tuple(_PROTOS.keys())
 
-_lib: Optional[C.CDLL] = None
+# CUDA kernels one call launches (for the launch accounting bench.py reports); 0 = host only
+KERNELS_PER_CALL = {
+    "zns_vqt_forward": 15, "zns_vqt_forward_host": 15, "zns_crop_gather": 1, "zns_conv1_fwd": 1, "zns_conv1_wgrad": 1,
+    "zns_conv_fwd": 1, "zns_conv_wgrad": 1, "zns_bias_grad": 1, "zns_pack_weights": 2, "zns_unpack_grads": 1,
+    "zns_pool_fwd": 1, "zns_pool_bwd": 1, "zns_head_fwd": 1, "zns_head_bwd": 1, "zns_merge": 1, "zns_act_from_nchw": 1,
+    "zns_act_to_nchw": 1, "zns_ntxent_fwd_bwd": 1, "zns_adam_flat": 1, "zns_counter_add": 1, "zns_dbg_conv_fwd_simt": 1,
+    "zns_dbg_conv_wgrad_simt": 1, "zns_dbg_umma_probe": 1,
+}
+CALL_COUNTS: dict = {}
 
 
-def lib() -> C.CDLL:
+class _LibProxy:
+    """Attribute access returns the ctypes function wrapped with a call counter."""
+
+    def __init__(self, handle: C.CDLL):
+        self._h = handle
+        self._fns = {}
+
+    def __getattr__(self, name):
+        fn = self._fns.get(name)
+        if fn is None:
+            raw = getattr(self._h, name)
+
+            def fn(*a, _raw=raw, _name=name):
+                CALL_COUNTS[_name] = CALL_COUNTS.get(_name, 0) + 1
+                return _raw(*a)
+
+            self._fns[name] = fn
+        return fn
+
+
+def kernel_launches(counts: Optional[dict] = None) -> int:
+    """Kernels launched by the calls recorded in ``counts`` (default: all calls so far)."""
+    c = CALL_COUNTS if counts is None else counts
+    return sum(n * KERNELS_PER_CALL.get(k, 0) for k, n in c.items())
+
+
+_lib: Optional[_LibProxy] = None
+
+
+def lib() -> _LibProxy:
     """Load the shared library once.  Raises ZnsError if it has not been built."""
     global _lib
     if _lib is None:
@@ -84,7 +121,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = handle
+        _lib = _LibProxy(handle)
     return _lib
 
 

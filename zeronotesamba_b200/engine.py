@@ -79,6 +79,31 @@ class EncoderEngine:
         self._x_stride = 0
         self._train = False
         self._p = 0.0
+        # optional per-launch timing (bench.py): list of (tag, flops, start_event, end_event)
+        self.timers: Optional[list] = None
+
+    def _timed(self, tag: str, flops: float):
+        eng = self
+
+        class _T:
+            def __enter__(self_inner):
+                if eng.timers is not None:
+                    self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                    self_inner.e0.record()
+                return self_inner
+
+            def __exit__(self_inner, *exc):
+                if eng.timers is not None:
+                    self_inner.e1.record()
+                    eng.timers.append((tag, flops, self_inner.e0, self_inner.e1))
+                return False
+
+        return _T()
+
+    def _conv_flops(self, name, H) -> float:
+        _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
+        return 2.0 * self.B * H * self.T * co * ci * kh * kw * self.n_br
 
     # -- workspaces needed only for backward -------------------------------------------------------
     def _ensure_grad_ws(self):
@@ -113,8 +138,9 @@ class EncoderEngine:
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw, relu=relu, dropout_p=self._p if drop else 0.0,
                         seed=self.seed, rng_stream=layer_id * 2, seed_dev=self.step_ctr if drop and self._p > 0 else None)
         bias = [params[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]
-        L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(ins), L.ptr_array(self.wf[name]),
-                                     L.ptr_array(bias), None, L.ptr_array(outs), L.current_stream()))
+        with self._timed(f"conv_fwd_umma<{co}>", self._conv_flops(name, H)):
+            L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(ins), L.ptr_array(self.wf[name]),
+                                         L.ptr_array(bias), None, L.ptr_array(outs), L.current_stream()))
 
     def _pool(self, H, Cc, pool, ys, outs, layer_id):
         lib, st = L.lib(), L.current_stream()
@@ -155,7 +181,8 @@ class EncoderEngine:
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
         lib, st = L.lib(), L.current_stream()
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw)
-        L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xs), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
+        with self._timed(f"conv_wgrad_umma<{min(co, 128)}>", self._conv_flops(name, H)):
+            L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xs), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
         for br in range(self.n_br):
             L.check(lib.zns_bias_grad(L.ptr(dys[br]), self.B, H, self.T, co, L.ptr(grads[br][f"pretrained.{name}.bias"]), st))
 
@@ -163,8 +190,9 @@ class EncoderEngine:
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
         scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
         d = L.conv_desc(self.B, H, self.T, co, ci, kh, kw, relu=0, out_scale=scale)
-        L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(dys), L.ptr_array(self.wd[name]), None,
-                                     L.ptr_array(masks), L.ptr_array(outs), L.current_stream()))
+        with self._timed(f"conv_fwd_umma<{ci}>", self._conv_flops(name, H)):
+            L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(dys), L.ptr_array(self.wd[name]), None,
+                                         L.ptr_array(masks), L.ptr_array(outs), L.current_stream()))
 
     def _unpool(self, H, Cc, pool, ys, dps, outs):
         lib, st = L.lib(), L.current_stream()

@@ -1,0 +1,197 @@
+"""Drop-in for /root/reference/zeroNoteSamba/models/models.py (lines 7-150).
+
+Same classes, constructor arguments, forward signatures, parameter names and shapes, so
+``Pretext_CNN().state_dict()`` has the reference's 36 keys and ``model.pretext.load_state_dict(
+torch.load("shift_pret_cnn_16.pth"))`` works unchanged (sample_script.py:41-42, loader.py:25-27).
+The layers are containers for the fp32 master weights only: the arithmetic is libzns_sm100
+(cv1 SIMT, cv2..cv8 tcgen05 implicit GEMM, fused pool/ReLU/dropout, fc1+sigmoid head) driven by
+``EncoderEngine``; bf16 operands, fp32 accumulation.  CUDA tensors only -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from ..engine import CONV_SPECS, EncoderEngine, branch_param_names
+
+DROPOUT_P = 0.1   # models.py:30
+
+
+def _require_cuda(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise RuntimeError("zeronotesamba_b200 models run on a CUDA device only (no CPU fallback); "
+                           "move the model and its inputs to cuda first")
+
+
+class _EngineCache:
+    """One EncoderEngine per (batch, T, n_br) geometry, kept on the owning module."""
+
+    def __init__(self):
+        self._engines: Dict[Tuple[int, int, int], EncoderEngine] = {}
+
+    def get(self, batch: int, T: int, n_br: int, device) -> EncoderEngine:
+        key = (batch, T, n_br)
+        eng = self._engines.get(key)
+        if eng is None:
+            if len(self._engines) >= 4:   # bounded: variable-length inference would otherwise pile up workspaces
+                self._engines.pop(next(iter(self._engines)))
+            eng = self._engines[key] = EncoderEngine(batch, T, n_br, device)
+        return eng
+
+
+def _check_input(x: torch.Tensor) -> Tuple[int, int]:
+    _require_cuda(x)
+    if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] != 96:
+        raise ValueError(f"expected input of shape (B, 1, 96, T), got {tuple(x.shape)}")
+    return x.shape[0], x.shape[3]
+
+
+class _EncoderFunction(torch.autograd.Function):
+    """n_br DS_CNN branches: (x_0 [, x_1], *params) -> emb_0 [, emb_1].  No gradient w.r.t. inputs."""
+
+    @staticmethod
+    def forward(ctx, cache: _EngineCache, n_br: int, train: bool, dropout_p: float, *tensors):
+        xs = [t.contiguous().float() for t in tensors[:n_br]]
+        flat = tensors[n_br:]
+        names = branch_param_names()
+        params = [dict(zip(names, flat[br * len(names):(br + 1) * len(names)])) for br in range(n_br)]
+        B, T = xs[0].shape[0], xs[0].shape[3]
+        eng = cache.get(B, T, n_br, xs[0].device)
+        need_grad = any(p.requires_grad for p in flat) and torch.is_grad_enabled()
+        eng.pack_weights(params, need_dgrad=True)
+        embs = eng.forward(xs, 96 * T, params, train=train, dropout_p=dropout_p)
+        ctx.eng, ctx.params, ctx.n_br, ctx.n_names = eng, params, n_br, len(names)
+        ctx.version = getattr(eng, "_version", 0) + 1
+        eng._version = ctx.version
+        out = tuple(e.clone() for e in embs)
+        return out if n_br > 1 else out[0]
+
+    @staticmethod
+    def backward(ctx, *d_embs):
+        eng: EncoderEngine = ctx.eng
+        if eng._version != ctx.version:
+            raise RuntimeError("encoder workspaces were overwritten by a later forward of the same geometry; "
+                               "call backward before the next forward")
+        names = branch_param_names()
+        grads = [{n: torch.zeros_like(ctx.params[br][n]) for n in names} for br in range(ctx.n_br)]
+        d = [(g if g is not None else torch.zeros_like(eng.emb[i])).contiguous().float() for i, g in enumerate(d_embs)]
+        eng.backward(d, ctx.params, grads)
+        flat = [grads[br][n] for br in range(ctx.n_br) for n in names]
+        return (None, None, None, None) + (None,) * ctx.n_br + tuple(flat)
+
+
+class _CNN(nn.Module):
+    """
+    Convolutional layers (parameter container; models.py:7-74).
+    """
+
+    def __init__(self) -> None:
+        super(_CNN, self).__init__()
+        for name, co, ci, kh, kw, _ in CONV_SPECS:
+            setattr(self, name, nn.Conv2d(in_channels=ci, out_channels=co, kernel_size=(kh, kw), padding=(kh // 2, kw // 2)))
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpl1 = nn.MaxPool2d((3, 1), padding=(0, 0))
+        self.maxpl2 = nn.MaxPool2d((4, 1), padding=(0, 0))
+        self.maxpl3 = nn.MaxPool2d((8, 1), padding=(0, 0))
+        self.dp = nn.Dropout(p=DROPOUT_P)
+        self._cache = _EngineCache()
+
+    def forward(self, x: torch.Tensor) -> Any:
+        """
+        Pass input through convolutional layers: (B, 1, 96, T) -> (B, 128, T).  Forward only
+        (inference / feature extraction); training goes through DS_CNN / Pretext_CNN / Down_CNN.
+        -- x: input (vqt)
+        """
+        B, T = _check_input(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("_CNN.forward on its own is forward-only; wrap it in torch.no_grad() "
+                               "or train through DS_CNN / Pretext_CNN / Down_CNN")
+        xs = [x.contiguous().float()]
+        names = branch_param_names()[:-2]
+        params = [{n: dict(self.named_parameters())[n.replace("pretrained.", "")] for n in names}]
+        zero_fc = torch.zeros(1, 128, 1, device=x.device), torch.zeros(1, device=x.device)
+        params[0]["fc1.weight"], params[0]["fc1.bias"] = zero_fc
+        eng = self._cache.get(B, T, 1, x.device)
+        eng.pack_weights(params, need_dgrad=False)
+        eng.forward(xs, 96 * T, params, train=self.training, dropout_p=self.dp.p)
+        out = torch.empty(B, 128, 1, T, device=x.device)
+        L.check(L.lib().zns_act_to_nchw(L.ptr(eng.x8[0]), L.ptr(out), B, 128, 1, T, L.current_stream()))
+        return torch.squeeze(out, dim=2)
+
+
+class DS_CNN(nn.Module):
+    """
+    Fully-convolutional architecture for beat tracking (models.py:77-103).
+    """
+
+    def __init__(self) -> None:
+        super(DS_CNN, self).__init__()
+        self.pretrained = _CNN()
+        # Output
+        self.fc1 = nn.Conv1d(in_channels=128, out_channels=1, kernel_size=1, padding=0)
+        self.sig = nn.Sigmoid()
+        self._cache = _EngineCache()
+
+    def _flat_params(self) -> List[torch.Tensor]:
+        named = dict(self.named_parameters())
+        return [named[n] for n in branch_param_names()]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """
+        Pass input through the encoder: (B, 1, 96, T) -> (B, T) sigmoid activations.
+        -- x: input (vqt)
+        """
+        _check_input(x)
+        return _EncoderFunction.apply(self._cache, 1, self.training, self.pretrained.dp.p, x, *self._flat_params())
+
+
+class Pretext_CNN(nn.Module):
+    """
+    DS_CNN tailored for percussive and non-percussive stems (models.py:106-124).
+    """
+
+    def __init__(self) -> None:
+        super(Pretext_CNN, self).__init__()
+        self.anchor = DS_CNN()
+        self.postve = DS_CNN()
+        self._cache = _EngineCache()
+
+    def forward(self, anc: torch.Tensor, pos: torch.Tensor) -> Tuple[Any, Any]:
+        """
+        Pass vqts through each model (both branches share every tensor-core launch).
+        """
+        ba, ta = _check_input(anc)
+        bp, tp = _check_input(pos)
+        if (ba, ta) != (bp, tp):
+            return self.anchor(anc), self.postve(pos)
+        train = self.anchor.training
+        anc_emb, pos_emb = _EncoderFunction.apply(self._cache, 2, train, self.anchor.pretrained.dp.p, anc, pos,
+                                                  *self.anchor._flat_params(), *self.postve._flat_params())
+        return anc_emb, pos_emb
+
+
+class Down_CNN(nn.Module):
+    """
+    Use of Pretext_CNN for downstream tasks (models.py:127-150).
+    """
+
+    def __init__(self, reduction: str = "max") -> None:
+        super(Down_CNN, self).__init__()
+        self.pretext = Pretext_CNN()
+        self.reduction = reduction
+
+    def forward(self, anc: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        """
+        Pass each input through each model. Merge (maximum, or mean) and output.
+        """
+        anc_emb, pos_emb = self.pretext(anc, pos)
+        if anc_emb.requires_grad or pos_emb.requires_grad:
+            # autograd needs the merge on the tape
+            return torch.div(anc_emb + pos_emb, 2) if self.reduction == "mean" else torch.maximum(anc_emb, pos_emb)
+        emb = torch.empty_like(anc_emb)
+        L.check(L.lib().zns_merge(L.ptr(anc_emb), L.ptr(pos_emb), L.ptr(emb), emb.numel(),
+                                  1 if self.reduction == "mean" else 0, L.current_stream()))
+        return emb

@@ -1,0 +1,342 @@
+"""Pretext (ZeroNS) training hot path -- drop-in for the step semantics of
+/root/reference/zeroNoteSamba/pretext.py: ``train_epoch`` (:453-524), ``val_epoch`` (:527-592), the
+crop sampler (:308-321) and ``Adam(lr=1e-6)`` (:202), plus what the north star adds: VQT inside
+the loop on the GPU and data-parallel training over the GPUs of one node.
+
+Two ways in:
+  * ``train_epoch(model, loader, criterion, optimizer)`` / ``val_epoch(...)`` -- the reference's
+    signatures and return values.  With a stock ``torch.optim`` optimizer the loop is the
+    reference's (autograd through the fused kernels, ``optimizer.step()``); with this module's
+    ``FusedAdam`` it runs ``PretextTrainer.step`` (whole step in one CUDA graph, no host syncs).
+  * ``PretextTrainer`` -- flat fp32 parameter / gradient / moment buffers (the nn.Parameters become
+    views, so ``state_dict()`` keeps the reference layout), one gradient all-reduce per step over
+    NCCL when ``torch.distributed`` is initialised, fused Adam.
+
+Bank building, pickling, plotting and Spleeter (pretext.py:30-172,418-448) are out of scope.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .engine import EncoderEngine, branch_param_names
+from .models.loss_functions import NTXent
+from .models.models import Pretext_CNN
+
+CROP_FRAMES = 313          # pretext.py:285,312
+CLIP_FRAMES = 626          # pretext.py:255-256
+
+
+def sample_crop_starts(batch_len: int, rng: Optional[random.Random] = None, n_frames: int = CLIP_FRAMES,
+                       crop: int = CROP_FRAMES) -> List[int]:
+    """``random.sample(range(0, 313), batch_len)`` -- distinct crop starts of one clip (pretext.py:312)."""
+    r = rng if rng is not None else random
+    return r.sample(range(0, n_frames - crop), batch_len)
+
+
+def crop_batch(vqt_pair: torch.Tensor, starts: torch.Tensor, out: Optional[torch.Tensor] = None,
+               crop: int = CROP_FRAMES) -> torch.Tensor:
+    """vqt_pair (2, 96, F) CUDA fp32, starts int32 CUDA (n,) -> (n, 2, 96, crop): one batch == the n
+    shifts of ONE clip (pretext.py:314-321, DataLoader(shuffle=False))."""
+    c, bins, frames = vqt_pair.shape
+    n = starts.numel()
+    if out is None:
+        out = torch.empty(n, c, bins, crop, device=vqt_pair.device, dtype=torch.float32)
+    L.check(L.lib().zns_crop_gather(L.ptr(vqt_pair), c, bins, frames, L.ptr(starts), n, crop, L.ptr(out), L.current_stream()))
+    return out
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` defaults (betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad) as one
+    flat fused kernel.  Passing it to ``train_epoch`` selects the graph-captured trainer."""
+
+    def __init__(self, params, lr: float = 1e-6, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._trainer: Optional["PretextTrainer"] = None
+
+    def step(self, closure=None):  # generic path: per-tensor fused update
+        assert closure is None
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                stt = self.state[p]
+                if not stt:
+                    stt["step"] = 0
+                    stt["exp_avg"] = torch.zeros_like(p)
+                    stt["exp_avg_sq"] = torch.zeros_like(p)
+                stt["step"] += 1
+                g = p.grad.contiguous()
+                L.check(L.lib().zns_adam_flat(L.ptr(p), L.ptr(g), L.ptr(stt["exp_avg"]), L.ptr(stt["exp_avg_sq"]), p.numel(),
+                                              group["lr"], b1, b2, group["eps"], stt["step"], None, 1.0, L.current_stream()))
+
+
+class PretextTrainer:
+    """Fused ZeroNS pretext step on one GPU (one process per GPU under torchrun)."""
+
+    def __init__(self, model: Pretext_CNN, batch_len: int = 16, temperature: float = 0.25, lr: float = 1e-6,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, crop_frames: int = CROP_FRAMES,
+                 dropout_p: Optional[float] = None, use_graph: bool = True, seed: int = 0):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PretextTrainer needs the model on a CUDA device (no CPU fallback)")
+        self.model, self.device = model, dev
+        self.B, self.T = int(batch_len), int(crop_frames)
+        self.temperature, self.lr, self.betas, self.eps = float(temperature), float(lr), betas, float(eps)
+        self.dropout_p = model.anchor.pretrained.dp.p if dropout_p is None else float(dropout_p)
+        self.use_graph = use_graph
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        names = branch_param_names()
+        named = [dict(model.anchor.named_parameters()), dict(model.postve.named_parameters())]
+        plist = [named[br][n] for br in range(2) for n in names]
+        # flat buffers (every segment 16-byte aligned); parameters become views
+        offs, total = [], 0
+        for p in plist:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat_p = torch.zeros(total, device=dev)
+        self.flat_g = torch.zeros(total, device=dev)
+        self.flat_m = torch.zeros(total, device=dev)
+        self.flat_v = torch.zeros(total, device=dev)
+        self.params: List[Dict[str, torch.Tensor]] = [{}, {}]
+        self.grads: List[Dict[str, torch.Tensor]] = [{}, {}]
+        for i, p in enumerate(plist):
+            seg = self.flat_p[offs[i]:offs[i] + p.numel()].view_as(p)
+            seg.copy_(p.data)
+            p.data = seg
+            gseg = self.flat_g[offs[i]:offs[i] + p.numel()].view_as(p)
+            p.grad = gseg
+            br, n = divmod(i, len(names))
+            self.params[br][names[n]] = seg
+            self.grads[br][names[n]] = gseg
+        if self.world > 1:   # replicas start from rank 0's weights
+            torch.distributed.broadcast(self.flat_p, 0)
+        self.engine = EncoderEngine(self.B, self.T, 2, dev, seed=seed)
+        self.engine._ensure_grad_ws()
+        self.batch_buf = torch.zeros(self.B, 2, 96, self.T, device=dev)
+        self.result = torch.zeros(3, device=dev)
+        self.d_emb = [torch.zeros(self.B, self.T, device=dev) for _ in range(2)]
+        self._graph_fb: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_opt: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_eval: Optional[torch.cuda.CUDAGraph] = None
+        self.n_launches_step = 0
+        # front-end (VQT in the loop)
+        self._vqt_plan = None
+        self._audio_buf: Optional[torch.Tensor] = None
+        self._vqt_buf: Optional[torch.Tensor] = None
+        self._starts_buf = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self._graph_front: Optional[torch.cuda.CUDAGraph] = None
+
+    # ---- pieces ------------------------------------------------------------------------------
+    def _forward_backward(self):
+        lib, st = L.lib(), L.current_stream()
+        eng = self.engine
+        L.check(lib.zns_counter_add(L.ptr(eng.step_ctr), 1, st))
+        eng.pack_weights(self.params, need_dgrad=True)
+        self.flat_g.zero_()
+        eng.forward([self.batch_buf[:, 0], self.batch_buf[:, 1]], 2 * 96 * self.T, self.params, train=True,
+                    dropout_p=self.dropout_p)
+        L.check(lib.zns_ntxent_fwd_bwd(L.ptr(eng.emb[0]), L.ptr(eng.emb[1]), self.B, self.T, self.B, self.temperature,
+                                       L.ptr(self.result), L.ptr(self.d_emb[0]), L.ptr(self.d_emb[1]), st))
+        eng.backward(self.d_emb, self.params, self.grads)
+
+    def _optimizer(self):
+        L.check(L.lib().zns_adam_flat(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
+                                      self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0,
+                                      L.ptr(self.engine.step_ctr), 1.0 / self.world, L.current_stream()))
+
+    def _eval_forward(self):
+        lib, st = L.lib(), L.current_stream()
+        eng = self.engine
+        eng.pack_weights(self.params, need_dgrad=False)
+        eng.forward([self.batch_buf[:, 0], self.batch_buf[:, 1]], 2 * 96 * self.T, self.params, train=False)
+        L.check(lib.zns_ntxent_fwd_bwd(L.ptr(eng.emb[0]), L.ptr(eng.emb[1]), self.B, self.T, self.B, self.temperature,
+                                       L.ptr(self.result), None, None, st))
+
+    def _capture(self, fn) -> torch.cuda.CUDAGraph:
+        # warm-up on a side stream (first-call attribute setting, lazy module loading), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    # ---- public ------------------------------------------------------------------------------
+    def load_batch(self, batch: torch.Tensor) -> None:
+        """batch (B, 2, 96, T): channel 0 -> anchor branch, channel 1 -> positive branch (pretext.py:476-477)."""
+        if batch.data_ptr() != self.batch_buf.data_ptr():
+            self.batch_buf.copy_(batch, non_blocking=True)
+
+    def step(self, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One training step (pretext.py:479-488).  Returns the device tensor
+        [loss, mean cos(anchor,pos), mean cos(anchor,neg)] of this step (no host sync)."""
+        if batch is not None:
+            self.load_batch(batch)
+        if self.use_graph:
+            if self._graph_fb is None:
+                snap = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.engine.step_ctr.clone())
+                self._graph_fb = self._capture(self._forward_backward)
+                self._graph_opt = self._capture(self._optimizer)
+                # capture warm-ups really ran: restore the state they touched
+                self.flat_p.copy_(snap[0]); self.flat_m.copy_(snap[1]); self.flat_v.copy_(snap[2])
+                self.engine.step_ctr.copy_(snap[3])
+            self._graph_fb.replay()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.flat_g)
+            self._graph_opt.replay()
+        else:
+            self._forward_backward()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.flat_g)
+            self._optimizer()
+        return self.result
+
+    def eval_step(self, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Forward + loss only (val_epoch, pretext.py:546-564)."""
+        if batch is not None:
+            self.load_batch(batch)
+        if self.use_graph:
+            if self._graph_eval is None:
+                self._graph_eval = self._capture(self._eval_forward)
+            self._graph_eval.replay()
+        else:
+            self._eval_forward()
+        return self.result
+
+    # ---- VQT in the loop ---------------------------------------------------------------------------
+    def _front(self):
+        self._vqt_plan.forward(self._audio_buf, out=self._vqt_buf)
+        crop_batch(self._vqt_buf, self._starts_buf, out=self.batch_buf, crop=self.T)
+
+    def step_from_audio(self, anchor_audio: torch.Tensor, positive_audio: torch.Tensor, starts: torch.Tensor,
+                        sample_rate: int = 16000, mode: str = "vqt") -> torch.Tensor:
+        """Whole in-loop path on the device: two 16 kHz stems of one source clip (anchor = other stems,
+        positive = drums; pretext.py:83-84,144) -> VQT (2, 96, F) -> B crops at ``starts`` -> training step."""
+        from .processing.input_rep import VQTPlan
+        n = anchor_audio.numel()
+        if self._vqt_plan is None or self._audio_buf is None or self._audio_buf.shape[1] != n:
+            self._vqt_plan = VQTPlan(sample_rate, mode, 2, n)
+            self._audio_buf = torch.zeros(2, n, device=self.device)
+            self._vqt_buf = torch.zeros(2, 96, self._vqt_plan.frames(n), device=self.device)
+            self._graph_front = None
+        self._audio_buf[0].copy_(anchor_audio, non_blocking=True)
+        self._audio_buf[1].copy_(positive_audio, non_blocking=True)
+        self._starts_buf.copy_(starts, non_blocking=True)
+        if self.use_graph:
+            if self._graph_front is None:
+                self._graph_front = self._capture(self._front)
+            self._graph_front.replay()
+        else:
+            self._front()
+        return self.step()
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-signature epoch functions
+# ---------------------------------------------------------------------------------------------------
+def _trainer_for(model: Pretext_CNN, criterion: NTXent, optimizer: FusedAdam, T: int) -> PretextTrainer:
+    tr = optimizer._trainer
+    if tr is None or tr.model is not model or tr.T != T or tr.B != criterion.batch_len:
+        g = optimizer.param_groups[0]
+        tr = PretextTrainer(model, batch_len=criterion.batch_len, temperature=criterion.temperature, lr=g["lr"],
+                            betas=g["betas"], eps=g["eps"], crop_frames=T)
+        optimizer._trainer = tr
+    return tr
+
+
+def train_epoch(model: torch.nn.Module, train_loader: Iterable, criterion: NTXent, optimizer: torch.optim.Optimizer,
+                pt_task: str = "zerons") -> Tuple[torch.nn.Module, float, float, float]:
+    """
+    Function for CL model training (reference signature and return values, pretext.py:453-524).
+    -- model: model to train
+    -- train_loader: loader with batches that contain 1 anchor, 1 positive, and negatives
+    -- criterion: loss function
+    -- optimizer: optimizer defined
+    -- pt_task: pretext task to run
+    """
+    if pt_task == "clmr":
+        raise NotImplementedError("the CLMR baseline path (pretext.py:494-511) is not built")
+    if pt_task != "zerons":
+        raise ValueError("Which pretext task are we running?")
+    device = next(model.parameters()).device
+    model.train()
+    n_batches = 0
+    if isinstance(optimizer, FusedAdam) and isinstance(model, Pretext_CNN):
+        acc = torch.zeros(3, device=device)
+        for [batch] in train_loader:
+            if batch.shape[0] != criterion.batch_len:
+                raise ValueError("fused trainer needs full batches (the reference's loader always yields batch_len crops)")
+            tr = _trainer_for(model, criterion, optimizer, batch.shape[3])
+            acc += tr.step(batch.to(device, non_blocking=True))
+            n_batches += 1
+        full_train_loss, full_train_anpos, full_train_anneg = (acc / max(n_batches, 1)).tolist()
+    else:
+        full_train_loss = full_train_anpos = full_train_anneg = 0.0
+        for [batch] in train_loader:
+            anchors = batch[:, 0:1, :, :].to(device)
+            postves = batch[:, 1:2, :, :].to(device)
+            optimizer.zero_grad()
+            anc_emb, pos_emb = model(anchors, postves)
+            loss, sim_an_pos, sim_an_neg = criterion(anc_emb, pos_emb)
+            loss.backward()
+            optimizer.step()
+            full_train_loss += loss.item()
+            full_train_anpos += sim_an_pos
+            full_train_anneg += sim_an_neg
+            n_batches += 1
+        full_train_loss /= n_batches
+        full_train_anpos /= n_batches
+        full_train_anneg /= n_batches
+    print("*** Mean training batch loss is {:.3f}.".format(full_train_loss))
+    print("*** Mean training anchor / positive similiarity is {:.3f}.".format(full_train_anpos))
+    print("*** Mean training anchor / negative similiarity is {:.3f}.".format(full_train_anneg))
+    return model, full_train_loss, full_train_anpos, full_train_anneg
+
+
+def val_epoch(model: torch.nn.Module, val_loader: Iterable, criterion: NTXent, optimizer: torch.optim.Optimizer,
+              pt_task: str = "zerons") -> Tuple[float, float, float]:
+    """
+    Validation pass (reference signature and return values, pretext.py:527-592).
+    """
+    if pt_task != "zerons":
+        raise ValueError("Which pretext task are we running?")
+    device = next(model.parameters()).device
+    model.eval()
+    full_val_loss = full_val_anpos = full_val_anneg = 0.0
+    n_batches = 0
+    for [batch] in val_loader:
+        with torch.no_grad():
+            anchors = batch[:, 0:1, :, :].to(device)
+            postves = batch[:, 1:2, :, :].to(device)
+            anc_emb, pos_emb = model(anchors, postves)
+            loss, sim_an_pos, sim_an_neg = criterion(anc_emb, pos_emb)
+            full_val_loss += loss.item()
+            full_val_anpos += sim_an_pos
+            full_val_anneg += sim_an_neg
+            n_batches += 1
+    return full_val_loss / n_batches, full_val_anpos / n_batches, full_val_anneg / n_batches
+
+
+def build_from_config(ymldict: Dict, device: Optional[torch.device] = None):
+    """Model / criterion / optimizer as ``train_model`` builds them (pretext.py:185-202), reading the
+    same YAML keys (``batch_size``, ``temp``, ``pt_task``) plus ``lr`` (which the reference ignores)."""
+    batch_len = int(float(ymldict.get("batch_size", -1)))
+    tmp = float(ymldict.get("temp", -1.0))
+    pt_task = ymldict.get("pt_task")
+    lr = float(ymldict.get("lr", 0.000001))
+    if pt_task != "zerons":
+        raise ValueError("Which pretext task are we running?")
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    model = Pretext_CNN().to(device)
+    criterion = NTXent(batch_len=batch_len, temperature=tmp)
+    optimizer = FusedAdam(model.parameters(), lr=lr)
+    return model, criterion, optimizer
