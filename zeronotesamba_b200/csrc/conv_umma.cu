@@ -146,83 +146,95 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int a_cnt = 0, b_cnt = 0;
-      for (int c = 0; c < p.n_chunks; ++c) {
-        int next_row = rr_lo;
-        for (int r = 0; r < p.kh; ++r) {
-          const int need_hi = min(r + ht_eff, rr_hi);
-          while (next_row < need_hi) {
-            const int slot = a_cnt % p.n_slots;
-            mbar_wait(smem_u32(&bars->a_empty[slot]), ((a_cnt / p.n_slots) & 1) ^ 1);
+    // ===== TMA producer (whole warp runs the control flow, one elected lane issues) =====
+    int a_cnt = 0, b_cnt = 0;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      int next_row = rr_lo;
+      for (int r = 0; r < p.kh; ++r) {
+        const int need_hi = min(r + ht_eff, rr_hi);
+        while (next_row < need_hi) {
+          const int slot = a_cnt % p.n_slots;
+          mbar_wait(smem_u32(&bars->a_empty[slot]), ((a_cnt / p.n_slots) & 1) ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(smem_u32(&bars->a_full[slot]), p.slot_bytes);
             tma_load_5d(a_base + slot * p.slot_bytes, tm_in, smem_u32(&bars->a_full[slot]), c * 64, 0, w0 - p.pw,
                         h0 - p.ph + next_row, g);
-            ++a_cnt;
-            ++next_row;
           }
-          if (max(r, rr_lo) >= min(r + ht_eff, rr_hi)) continue;  // tap row touches no valid input row
-          for (int s = 0; s < p.kw; ++s) {
-            const int st = b_cnt % p.n_bstages;
-            mbar_wait(smem_u32(&bars->b_empty[st]), ((b_cnt / p.n_bstages) & 1) ^ 1);
+          __syncwarp();
+          ++a_cnt;
+          ++next_row;
+        }
+        if (max(r, rr_lo) >= min(r + ht_eff, rr_hi)) continue;  // tap row touches no valid input row
+        for (int s = 0; s < p.kw; ++s) {
+          const int st = b_cnt % p.n_bstages;
+          mbar_wait(smem_u32(&bars->b_empty[st]), ((b_cnt / p.n_bstages) & 1) ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(smem_u32(&bars->b_full[st]), kBTile);
             tma_load_3d(b_base + st * kBTile, tm_w, smem_u32(&bars->b_full[st]), c * 64, 0, r * p.kw + s);
-            ++b_cnt;
           }
+          __syncwarp();
+          ++b_cnt;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
-      int a_wait = 0, b_cnt = 0;
-      uint32_t started = 0;  // bit h: accumulator h holds data
-      for (int c = 0; c < p.n_chunks; ++c) {
-        const int row_base = c * n_valid - rr_lo;  // sequence number of relative row rr is row_base + rr
-        int next_row = rr_lo, rel_row = rr_lo;
-        for (int r = 0; r < p.kh; ++r) {
-          const int need_hi = min(r + ht_eff, rr_hi);
-          while (next_row < need_hi) {
-            const int slot = a_wait % p.n_slots;
-            mbar_wait(smem_u32(&bars->a_full[slot]), (a_wait / p.n_slots) & 1);
-            ++a_wait;
-            ++next_row;
-          }
-          const int lo = max(r, rr_lo), hi = min(r + ht_eff, rr_hi);
-          if (lo < hi) {
-            for (int s = 0; s < p.kw; ++s) {
-              const int st = b_cnt % p.n_bstages;
-              mbar_wait(smem_u32(&bars->b_full[st]), (b_cnt / p.n_bstages) & 1);
-              tc_fence_after();
-              const uint32_t b_addr = b_base + st * kBTile;
+    // ===== MMA issuer (warp-uniform control flow; one elected lane issues tcgen05.mma / commit) =====
+    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+    int a_wait = 0, b_cnt = 0;
+    uint32_t started = 0;  // bit h: accumulator h holds data
+    for (int c = 0; c < p.n_chunks; ++c) {
+      const int row_base = c * n_valid - rr_lo;  // sequence number of relative row rr is row_base + rr
+      int next_row = rr_lo, rel_row = rr_lo;
+      for (int r = 0; r < p.kh; ++r) {
+        const int need_hi = min(r + ht_eff, rr_hi);
+        while (next_row < need_hi) {
+          const int slot = a_wait % p.n_slots;
+          mbar_wait(smem_u32(&bars->a_full[slot]), (a_wait / p.n_slots) & 1);
+          ++a_wait;
+          ++next_row;
+        }
+        const int lo = max(r, rr_lo), hi = min(r + ht_eff, rr_hi);
+        if (lo < hi) {
+          for (int s = 0; s < p.kw; ++s) {
+            const int st = b_cnt % p.n_bstages;
+            mbar_wait(smem_u32(&bars->b_full[st]), (b_cnt / p.n_bstages) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_lo = (((b_base + st * kBTile) & 0x3FFFF) >> 4) | (1u << 16);
               for (int rr = lo; rr < hi; ++rr) {
                 const int h = rr - r;
                 const uint32_t a_addr = a_base + ((row_base + rr) % p.n_slots) * p.slot_bytes + s * 1024;
+                const uint32_t a_lo = ((a_addr & 0x3FFFF) >> 4) | (1u << 16);
+                const uint32_t acc = (started >> h) & 1;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_bf16(tmem + h * N, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                            umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, ((started >> h) & 1) | (k > 0));
+                  umma_bf16(tmem + h * N, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
+                            idesc, acc | (k > 0));
                 }
-                started |= 1u << h;
               }
               umma_commit(smem_u32(&bars->b_empty[st]));
-              ++b_cnt;
             }
-          }
-          while (rel_row <= r && rel_row < rr_hi) {
-            umma_commit(smem_u32(&bars->a_empty[(row_base + rel_row) % p.n_slots]));
-            ++rel_row;
+            __syncwarp();
+            for (int rr = lo; rr < hi; ++rr) started |= 1u << (rr - r);
+            ++b_cnt;
           }
         }
-        while (rel_row < rr_hi) {
-          umma_commit(smem_u32(&bars->a_empty[(row_base + rel_row) % p.n_slots]));
-          ++rel_row;
+        if (elect_one()) {
+          for (int q = rel_row; q <= r && q < rr_hi; ++q)
+            umma_commit(smem_u32(&bars->a_empty[(row_base + q) % p.n_slots]));
         }
+        __syncwarp();
+        while (rel_row <= r && rel_row < rr_hi) ++rel_row;
       }
-      umma_commit(smem_u32(&bars->acc_full));
+      if (elect_one()) {
+        for (int q = rel_row; q < rr_hi; ++q) umma_commit(smem_u32(&bars->a_empty[(row_base + q) % p.n_slots]));
+      }
+      __syncwarp();
+      rel_row = rr_hi;
     }
+    if (elect_one()) umma_commit(smem_u32(&bars->acc_full));
+    __syncwarp();
   } else {
     // ===== epilogue: TMEM -> registers -> bias / ReLU / dropout / mask -> bf16 act =====
     mbar_wait(smem_u32(&bars->acc_full), 0);
@@ -436,16 +448,16 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   const uint32_t dy_off = n_xchunks * p.x_chunk_bytes;  // dy tiles follow the x chunks inside a stage
 
   if (warp == 0) {
-    if (lane == 0) {
-      int cnt = 0;
-      for (int q = q0; q < q1; ++q) {
-        const int wt = q % p.n_wtiles;
-        const int gh = q / p.n_wtiles;
-        const int h = gh % p.H, g = gh / p.H;
-        const int hh = h + r - p.ph;
-        if (hh < 0 || hh >= p.H) continue;
-        const int st = cnt % p.n_stages;
-        mbar_wait(smem_u32(&bars->empty[st]), ((cnt / p.n_stages) & 1) ^ 1);
+    int cnt = 0;
+    for (int q = q0; q < q1; ++q) {
+      const int wt = q % p.n_wtiles;
+      const int gh = q / p.n_wtiles;
+      const int h = gh % p.H, g = gh / p.H;
+      const int hh = h + r - p.ph;
+      if (hh < 0 || hh >= p.H) continue;
+      const int st = cnt % p.n_stages;
+      mbar_wait(smem_u32(&bars->empty[st]), ((cnt / p.n_stages) & 1) ^ 1);
+      if (elect_one()) {
         const uint32_t base = smem_base + st * p.stage_bytes;
         mbar_expect_tx(smem_u32(&bars->full[st]), p.stage_bytes);
         for (int xc = 0; xc < n_xchunks; ++xc)
@@ -453,34 +465,41 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
                       wt * WT - p.pw + s0, hh, g);
         for (int j = 0; j < NB / 64; ++j)
           tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, smem_u32(&bars->full[st]), cob * NB + j * 64, 0, wt * WT, h, g);
-        ++cnt;
       }
+      __syncwarp();
+      ++cnt;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, NB, 1, 1);
-      const uint32_t a_lbo = p.fold ? 1024u : p.x_chunk_bytes;
-      int cnt = 0;
-      for (int q = q0; q < q1; ++q) {
-        const int gh = q / p.n_wtiles;
-        const int h = gh % p.H;
-        const int hh = h + r - p.ph;
-        if (hh < 0 || hh >= p.H) continue;
-        const int st = cnt % p.n_stages;
-        mbar_wait(smem_u32(&bars->full[st]), (cnt / p.n_stages) & 1);
-        tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, NB, 1, 1);
+    const uint32_t a_lbo = p.fold ? 1024u : p.x_chunk_bytes;
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+    int cnt = 0;
+    for (int q = q0; q < q1; ++q) {
+      const int gh = q / p.n_wtiles;
+      const int h = gh % p.H;
+      const int hh = h + r - p.ph;
+      if (hh < 0 || hh >= p.H) continue;
+      const int st = cnt % p.n_stages;
+      mbar_wait(smem_u32(&bars->full[st]), (cnt / p.n_stages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t base = smem_base + st * p.stage_bytes;
+        const uint32_t b_lo = (((base + dy_off) & 0x3FFFF) >> 4) | ((kDyChunk >> 4) << 16);
         for (int a = 0; a < n_acc_eff; ++a) {
           const uint32_t xa = base + (uint32_t)(p.fold ? 2 * a : a) * 1024u;
+          const uint32_t a_lo = ((xa & 0x3FFFF) >> 4) | (((a_lbo >> 4) & 0x3FFF) << 16);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            umma_bf16(tmem + a * NB, umma_desc_sw128(xa + k * 2048, a_lbo, 1024),
-                      umma_desc_sw128(base + dy_off + k * 2048, kDyChunk, 1024), idesc, (cnt > 0) | (k > 0));
+            umma_bf16(tmem + a * NB, ((uint64_t)kDescHi << 32) | (a_lo + 128 * k), ((uint64_t)kDescHi << 32) | (b_lo + 128 * k),
+                      idesc, (cnt > 0) | (k > 0));
           }
         }
         umma_commit(smem_u32(&bars->empty[st]));
-        ++cnt;
       }
+      __syncwarp();
+      ++cnt;
+    }
+    if (elect_one()) {
       if (cnt > 0) {
         *reinterpret_cast<volatile uint32_t*>(&bars->any_step) = 1;
         umma_commit(smem_u32(&bars->acc_full));
@@ -488,6 +507,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
         mbar_arrive(smem_u32(&bars->acc_full));
       }
     }
+    __syncwarp();
   } else {
     mbar_wait(smem_u32(&bars->acc_full), 0);
     tc_fence_after();

@@ -486,20 +486,30 @@ extern "C" int zns_unpack_grads(const float* gpk, int c_out, int c_in, int kh, i
 // ---------------------------------------------------------------------------------------------
 // bias gradient: db[c] += sum_p dy[p][c]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dy, size_t n_pos, int C,
+__global__ void __launch_bounds__(256) bias_grad_kernel(const uint4* __restrict__ dy, size_t n_pos, int C,
                                                         float* __restrict__ db) {
-  __shared__ float red[256];
-  const int c = threadIdx.x % C;            // C in {64,128,256}
-  const int lane_row = threadIdx.x / C;
-  const int rows_per_it = 256 / C;
-  float acc = 0.f;
-  for (size_t p = (size_t)blockIdx.x * rows_per_it + lane_row; p < n_pos; p += (size_t)gridDim.x * rows_per_it)
-    acc += __bfloat162float(dy[p * C + c]);
-  red[threadIdx.x] = acc;
+  // a thread owns 8 consecutive channels (one 16-byte load per position); C/8 threads span a position
+  __shared__ float red[256 * 8];
+  const int tpr = C / 8;                     // threads per position: 8, 16 or 32
+  const int cg = threadIdx.x % tpr;          // channel group
+  const int lane_row = threadIdx.x / tpr;
+  const int rows_per_it = 256 / tpr;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (size_t p = (size_t)blockIdx.x * rows_per_it + lane_row; p < n_pos; p += (size_t)gridDim.x * rows_per_it) {
+    float v[8];
+    unpack8(__ldg(dy + p * tpr + cg), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
   __syncthreads();
   if (threadIdx.x < C) {
+    const int g = threadIdx.x / 8, j = threadIdx.x % 8;
     float s = 0.f;
-    for (int r = 0; r < rows_per_it; ++r) s += red[r * C + threadIdx.x];
+    for (int r = 0; r < rows_per_it; ++r) s += red[(r * tpr + g) * 8 + j];
     atomicAdd(db + threadIdx.x, s);
   }
 }
@@ -508,8 +518,9 @@ extern "C" int zns_bias_grad(const void* dy_act, int batch, int H, int W, int C,
   ZNS_REQUIRE(dy_act && db, "NULL argument");
   ZNS_REQUIRE(C == 64 || C == 128 || C == 256, "bias_grad supports C in {64,128,256}");
   const size_t n_pos = (size_t)zns_groups(batch) * H * W * 8;
-  const int blocks = (int)std::min<size_t>((n_pos * C + 65535) / 65536, 148 * 4);
-  bias_grad_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, n_pos, C, db);
+  const int rows_per_it = 256 / (C / 8);
+  const int blocks = (int)std::min<size_t>((n_pos + (size_t)rows_per_it * 8 - 1) / ((size_t)rows_per_it * 8), 148 * 8);
+  bias_grad_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy_act, n_pos, C, db);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }

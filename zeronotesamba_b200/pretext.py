@@ -22,6 +22,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
+from . import dist_utils
 from .engine import EncoderEngine, branch_param_names
 from .models.loss_functions import NTXent
 from .models.models import Pretext_CNN
@@ -113,8 +114,7 @@ class PretextTrainer:
             br, n = divmod(i, len(names))
             self.params[br][names[n]] = seg
             self.grads[br][names[n]] = gseg
-        if self.world > 1:   # replicas start from rank 0's weights
-            torch.distributed.broadcast(self.flat_p, 0)
+        dist_utils.broadcast_parameters(self.flat_p, 0)   # replicas start from rank 0's weights
         self.engine = EncoderEngine(self.B, self.T, 2, dev, seed=seed)
         self.engine._ensure_grad_ws()
         self.batch_buf = torch.zeros(self.B, 2, 96, self.T, device=dev)
@@ -190,13 +190,11 @@ class PretextTrainer:
                 self.flat_p.copy_(snap[0]); self.flat_m.copy_(snap[1]); self.flat_v.copy_(snap[2])
                 self.engine.step_ctr.copy_(snap[3])
             self._graph_fb.replay()
-            if self.world > 1:
-                torch.distributed.all_reduce(self.flat_g)
+            dist_utils.allreduce_gradients(self.flat_g)     # NCCL over NVLink; Adam applies 1/world
             self._graph_opt.replay()
         else:
             self._forward_backward()
-            if self.world > 1:
-                torch.distributed.all_reduce(self.flat_g)
+            dist_utils.allreduce_gradients(self.flat_g)
             self._optimizer()
         return self.result
 
