@@ -15,8 +15,10 @@
 //   * wgrad: the reduction runs over positions; both operands are MN-major views of the same
 //     kind of tile (x halo row shifted by the tap, dy tile), accumulators are per-tap
 //     [c_in x c_out] blocks in TMEM, reduced across position slices with fp32 atomics.
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
-#include <mutex>
 
 #include "common.cuh"
 
@@ -302,6 +304,298 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// transposed forward / data-gradient kernel for C_out <= 128
+//   The 128 x N x 16 MMA reads a 4 KB A tile however small N is, and shared-memory operand
+//   bandwidth (~90 B/clk measured) bounds the N = 64 / 128 kernels above at 38 % / 63 % of peak.
+//   Here the roles are swapped: A (M = 128) = weight tile, B (N = 256) = 32 frames x 8 clips of an
+//   input row -> 12 KB per 128-cycle MMA, like the N = 256 kernel.  D[c_out, position] lives in
+//   TMEM with channels on lanes; the epilogue writes 2-byte values, 32 consecutive channels per
+//   warp store.  For c_out = 64 two adjacent output rows are stacked on M: rows (h, h-1) use
+//   weight tap rows (r, r+1) on the same input row, so the tap-row loop has kh + 1 steps.
+// ---------------------------------------------------------------------------------------------
+#define WTT 32  // frames per tile in the transposed kernel
+
+struct FwdTParams {
+  int G, H, W, batch;
+  int kh, kw, ph, pw;
+  int n_chunks;
+  int n_wtiles, n_htiles;
+  int cout;          // 64 or 128
+  int stack;         // output rows stacked on M: 128 / cout
+  int n_acc;         // accumulators (of 256 TMEM columns) per CTA
+  int n_slots, n_wstages;
+  uint32_t slot_bytes;  // (WTT + kw - 1) * 1024
+  int relu;
+  float drop_p, scale;
+  uint32_t seed, stream_id;
+  const uint32_t* seed_dev;
+  const float* bias[2];
+  const bf16* mask[2];
+  bf16* out[2];
+};
+
+struct FwdTBarriers {
+  uint64_t x_full[MAX_RING], x_empty[MAX_RING], w_full[MAX_RING], w_empty[MAX_RING], acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_fwdT_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+                      const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                      const FwdTParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x_base = smem_base;
+  const uint32_t w_base = x_base + p.n_slots * p.slot_bytes;
+  constexpr uint32_t kWTile = 128 * 128;  // 128 rows x 64 channels bf16
+  FwdTBarriers* bars = reinterpret_cast<FwdTBarriers*>(smem_raw + (w_base + p.n_wstages * kWTile - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int br = blockIdx.z;
+  const CUtensorMap* tm_in = br ? &tm_in1 : &tm_in0;
+  const CUtensorMap* tm_w = br ? &tm_w1 : &tm_w0;
+
+  int t = blockIdx.x;
+  const int wt = t % p.n_wtiles; t /= p.n_wtiles;
+  const int htile = t % p.n_htiles; t /= p.n_htiles;
+  const int g = t;
+  const int rows_per_cta = p.n_acc * p.stack;
+  const int w0 = wt * WTT, h0 = htile * rows_per_cta;
+  const int acc_eff = min(p.n_acc, (p.H - h0 + p.stack - 1) / p.stack);
+  const int n_iter = p.kh + p.stack - 1;                     // tap-row steps r' = 0 .. kh + stack - 2
+  // relative input rows rr: hh = h0 - ph + rr; accumulator a needs row r' + a*stack at step r'
+  const int rr_lo = max(0, p.ph - h0);
+  const int rr_hi = min(acc_eff * p.stack + p.kh - 1, p.H + p.ph - h0);
+  const int n_valid = rr_hi - rr_lo;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_slots; ++i) { mbar_init(smem_u32(&bars->x_full[i]), 1); mbar_init(smem_u32(&bars->x_empty[i]), 1); }
+    for (int i = 0; i < p.n_wstages; ++i) { mbar_init(smem_u32(&bars->w_full[i]), 1); mbar_init(smem_u32(&bars->w_empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tm_in);
+    tma_prefetch_desc(tm_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  // does step r' touch a valid input row for some accumulator?
+  auto step_active = [&](int rp) {
+    for (int a = 0; a < acc_eff; ++a) {
+      const int rr = rp + a * p.stack;
+      if (rr >= rr_lo && rr < rr_hi) return true;
+    }
+    return false;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int x_cnt = 0, w_cnt = 0;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      int next_row = rr_lo;
+      for (int rp = 0; rp < n_iter; ++rp) {
+        const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
+        while (next_row < need_hi) {
+          const int slot = x_cnt % p.n_slots;
+          mbar_wait(smem_u32(&bars->x_empty[slot]), ((x_cnt / p.n_slots) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(smem_u32(&bars->x_full[slot]), p.slot_bytes);
+            tma_load_5d(x_base + slot * p.slot_bytes, tm_in, smem_u32(&bars->x_full[slot]), c * 64, 0, w0 - p.pw,
+                        h0 - p.ph + next_row, g);
+          }
+          __syncwarp();
+          ++x_cnt;
+          ++next_row;
+        }
+        if (!step_active(rp)) continue;
+        for (int s = 0; s < p.kw; ++s) {
+          const int st = w_cnt % p.n_wstages;
+          mbar_wait(smem_u32(&bars->w_empty[st]), ((w_cnt / p.n_wstages) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(smem_u32(&bars->w_full[st]), kWTile);
+            for (int j = 0; j < p.stack; ++j) {
+              const int r = rp - (p.stack - 1) + j;      // weight tap row of M block j (out of range -> TMA zero fill)
+              const int tap = (r < 0 || r >= p.kh) ? -1 : r * p.kw + s;
+              tma_load_3d(w_base + st * kWTile + j * p.cout * 128, tm_w, smem_u32(&bars->w_full[st]), c * 64, 0, tap);
+            }
+          }
+          __syncwarp();
+          ++w_cnt;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    int x_wait = 0, w_cnt = 0;
+    uint32_t started = 0;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      const int row_base = c * n_valid - rr_lo;
+      int next_row = rr_lo, rel_row = rr_lo;
+      for (int rp = 0; rp < n_iter; ++rp) {
+        const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
+        while (next_row < need_hi) {
+          const int slot = x_wait % p.n_slots;
+          mbar_wait(smem_u32(&bars->x_full[slot]), (x_wait / p.n_slots) & 1);
+          ++x_wait;
+          ++next_row;
+        }
+        if (step_active(rp)) {
+          for (int s = 0; s < p.kw; ++s) {
+            const int st = w_cnt % p.n_wstages;
+            mbar_wait(smem_u32(&bars->w_full[st]), (w_cnt / p.n_wstages) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = (((w_base + st * kWTile) & 0x3FFFF) >> 4) | (1u << 16);
+              for (int a = 0; a < acc_eff; ++a) {
+                const int rr = rp + a * p.stack;
+                if (rr < rr_lo || rr >= rr_hi) continue;
+                const uint32_t b_addr = x_base + ((row_base + rr) % p.n_slots) * p.slot_bytes + s * 1024;
+                const uint32_t b_lo = ((b_addr & 0x3FFFF) >> 4) | (1u << 16);
+                const uint32_t acc = (started >> a) & 1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(tmem + a * 256, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
+                            idesc, acc | (k > 0));
+                }
+              }
+              umma_commit(smem_u32(&bars->w_empty[st]));
+            }
+            __syncwarp();
+            for (int a = 0; a < acc_eff; ++a) {
+              const int rr = rp + a * p.stack;
+              if (rr >= rr_lo && rr < rr_hi) started |= 1u << a;
+            }
+            ++w_cnt;
+          }
+        }
+        // row rr = rp has had its last use (accumulator 0)
+        if (elect_one()) {
+          for (int q = rel_row; q <= rp && q < rr_hi; ++q)
+            umma_commit(smem_u32(&bars->x_empty[(row_base + q) % p.n_slots]));
+        }
+        __syncwarp();
+        while (rel_row <= rp && rel_row < rr_hi) ++rel_row;
+      }
+      if (elect_one()) {
+        for (int q = rel_row; q < rr_hi; ++q) umma_commit(smem_u32(&bars->x_empty[(row_base + q) % p.n_slots]));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(smem_u32(&bars->acc_full));
+    __syncwarp();
+  } else {
+    // ===== epilogue: lane = output channel (and stacked row), columns = positions =====
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int j = m / p.cout, co = m - j * p.cout;
+    const float bias = p.bias[br] ? __ldg(p.bias[br] + co) : 0.f;
+    const bf16* mask = p.mask[br];
+    bf16* out = p.out[br];
+    uint32_t seed = p.seed;
+    if (p.seed_dev) seed ^= __ldg(p.seed_dev) * 0x9E3779B9u;
+    const bool do_drop = p.drop_p > 0.f;
+    const double thr_d = (double)p.drop_p * 4294967296.0;
+    const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
+    const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const int n_valid_cols = min(WTT, p.W - w0) * 8;
+    for (int a = 0; a < acc_eff; ++a) {
+      const int h = h0 + a * p.stack + (p.stack - 1 - j);
+      const bool row_ok = h < p.H;
+      const size_t e0 = zns_act_index(g, row_ok ? h : 0, w0, 0, co, p.H, p.W, p.cout);
+#pragma unroll 1
+      for (int nb = 0; nb < 8; ++nb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + a * 256 + nb * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = nb * 32 + i;
+          if (n < n_valid_cols) {
+            const size_t e = e0 + (size_t)n * p.cout;
+            float x = __uint_as_float(v[i]) + bias;
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (do_drop) x = (zns_hash32(e, seed, p.stream_id + br) >= thr) ? x * keep : 0.f;
+            if (mask && !(__bfloat162float(mask[e]) > 0.f)) x = 0.f;
+            out[e] = __float2bfloat16(x * p.scale);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static bool fwdT_config(const zns_conv_desc* d, FwdTParams* p) {
+  if (d->c_out != 64 && d->c_out != 128) return false;
+  const int stack = 128 / d->c_out;
+  if (stack == 2 && (d->H & 1)) return false;
+  const uint32_t slot = (uint32_t)(WTT + d->kw - 1) * 1024u;
+  const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdTBarriers) - 64;
+  int n_acc = 2;
+  if (d->H <= stack) n_acc = 1;
+  int slots = (n_acc - 1) * stack + 2;
+  if ((uint64_t)slots * slot + 2ull * 16384 > budget) return false;
+  int wst = 2;
+  while (wst < 4 && (uint64_t)slots * slot + (uint64_t)(wst + 1) * 16384 <= budget) ++wst;
+  if (slots < MAX_RING && (uint64_t)(slots + 1) * slot + (uint64_t)wst * 16384 <= budget && d->H > stack) ++slots;
+  while (wst < MAX_RING && (uint64_t)slots * slot + (uint64_t)(wst + 1) * 16384 <= budget) ++wst;
+  p->cout = d->c_out; p->stack = stack; p->n_acc = n_acc; p->n_slots = slots; p->n_wstages = wst; p->slot_bytes = slot;
+  return true;
+}
+
+static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, const void* const* in,
+                       const void* const* wpk, const float* const* bias, const void* const* mask, void* const* out,
+                       cudaStream_t st) {
+  const int G = zns_groups(d->batch);
+  FwdTParams p = cfg;
+  p.G = G; p.H = d->H; p.W = d->W; p.batch = d->batch;
+  p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
+  p.n_chunks = d->c_in / 64;
+  p.n_wtiles = (d->W + WTT - 1) / WTT;
+  const int rows_per_cta = p.n_acc * p.stack;
+  p.n_htiles = (d->H + rows_per_cta - 1) / rows_per_cta;
+  p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
+  const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * 16384 + sizeof(FwdTBarriers) + 64;
+  CUtensorMap tm_in[2], tm_w[2];
+  for (int b = 0; b < 2; ++b) {
+    const int s = b < n_br ? b : 0;
+    int rc = make_act_map(&tm_in[b], in[s], G, d->H, d->W, d->c_in, WTT + d->kw - 1);
+    if (rc) return rc;
+    rc = make_w_map(&tm_w[b], wpk[s], d->kh * d->kw, d->c_out, d->c_in, d->c_out);
+    if (rc) return rc;
+    p.bias[b] = bias ? bias[s] : nullptr;
+    p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
+    p.out[b] = (bf16*)out[s];
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(conv_fwdT_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    attr_set = true;
+  }
+  dim3 grid(p.n_wtiles * p.n_htiles * G, 1, n_br);
+  conv_fwdT_umma_kernel<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
 template <int N, int HT>
 static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
                       const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st) {
@@ -363,6 +657,13 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
   ZNS_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout_p out of range");
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // C_out <= 128: transposed kernel (weights on M, 256 positions on N) unless disabled for A/B tests
+    static const bool no_t = getenv("ZNS_CONV_NO_TRANSPOSED") != nullptr;
+    FwdTParams cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    if (!no_t && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
+  }
   switch (d->c_out) {
     case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);
     case 128: return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st);

@@ -38,6 +38,13 @@ def branch_param_names() -> List[str]:
     return names + ["fc1.weight", "fc1.bias"]
 
 
+def _fwd_tag(c_out: int, H: int) -> str:
+    """Which tensor-core kernel zns_conv_fwd dispatches to (csrc/conv_umma.cu)."""
+    if c_out == 128 or (c_out == 64 and H % 2 == 0):
+        return f"conv_fwdT_umma(c_out={c_out})"
+    return f"conv_fwd_umma<{c_out}>"
+
+
 class EncoderEngine:
     """Workspaces + launch sequences for ``n_br`` encoders on a fixed (batch, T) geometry."""
 
@@ -138,7 +145,7 @@ class EncoderEngine:
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw, relu=relu, dropout_p=self._p if drop else 0.0,
                         seed=self.seed, rng_stream=layer_id * 2, seed_dev=self.step_ctr if drop and self._p > 0 else None)
         bias = [params[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]
-        with self._timed(f"conv_fwd_umma<{co}>", self._conv_flops(name, H)):
+        with self._timed(_fwd_tag(co, H), self._conv_flops(name, H)):
             L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(ins), L.ptr_array(self.wf[name]),
                                          L.ptr_array(bias), None, L.ptr_array(outs), L.current_stream()))
 
@@ -190,7 +197,7 @@ class EncoderEngine:
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
         scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
         d = L.conv_desc(self.B, H, self.T, co, ci, kh, kw, relu=0, out_scale=scale)
-        with self._timed(f"conv_fwd_umma<{ci}>", self._conv_flops(name, H)):
+        with self._timed(_fwd_tag(ci, H), self._conv_flops(name, H)):
             L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(dys), L.ptr_array(self.wd[name]), None,
                                          L.ptr_array(masks), L.ptr_array(outs), L.current_stream()))
 
