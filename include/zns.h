@@ -181,6 +181,8 @@ int zns_dbg_conv_fwd_simt(const zns_conv_desc* d, const void* in, const void* wp
 int zns_dbg_conv_wgrad_simt(const zns_conv_desc* d, const void* x, const void* dy, float* dwpk, void* stream);
 /* Raw tcgen05 GEMM probe (descriptor self-test); see csrc/umma_probe.cu. */
 int zns_dbg_umma_probe(int variant, const void* a, const void* b, float* d, int n, int k, void* stream);
+/* tcgen05 issue/throughput microbenchmark (diagnostic): cycles[n_ctas] per CTA. */
+int zns_dbg_umma_rate(int n, int iters, int per_group, int mode, int n_ctas, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

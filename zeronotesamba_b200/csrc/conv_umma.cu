@@ -128,7 +128,6 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   // input rows rr (relative): hh = h0 - ph + rr, valid when 0 <= hh < H
   const int rr_lo = max(0, p.ph - h0);
   const int rr_hi = min(ht_eff + p.kh - 1, p.H + p.ph - h0);
-  const int n_valid = rr_hi - rr_lo;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
@@ -147,95 +146,101 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
+  const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
+  const uint32_t n_slots = p.n_slots, n_bst = p.n_bstages;
+  // Producer and MMA issuer are each ONE elected thread running the whole loop: tcgen05.mma is
+  // asynchronous, so the issuing instruction stream only has to be shorter than the MMAs it feeds
+  // (measured: ~80 clk of scalar work per MMA and ~330 clk per elect block in a naive loop, which is
+  // why nothing below divides, takes a modulo or re-elects).
   if (warp == 0) {
-    // ===== TMA producer (whole warp runs the control flow, one elected lane issues) =====
-    int a_cnt = 0, b_cnt = 0;
-    for (int c = 0; c < p.n_chunks; ++c) {
-      int next_row = rr_lo;
-      for (int r = 0; r < p.kh; ++r) {
-        const int need_hi = min(r + ht_eff, rr_hi);
-        while (next_row < need_hi) {
-          const int slot = a_cnt % p.n_slots;
-          mbar_wait(smem_u32(&bars->a_empty[slot]), ((a_cnt / p.n_slots) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->a_full[slot]), p.slot_bytes);
-            tma_load_5d(a_base + slot * p.slot_bytes, tm_in, smem_u32(&bars->a_full[slot]), c * 64, 0, w0 - p.pw,
+    if (elect_one()) {
+      // ===== TMA producer =====
+      uint32_t a_slot = 0, a_par = 1, b_st = 0, b_par = 1;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo;
+        for (int r = 0; r < p.kh; ++r) {
+          const int need_hi = min(r + ht_eff, rr_hi);
+          while (next_row < need_hi) {
+            mbar_wait(bar_a_empty + 8 * a_slot, a_par);
+            mbar_expect_tx(bar_a_full + 8 * a_slot, p.slot_bytes);
+            tma_load_5d(a_base + a_slot * p.slot_bytes, tm_in, bar_a_full + 8 * a_slot, c * 64, 0, w0 - p.pw,
                         h0 - p.ph + next_row, g);
+            if (++a_slot == n_slots) { a_slot = 0; a_par ^= 1; }
+            ++next_row;
           }
-          __syncwarp();
-          ++a_cnt;
-          ++next_row;
-        }
-        if (max(r, rr_lo) >= min(r + ht_eff, rr_hi)) continue;  // tap row touches no valid input row
-        for (int s = 0; s < p.kw; ++s) {
-          const int st = b_cnt % p.n_bstages;
-          mbar_wait(smem_u32(&bars->b_empty[st]), ((b_cnt / p.n_bstages) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->b_full[st]), kBTile);
-            tma_load_3d(b_base + st * kBTile, tm_w, smem_u32(&bars->b_full[st]), c * 64, 0, r * p.kw + s);
+          if (max(r, rr_lo) >= need_hi) continue;  // tap row touches no valid input row
+          const int tap0 = r * p.kw;
+          for (int s = 0; s < p.kw; ++s) {
+            mbar_wait(bar_b_empty + 8 * b_st, b_par);
+            mbar_expect_tx(bar_b_full + 8 * b_st, kBTile);
+            tma_load_3d(b_base + b_st * kBTile, tm_w, bar_b_full + 8 * b_st, c * 64, 0, tap0 + s);
+            if (++b_st == n_bst) { b_st = 0; b_par ^= 1; }
           }
-          __syncwarp();
-          ++b_cnt;
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform control flow; one elected lane issues tcgen05.mma / commit) =====
-    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
-    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
-    int a_wait = 0, b_cnt = 0;
-    uint32_t started = 0;  // bit h: accumulator h holds data
-    for (int c = 0; c < p.n_chunks; ++c) {
-      const int row_base = c * n_valid - rr_lo;  // sequence number of relative row rr is row_base + rr
-      int next_row = rr_lo, rel_row = rr_lo;
-      for (int r = 0; r < p.kh; ++r) {
-        const int need_hi = min(r + ht_eff, rr_hi);
-        while (next_row < need_hi) {
-          const int slot = a_wait % p.n_slots;
-          mbar_wait(smem_u32(&bars->a_full[slot]), (a_wait / p.n_slots) & 1);
-          ++a_wait;
-          ++next_row;
-        }
-        const int lo = max(r, rr_lo), hi = min(r + ht_eff, rr_hi);
-        if (lo < hi) {
-          for (int s = 0; s < p.kw; ++s) {
-            const int st = b_cnt % p.n_bstages;
-            mbar_wait(smem_u32(&bars->b_full[st]), (b_cnt / p.n_bstages) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t b_lo = (((b_base + st * kBTile) & 0x3FFFF) >> 4) | (1u << 16);
+    if (elect_one()) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+      uint32_t a_slot = 0, a_par = 0, b_st = 0, b_par = 0;
+      uint32_t rel_slot = 0;      // slot of the oldest unreleased row (rel_row)
+      uint32_t started = 0;       // bit h: accumulator h holds data
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo, rel_row = rr_lo;
+        for (int r = 0; r < p.kh; ++r) {
+          const int need_hi = min(r + ht_eff, rr_hi);
+          while (next_row < need_hi) {
+            mbar_wait(bar_a_full + 8 * a_slot, a_par);
+            if (++a_slot == n_slots) { a_slot = 0; a_par ^= 1; }
+            ++next_row;
+          }
+          const int lo = max(r, rr_lo), hi = need_hi;
+          if (lo < hi) {
+            // rows lo..hi-1 are live, rel_row <= lo: slot(lo) = rel_slot + (lo - rel_row) (mod n_slots)
+            uint32_t lo_slot = rel_slot + (uint32_t)(lo - rel_row);
+            if (lo_slot >= n_slots) lo_slot -= n_slots;
+            const uint32_t lo_addr = a_base + lo_slot * p.slot_bytes;
+            const uint32_t wrap_addr = a_base + n_slots * p.slot_bytes;
+            for (int s = 0; s < p.kw; ++s) {
+              mbar_wait(bar_b_full + 8 * b_st, b_par);
+              tc_fence_after();
+              const uint32_t b_lo = ((b_base + b_st * kBTile) >> 4) | (1u << 16);
+              uint32_t row_addr = lo_addr + s * 1024;
               for (int rr = lo; rr < hi; ++rr) {
                 const int h = rr - r;
-                const uint32_t a_addr = a_base + ((row_base + rr) % p.n_slots) * p.slot_bytes + s * 1024;
-                const uint32_t a_lo = ((a_addr & 0x3FFFF) >> 4) | (1u << 16);
-                const uint32_t acc = (started >> h) & 1;
+                const uint32_t a_lo = (row_addr >> 4) | (1u << 16);
+                const uint32_t acc = ((started >> h) & 1) | (s > 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   umma_bf16(tmem + h * N, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
                             idesc, acc | (k > 0));
                 }
+                row_addr += p.slot_bytes;
+                if (row_addr >= wrap_addr) row_addr -= n_slots * p.slot_bytes;
               }
-              umma_commit(smem_u32(&bars->b_empty[st]));
+              umma_commit(bar_b_empty + 8 * b_st);
+              if (++b_st == n_bst) { b_st = 0; b_par ^= 1; }
             }
-            __syncwarp();
-            for (int rr = lo; rr < hi; ++rr) started |= 1u << (rr - r);
-            ++b_cnt;
+            started |= ((1u << (hi - lo)) - 1u) << (lo - r);
+          }
+          while (rel_row <= r && rel_row < rr_hi) {   // row r has had its last use
+            umma_commit(bar_a_empty + 8 * rel_slot);
+            if (++rel_slot == n_slots) rel_slot = 0;
+            ++rel_row;
           }
         }
-        if (elect_one()) {
-          for (int q = rel_row; q <= r && q < rr_hi; ++q)
-            umma_commit(smem_u32(&bars->a_empty[(row_base + q) % p.n_slots]));
+        while (rel_row < rr_hi) {
+          umma_commit(bar_a_empty + 8 * rel_slot);
+          if (++rel_slot == n_slots) rel_slot = 0;
+          ++rel_row;
         }
-        __syncwarp();
-        while (rel_row <= r && rel_row < rr_hi) ++rel_row;
       }
-      if (elect_one()) {
-        for (int q = rel_row; q < rr_hi; ++q) umma_commit(smem_u32(&bars->a_empty[(row_base + q) % p.n_slots]));
-      }
-      __syncwarp();
-      rel_row = rr_hi;
+      umma_commit(smem_u32(&bars->acc_full));
     }
-    if (elect_one()) umma_commit(smem_u32(&bars->acc_full));
     __syncwarp();
   } else {
     // ===== epilogue: TMEM -> registers -> bias / ReLU / dropout / mask -> bf16 act =====
@@ -367,7 +372,6 @@ conv_fwdT_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
   // relative input rows rr: hh = h0 - ph + rr; accumulator a needs row r' + a*stack at step r'
   const int rr_lo = max(0, p.ph - h0);
   const int rr_hi = min(acc_eff * p.stack + p.kh - 1, p.H + p.ph - h0);
-  const int n_valid = rr_hi - rr_lo;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_slots; ++i) { mbar_init(smem_u32(&bars->x_full[i]), 1); mbar_init(smem_u32(&bars->x_empty[i]), 1); }
@@ -395,102 +399,106 @@ conv_fwdT_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
     return false;
   };
 
+  const uint32_t bar_x_full = smem_u32(&bars->x_full[0]), bar_x_empty = smem_u32(&bars->x_empty[0]);
+  const uint32_t bar_w_full = smem_u32(&bars->w_full[0]), bar_w_empty = smem_u32(&bars->w_empty[0]);
+  const uint32_t n_slots = p.n_slots, n_wst = p.n_wstages;
   if (warp == 0) {
-    // ===== TMA producer =====
-    int x_cnt = 0, w_cnt = 0;
-    for (int c = 0; c < p.n_chunks; ++c) {
-      int next_row = rr_lo;
-      for (int rp = 0; rp < n_iter; ++rp) {
-        const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
-        while (next_row < need_hi) {
-          const int slot = x_cnt % p.n_slots;
-          mbar_wait(smem_u32(&bars->x_empty[slot]), ((x_cnt / p.n_slots) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->x_full[slot]), p.slot_bytes);
-            tma_load_5d(x_base + slot * p.slot_bytes, tm_in, smem_u32(&bars->x_full[slot]), c * 64, 0, w0 - p.pw,
+    if (elect_one()) {
+      // ===== TMA producer (one elected thread, no div/mod) =====
+      uint32_t x_slot = 0, x_par = 1, w_st = 0, w_par = 1;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo;
+        for (int rp = 0; rp < n_iter; ++rp) {
+          const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
+          while (next_row < need_hi) {
+            mbar_wait(bar_x_empty + 8 * x_slot, x_par);
+            mbar_expect_tx(bar_x_full + 8 * x_slot, p.slot_bytes);
+            tma_load_5d(x_base + x_slot * p.slot_bytes, tm_in, bar_x_full + 8 * x_slot, c * 64, 0, w0 - p.pw,
                         h0 - p.ph + next_row, g);
+            if (++x_slot == n_slots) { x_slot = 0; x_par ^= 1; }
+            ++next_row;
           }
-          __syncwarp();
-          ++x_cnt;
-          ++next_row;
-        }
-        if (!step_active(rp)) continue;
-        for (int s = 0; s < p.kw; ++s) {
-          const int st = w_cnt % p.n_wstages;
-          mbar_wait(smem_u32(&bars->w_empty[st]), ((w_cnt / p.n_wstages) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->w_full[st]), kWTile);
+          if (!step_active(rp)) continue;
+          for (int s = 0; s < p.kw; ++s) {
+            mbar_wait(bar_w_empty + 8 * w_st, w_par);
+            mbar_expect_tx(bar_w_full + 8 * w_st, kWTile);
             for (int j = 0; j < p.stack; ++j) {
               const int r = rp - (p.stack - 1) + j;      // weight tap row of M block j (out of range -> TMA zero fill)
               const int tap = (r < 0 || r >= p.kh) ? -1 : r * p.kw + s;
-              tma_load_3d(w_base + st * kWTile + j * p.cout * 128, tm_w, smem_u32(&bars->w_full[st]), c * 64, 0, tap);
+              tma_load_3d(w_base + w_st * kWTile + j * p.cout * 128, tm_w, bar_w_full + 8 * w_st, c * 64, 0, tap);
             }
+            if (++w_st == n_wst) { w_st = 0; w_par ^= 1; }
           }
-          __syncwarp();
-          ++w_cnt;
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
-    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    int x_wait = 0, w_cnt = 0;
-    uint32_t started = 0;
-    for (int c = 0; c < p.n_chunks; ++c) {
-      const int row_base = c * n_valid - rr_lo;
-      int next_row = rr_lo, rel_row = rr_lo;
-      for (int rp = 0; rp < n_iter; ++rp) {
-        const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
-        while (next_row < need_hi) {
-          const int slot = x_wait % p.n_slots;
-          mbar_wait(smem_u32(&bars->x_full[slot]), (x_wait / p.n_slots) & 1);
-          ++x_wait;
-          ++next_row;
-        }
-        if (step_active(rp)) {
-          for (int s = 0; s < p.kw; ++s) {
-            const int st = w_cnt % p.n_wstages;
-            mbar_wait(smem_u32(&bars->w_full[st]), (w_cnt / p.n_wstages) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a_lo = (((w_base + st * kWTile) & 0x3FFFF) >> 4) | (1u << 16);
-              for (int a = 0; a < acc_eff; ++a) {
-                const int rr = rp + a * p.stack;
-                if (rr < rr_lo || rr >= rr_hi) continue;
-                const uint32_t b_addr = x_base + ((row_base + rr) % p.n_slots) * p.slot_bytes + s * 1024;
-                const uint32_t b_lo = ((b_addr & 0x3FFFF) >> 4) | (1u << 16);
-                const uint32_t acc = (started >> a) & 1;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(tmem + a * 256, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
-                            idesc, acc | (k > 0));
-                }
-              }
-              umma_commit(smem_u32(&bars->w_empty[st]));
-            }
-            __syncwarp();
+    if (elect_one()) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      uint32_t x_slot = 0, x_par = 0, w_st = 0, w_par = 0;
+      uint32_t rel_slot = 0;
+      uint32_t started = 0;
+      const uint32_t ring_bytes = n_slots * p.slot_bytes;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo, rel_row = rr_lo;
+        for (int rp = 0; rp < n_iter; ++rp) {
+          const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
+          while (next_row < need_hi) {
+            mbar_wait(bar_x_full + 8 * x_slot, x_par);
+            if (++x_slot == n_slots) { x_slot = 0; x_par ^= 1; }
+            ++next_row;
+          }
+          if (step_active(rp)) {
+            // live rows are >= rel_row and fewer than n_slots: address of row rr by offset from rel_slot
+            uint32_t row_off[2];
+            uint32_t use = 0;
             for (int a = 0; a < acc_eff; ++a) {
               const int rr = rp + a * p.stack;
-              if (rr >= rr_lo && rr < rr_hi) started |= 1u << a;
+              if (rr >= rr_lo && rr < rr_hi) {
+                uint32_t off = (rel_slot + (uint32_t)(rr - rel_row)) * p.slot_bytes;
+                if (off >= ring_bytes) off -= ring_bytes;
+                row_off[a] = off;
+                use |= 1u << a;
+              }
             }
-            ++w_cnt;
+            for (int s = 0; s < p.kw; ++s) {
+              mbar_wait(bar_w_full + 8 * w_st, w_par);
+              tc_fence_after();
+              const uint32_t a_lo = ((w_base + w_st * kWTile) >> 4) | (1u << 16);
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                if ((use >> a) & 1) {
+                  const uint32_t b_lo = ((x_base + row_off[a] + s * 1024) >> 4) | (1u << 16);
+                  const uint32_t acc = ((started >> a) & 1) | (s > 0);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    umma_bf16(tmem + a * 256, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
+                              idesc, acc | (k > 0));
+                  }
+                }
+              }
+              umma_commit(bar_w_empty + 8 * w_st);
+              if (++w_st == n_wst) { w_st = 0; w_par ^= 1; }
+            }
+            started |= use;
+          }
+          while (rel_row <= rp && rel_row < rr_hi) {   // row rp has had its last use (accumulator 0)
+            umma_commit(bar_x_empty + 8 * rel_slot);
+            if (++rel_slot == n_slots) rel_slot = 0;
+            ++rel_row;
           }
         }
-        // row rr = rp has had its last use (accumulator 0)
-        if (elect_one()) {
-          for (int q = rel_row; q <= rp && q < rr_hi; ++q)
-            umma_commit(smem_u32(&bars->x_empty[(row_base + q) % p.n_slots]));
+        while (rel_row < rr_hi) {
+          umma_commit(bar_x_empty + 8 * rel_slot);
+          if (++rel_slot == n_slots) rel_slot = 0;
+          ++rel_row;
         }
-        __syncwarp();
-        while (rel_row <= rp && rel_row < rr_hi) ++rel_row;
       }
-      if (elect_one()) {
-        for (int q = rel_row; q < rr_hi; ++q) umma_commit(smem_u32(&bars->x_empty[(row_base + q) % p.n_slots]));
-      }
-      __syncwarp();
+      umma_commit(smem_u32(&bars->acc_full));
     }
-    if (elect_one()) umma_commit(smem_u32(&bars->acc_full));
     __syncwarp();
   } else {
     // ===== epilogue: lane = output channel (and stacked row), columns = positions =====
@@ -748,60 +756,65 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   const uint32_t tmem = bars->tmem_base;
   const uint32_t dy_off = n_xchunks * p.x_chunk_bytes;  // dy tiles follow the x chunks inside a stage
 
+  const uint32_t bar_full = smem_u32(&bars->full[0]), bar_empty = smem_u32(&bars->empty[0]);
+  const uint32_t n_st = p.n_stages;
+  // position-step cursor (wt, h, g) of step q0, advanced incrementally (no div/mod in the loops)
+  const int wt_0 = q0 % p.n_wtiles, gh_0 = q0 / p.n_wtiles;
+  const int h_0 = gh_0 % p.H, g_0 = gh_0 / p.H;
   if (warp == 0) {
-    int cnt = 0;
-    for (int q = q0; q < q1; ++q) {
-      const int wt = q % p.n_wtiles;
-      const int gh = q / p.n_wtiles;
-      const int h = gh % p.H, g = gh / p.H;
-      const int hh = h + r - p.ph;
-      if (hh < 0 || hh >= p.H) continue;
-      const int st = cnt % p.n_stages;
-      mbar_wait(smem_u32(&bars->empty[st]), ((cnt / p.n_stages) & 1) ^ 1);
-      if (elect_one()) {
-        const uint32_t base = smem_base + st * p.stage_bytes;
-        mbar_expect_tx(smem_u32(&bars->full[st]), p.stage_bytes);
-        for (int xc = 0; xc < n_xchunks; ++xc)
-          tma_load_5d(base + xc * p.x_chunk_bytes, tm_x, smem_u32(&bars->full[st]), (cib * n_xchunks + xc) * 64, 0,
-                      wt * WT - p.pw + s0, hh, g);
-        for (int j = 0; j < NB / 64; ++j)
-          tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, smem_u32(&bars->full[st]), cob * NB + j * 64, 0, wt * WT, h, g);
-      }
-      __syncwarp();
-      ++cnt;
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(128, NB, 1, 1);
-    const uint32_t a_lbo = p.fold ? 1024u : p.x_chunk_bytes;
-    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
-    int cnt = 0;
-    for (int q = q0; q < q1; ++q) {
-      const int gh = q / p.n_wtiles;
-      const int h = gh % p.H;
-      const int hh = h + r - p.ph;
-      if (hh < 0 || hh >= p.H) continue;
-      const int st = cnt % p.n_stages;
-      mbar_wait(smem_u32(&bars->full[st]), (cnt / p.n_stages) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t base = smem_base + st * p.stage_bytes;
-        const uint32_t b_lo = (((base + dy_off) & 0x3FFFF) >> 4) | ((kDyChunk >> 4) << 16);
-        for (int a = 0; a < n_acc_eff; ++a) {
-          const uint32_t xa = base + (uint32_t)(p.fold ? 2 * a : a) * 1024u;
-          const uint32_t a_lo = ((xa & 0x3FFFF) >> 4) | (((a_lbo >> 4) & 0x3FFF) << 16);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            umma_bf16(tmem + a * NB, ((uint64_t)kDescHi << 32) | (a_lo + 128 * k), ((uint64_t)kDescHi << 32) | (b_lo + 128 * k),
-                      idesc, (cnt > 0) | (k > 0));
-          }
-        }
-        umma_commit(smem_u32(&bars->empty[st]));
-      }
-      __syncwarp();
-      ++cnt;
-    }
     if (elect_one()) {
-      if (cnt > 0) {
+      uint32_t st = 0, par = 1;
+      int wt = wt_0, h = h_0, g = g_0;
+      for (int q = q0; q < q1; ++q) {
+        const int hh = h + r - p.ph;
+        if (hh >= 0 && hh < p.H) {
+          mbar_wait(bar_empty + 8 * st, par);
+          const uint32_t base = smem_base + st * p.stage_bytes;
+          mbar_expect_tx(bar_full + 8 * st, p.stage_bytes);
+          for (int xc = 0; xc < n_xchunks; ++xc)
+            tma_load_5d(base + xc * p.x_chunk_bytes, tm_x, bar_full + 8 * st, (cib * n_xchunks + xc) * 64, 0,
+                        wt * WT - p.pw + s0, hh, g);
+          for (int j = 0; j < NB / 64; ++j)
+            tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, bar_full + 8 * st, cob * NB + j * 64, 0, wt * WT, h, g);
+          if (++st == n_st) { st = 0; par ^= 1; }
+        }
+        if (++wt == p.n_wtiles) { wt = 0; if (++h == p.H) { h = 0; ++g; } }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, NB, 1, 1);
+      const uint32_t a_lbo = p.fold ? 1024u : p.x_chunk_bytes;
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+      const uint32_t a_hi16 = ((a_lbo >> 4) & 0x3FFF) << 16, b_hi16 = (kDyChunk >> 4) << 16;
+      const uint32_t a_step = p.fold ? 2048u : 1024u;
+      uint32_t st = 0, par = 0, any = 0;
+      int wt = wt_0, h = h_0;
+      for (int q = q0; q < q1; ++q) {
+        const int hh = h + r - p.ph;
+        if (hh >= 0 && hh < p.H) {
+          mbar_wait(bar_full + 8 * st, par);
+          tc_fence_after();
+          const uint32_t base = smem_base + st * p.stage_bytes;
+          const uint32_t b_lo = ((base + dy_off) >> 4) | b_hi16;
+          uint32_t xa = base;
+          for (int a = 0; a < n_acc_eff; ++a) {
+            const uint32_t a_lo = (xa >> 4) | a_hi16;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              umma_bf16(tmem + a * NB, ((uint64_t)kDescHi << 32) | (a_lo + 128 * k), ((uint64_t)kDescHi << 32) | (b_lo + 128 * k),
+                        idesc, any | (k > 0));
+            }
+            xa += a_step;
+          }
+          umma_commit(bar_empty + 8 * st);
+          if (++st == n_st) { st = 0; par ^= 1; }
+          any = 1;
+        }
+        if (++wt == p.n_wtiles) { wt = 0; if (++h == p.H) h = 0; }
+      }
+      if (any) {
         *reinterpret_cast<volatile uint32_t*>(&bars->any_step) = 1;
         umma_commit(smem_u32(&bars->acc_full));
       } else {
@@ -1018,6 +1031,72 @@ extern "C" int zns_dbg_umma_probe(int variant, const void* a, const void* b, flo
     attr_set = true;
   }
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const bf16*)a, (const bf16*)b, d, n, k);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 rate microbenchmark (test/diagnostic only): one CTA per SM issues `iters` groups of
+// `per_group` MMAs (128 x n x 16, bf16) on shared-memory-resident garbage and reports cycles.
+//   mode bit0: rotate over `n_acc` accumulators instead of one
+//   mode bit1: commit + wait on an mbarrier after every group (pipeline round trip)
+//   mode bit2: B operand address changes per MMA (different smem tiles)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int n, int iters, int per_group, int mode, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const int n_acc = (mode & 1) ? 512 / n : 1;
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+        for (int g = 0; g < per_group; ++g) {
+          const int q = it * per_group + g;
+          const uint32_t a_addr = base + (q % 16) * 1024 + (g & 3) * 32;
+          const uint32_t b_addr = base + 64 * 1024 + ((mode & 4) ? (q % 3) * 32768 : 0) + (g & 3) * 32;
+          umma_bf16(tmem + (q % n_acc) * n, ((uint64_t)kDescHi << 32) | ((a_addr & 0x3FFFF) >> 4) | (1u << 16),
+                    ((uint64_t)kDescHi << 32) | ((b_addr & 0x3FFFF) >> 4) | (1u << 16), idesc, 1);
+        }
+        if (mode & 2) umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+      if (mode & 2) { mbar_wait(smem_u32(&bar), phase); phase ^= 1; }
+    }
+    if (!(mode & 2)) {
+      if (elect_one()) umma_commit(smem_u32(&bar));
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), 0);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+extern "C" int zns_dbg_umma_rate(int n, int iters, int per_group, int mode, int n_ctas, long long* cycles, void* stream) {
+  ZNS_REQUIRE(cycles && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && per_group > 0 && n_ctas > 0, "bad arguments");
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  umma_rate_kernel<<<n_ctas, 128, 170 * 1024, (cudaStream_t)stream>>>(n, iters, per_group, mode, cycles);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
