@@ -15,7 +15,7 @@ run simple 600 tests/test_gpu_ops.py -k "not umma and not conv_fwd and not conv_
 run convfwd 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad"
 run wgrad 600 tests/test_gpu_ops.py -k "conv_wgrad_umma"
 run full 900 tests/test_gpu_ops.py -k "conv_full"
-export ZNS_CONV_NO_TRANSPOSED=1
-run convfwd_notransposed 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full"
-unset ZNS_CONV_NO_TRANSPOSED
+export ZNS_CONV_TRANSPOSED=1
+run convfwd_transposed 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full"
+unset ZNS_CONV_TRANSPOSED
 cat gpurun_out/summary.txt

@@ -15,7 +15,7 @@ if __name__ == "__main__":
     print("n per_group mode ctas -> cycles/MMA (mean, max over CTAs); ideal = n/2")
     for ctas in (1, 148):
         for n in (64, 128, 256):
-            for mode in (0, 1, 4, 5, 2, 3, 7):
+            for mode in (0, 1, 8, 9):
                 for pg in (4, 16):
                     run(n, 50, pg, mode, ctas)
                     m, mx = run(n, 2000, pg, mode, ctas)

@@ -666,11 +666,12 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
   cudaStream_t st = (cudaStream_t)stream;
   {
-    // C_out <= 128: transposed kernel (weights on M, 256 positions on N) unless disabled for A/B tests
-    static const bool no_t = getenv("ZNS_CONV_NO_TRANSPOSED") != nullptr;
+    // Experimental transposed kernel (weights on M, 256 positions on N) for C_out <= 128: measured
+    // slower than the direct kernel once the issue loops were fixed (profiles/README.md); opt-in only.
+    static const bool use_t = getenv("ZNS_CONV_TRANSPOSED") != nullptr;
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    if (!no_t && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
+    if (use_t && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
   switch (d->c_out) {
     case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);
@@ -1062,6 +1063,24 @@ umma_rate_kernel(int n, int iters, int per_group, int mode, long long* __restric
     const int n_acc = (mode & 1) ? 512 / n : 1;
     uint32_t phase = 0;
     const long long t0 = clock64();
+    if (mode & 8) {
+      // tight loop: one elected thread, descriptors precomputed, 4 MMAs unrolled (like the conv kernels)
+      if (elect_one()) {
+        const uint32_t a_lo = (base >> 4) | (1u << 16), b_lo = ((base + 64 * 1024) >> 4) | (1u << 16);
+        const int n_acc8 = (mode & 1) ? 512 / n : 1;
+        uint32_t acc = 0, a_off = 0;
+        for (int it = 0; it < iters * per_group / 4; ++it) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + acc * n, ((uint64_t)kDescHi << 32) | (a_lo + a_off + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k), idesc, 1);
+          if (++acc == (uint32_t)n_acc8) acc = 0;
+          a_off += 64; if (a_off >= 1024) a_off = 0;
+        }
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), 0);
+    } else
     for (int it = 0; it < iters; ++it) {
       if (elect_one()) {
         for (int g = 0; g < per_group; ++g) {
@@ -1076,7 +1095,7 @@ umma_rate_kernel(int n, int iters, int per_group, int mode, long long* __restric
       __syncwarp();
       if (mode & 2) { mbar_wait(smem_u32(&bar), phase); phase ^= 1; }
     }
-    if (!(mode & 2)) {
+    if (!(mode & 2) && !(mode & 8)) {
       if (elect_one()) umma_commit(smem_u32(&bar));
       __syncwarp();
       mbar_wait(smem_u32(&bar), 0);

@@ -40,7 +40,8 @@ def branch_param_names() -> List[str]:
 
 def _fwd_tag(c_out: int, H: int) -> str:
     """Which tensor-core kernel zns_conv_fwd dispatches to (csrc/conv_umma.cu)."""
-    if c_out == 128 or (c_out == 64 and H % 2 == 0):
+    import os
+    if os.environ.get("ZNS_CONV_TRANSPOSED") and (c_out == 128 or (c_out == 64 and H % 2 == 0)):
         return f"conv_fwdT_umma(c_out={c_out})"
     return f"conv_fwd_umma<{c_out}>"
 
