@@ -192,6 +192,20 @@ extern "C" int zns_vqt_basis_host(int sr, int n_bins, int bpo, double fmin, doub
   return ZNS_OK;
 }
 
+static uint16_t host_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static float host_bf16_to_float(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +215,8 @@ struct zns_vqt_plan {
   int sr, hop, n_bins, bpo, n_oct;
   int max_batch, max_samples;
   int n_fft[ZNS_VQT_MAX_OCT];
-  float* d_coef[ZNS_VQT_MAX_OCT];  // [n_fft][2][bpo/2][2] interleaved (see filterbank kernel)
+  float* d_coef[ZNS_VQT_MAX_OCT];  // [n_fft][2][bpo/2][2] interleaved (SIMT filterbank kernel)
+  uint16_t* d_coef_bf[ZNS_VQT_MAX_OCT];  // [3 splits][2*bpo columns][n_fft] bf16 (tensor-core filterbank)
   float* d_inv_sqrt_len;           // [n_bins]
   float* d_scratch[ZNS_VQT_MAX_OCT];  // decimated signals, octave >= 1
   float* d_stage_in;               // for *_host: [max_batch][max_samples]
@@ -272,6 +287,23 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
       }
     ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef[i], coef.size() * sizeof(float)));
     ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef[i], coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // three-term bf16 split g = g1 + g2 + g3 (round to nearest even), column = 2*filter + {re, im}
+    {
+      const int ncol = 2 * bpo;
+      std::vector<uint16_t> sp((size_t)3 * ncol * nf);
+      for (int k = 0; k < bpo; ++k)
+        for (int ri = 0; ri < 2; ++ri)
+          for (int n = 0; n < nf; ++n) {
+            float v = ri ? im[k * nf + n] : re[k * nf + n];
+            for (int t = 0; t < 3; ++t) {
+              const uint16_t hb = host_bf16_rn(v);
+              sp[((size_t)t * ncol + 2 * k + ri) * nf + n] = hb;
+              v -= host_bf16_to_float(hb);
+            }
+          }
+      ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef_bf[i], sp.size() * sizeof(uint16_t)));
+      ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef_bf[i], sp.data(), sp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
   }
   std::vector<double> lens;
   cq_lengths((double)sr, fmin, n_bins, bpo, gamma, lens);
@@ -293,6 +325,7 @@ extern "C" int zns_vqt_plan_destroy(zns_vqt_plan* p) {
   if (!p) return ZNS_OK;
   for (int i = 0; i < ZNS_VQT_MAX_OCT; ++i) {
     if (p->d_coef[i]) cudaFree(p->d_coef[i]);
+    if (p->d_coef_bf[i]) cudaFree(p->d_coef_bf[i]);
     if (p->d_scratch[i]) cudaFree(p->d_scratch[i]);
   }
   if (p->d_inv_sqrt_len) cudaFree(p->d_inv_sqrt_len);
@@ -306,49 +339,96 @@ extern "C" int zns_vqt_plan_destroy(zns_vqt_plan* p) {
 // device: stride-2 decimation  y[t] = (sum_{|j|<=31} h[|j|] x[2t+j]) / sqrt(0.5), zero extended
 // (resampy._resample_loop at ratio 1/2 + librosa fix_length + scale)
 // ---------------------------------------------------------------------------------------------
-#define DEC_TILE 1024  // outputs per block
-#define DEC_THREADS 256
+#define DEC_TILE 2048    // outputs per block
+#define DEC_THREADS 256  // 8 consecutive outputs per thread
+#define DEC_PAIRS (DEC_TILE + 48)  // even/odd sample pairs staged per block (16 before, 32 after)
+
+// even / odd phases live in separate arrays, each skewed by one word per eight so that lanes
+// (stride 8 outputs) hit distinct banks: pos(m) = m + (m >> 3)
+__device__ __forceinline__ int dec_pos(int m) { return m + (m >> 3); }
+
+#define DEC_TILES_PER_BLOCK 4
+
+// loads the even/odd pairs of tile t0 into registers (all loads in flight before first use)
+__device__ __forceinline__ void dec_load_tile(const float* __restrict__ xb, int n_in, int t0, float2* v) {
+  constexpr int kIter = (DEC_PAIRS + DEC_THREADS - 1) / DEC_THREADS;
+  const long first = 2L * (t0 - 16);
+  const bool interior = first >= 0 && first + 2L * DEC_PAIRS <= (long)n_in && ((reinterpret_cast<uintptr_t>(xb + first) & 7) == 0);
+  if (interior) {
+    const float2* src = reinterpret_cast<const float2*>(xb + first);
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+      const int i = threadIdx.x + k * DEC_THREADS;
+      v[k] = (i < DEC_PAIRS) ? __ldg(src + i) : make_float2(0.f, 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+      const int i = threadIdx.x + k * DEC_THREADS;
+      const long s0 = first + 2L * i;
+      v[k].x = (i < DEC_PAIRS && s0 >= 0 && s0 < n_in) ? __ldg(xb + s0) : 0.f;
+      v[k].y = (i < DEC_PAIRS && s0 + 1 >= 0 && s0 + 1 < n_in) ? __ldg(xb + s0 + 1) : 0.f;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(DEC_THREADS) vqt_decimate_kernel(const float* __restrict__ x, int n_in,
                                                                    float* __restrict__ y, int n_out_valid, int n_out) {
-  // even / odd phases in separate arrays so that lanes read consecutive words
-  __shared__ float xe[DEC_TILE + 32];
-  __shared__ float xo[DEC_TILE + 32];
+  __shared__ float xe[DEC_PAIRS + DEC_PAIRS / 8 + 2];
+  __shared__ float xo[DEC_PAIRS + DEC_PAIRS / 8 + 2];
+  constexpr int kIter = (DEC_PAIRS + DEC_THREADS - 1) / DEC_THREADS;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * DEC_TILE;
   const float* xb = x + (size_t)b * n_in;
-  // sample index range needed: 2*t0 - 31 .. 2*(t0+DEC_TILE-1) + 31  ->  pairs m = t0-16 .. t0+DEC_TILE+15
-  for (int i = threadIdx.x; i < DEC_TILE + 32; i += DEC_THREADS) {
-    int m = t0 - 16 + i;
-    long s0 = 2L * m, s1 = 2L * m + 1;
-    xe[i] = (s0 >= 0 && s0 < n_in) ? __ldg(xb + s0) : 0.f;
-    xo[i] = (s1 >= 0 && s1 < n_in) ? __ldg(xb + s1) : 0.f;
-  }
-  __syncthreads();
   float* yb = y + (size_t)b * n_out;
+  const int tile0 = blockIdx.x * DEC_TILES_PER_BLOCK;
+  const int n_tiles = (n_out + DEC_TILE - 1) / DEC_TILE;
+  const int tile_end = min(tile0 + DEC_TILES_PER_BLOCK, n_tiles);
+  float2 v[kIter];
+  dec_load_tile(xb, n_in, tile0 * DEC_TILE, v);
+  for (int tile = tile0; tile < tile_end; ++tile) {
+    const int t0 = tile * DEC_TILE;
+    // pair index m (local) <-> global pair t0 - 16 + m
 #pragma unroll
-  for (int r = 0; r < DEC_TILE / DEC_THREADS; ++r) {
-    int tl = threadIdx.x + r * DEC_THREADS;
-    int t = t0 + tl;
-    if (t >= n_out) continue;
-    float acc = 0.f;
-    if (t < n_out_valid) {
-      // x[2t + j]: j even -> xe[tl + 16 + j/2]; j odd -> xo[tl + 16 + (j-1)/2]
-      // left wing first (j = 0, -1, ..., -31), then right wing (j = 1..31), as the reference sums
-      const int c = tl + 16;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float v = (i & 1) ? xo[c - (i + 1) / 2] : xe[c - i / 2];
-        acc = fmaf(c_dec_taps[i], v, acc);
+    for (int k = 0; k < kIter; ++k) {
+      const int i = threadIdx.x + k * DEC_THREADS;
+      if (i < DEC_PAIRS) {
+        xe[dec_pos(i)] = v[k].x;
+        xo[dec_pos(i)] = v[k].y;
       }
-#pragma unroll
-      for (int k = 1; k < 32; ++k) {
-        float v = (k & 1) ? xo[c + (k - 1) / 2] : xe[c + k / 2];
-        acc = fmaf(c_dec_taps[k], v, acc);
-      }
-      acc = acc / 0.70710678118654752f;
     }
-    yb[t] = acc;
+    __syncthreads();
+    if (tile + 1 < tile_end) dec_load_tile(xb, n_in, t0 + DEC_TILE, v);   // next tile's loads fly during the FMAs
+    // thread -> outputs tl0 .. tl0+7 (local), tl0 = 8 * threadIdx.x; output t uses
+    //   even taps j = -30..30:  xe[t + j/2]      -> local pairs (tl + 16) - 15 .. + 15
+    //   odd  taps j = -31..31:  xo[t + (j-1)/2]  -> local pairs (tl + 16) - 16 .. + 15
+    const int c0 = 8 * threadIdx.x + 16;
+    float ev[38], od[39];
+#pragma unroll
+    for (int i = 0; i < 38; ++i) ev[i] = xe[dec_pos(c0 - 15 + i)];
+#pragma unroll
+    for (int i = 0; i < 39; ++i) od[i] = xo[dec_pos(c0 - 16 + i)];
+    __syncthreads();   // smem may be overwritten by the next iteration
+    float res[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float acc = c_dec_taps[0] * ev[o + 15];
+#pragma unroll
+      for (int q = 1; q <= 15; ++q) acc = fmaf(c_dec_taps[2 * q], ev[o + 15 - q] + ev[o + 15 + q], acc);   // j = -2q, +2q
+#pragma unroll
+      for (int q = 0; q <= 15; ++q) acc = fmaf(c_dec_taps[2 * q + 1], od[o + 15 - q] + od[o + 16 + q], acc);  // j = -(2q+1), +(2q+1)
+      res[o] = acc / 0.70710678118654752f;
+    }
+    const int tbase = t0 + 8 * threadIdx.x;
+    if (tbase + 8 <= n_out_valid && ((reinterpret_cast<uintptr_t>(yb + tbase) & 15) == 0)) {
+      reinterpret_cast<float4*>(yb + tbase)[0] = make_float4(res[0], res[1], res[2], res[3]);
+      reinterpret_cast<float4*>(yb + tbase)[1] = make_float4(res[4], res[5], res[6], res[7]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int t = tbase + o;
+        if (t < n_out) yb[t] = (t < n_out_valid) ? res[o] : 0.f;
+      }
+    }
   }
 }
 
@@ -421,10 +501,191 @@ vqt_filterbank_kernel(const float* __restrict__ y, int n_sig, long long sig_stri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// device: tensor-core filterbank.  C[t, col] = sum_n frame[t][n] * g[col][n] is a dense GEMM
+// (128 frames x 24 columns x n_fft per block); fp32 inputs are split into three bf16 terms
+// x = x1 + x2 + x3, g = g1 + g2 + g3 and the six leading products (x1g1, x1g2, x1g3, x2g1, x2g2,
+// x3g1) are accumulated in fp32 by mma.sync m16n8k16 -- 1e-8 of full scale from exact
+// (tools check in DESIGN.md), below the reference's own fp32 noise.  Frames are materialised in
+// shared memory with pitch n_fft + 8 halfwords, which makes every fragment load conflict-free.
+// (mma.sync rather than tcgen05: N = 24 is far below a UMMA tile and the operand is a Toeplitz
+// view; the warp-level path lets the fragments be addressed directly.)
+// ---------------------------------------------------------------------------------------------
+#define FBT_COLS 24
+#define FBT_TILES 4   // consecutive frame tiles per block (coefficients staged once)
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// x = x1 + x2 + x3 for two values at once: one packed cvt.rn.bf16x2.f32 per term; a bf16 is the
+// high half of its fp32, so unpacking is a shift / mask.
+__device__ __forceinline__ void split3_pair(float v0, float v1, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+  s1 = pack_bf16x2(v0, v1);
+  const float r0 = v0 - __uint_as_float(s1 << 16), r1 = v1 - __uint_as_float(s1 & 0xFFFF0000u);
+  s2 = pack_bf16x2(r0, r1);
+  const float q0 = r0 - __uint_as_float(s2 << 16), q1 = r1 - __uint_as_float(s2 & 0xFFFF0000u);
+  s3 = pack_bf16x2(q0, q1);
+}
+
+template <int NFFT, int FBT_FRAMES>
+__global__ void __launch_bounds__(FBT_FRAMES * 2)
+vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_stride,
+                          const uint16_t* __restrict__ coef_bf, int hop, const float* __restrict__ inv_sqrt_len, int bin0,
+                          int n_bins, int n_frames, float* __restrict__ out) {
+  constexpr int FBT_THREADS = FBT_FRAMES * 2;  // one warp per 16 frames
+  constexpr int PITCH = NFFT + 8;           // halfwords; PITCH/2 = 4 (mod 8) -> conflict-free fragments
+  constexpr int PW = PITCH / 2;             // 32-bit words per row
+  extern __shared__ uint32_t fsm[];
+  uint32_t* fr = fsm;                        // [3][FBT_FRAMES][PW]
+  uint32_t* cf = fsm + 3 * FBT_FRAMES * PW;  // [3][FBT_COLS][PW]
+  const int b = blockIdx.z;
+  const float* yb = y + (size_t)b * sig_stride;
+
+  // coefficients: global [3][24][NFFT] halfwords -> smem rows of PITCH (once per block, 16-byte loads)
+  {
+    constexpr int kVec = 3 * FBT_COLS * (NFFT / 2) / 4;   // uint4 count
+    const uint4* src = reinterpret_cast<const uint4*>(coef_bf);
+    for (int i = threadIdx.x; i < kVec; i += FBT_THREADS) {
+      const uint4 c = __ldg(src + i);
+      const int row = (i * 4) / (NFFT / 2), w = (i * 4) - row * (NFFT / 2);
+      uint32_t* d = cf + row * PW + w;
+      d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+    }
+  }
+  for (int tile = 0; tile < FBT_TILES; ++tile) {
+  const int f0 = (blockIdx.x * FBT_TILES + tile) * FBT_FRAMES;
+  if (f0 >= n_frames) break;
+  if (tile > 0) __syncthreads();   // the previous tile's fragments have been consumed
+  // frames: (t, n-pair) -> three bf16 split words.  Loads are issued in batches of 8 pairs per
+  // thread before any conversion so that their latency overlaps.
+  constexpr int HALF = NFFT / 2;
+  constexpr int kPairs = FBT_FRAMES * HALF / FBT_THREADS;   // pairs per thread
+  constexpr int kBatch = kPairs < 8 ? kPairs : 8;
+  const long span_lo = (long)f0 * hop - HALF;
+  const long span_hi = (long)(min(f0 + FBT_FRAMES, n_frames) - 1) * hop + HALF;   // exclusive end of the last frame
+  const bool interior = span_lo >= 0 && span_hi <= (long)n_sig && f0 + FBT_FRAMES <= n_frames &&
+                        ((reinterpret_cast<uintptr_t>(yb) & 7) == 0);
+#pragma unroll 1
+  for (int i0 = 0; i0 < kPairs; i0 += kBatch) {
+    float2 v[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int i = threadIdx.x + (i0 + k) * FBT_THREADS;
+      const int t = i / HALF, w = i - t * HALF;
+      const int f = f0 + t;
+      const long q = (long)f * hop + 2 * w - HALF;       // even: hop and HALF are even
+      if (interior) {
+        v[k] = __ldg(reinterpret_cast<const float2*>(yb + q));
+      } else if (f < n_frames) {
+        v[k].x = __ldg(yb + reflect_index(q, n_sig));
+        v[k].y = __ldg(yb + reflect_index(q + 1, n_sig));
+      } else {
+        v[k] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int i = threadIdx.x + (i0 + k) * FBT_THREADS;
+      const int t = i / HALF, w = i - t * HALF;
+      uint32_t s1, s2, s3;
+      split3_pair(v[k].x, v[k].y, s1, s2, s3);
+      fr[(0 * FBT_FRAMES + t) * PW + w] = s1;
+      fr[(1 * FBT_FRAMES + t) * PW + w] = s2;
+      fr[(2 * FBT_FRAMES + t) * PW + w] = s3;
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tid = lane & 3;
+  float acc[3][4];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  const int row0 = warp * 16 + g;
+#pragma unroll
+  for (int ks = 0; ks < NFFT / 16; ++ks) {
+    uint32_t a[3][4];
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp) {
+      const uint32_t* base = fr + (sp * FBT_FRAMES + row0) * PW + ks * 8 + tid;
+      a[sp][0] = base[0];
+      a[sp][1] = base[8 * PW];
+      a[sp][2] = base[4];
+      a[sp][3] = base[8 * PW + 4];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      uint32_t bb[3][2];
+#pragma unroll
+      for (int sp = 0; sp < 3; ++sp) {
+        const uint32_t* cb = cf + (sp * FBT_COLS + j * 8 + g) * PW + ks * 8 + tid;
+        bb[sp][0] = cb[0];
+        bb[sp][1] = cb[4];
+      }
+      // smallest products first
+      mma_bf16_16816(acc[j], a[2], bb[0][0], bb[0][1]);  // x3 g1
+      mma_bf16_16816(acc[j], a[0], bb[2][0], bb[2][1]);  // x1 g3
+      mma_bf16_16816(acc[j], a[1], bb[1][0], bb[1][1]);  // x2 g2
+      mma_bf16_16816(acc[j], a[1], bb[0][0], bb[0][1]);  // x2 g1
+      mma_bf16_16816(acc[j], a[0], bb[1][0], bb[1][1]);  // x1 g2
+      mma_bf16_16816(acc[j], a[0], bb[0][0], bb[0][1]);  // x1 g1
+    }
+  }
+  // epilogue: thread holds (re, im) of filter 4j + tid for frames row0 and row0 + 8
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int bin = bin0 + 4 * j + tid;
+    const float isl = __ldg(inv_sqrt_len + bin);
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int f = f0 + row0 + 8 * hrow;
+      if (f < n_frames) {
+        const float re = acc[j][2 * hrow], im = acc[j][2 * hrow + 1];
+        out[((size_t)b * n_bins + bin) * n_frames + f] = logf(sqrtf(re * re + im * im) * isl + 1e-9f);
+      }
+    }
+  }
+  }  // tile loop
+}
+
+template <int NFFT, int FBT_FRAMES>
+static int fbt_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
+                        int n_frames, float* out, cudaStream_t st) {
+  const size_t smem = (size_t)(3 * FBT_FRAMES + 3 * FBT_COLS) * ((NFFT + 8) / 2) * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute((vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES>),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((n_frames + FBT_FRAMES * FBT_TILES - 1) / (FBT_FRAMES * FBT_TILES), 1, batch);
+  vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES><<<grid, FBT_FRAMES * 2, smem, st>>>(sig, n_sig, stride, p->d_coef_bf[oct], hop_i,
+                                                                    p->d_inv_sqrt_len, p->n_bins - p->bpo * (oct + 1),
+                                                                    p->n_bins, n_frames, out);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
 static int fb_launch(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
                      int n_frames, float* out, cudaStream_t st) {
   const int nf = p->n_fft[oct];
   const int hb = p->bpo / 2;
+  static const bool simt = getenv("ZNS_VQT_SIMT") != nullptr;   // A/B switch: the round-1 SIMT filterbank
+  if (!simt && p->bpo == 12) {
+    switch (nf) {
+      case 16: return fbt_launch_t<16, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      case 32: return fbt_launch_t<32, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      case 64: return fbt_launch_t<64, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      case 128: return fbt_launch_t<128, 64>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);  // 72 KB -> 3 CTAs/SM
+      default: break;
+    }
+  }
   size_t smem = ((size_t)FB_FRAMES * (nf + 1) + (size_t)nf * hb * 4) * sizeof(float);
   dim3 grid((n_frames + FB_FRAMES - 1) / FB_FRAMES, 1, batch);
   const int bin0 = p->n_bins - p->bpo * (oct + 1);
@@ -459,7 +720,7 @@ extern "C" int zns_vqt_forward(zns_vqt_plan* p, const float* y, int batch, int n
     if (i > 0) {
       const int n_valid = n_cur / 2;        // resampy output length
       const int n_next = (n_cur + 1) / 2;   // librosa fix_length
-      dim3 grid((n_next + DEC_TILE - 1) / DEC_TILE, batch);
+      dim3 grid((n_next + DEC_TILE * DEC_TILES_PER_BLOCK - 1) / (DEC_TILE * DEC_TILES_PER_BLOCK), batch);
       vqt_decimate_kernel<<<grid, DEC_THREADS, 0, st>>>(cur, n_cur, p->d_scratch[i], n_valid, n_next);
       ZNS_CHECK_LAUNCH();
       cur = p->d_scratch[i];

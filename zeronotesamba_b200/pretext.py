@@ -81,7 +81,7 @@ class PretextTrainer:
 
     def __init__(self, model: Pretext_CNN, batch_len: int = 16, temperature: float = 0.25, lr: float = 1e-6,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, crop_frames: int = CROP_FRAMES,
-                 dropout_p: Optional[float] = None, use_graph: bool = True, seed: int = 0):
+                 dropout_p: Optional[float] = None, use_graph: bool = True, seed: int = 0, distributed: bool = True):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("PretextTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -90,7 +90,8 @@ class PretextTrainer:
         self.temperature, self.lr, self.betas, self.eps = float(temperature), float(lr), betas, float(eps)
         self.dropout_p = model.anchor.pretrained.dp.p if dropout_p is None else float(dropout_p)
         self.use_graph = use_graph
-        self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self.distributed = bool(distributed) and dist_utils.is_distributed()
+        self.world = torch.distributed.get_world_size() if self.distributed else 1
         names = branch_param_names()
         named = [dict(model.anchor.named_parameters()), dict(model.postve.named_parameters())]
         plist = [named[br][n] for br in range(2) for n in names]
@@ -114,7 +115,8 @@ class PretextTrainer:
             br, n = divmod(i, len(names))
             self.params[br][names[n]] = seg
             self.grads[br][names[n]] = gseg
-        dist_utils.broadcast_parameters(self.flat_p, 0)   # replicas start from rank 0's weights
+        if self.distributed:
+            dist_utils.broadcast_parameters(self.flat_p, 0)   # replicas start from rank 0's weights
         self.engine = EncoderEngine(self.B, self.T, 2, dev, seed=seed)
         self.engine._ensure_grad_ws()
         self.batch_buf = torch.zeros(self.B, 2, 96, self.T, device=dev)
@@ -190,11 +192,13 @@ class PretextTrainer:
                 self.flat_p.copy_(snap[0]); self.flat_m.copy_(snap[1]); self.flat_v.copy_(snap[2])
                 self.engine.step_ctr.copy_(snap[3])
             self._graph_fb.replay()
-            dist_utils.allreduce_gradients(self.flat_g)     # NCCL over NVLink; Adam applies 1/world
+            if self.distributed:
+                dist_utils.allreduce_gradients(self.flat_g)     # NCCL over NVLink; Adam applies 1/world
             self._graph_opt.replay()
         else:
             self._forward_backward()
-            dist_utils.allreduce_gradients(self.flat_g)
+            if self.distributed:
+                dist_utils.allreduce_gradients(self.flat_g)
             self._optimizer()
         return self.result
 
@@ -216,7 +220,7 @@ class PretextTrainer:
         crop_batch(self._vqt_buf, self._starts_buf, out=self.batch_buf, crop=self.T)
 
     def step_from_audio(self, anchor_audio: torch.Tensor, positive_audio: torch.Tensor, starts: torch.Tensor,
-                        sample_rate: int = 16000, mode: str = "vqt") -> torch.Tensor:
+                        sample_rate: int = 16000, mode: str = "vqt", run_step: bool = True) -> torch.Tensor:
         """Whole in-loop path on the device: two 16 kHz stems of one source clip (anchor = other stems,
         positive = drums; pretext.py:83-84,144) -> VQT (2, 96, F) -> B crops at ``starts`` -> training step."""
         from .processing.input_rep import VQTPlan
@@ -235,7 +239,7 @@ class PretextTrainer:
             self._graph_front.replay()
         else:
             self._front()
-        return self.step()
+        return self.step() if run_step else self.result
 
 
 # ---------------------------------------------------------------------------------------------------
