@@ -76,16 +76,19 @@ int zns_crop_gather(const float* vqt, int channels, int bins, int frames, const 
 /* ------------------------------------------------------------------------------------------
  * Encoder layers (models.py:16-74).  "Same" convolutions, stride 1.
  * ---------------------------------------------------------------------------------------- */
-/* cv1 (models.py:16,37-39): x fp32 [B][H][W] (the (B,1,96,T) NCHW input, optionally with a
- * per-clip element stride `x_clip_stride`, so that channel 0 / 1 of a (B,2,96,T) crop batch can be
- * read in place, pretext.py:476-477) -> act bf16 [G][H][W][8][64] = dropout(relu(conv + bias)). */
-int zns_conv1_fwd(const float* x, long long x_clip_stride, const float* weight, const float* bias, void* out_act,
+/* cv1 (models.py:16,37-39): x fp32, clip b / row h / frame w at x[b*x_clip_stride + h*x_row_stride + w]
+ * (the (B,1,96,T) NCHW input; the strides let channel 0 / 1 of a (B,2,96,T) crop batch be read in
+ * place, pretext.py:476-477, and let overlapping time segments of ONE long clip act as the "clips" of a
+ * group: x_clip_stride = segment hop, x_row_stride = T)
+ * -> act bf16 [G][H][W][8][64] = dropout(relu(conv + bias)). */
+int zns_conv1_fwd(const float* x, long long x_clip_stride, long long x_row_stride, const float* weight, const float* bias,
+                  void* out_act,
                   int batch, int H, int W, float dropout_p, uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream,
                   void* stream);
 /* cv1 weight/bias gradient: dy act bf16 [G][H][W][8][64]; dw fp32 [64][1][3][11] and db [64] are
  * accumulated into (+=). */
-int zns_conv1_wgrad(const void* dy_act, const float* x, long long x_clip_stride, float* dw, float* db, int batch,
-                    int H, int W, void* stream);
+int zns_conv1_wgrad(const void* dy_act, const float* x, long long x_clip_stride, long long x_row_stride, float* dw,
+                    float* db, int batch, int H, int W, void* stream);
 
 typedef struct {
   int batch;      /* B clips (act tensors hold ceil(B/8) groups) */

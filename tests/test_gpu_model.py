@@ -202,3 +202,68 @@ def test_smoke_entry():
     from zeronotesamba_b200 import smoke
     out = smoke.run(verbose=False)
     assert out["vqt_max_rel"] < 1e-4
+
+
+def test_batch1_time_folding_matches_unfolded_and_reference(gold, sd):
+    """Batch-1 inputs run time-folded over the eight clip slots: same result as the unfolded path
+    (the clip duplicated to a batch of two, which is not folded) and as the reference's Down_CNN."""
+    from zeronotesamba_b200.models.models import Down_CNN, fold_plan
+    x = torch.from_numpy(gold["ft_in"]).to(DEV)
+    assert fold_plan(x.shape[3]) is not None
+    model = Down_CNN().to(DEV)
+    model.pretext.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        folded = model(x[:, 0:1], x[:, 1:2])
+        x2 = torch.cat([x, x], dim=0)
+        unfolded = model(x2[:, 0:1], x2[:, 1:2])[0:1]
+    assert folded.shape == (1, x.shape[3])
+    assert float((folded - unfolded).abs().max()) < 2e-3
+    assert _rel(folded, gold["ft_out"]) < 1e-2
+
+
+def test_finetune_step_batch1_golden(gold, sd):
+    """epochs.train_epoch (reference signature): Down_CNN -> BCELoss -> backward -> Adam, one file per step."""
+    from zeronotesamba_b200 import epochs
+    from zeronotesamba_b200.loader import load_models
+    criterion, optimizer, model = load_models("pretrained", "finetune", 1e-5, state_dict=sd)
+    for br in (model.pretext.anchor, model.pretext.postve):
+        br.pretrained.dp.p = 0.0
+    assert abs(optimizer.param_groups[0]["lr"] - 0.5 * 1e-5 * 10e-2) < 1e-18       # loader.py:43
+    x = torch.from_numpy(gold["ft_in"])[0]                      # (2, 96, T)
+    msk = torch.from_numpy(gold["ft_mask"])[0]
+    vl = epochs.val_epoch(model, criterion, "pretrained", ["a"], {"a": None}, {"a": x}, {"a": msk}, False, False)
+    assert abs(vl[0] - float(gold["ft_loss"])) <= 1e-2 * float(gold["ft_loss"])
+    res = epochs.train_epoch(model, criterion, optimizer, "pretrained", ["a"], {"a": None}, {"a": x}, {"a": msk}, False, False)
+    assert res[0] is model and abs(res[2] - float(gold["ft_loss"])) <= 1e-2 * float(gold["ft_loss"])
+    keys = [str(k) for k in gold["layout_keys"]]
+    named = dict(model.pretext.named_parameters())
+    off = gold["sample_off"]
+    cosines = []
+    for i, k in enumerate(keys):
+        g = named[k].grad
+        assert abs(float(g.double().norm()) - gold["ft_grad_l2"][i]) <= 0.1 * gold["ft_grad_l2"][i] + 1e-9, k
+        idx = gold["sample_idx"][off[i]:off[i + 1]]
+        gs = g.reshape(-1)[idx].double().cpu().numpy()
+        ref = gold["ft_grad_samples"][off[i]:off[i + 1]]
+        cosines.append(float(gs @ ref / (np.linalg.norm(gs) * np.linalg.norm(ref) + 1e-30)))
+    assert min(cosines) > 0.99, cosines
+    # vanilla / clmr status: single DS_CNN
+    criterion, optimizer, single = load_models("vanilla", "finetune", 1e-5)
+    out = epochs.train_epoch(single, criterion, optimizer, "vanilla", ["a"], {"a": None}, {"a": x[0]}, {"a": msk}, False, False)
+    assert np.isfinite(out[2])
+
+
+def test_batched_inference_long_clips(sd):
+    """cfg5 shape: a batch of 30 s clips (T = 1876) through Down_CNN; batch rows are independent."""
+    from zeronotesamba_b200.models.models import Down_CNN
+    model = Down_CNN().to(DEV)
+    model.pretext.load_state_dict(sd)
+    model.eval()
+    g = torch.Generator().manual_seed(8)
+    x = (torch.rand(3, 2, 96, 1876, generator=g) * 10 - 9 + 2 * torch.randn(3, 2, 96, 1876, generator=g)).to(DEV)
+    with torch.no_grad():
+        out = model(x[:, 0:1], x[:, 1:2])
+        one = model(x[1:2, 0:1], x[1:2, 1:2])      # folded batch-1 path
+    assert out.shape == (3, 1876) and float(out.min()) >= 0 and float(out.max()) <= 1
+    assert float((out[1:2] - one).abs().max()) < 2e-3

@@ -135,7 +135,7 @@ def test_conv1_fwd_wgrad(B, H, W):
     for ch in (0, 1):
         x = x2[:, ch]
         out = torch.empty(G, H, W, 8, 64, dtype=torch.bfloat16, device=DEV)
-        L.check(L.lib().zns_conv1_fwd(L.ptr(x2) + ch * H * W * 4, 2 * H * W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.0,
+        L.check(L.lib().zns_conv1_fwd(L.ptr(x2) + ch * H * W * 4, 2 * H * W, W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.0,
                                       0, None, 0, st()))
         ref = F.relu(F.conv2d(x.unsqueeze(1), w, b, padding=(1, 5)))
         got = from_act(out, B)
@@ -147,7 +147,7 @@ def test_conv1_fwd_wgrad(B, H, W):
         dy_act = to_act(dy)
         dw = torch.zeros_like(w)
         db = torch.zeros_like(b)
-        L.check(L.lib().zns_conv1_wgrad(L.ptr(dy_act), L.ptr(x2) + ch * H * W * 4, 2 * H * W, L.ptr(dw), L.ptr(db), B, H, W,
+        L.check(L.lib().zns_conv1_wgrad(L.ptr(dy_act), L.ptr(x2) + ch * H * W * 4, 2 * H * W, W, L.ptr(dw), L.ptr(db), B, H, W,
                                         st()))
         wr = w.clone().requires_grad_(True)
         br = b.clone().requires_grad_(True)
@@ -163,8 +163,8 @@ def test_conv1_dropout_statistics():
     b = torch.ones(64, device=DEV)
     out = torch.empty(1, H, W, 8, 64, dtype=torch.bfloat16, device=DEV)
     ref = torch.empty_like(out)
-    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, L.ptr(w), L.ptr(b), L.ptr(ref), B, H, W, 0.0, 7, None, 3, st()))
-    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.1, 7, None, 3, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(ref), B, H, W, 0.0, 7, None, 3, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.1, 7, None, 3, st()))
     kept = out.float() != 0
     rate = float(kept.float().mean())
     assert abs(rate - 0.9) < 3e-3, rate
@@ -172,7 +172,7 @@ def test_conv1_dropout_statistics():
     assert float((ratio - 1 / 0.9).abs().max()) < 1e-2
     out2 = torch.empty_like(out)
     ctr = torch.tensor([5], dtype=torch.int32, device=DEV)
-    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, L.ptr(w), L.ptr(b), L.ptr(out2), B, H, W, 0.1, 7, L.ptr(ctr), 3, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(out2), B, H, W, 0.1, 7, L.ptr(ctr), 3, st()))
     assert float(((out2.float() != 0) != kept).float().mean()) > 0.1  # a different mask with a device seed word
 
 

@@ -76,3 +76,19 @@ def test_training_step(gold, sd):
         assert np.allclose(gs, ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max() + 1e-12), k
         delta = (res["new_sd"][k].double() - sd[k].double())
         assert np.isclose(float(delta.norm()), gold["delta_l2"][i], rtol=2e-3), k
+
+
+def test_finetune_step_batch1(gold, sd):
+    """Down_CNN -> BCELoss -> backward at batch size 1 (epochs.py:45-63) against the reference's vectors."""
+    torch.set_num_threads(8)
+    x = torch.from_numpy(gold["ft_in"])
+    msk = torch.from_numpy(gold["ft_mask"])
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = eo.down_forward(params, x[:, 0:1], x[:, 1:2], "max")
+    loss = torch.nn.functional.binary_cross_entropy(out, msk)
+    loss.backward()
+    assert np.allclose(out.detach().numpy(), gold["ft_out"], rtol=1e-5, atol=1e-6)
+    assert np.isclose(float(loss), float(gold["ft_loss"]), rtol=1e-5)
+    keys = list(eo.state_dict_layout().keys())
+    for i, k in enumerate(keys):
+        assert np.isclose(float(params[k].grad.double().norm()), gold["ft_grad_l2"][i], rtol=1e-3, atol=1e-9), k

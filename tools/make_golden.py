@@ -118,6 +118,26 @@ def main():
         out["down_max"] = down(x[:, 0:1], x[:, 1:2]).numpy()
         out["down_mean"] = _with_sd(mm.Down_CNN("mean"), sd)(x[:, 0:1], x[:, 1:2]).numpy()
 
+    # ---- downstream fine-tune step, batch size 1 (epochs.py:45-63): Down_CNN -> BCELoss -> backward -----
+    T1 = 400
+    x1 = (torch.rand(1, 2, 96, T1, generator=g) * 10.0 - 9.0 + 2.0 * torch.randn(1, 2, 96, T1, generator=g)).float()
+    msk = torch.tensor(np.random.default_rng(3).choice([0.0, 0.5, 1.0], size=(1, T1), p=[0.8, 0.1, 0.1]), dtype=torch.float32)
+    ft = mm.Down_CNN()
+    ft.pretext.load_state_dict(sd)
+    ft.train()
+    for br in (ft.pretext.anchor, ft.pretext.postve):
+        br.pretrained.dp.p = 0.0
+    out1 = ft(x1[:, 0:1], x1[:, 1:2])
+    loss1 = torch.nn.BCELoss()(out1, msk)
+    loss1.backward()
+    out["ft_in"] = x1.numpy()
+    out["ft_mask"] = msk.numpy()
+    out["ft_out"] = out1.detach().numpy()
+    out["ft_loss"] = np.array(float(loss1))
+    ftp = dict(ft.pretext.named_parameters())
+    out["ft_grad_l2"] = np.array([float(ftp[k].grad.double().norm()) for k in keys])
+    out["ft_grad_samples"] = np.concatenate([ftp[k].grad.reshape(-1)[samp_idx[k]].numpy() for k in keys])
+
     # ---- NT-Xent on its own, incl. a short last batch (loss_functions.py:30) --------------------
     e1 = torch.rand(16, 313, generator=g)
     e2 = torch.rand(16, 313, generator=g)

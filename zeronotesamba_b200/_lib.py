@@ -37,9 +37,9 @@ _PROTOS = {
     "zns_vqt_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_vqt_forward_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_crop_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "zns_conv1_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_u32,
+    "zns_conv1_fwd": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_u32,
                               c_void_p, c_u32, c_void_p]),
-    "zns_conv1_wgrad": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "zns_conv1_wgrad": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "zns_conv_fwd": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
                              C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p]),
     "zns_conv_wgrad": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),

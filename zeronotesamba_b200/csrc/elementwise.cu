@@ -25,7 +25,7 @@ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 #define C1_CO 64
 
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, long long clip_stride,
-                                                        const float* __restrict__ weight,
+                                                        long long row_stride, const float* __restrict__ weight,
                                                         const float* __restrict__ bias, bf16* __restrict__ out,
                                                         int B, int H, int W, float drop_p, uint32_t seed,
                                                         const uint32_t* __restrict__ seed_dev, uint32_t stream_id) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int s = 0; s < C1_KW; ++s) {
       int hh = h + r - 1, ww = w + s - 5;
-      xin[r * C1_KW + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * W + ww) : 0.f;
+      xin[r * C1_KW + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * row_stride + ww) : 0.f;
     }
   const uint32_t thr = dropout_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -86,13 +86,13 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   }
 }
 
-extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, const float* weight, const float* bias,
-                             void* out_act, int batch, int H, int W, float drop_p, uint32_t seed,
+extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long row_stride, const float* weight,
+                             const float* bias, void* out_act, int batch, int H, int W, float drop_p, uint32_t seed,
                              const uint32_t* seed_dev, uint32_t rng_stream, void* stream) {
   ZNS_REQUIRE(x && weight && bias && out_act, "NULL argument");
   ZNS_REQUIRE(batch > 0 && H > 0 && W > 0 && drop_p >= 0.f && drop_p < 1.f, "bad conv1 geometry");
   dim3 grid((W + 31) / 32, H, zns_groups(batch));
-  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, clip_stride, weight, bias, (bf16*)out_act, batch, H, W,
+  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, clip_stride, row_stride, weight, bias, (bf16*)out_act, batch, H, W,
                                                            drop_p, seed, seed_dev, rng_stream);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
@@ -102,7 +102,7 @@ extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, const float*
 // cv1 weight / bias gradient
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
-                                                          long long clip_stride, float* __restrict__ dw,
+                                                          long long clip_stride, long long row_stride, float* __restrict__ dw,
                                                           float* __restrict__ db, int B, int H, int W) {
   __shared__ float xs[C1_KH][8][32 + C1_KW - 1];
   const int g = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 32;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const bf16* __restrict
     int r = i / (8 * 42), rem = i - r * 8 * 42;
     int b8 = rem / 42, j = rem - b8 * 42;
     int hh = h + r - 1, ww = w0 + j - 5, b = g * 8 + b8;
-    xs[r][b8][j] = (b < B && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (size_t)b * clip_stride + (size_t)hh * W + ww)
+    xs[r][b8][j] = (b < B && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (size_t)b * clip_stride + (size_t)hh * row_stride + ww)
                                                                     : 0.f;
   }
   __syncthreads();
@@ -143,11 +143,12 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const bf16* __restrict
   if (q == 0) atomicAdd(db + n, accb);
 }
 
-extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long clip_stride, float* dw, float* db, int batch,
-                               int H, int W, void* stream) {
+extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long clip_stride, long long row_stride, float* dw,
+                               float* db, int batch, int H, int W, void* stream) {
   ZNS_REQUIRE(dy_act && x && dw && db, "NULL argument");
   dim3 grid((W + 31) / 32, H, zns_groups(batch));
-  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, x, clip_stride, dw, db, batch, H, W);
+  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, x, clip_stride, row_stride, dw, db, batch, H,
+                                                             W);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }

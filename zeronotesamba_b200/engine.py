@@ -157,15 +157,17 @@ class EncoderEngine:
                                      L.ptr(self.step_ctr) if self._p > 0 else None, layer_id * 2 + br, st))
 
     def forward(self, xs: Sequence[torch.Tensor], x_clip_stride: int, params: Sequence[Dict[str, torch.Tensor]],
-                train: bool, dropout_p: float = 0.1) -> List[torch.Tensor]:
-        """xs[br]: fp32 CUDA tensor whose clip b starts ``b * x_clip_stride`` elements after its
-        data pointer and holds a contiguous (96, T) VQT.  Returns [emb (B, T)] per branch."""
+                train: bool, dropout_p: float = 0.1, x_row_stride: Optional[int] = None) -> List[torch.Tensor]:
+        """xs[br]: fp32 CUDA tensor; clip b / row h / frame w is read at
+        ``data_ptr + b * x_clip_stride + h * x_row_stride + w`` (x_row_stride defaults to T).
+        Returns [emb (B, T)] per branch."""
         lib, st = L.lib(), L.current_stream()
         self._train, self._p = train, (dropout_p if train else 0.0)
         self._x_in, self._x_stride = list(xs), x_clip_stride
+        self._x_row = self.T if x_row_stride is None else int(x_row_stride)
         for br in range(self.n_br):
             p = params[br]
-            L.check(lib.zns_conv1_fwd(L.ptr(xs[br]), x_clip_stride, L.ptr(p["pretrained.cv1.weight"]),
+            L.check(lib.zns_conv1_fwd(L.ptr(xs[br]), x_clip_stride, self._x_row, L.ptr(p["pretrained.cv1.weight"]),
                                       L.ptr(p["pretrained.cv1.bias"]), L.ptr(self.x1[br]), self.B, N_BINS, self.T,
                                       self._p, self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, 100 + br, st))
         self._conv("cv2", 96, self.x1, self.y2, params, relu=0, drop=False, layer_id=2)
@@ -239,7 +241,7 @@ class EncoderEngine:
         self._dgrad("cv2", 96, gb, self.x1, ga)         # dy1
         for br in range(self.n_br):
             g = grads[br]
-            L.check(lib.zns_conv1_wgrad(L.ptr(ga[br]), L.ptr(self._x_in[br]), self._x_stride,
+            L.check(lib.zns_conv1_wgrad(L.ptr(ga[br]), L.ptr(self._x_in[br]), self._x_stride, self._x_row,
                                         L.ptr(g["pretrained.cv1.weight"]), L.ptr(g["pretrained.cv1.bias"]), self.B, N_BINS,
                                         self.T, st))
             for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:

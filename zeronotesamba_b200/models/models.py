@@ -42,6 +42,50 @@ class _EngineCache:
         return eng
 
 
+# Cumulative time-axis receptive-field halo of the eight convolutions: sum of (kw - 1) / 2 over
+# kw = 11, 13, 15, 17, 19, 21, 23, 25 (models.py:16-23).
+TIME_HALO = 68
+FOLD_SLOTS = 8
+
+
+def fold_plan(T: int, slots: int = FOLD_SLOTS, halo: int = TIME_HALO):
+    """Time folding for batch-1 inputs (the reference fine-tunes and infers one file at a time,
+    epochs.py:45-63, sample_script.py:46-48).  The act layout always carries eight clip slots; with a
+    single clip seven would be padding.  Instead the T frames are cut into eight overlapping segments
+    of W_s frames at hop delta (7 * delta + W_s == T, W_s - delta >= 2 * halo): every output frame is
+    taken from a segment in which it lies >= `halo` frames away from an artificial edge, so its whole
+    receptive field -- forward and backward -- is real data and the result equals the unfolded
+    computation; true clip edges coincide with segment edges, where zero "same" padding is right.
+    Returns (W_s, delta, cuts) with cuts[s]..cuts[s+1] the output frames segment s owns, or None when
+    the clip is too short to fold."""
+    w_min = -(-(T + (slots - 1) * 2 * halo) // slots)
+    for w_s in range(w_min, w_min + slots):
+        if w_s >= T:
+            break
+        if (T - w_s) % (slots - 1) == 0:
+            delta = (T - w_s) // (slots - 1)
+            if delta > 0 and w_s - delta >= 2 * halo:
+                cuts = [0] + [(s + 1) * delta + halo for s in range(slots - 1)] + [T]
+                return w_s, delta, cuts
+    return None
+
+
+def _unfold(emb: torch.Tensor, plan, T: int) -> torch.Tensor:
+    _, delta, cuts = plan
+    out = torch.empty(1, T, device=emb.device, dtype=emb.dtype)
+    for s in range(FOLD_SLOTS):
+        out[0, cuts[s]:cuts[s + 1]] = emb[s, cuts[s] - s * delta:cuts[s + 1] - s * delta]
+    return out
+
+
+def _fold_grad(d_full: torch.Tensor, plan) -> torch.Tensor:
+    w_s, delta, cuts = plan
+    out = torch.zeros(FOLD_SLOTS, w_s, device=d_full.device, dtype=torch.float32)
+    for s in range(FOLD_SLOTS):
+        out[s, cuts[s] - s * delta:cuts[s + 1] - s * delta] = d_full[0, cuts[s]:cuts[s + 1]]
+    return out
+
+
 def _check_input(x: torch.Tensor) -> Tuple[int, int]:
     _require_cuda(x)
     if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] != 96:
@@ -59,14 +103,21 @@ class _EncoderFunction(torch.autograd.Function):
         names = branch_param_names()
         params = [dict(zip(names, flat[br * len(names):(br + 1) * len(names)])) for br in range(n_br)]
         B, T = xs[0].shape[0], xs[0].shape[3]
-        eng = cache.get(B, T, n_br, xs[0].device)
-        need_grad = any(p.requires_grad for p in flat) and torch.is_grad_enabled()
+        plan = fold_plan(T) if B == 1 else None
+        if plan is not None:
+            eng = cache.get(FOLD_SLOTS, plan[0], n_br, xs[0].device)
+        else:
+            eng = cache.get(B, T, n_br, xs[0].device)
         eng.pack_weights(params, need_dgrad=True)
-        embs = eng.forward(xs, 96 * T, params, train=train, dropout_p=dropout_p)
-        ctx.eng, ctx.params, ctx.n_br, ctx.n_names = eng, params, n_br, len(names)
+        if plan is not None:
+            embs = eng.forward(xs, plan[1], params, train=train, dropout_p=dropout_p, x_row_stride=T)
+            out = tuple(_unfold(e, plan, T) for e in embs)
+        else:
+            embs = eng.forward(xs, 96 * T, params, train=train, dropout_p=dropout_p)
+            out = tuple(e.clone() for e in embs)
+        ctx.eng, ctx.params, ctx.n_br, ctx.n_names, ctx.plan = eng, params, n_br, len(names), plan
         ctx.version = getattr(eng, "_version", 0) + 1
         eng._version = ctx.version
-        out = tuple(e.clone() for e in embs)
         return out if n_br > 1 else out[0]
 
     @staticmethod
@@ -77,7 +128,10 @@ class _EncoderFunction(torch.autograd.Function):
                                "call backward before the next forward")
         names = branch_param_names()
         grads = [{n: torch.zeros_like(ctx.params[br][n]) for n in names} for br in range(ctx.n_br)]
-        d = [(g if g is not None else torch.zeros_like(eng.emb[i])).contiguous().float() for i, g in enumerate(d_embs)]
+        if ctx.plan is not None:
+            d = [_fold_grad(g.float(), ctx.plan) if g is not None else torch.zeros_like(eng.emb[i]) for i, g in enumerate(d_embs)]
+        else:
+            d = [(g if g is not None else torch.zeros_like(eng.emb[i])).contiguous().float() for i, g in enumerate(d_embs)]
         eng.backward(d, ctx.params, grads)
         flat = [grads[br][n] for br in range(ctx.n_br) for n in names]
         return (None, None, None, None) + (None,) * ctx.n_br + tuple(flat)
