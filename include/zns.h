@@ -73,6 +73,11 @@ int zns_vqt_forward_host(zns_vqt_plan* plan, const float* y_host, int batch, int
 int zns_crop_gather(const float* vqt, int channels, int bins, int frames, const int32_t* starts, int n_crops,
                     int crop_frames, float* out, void* stream);
 
+/* RMS stem gate, check_CL_clips of processing/stem_check.py:21-51 (used at pretext.py:66-81):
+ * counts[clip] = number of librosa.feature.rms frames (2048 / hop 512, centred, reflect) with
+ * rms(ros)/2 < rms(stem) < 4 rms(ros); there are 1 + n_samples/512 frames.  stem/ros fp32 [batch][n]. */
+int zns_rms_gate(const float* stem, const float* ros, int batch, int n_samples, int32_t* counts, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Encoder layers (models.py:16-74).  "Same" convolutions, stride 1.
  * ---------------------------------------------------------------------------------------- */

@@ -272,3 +272,20 @@ def octave_time_kernels(octave: int, sr: float, gamma: float) -> Tuple[np.ndarra
     n = np.arange(n_fft)[None, :]
     e = np.exp(-2j * np.pi * b * n / n_fft)
     return fft_basis.astype(np.complex128) @ e, n_fft
+
+
+# ---- RMS stem gate (row f3): librosa.feature.rms + check_CL_clips --------------------------------
+def rms_frames(y: np.ndarray, frame_length: int = 2048, hop_length: int = 512) -> np.ndarray:
+    """librosa.feature.rms(y=y, frame_length=2048, hop_length=512) (center=True, reflect), shape (F,)."""
+    y = np.asarray(y, dtype=np.float32)
+    ypad = np.pad(y, int(frame_length // 2), mode="reflect")
+    n_frames = 1 + (len(ypad) - frame_length) // hop_length
+    idx = (np.arange(n_frames) * hop_length)[None, :] + np.arange(frame_length)[:, None]
+    return np.sqrt(np.mean(np.abs(ypad[idx]) ** 2, axis=0))
+
+
+def rms_fraction(anchor: np.ndarray, positive: np.ndarray) -> float:
+    """Fraction used by check_CL_clips (/root/reference/zeroNoteSamba/processing/stem_check.py:33-45)."""
+    stem, ros = rms_frames(anchor), rms_frames(positive)
+    ok = (stem > ros / 2).astype(int) * (stem < ros * 4).astype(int)
+    return float(np.sum(ok) / len(ok))

@@ -267,3 +267,68 @@ def test_batched_inference_long_clips(sd):
         one = model(x[1:2, 0:1], x[1:2, 1:2])      # folded batch-1 path
     assert out.shape == (3, 1876) and float(out.min()) >= 0 and float(out.max()) <= 1
     assert float((out[1:2] - one).abs().max()) < 2e-3
+
+
+def test_rms_stem_gate_vs_oracle():
+    """Row f3: check_CL_clips (stem_check.py:21-51) on the GPU against the librosa.feature.rms restatement."""
+    from oracle import vqt_oracle as vo
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.processing import stem_check
+    pairs = [synth.stem_pair(i, 10.0) for i in range(4)]
+    drums = torch.from_numpy(np.stack([p[0] for p in pairs])).to(DEV)
+    other = torch.from_numpy(np.stack([p[1] for p in pairs])).to(DEV)
+    frac = stem_check.rms_fraction_batch(other, drums).cpu().numpy()
+    for i, (d, o) in enumerate(pairs):
+        want = vo.rms_fraction(o, d)
+        assert abs(frac[i] - want) <= 1.5 / 313, (i, frac[i], want)       # a frame on the threshold may flip
+        for lo, hi in ((0.3, 1.0), (0.0, 0.2), (0.9, 1.0)):
+            if abs(want - lo) > 0.01 and abs(want - hi) > 0.01:
+                assert stem_check.check_CL_clips(o, d, lo, hi) == (lo < want <= hi)
+    scaled = stem_check.rms_fraction_batch(other, other * 0.6).cpu().numpy()
+    assert np.allclose(scaled, 1.0)                                          # ros/2 < stem < 4 ros everywhere
+    assert np.allclose(stem_check.rms_fraction_batch(other, other * 5.0).cpu().numpy(), 0.0)
+
+
+def test_clmr_shared_weight_step_golden(gold, sd):
+    """Row f4: CLMR baseline -- one DS_CNN on both views (pretext.py:494-511), reference signature."""
+    from zeronotesamba_b200.models.loss_functions import NTXent
+    from zeronotesamba_b200.models.models import DS_CNN
+    from zeronotesamba_b200.pretext import FusedAdam, train_epoch, val_epoch
+    batch = torch.from_numpy(gold["step_batch"])
+    B = batch.shape[0]
+    model = DS_CNN().to(DEV)
+    model.load_state_dict({k[len("anchor."):]: v for k, v in sd.items() if k.startswith("anchor.")})
+    model.pretrained.dp.p = 0.0
+    crit = NTXent(batch_len=B, temperature=0.25)
+    opt = FusedAdam(model.parameters(), lr=1e-5)
+    vl = val_epoch(model, [[batch]], crit, opt, pt_task="clmr")
+    assert np.allclose(vl, gold["clmr_loss_cos"], rtol=1e-2, atol=1e-2)
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    _, tl, tp, tn = train_epoch(model, [[batch]], crit, opt, pt_task="clmr")
+    assert np.allclose([tl, tp, tn], gold["clmr_loss_cos"], rtol=1e-2, atol=1e-2)
+    akeys = [str(k)[len("anchor."):] for k in gold["layout_keys"] if str(k).startswith("anchor.")]
+    named = dict(model.named_parameters())
+    for i, k in enumerate(akeys):
+        assert abs(float(named[k].grad.double().norm()) - gold["clmr_grad_l2"][i]) <= 0.3 * gold["clmr_grad_l2"][i] + 1e-9, k
+        assert not torch.equal(named[k].detach(), before[k])
+    with pytest.raises(ValueError, match="Which pretext task"):
+        train_epoch(model, [[batch]], crit, opt, pt_task="other")
+
+
+def test_vqt_bank_and_index_only_crops():
+    """Row f2: on-GPU bank (n, 2, 96, 626) + index-only crop sampling (pretext.py:308-321)."""
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.pretext import crop_batches, vqt_bank
+    drums, other = synth.stem_batch(20, 3, 10.0)
+    bank = vqt_bank(torch.from_numpy(other).to(DEV), torch.from_numpy(drums).to(DEV))
+    assert bank.shape == (3, 2, 96, 626)
+    rng = random.Random(4)
+    expect = random.Random(4)
+    n = 0
+    for i, [batch] in enumerate(crop_batches(bank, 16, rng)):
+        starts = expect.sample(range(0, 313), 16)
+        assert batch.shape == (16, 2, 96, 313)
+        for j, s0 in enumerate(starts):
+            assert torch.equal(batch[j], bank[i, :, :, s0:s0 + 313])
+        n += 1
+    assert n == 3

@@ -92,3 +92,28 @@ def test_finetune_step_batch1(gold, sd):
     keys = list(eo.state_dict_layout().keys())
     for i, k in enumerate(keys):
         assert np.isclose(float(params[k].grad.double().norm()), gold["ft_grad_l2"][i], rtol=1e-3, atol=1e-9), k
+
+
+def test_clmr_shared_weights(gold, sd):
+    """CLMR baseline (pretext.py:494-511): the oracle's DS_CNN applied to both views with shared weights."""
+    torch.set_num_threads(8)
+    batch = torch.from_numpy(gold["step_batch"])
+    single = {k[len("anchor."):]: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("anchor.")}
+    shared = {("anchor." + k): v for k, v in single.items()}
+    a = eo.ds_cnn_forward(shared, "anchor", batch[:, 0:1])
+    p = eo.ds_cnn_forward(shared, "anchor", batch[:, 1:2])
+    loss, cp, cn = eo.ntxent(a, p, batch.shape[0], 0.25)
+    loss.backward()
+    assert np.allclose([float(loss.detach()), cp, cn], gold["clmr_loss_cos"], rtol=1e-5)
+    for i, k in enumerate(single):
+        assert np.isclose(float(single[k].grad.double().norm()), gold["clmr_grad_l2"][i], rtol=1e-3, atol=1e-9), k
+
+
+def test_rms_gate_oracle_properties():
+    from oracle import vqt_oracle as vo
+    from zeronotesamba_b200 import synth
+    d, o = synth.stem_pair(0, 10.0)
+    r = vo.rms_frames(o)
+    assert r.shape == (313,) and np.all(r >= 0)
+    assert vo.rms_fraction(o, o * 0.6) == 1.0 and vo.rms_fraction(o, o * 5.0) == 0.0
+    assert 0.0 <= vo.rms_fraction(o, d) <= 1.0

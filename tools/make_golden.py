@@ -138,6 +138,17 @@ def main():
     out["ft_grad_l2"] = np.array([float(ftp[k].grad.double().norm()) for k in keys])
     out["ft_grad_samples"] = np.concatenate([ftp[k].grad.reshape(-1)[samp_idx[k]].numpy() for k in keys])
 
+    # ---- CLMR baseline step (pretext.py:494-511): one DS_CNN on both views, shared weights ---------------
+    ds = mm.DS_CNN()
+    ds.load_state_dict({k[len("anchor."):]: v for k, v in sd.items() if k.startswith("anchor.")})
+    ds.pretrained.dp.p = 0.0
+    opt_c = torch.optim.Adam(params=ds.parameters(), lr=0.00001)
+    _, cl, cp_, cn_ = pt.train_epoch(ds, loader, lf.NTXent(batch_len=B, temperature=0.25), opt_c, pt_task="clmr")
+    out["clmr_loss_cos"] = np.array([cl, cp_, cn_])
+    dsp = dict(ds.named_parameters())
+    akeys = [k[len("anchor."):] for k in keys if k.startswith("anchor.")]
+    out["clmr_grad_l2"] = np.array([float(dsp[k].grad.double().norm()) for k in akeys])
+
     # ---- NT-Xent on its own, incl. a short last batch (loss_functions.py:30) --------------------
     e1 = torch.rand(16, 313, generator=g)
     e2 = torch.rand(16, 313, generator=g)

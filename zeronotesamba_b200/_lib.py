@@ -37,6 +37,7 @@ _PROTOS = {
     "zns_vqt_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_vqt_forward_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_crop_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "zns_rms_gate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_conv1_fwd": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_u32,
                               c_void_p, c_u32, c_void_p]),
     "zns_conv1_wgrad": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -71,7 +72,7 @@ EXPORTS = tuple(_PROTOS.keys())
 
 # CUDA kernels one call launches (for the launch accounting bench.py reports); 0 = host only
 KERNELS_PER_CALL = {
-    "zns_vqt_forward": 15, "zns_vqt_forward_host": 15, "zns_crop_gather": 1, "zns_conv1_fwd": 1, "zns_conv1_wgrad": 1,
+    "zns_vqt_forward": 15, "zns_vqt_forward_host": 15, "zns_crop_gather": 1, "zns_rms_gate": 1, "zns_conv1_fwd": 1, "zns_conv1_wgrad": 1,
     "zns_conv_fwd": 1, "zns_conv_wgrad": 1, "zns_bias_grad": 1, "zns_pack_weights": 2, "zns_unpack_grads": 1,
     "zns_pool_fwd": 1, "zns_pool_bwd": 1, "zns_head_fwd": 1, "zns_head_bwd": 1, "zns_merge": 1, "zns_act_from_nchw": 1,
     "zns_act_to_nchw": 1, "zns_ntxent_fwd_bwd": 1, "zns_adam_flat": 1, "zns_counter_add": 1, "zns_dbg_conv_fwd_simt": 1,

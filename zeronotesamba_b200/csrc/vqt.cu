@@ -776,3 +776,51 @@ extern "C" int zns_crop_gather(const float* vqt, int channels, int bins, int fra
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// RMS stem gate (row f3): check_CL_clips of /root/reference/zeroNoteSamba/processing/stem_check.py:21-51
+// = librosa.feature.rms(frame_length=2048, hop_length=512, center=True, reflect) of both stems, then
+// the fraction of frames with  ros/2 < stem < 4*ros.  One warp per frame; counts[clip] accumulates
+// the number of accepted frames (the caller divides by 1 + N/512 and applies lower_p < . <= upper_p).
+// ---------------------------------------------------------------------------------------------
+#define RMS_FRAME 2048
+#define RMS_HOP 512
+
+__global__ void __launch_bounds__(256) rms_gate_kernel(const float* __restrict__ stem, const float* __restrict__ ros,
+                                                       int n, int n_frames, int32_t* __restrict__ counts) {
+  const int clip = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 8 + warp;
+  if (f >= n_frames) return;
+  const float* a = stem + (size_t)clip * n;
+  const float* b = ros + (size_t)clip * n;
+  const long q0 = (long)f * RMS_HOP - RMS_FRAME / 2;
+  float sa = 0.f, sb = 0.f;
+  const bool interior = q0 >= 0 && q0 + RMS_FRAME <= n;
+  for (int i = lane; i < RMS_FRAME; i += 32) {
+    const int idx = interior ? (int)(q0 + i) : reflect_index(q0 + i, n);
+    const float va = __ldg(a + idx), vb = __ldg(b + idx);
+    sa = fmaf(va, va, sa);
+    sb = fmaf(vb, vb, sb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if (lane == 0) {
+    const float ra = sqrtf(sa / RMS_FRAME), rb = sqrtf(sb / RMS_FRAME);
+    if (ra > rb / 2.f && ra < rb * 4.f) atomicAdd(counts + clip, 1);
+  }
+}
+
+extern "C" int zns_rms_gate(const float* stem, const float* ros, int batch, int n_samples, int32_t* counts, void* stream) {
+  ZNS_REQUIRE(stem && ros && counts, "NULL argument");
+  ZNS_REQUIRE(batch >= 1 && n_samples > RMS_FRAME / 2, "clip too short for a 2048-sample RMS frame");
+  const int n_frames = 1 + n_samples / RMS_HOP;
+  ZNS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)batch * sizeof(int32_t), (cudaStream_t)stream));
+  dim3 grid((n_frames + 7) / 8, batch);
+  rms_gate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(stem, ros, n_samples, n_frames, counts);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}

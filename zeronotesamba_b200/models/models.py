@@ -188,6 +188,7 @@ class DS_CNN(nn.Module):
         self.fc1 = nn.Conv1d(in_channels=128, out_channels=1, kernel_size=1, padding=0)
         self.sig = nn.Sigmoid()
         self._cache = _EngineCache()
+        self._pair_cache = _EngineCache()
 
     def _flat_params(self) -> List[torch.Tensor]:
         named = dict(self.named_parameters())
@@ -200,6 +201,17 @@ class DS_CNN(nn.Module):
         """
         _check_input(x)
         return _EncoderFunction.apply(self._cache, 1, self.training, self.pretrained.dp.p, x, *self._flat_params())
+
+    def forward_pair(self, a: torch.Tensor, p: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(self(a), self(p))`` in one pass with SHARED weights -- the CLMR baseline applies one DS_CNN
+        to both views (pretext.py:503-504); both views go through every tensor-core launch together and
+        autograd sums the two gradient contributions of each parameter."""
+        ba, ta = _check_input(a)
+        bp, tp = _check_input(p)
+        if (ba, ta) != (bp, tp):
+            raise ValueError("forward_pair needs two inputs of the same shape")
+        params = self._flat_params()
+        return _EncoderFunction.apply(self._pair_cache, 2, self.training, self.pretrained.dp.p, a, p, *params, *params)
 
 
 class Pretext_CNN(nn.Module):

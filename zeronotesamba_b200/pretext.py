@@ -265,14 +265,30 @@ def train_epoch(model: torch.nn.Module, train_loader: Iterable, criterion: NTXen
     -- optimizer: optimizer defined
     -- pt_task: pretext task to run
     """
-    if pt_task == "clmr":
-        raise NotImplementedError("the CLMR baseline path (pretext.py:494-511) is not built")
-    if pt_task != "zerons":
+    if pt_task not in ("zerons", "clmr"):
         raise ValueError("Which pretext task are we running?")
     device = next(model.parameters()).device
     model.train()
     n_batches = 0
-    if isinstance(optimizer, FusedAdam) and isinstance(model, Pretext_CNN):
+    if pt_task == "clmr":
+        # CLMR baseline (pretext.py:494-511): ONE DS_CNN applied to both views, shared weights
+        full_train_loss = full_train_anpos = full_train_anneg = 0.0
+        for [batch] in train_loader:
+            anchors = batch[:, 0:1, :, :].to(device)
+            postves = batch[:, 1:2, :, :].to(device)
+            optimizer.zero_grad()
+            anc_emb, pos_emb = model.forward_pair(anchors, postves)
+            loss, sim_an_pos, sim_an_neg = criterion(anc_emb, pos_emb)
+            loss.backward()
+            optimizer.step()
+            full_train_loss += loss.item()
+            full_train_anpos += sim_an_pos
+            full_train_anneg += sim_an_neg
+            n_batches += 1
+        full_train_loss /= n_batches
+        full_train_anpos /= n_batches
+        full_train_anneg /= n_batches
+    elif isinstance(optimizer, FusedAdam) and isinstance(model, Pretext_CNN):
         acc = torch.zeros(3, device=device)
         for [batch] in train_loader:
             if batch.shape[0] != criterion.batch_len:
@@ -309,7 +325,7 @@ def val_epoch(model: torch.nn.Module, val_loader: Iterable, criterion: NTXent, o
     """
     Validation pass (reference signature and return values, pretext.py:527-592).
     """
-    if pt_task != "zerons":
+    if pt_task not in ("zerons", "clmr"):
         raise ValueError("Which pretext task are we running?")
     device = next(model.parameters()).device
     model.eval()
@@ -319,7 +335,7 @@ def val_epoch(model: torch.nn.Module, val_loader: Iterable, criterion: NTXent, o
         with torch.no_grad():
             anchors = batch[:, 0:1, :, :].to(device)
             postves = batch[:, 1:2, :, :].to(device)
-            anc_emb, pos_emb = model(anchors, postves)
+            anc_emb, pos_emb = model(anchors, postves) if pt_task == "zerons" else model.forward_pair(anchors, postves)
             loss, sim_an_pos, sim_an_neg = criterion(anc_emb, pos_emb)
             full_val_loss += loss.item()
             full_val_anpos += sim_an_pos
@@ -335,10 +351,36 @@ def build_from_config(ymldict: Dict, device: Optional[torch.device] = None):
     tmp = float(ymldict.get("temp", -1.0))
     pt_task = ymldict.get("pt_task")
     lr = float(ymldict.get("lr", 0.000001))
-    if pt_task != "zerons":
-        raise ValueError("Which pretext task are we running?")
     device = device or torch.device("cuda", torch.cuda.current_device())
-    model = Pretext_CNN().to(device)
     criterion = NTXent(batch_len=batch_len, temperature=tmp)
-    optimizer = FusedAdam(model.parameters(), lr=lr)
+    if pt_task == "zerons":
+        model = Pretext_CNN().to(device)
+        optimizer = FusedAdam(model.parameters(), lr=lr)
+    elif pt_task == "clmr":
+        from .models.models import DS_CNN
+        model = DS_CNN().to(device)
+        optimizer = FusedAdam(model.parameters(), lr=0.00001)     # pretext.py:208
+    else:
+        raise ValueError("Which pretext task are we running?")
     return model, criterion, optimizer
+
+
+def vqt_bank(anchor_audio: torch.Tensor, positive_audio: torch.Tensor, sample_rate: int = 16000,
+             mode: str = "vqt") -> torch.Tensor:
+    """On-GPU replacement of the pickled banks of pretext.py:89-172: anchor / positive stems
+    (CUDA fp32 [n, N]) -> bank (n, 2, 96, 1 + N//256), channel 0 = anchor, 1 = positive (pretext.py:144-145)."""
+    from .processing.input_rep import xqt_batch
+    a = xqt_batch(anchor_audio.contiguous().float(), sample_rate, mode)
+    p = xqt_batch(positive_audio.contiguous().float(), sample_rate, mode)
+    return torch.stack([a, p], dim=1)
+
+
+def crop_batches(bank: torch.Tensor, batch_len: int, rng: Optional[random.Random] = None, crop: int = CROP_FRAMES):
+    """Index-only crop sampler over a bank (pretext.py:308-321): yields ``[batch]`` like the reference's
+    DataLoader -- one batch per source clip, ``batch_len`` distinct random starts -- without ever
+    materialising the (1440*16, 2, 96, 313) staging array."""
+    n, _, _, frames = bank.shape
+    for i in range(n):
+        starts = sample_crop_starts(batch_len, rng, n_frames=frames, crop=crop)
+        st = torch.tensor(starts, dtype=torch.int32, device=bank.device)
+        yield [crop_batch(bank[i], st, crop=crop)]
