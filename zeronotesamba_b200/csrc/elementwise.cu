@@ -24,66 +24,66 @@ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 #define C1_TAPS 33
 #define C1_CO 64
 
-// block = 32 frames x 8 channel groups; a thread computes 8 output channels of one (clip, frame):
-// the eight threads of a position store one contiguous 128-byte row.  grid.y enumerates (h, clip slot).
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, long long clip_stride,
                                                         long long row_stride, const float* __restrict__ weight,
                                                         const float* __restrict__ bias, bf16* __restrict__ out,
                                                         int B, int H, int W, float drop_p, uint32_t seed,
                                                         const uint32_t* __restrict__ seed_dev, uint32_t stream_id) {
   __shared__ __align__(16) float ws[C1_TAPS][C1_CO];
-  __shared__ float bs[C1_CO];
-  __shared__ float xs[C1_KH][32 + C1_KW - 1];
   if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
-  const int g = blockIdx.z, h = blockIdx.y >> 3, b8 = blockIdx.y & 7, w0 = blockIdx.x * 32;
-  const int b = g * 8 + b8;
+  __shared__ float bs[C1_CO];
   for (int i = threadIdx.x; i < C1_TAPS * C1_CO; i += 256) {
     int c = i / C1_TAPS, t = i - c * C1_TAPS;  // weight is [64][1][3][11]
     ws[t][c] = weight[i];
   }
   if (threadIdx.x < C1_CO) bs[threadIdx.x] = bias[threadIdx.x];
-  if (threadIdx.x < C1_KH * 42) {
-    const int r = threadIdx.x / 42, j = threadIdx.x - r * 42;
-    const int hh = h + r - 1, ww = w0 + j - 5;
-    xs[r][j] = (b < B && hh >= 0 && hh < H && ww >= 0 && ww < W)
-                   ? __ldg(x + (size_t)b * clip_stride + (size_t)hh * row_stride + ww) : 0.f;
-  }
   __syncthreads();
-  const int cg = threadIdx.x & 7, wl = threadIdx.x >> 3;
-  const int w = w0 + wl;
+  const int b8 = threadIdx.x & 7, wl = threadIdx.x >> 3;
+  const int g = blockIdx.z, h = blockIdx.y, w = blockIdx.x * 32 + wl;
   if (w >= W) return;
-  const size_t e0 = zns_act_index(g, h, w, b8, cg * 8, H, W, C1_CO);
-  uint4* dst = reinterpret_cast<uint4*>(out + e0);
+  const int b = g * 8 + b8;
+  uint4* dst = reinterpret_cast<uint4*>(out + zns_act_index(g, h, w, b8, 0, H, W, C1_CO));
   if (b >= B) {
-    *dst = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
     return;
   }
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = bs[cg * 8 + i];
+  float xin[C1_TAPS];
+  const float* xb = x + (size_t)b * clip_stride;
 #pragma unroll
   for (int r = 0; r < C1_KH; ++r)
 #pragma unroll
-    for (int sft = 0; sft < C1_KW; ++sft) {
-      const int t = r * C1_KW + sft;
-      const float4 w0v = *reinterpret_cast<const float4*>(&ws[t][cg * 8]);
-      const float4 w1v = *reinterpret_cast<const float4*>(&ws[t][cg * 8 + 4]);
-      const float v = xs[r][wl + sft];
-      acc[0] = fmaf(w0v.x, v, acc[0]); acc[1] = fmaf(w0v.y, v, acc[1]);
-      acc[2] = fmaf(w0v.z, v, acc[2]); acc[3] = fmaf(w0v.w, v, acc[3]);
-      acc[4] = fmaf(w1v.x, v, acc[4]); acc[5] = fmaf(w1v.y, v, acc[5]);
-      acc[6] = fmaf(w1v.z, v, acc[6]); acc[7] = fmaf(w1v.w, v, acc[7]);
+    for (int s = 0; s < C1_KW; ++s) {
+      int hh = h + r - 1, ww = w + s - 5;
+      xin[r * C1_KW + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * row_stride + ww) : 0.f;
     }
   const uint32_t thr = dropout_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const size_t e0 = zns_act_index(g, h, w, b8, 0, H, W, C1_CO);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float v = fmaxf(acc[i], 0.f);
-    if (drop_p > 0.f) v = (zns_hash32(e0 + i, seed, stream_id) >= thr) ? v * keep_scale : 0.f;
-    acc[i] = v;
+  for (int cb = 0; cb < C1_CO; cb += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bs[cb + i];
+#pragma unroll
+    for (int t = 0; t < C1_TAPS; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[t][cb]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[t][cb + 4]);
+      const float v = xin[t];
+      acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
+      acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
+      acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
+      acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaxf(acc[i], 0.f);
+      if (drop_p > 0.f) v = (zns_hash32(e0 + cb + i, seed, stream_id) >= thr) ? v * keep_scale : 0.f;
+      acc[i] = v;
+    }
+    dst[cb / 8] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                             pack_bf16x2(acc[6], acc[7]));
   }
-  *dst = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                    pack_bf16x2(acc[6], acc[7]));
 }
 
 extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long row_stride, const float* weight,
@@ -91,8 +91,7 @@ extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long ro
                              const uint32_t* seed_dev, uint32_t rng_stream, void* stream) {
   ZNS_REQUIRE(x && weight && bias && out_act, "NULL argument");
   ZNS_REQUIRE(batch > 0 && H > 0 && W > 0 && drop_p >= 0.f && drop_p < 1.f, "bad conv1 geometry");
-  ZNS_REQUIRE(H * 8 <= 65535, "conv1: H too large");
-  dim3 grid((W + 31) / 32, H * 8, zns_groups(batch));
+  dim3 grid((W + 31) / 32, H, zns_groups(batch));
   conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, clip_stride, row_stride, weight, bias, (bf16*)out_act, batch, H, W,
                                                            drop_p, seed, seed_dev, rng_stream);
   ZNS_CHECK_LAUNCH();
@@ -102,67 +101,75 @@ extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long ro
 // ---------------------------------------------------------------------------------------------
 // cv1 weight / bias gradient
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+// block = (group, row h, 32 frames); thread = (output channel n, kernel row r): the 42 input samples
+// of row r are held in registers and slide under the 11 taps, so the inner loop is 11 FMAs per
+// shared-memory load of dy.
+#define C1W_TILES 5   // 32-frame tiles per block: fewer same-address atomics on the 64 x 33 gradient
+
+__global__ void __launch_bounds__(192) conv1_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
                                                           long long clip_stride, long long row_stride, float* __restrict__ dw,
                                                           float* __restrict__ db, int B, int H, int W) {
   __shared__ float xs[C1_KH][8][32 + C1_KW - 1];
   __shared__ __align__(16) bf16 dys[32 * 8 * C1_CO];      // [frame][clip slot][64 channels], 32 KB
-  const int g = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 32;
-  const int wmax = min(32, W - w0);
-  {
-    // the 32-frame dy tile of this (group, row) is one contiguous run: all 16-byte loads in flight at once
-    const uint4* src = reinterpret_cast<const uint4*>(dy + zns_act_index(g, h, w0, 0, 0, H, W, C1_CO));
-    const int n_vec = wmax * 8 * C1_CO / 8;
-    uint4 v[8];
+  const int g = blockIdx.z, h = blockIdx.y;
+  const int n = threadIdx.x & 63, r = threadIdx.x >> 6;   // r = 0..2
+  float acc[C1_KW];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = threadIdx.x + k * 256;
-      v[k] = i < n_vec ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) reinterpret_cast<uint4*>(dys)[threadIdx.x + k * 256] = v[k];
-  }
-  for (int i = threadIdx.x; i < C1_KH * 8 * 42; i += 256) {
-    int r = i / (8 * 42), rem = i - r * 8 * 42;
-    int b8 = rem / 42, j = rem - b8 * 42;
-    int hh = h + r - 1, ww = w0 + j - 5, b = g * 8 + b8;
-    xs[r][b8][j] = (b < B && hh >= 0 && hh < H && ww >= 0 && ww < W)
-                       ? __ldg(x + (size_t)b * clip_stride + (size_t)hh * row_stride + ww) : 0.f;
-  }
-  __syncthreads();
-  const int n = threadIdx.x & 63, q = threadIdx.x >> 6;
-  float acc[9];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+  for (int j = 0; j < C1_KW; ++j) acc[j] = 0.f;
   float accb = 0.f;
-  for (int wl = 0; wl < wmax; ++wl) {
+  for (int tile = 0; tile < C1W_TILES; ++tile) {
+    const int w0 = (blockIdx.x * C1W_TILES + tile) * 32;
+    if (w0 >= W) break;
+    const int wmax = min(32, W - w0);
+    if (tile > 0) __syncthreads();
+    {
+      // the 32-frame dy tile of this (group, row) is one contiguous run: all 16-byte loads in flight at once
+      const uint4* src = reinterpret_cast<const uint4*>(dy + zns_act_index(g, h, w0, 0, 0, H, W, C1_CO));
+      const int n_vec = wmax * 8 * C1_CO / 8;
+      uint4 v[11];
 #pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const int i = threadIdx.x + k * 192;
+        v[k] = i < n_vec ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const int i = threadIdx.x + k * 192;
+        if (i < 2048) reinterpret_cast<uint4*>(dys)[i] = v[k];
+      }
+    }
+    for (int i = threadIdx.x; i < C1_KH * 8 * 42; i += 192) {
+      int rr = i / (8 * 42), rem = i - rr * 8 * 42;
+      int b8 = rem / 42, j = rem - b8 * 42;
+      int hh = h + rr - 1, ww = w0 + j - 5, b = g * 8 + b8;
+      xs[rr][b8][j] = (b < B && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                          ? __ldg(x + (size_t)b * clip_stride + (size_t)hh * row_stride + ww) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
     for (int b8 = 0; b8 < 8; ++b8) {
-      const float d = __bfloat162float(dys[(wl * 8 + b8) * C1_CO + n]);
-      accb += d;
+      float xr[32 + C1_KW - 1];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int t = q + 4 * j;
-        if (t < C1_TAPS) {
-          const int r = t / C1_KW, sft = t - r * C1_KW;
-          acc[j] = fmaf(d, xs[r][b8][wl + sft], acc[j]);
-        }
+      for (int j = 0; j < 32 + C1_KW - 1; ++j) xr[j] = xs[r][b8][j];
+#pragma unroll
+      for (int wl = 0; wl < 32; ++wl) {
+        const float d = __bfloat162float(dys[(wl * 8 + b8) * C1_CO + n]);   // zero beyond wmax
+        accb += d;
+#pragma unroll
+        for (int sft = 0; sft < C1_KW; ++sft) acc[sft] = fmaf(d, xr[wl + sft], acc[sft]);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    const int t = q + 4 * j;
-    if (t < C1_TAPS) atomicAdd(dw + n * C1_TAPS + t, acc[j]);
-  }
-  if (q == 0) atomicAdd(db + n, accb);
+  for (int sft = 0; sft < C1_KW; ++sft) atomicAdd(dw + n * C1_TAPS + r * C1_KW + sft, acc[sft]);
+  if (r == 0) atomicAdd(db + n, accb);
 }
 
 extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long clip_stride, long long row_stride, float* dw,
                                float* db, int batch, int H, int W, void* stream) {
   ZNS_REQUIRE(dy_act && x && dw && db, "NULL argument");
-  dim3 grid((W + 31) / 32, H, zns_groups(batch));
-  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, x, clip_stride, row_stride, dw, db, batch, H,
+  dim3 grid((W + 32 * C1W_TILES - 1) / (32 * C1W_TILES), H, zns_groups(batch));
+  conv1_wgrad_kernel<<<grid, 192, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, x, clip_stride, row_stride, dw, db, batch, H,
                                                              W);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
