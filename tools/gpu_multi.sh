@@ -1,15 +1,17 @@
 #!/bin/bash
-# usage: bash tools/gpu_multi.sh N   (under gpurun --gpus N)
+# usage: bash tools/gpu_multi.sh N   (under gpurun --gpus N): DDP check on N ranks + scaling bench at 1,2,4,..,N
 N=${1:-2}
 mkdir -p gpurun_out
-timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/ddp_check.py > gpurun_out/ddp_check_$N.log 2>&1
-echo "ddp_check exit=$?"; tail -3 gpurun_out/ddp_check_$N.log
-for n in 1 $N; do
+timeout -k 5 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/ddp_check.py > gpurun_out/ddp_check_$N.log 2>&1
+echo "ddp_check exit=$?"; grep -E "ddp_check|DDP_CHECK" gpurun_out/ddp_check_$N.log
+n=1
+while [ $n -le $N ]; do
   if [ $n -eq 1 ]; then
-    timeout -k 10 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-extras > gpurun_out/scale_1.json 2> gpurun_out/scale_1.err
+    timeout -k 5 150 python bench.py --gpus 1 --steps 30 --warmup 5 --no-extras > gpurun_out/scale_1.json 2> gpurun_out/scale_1.err
   else
-    NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 20 --warmup 5 --no-extras > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
+    NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 5 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29512+n)) bench.py --gpus $n --steps 30 --warmup 5 --no-extras > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
   fi
-  echo "bench $n exit=$?"; grep -h '"metric"' gpurun_out/scale_$n.json | cut -c1-400
+  echo "bench $n exit=$?"; grep -h '"metric"' gpurun_out/scale_$n.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['n_gpus'], round(d['value'],1), 'clips/s', round(d['ms_per_step'],3), 'ms/step e2e', round(d['e2e']['value'],1))"
+  n=$((n*2))
 done
-grep -h -i -E "NVLS|via P2P|NET/" gpurun_out/scale_$N.err | head -5
+grep -h -i -E "NVLS|Connected all|via P2P" gpurun_out/scale_$N.err | head -6
