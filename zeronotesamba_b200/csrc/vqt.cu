@@ -17,6 +17,8 @@
 #include <complex>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -192,20 +194,6 @@ extern "C" int zns_vqt_basis_host(int sr, int n_bins, int bpo, double fmin, doub
   return ZNS_OK;
 }
 
-static uint16_t host_bf16_rn(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-static float host_bf16_to_float(uint16_t h) {
-  uint32_t u = (uint32_t)h << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
@@ -216,7 +204,8 @@ struct zns_vqt_plan {
   int max_batch, max_samples;
   int n_fft[ZNS_VQT_MAX_OCT];
   float* d_coef[ZNS_VQT_MAX_OCT];  // [n_fft][2][bpo/2][2] interleaved (SIMT filterbank kernel)
-  uint16_t* d_coef_bf[ZNS_VQT_MAX_OCT];  // [3 splits][2*bpo columns][n_fft] bf16 (tensor-core filterbank)
+  uint16_t* d_coef_bf[ZNS_VQT_MAX_OCT];  // [2 terms][2*bpo columns][n_fft] fp16 (tensor-core filterbank)
+  float coef_inv_scale[ZNS_VQT_MAX_OCT]; // 1 / (power-of-two scale applied to the fp16 coefficients)
   float* d_inv_sqrt_len;           // [n_bins]
   float* d_scratch[ZNS_VQT_MAX_OCT];  // decimated signals, octave >= 1
   float* d_stage_in;               // for *_host: [max_batch][max_samples]
@@ -287,19 +276,23 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
       }
     ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef[i], coef.size() * sizeof(float)));
     ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef[i], coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice));
-    // three-term bf16 split g = g1 + g2 + g3 (round to nearest even), column = 2*filter + {re, im}
+    // two-term fp16 split of GS*g = g1 + g2/2048 (GS = power of two bringing max|g| into [0.5, 1)),
+    // column = 2*filter + {re, im}
     {
       const int ncol = 2 * bpo;
-      std::vector<uint16_t> sp((size_t)3 * ncol * nf);
+      float gmax = 0.f;
+      for (int k = 0; k < bpo * nf; ++k) gmax = std::max(gmax, std::max(fabsf(re[k]), fabsf(im[k])));
+      const float gs = gmax > 0.f ? exp2f(-1.f - floorf(log2f(gmax))) : 1.f;
+      p->coef_inv_scale[i] = 1.f / gs;
+      std::vector<uint16_t> sp((size_t)2 * ncol * nf);
       for (int k = 0; k < bpo; ++k)
         for (int ri = 0; ri < 2; ++ri)
           for (int n = 0; n < nf; ++n) {
-            float v = ri ? im[k * nf + n] : re[k * nf + n];
-            for (int t = 0; t < 3; ++t) {
-              const uint16_t hb = host_bf16_rn(v);
-              sp[((size_t)t * ncol + 2 * k + ri) * nf + n] = hb;
-              v -= host_bf16_to_float(hb);
-            }
+            const float v = (ri ? im[k * nf + n] : re[k * nf + n]) * gs;
+            const __half h1 = __float2half_rn(v);
+            const __half h2 = __float2half_rn((v - __half2float(h1)) * 2048.f);
+            sp[((size_t)0 * ncol + 2 * k + ri) * nf + n] = __half_as_ushort(h1);
+            sp[((size_t)1 * ncol + 2 * k + ri) * nf + n] = __half_as_ushort(h2);
           }
       ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef_bf[i], sp.size() * sizeof(uint16_t)));
       ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef_bf[i], sp.data(), sp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -503,51 +496,52 @@ vqt_filterbank_kernel(const float* __restrict__ y, int n_sig, long long sig_stri
 
 // ---------------------------------------------------------------------------------------------
 // device: tensor-core filterbank.  C[t, col] = sum_n frame[t][n] * g[col][n] is a dense GEMM
-// (128 frames x 24 columns x n_fft per block); fp32 inputs are split into three bf16 terms
-// x = x1 + x2 + x3, g = g1 + g2 + g3 and the six leading products (x1g1, x1g2, x1g3, x2g1, x2g2,
-// x3g1) are accumulated in fp32 by mma.sync m16n8k16 -- 1e-8 of full scale from exact
-// (tools check in DESIGN.md), below the reference's own fp32 noise.  Frames are materialised in
-// shared memory with pitch n_fft + 8 halfwords, which makes every fragment load conflict-free.
-// (mma.sync rather than tcgen05: N = 24 is far below a UMMA tile and the operand is a Toeplitz
-// view; the warp-level path lets the fragments be addressed directly.)
+// (frames x 24 columns x n_fft per block).  fp32 operands are split into two fp16 terms
+//   x = x1 + x2/2048,  GS*g = g1 + g2/2048   (22 mantissa bits each)
+// and the three leading products are accumulated in fp32 by mma.sync m16n8k16:
+//   Da = x1 g1,  Db = x1 g2 + x2 g1,  C = (Da + Db/2048) / GS
+// -- 1e-7 of full scale from exact, below the reference's own fp32 noise (3.6e-7).
+// Frames are materialised in shared memory with pitch n_fft + 8 halfwords, which makes every
+// fragment load conflict-free.  (mma.sync rather than tcgen05: N = 24 is far below a UMMA tile and
+// the operand is a Toeplitz view; the warp-level path lets the fragments be addressed directly.)
 // ---------------------------------------------------------------------------------------------
 #define FBT_COLS 24
 #define FBT_TILES 4   // consecutive frame tiles per block (coefficients staged once)
 
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// x = x1 + x2 + x3 for two values at once: one packed cvt.rn.bf16x2.f32 per term; a bf16 is the
-// high half of its fp32, so unpacking is a shift / mask.
-__device__ __forceinline__ void split3_pair(float v0, float v1, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
-  s1 = pack_bf16x2(v0, v1);
-  const float r0 = v0 - __uint_as_float(s1 << 16), r1 = v1 - __uint_as_float(s1 & 0xFFFF0000u);
-  s2 = pack_bf16x2(r0, r1);
-  const float q0 = r0 - __uint_as_float(s2 << 16), q1 = r1 - __uint_as_float(s2 & 0xFFFF0000u);
-  s3 = pack_bf16x2(q0, q1);
+// x = x1 + x2/2048 for two values at once (packed half2 conversions)
+__device__ __forceinline__ void split2_pair(float v0, float v1, uint32_t& s1, uint32_t& s2) {
+  const __half2 h1 = __floats2half2_rn(v0, v1);
+  const float2 f1 = __half22float2(h1);
+  const __half2 h2 = __floats2half2_rn((v0 - f1.x) * 2048.f, (v1 - f1.y) * 2048.f);
+  s1 = *reinterpret_cast<const uint32_t*>(&h1);
+  s2 = *reinterpret_cast<const uint32_t*>(&h2);
 }
 
 template <int NFFT, int FBT_FRAMES>
 __global__ void __launch_bounds__(FBT_FRAMES * 2)
 vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_stride,
-                          const uint16_t* __restrict__ coef_bf, int hop, const float* __restrict__ inv_sqrt_len, int bin0,
-                          int n_bins, int n_frames, float* __restrict__ out) {
+                          const uint16_t* __restrict__ coef_bf, float coef_inv_scale, int hop,
+                          const float* __restrict__ inv_sqrt_len, int bin0, int n_bins, int n_frames,
+                          float* __restrict__ out) {
   constexpr int FBT_THREADS = FBT_FRAMES * 2;  // one warp per 16 frames
   constexpr int PITCH = NFFT + 8;           // halfwords; PITCH/2 = 4 (mod 8) -> conflict-free fragments
   constexpr int PW = PITCH / 2;             // 32-bit words per row
   extern __shared__ uint32_t fsm[];
-  uint32_t* fr = fsm;                        // [3][FBT_FRAMES][PW]
-  uint32_t* cf = fsm + 3 * FBT_FRAMES * PW;  // [3][FBT_COLS][PW]
+  uint32_t* fr = fsm;                        // [2][FBT_FRAMES][PW]
+  uint32_t* cf = fsm + 2 * FBT_FRAMES * PW;  // [2][FBT_COLS][PW]
   const int b = blockIdx.z;
   const float* yb = y + (size_t)b * sig_stride;
 
-  // coefficients: global [3][24][NFFT] halfwords -> smem rows of PITCH (once per block, 16-byte loads)
+  // coefficients: global [2][24][NFFT] halfwords -> smem rows of PITCH (once per block, 16-byte loads)
   {
-    constexpr int kVec = 3 * FBT_COLS * (NFFT / 2) / 4;   // uint4 count
+    constexpr int kVec = 2 * FBT_COLS * (NFFT / 2) / 4;   // uint4 count
     const uint4* src = reinterpret_cast<const uint4*>(coef_bf);
     for (int i = threadIdx.x; i < kVec; i += FBT_THREADS) {
       const uint4 c = __ldg(src + i);
@@ -560,7 +554,7 @@ vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_
   const int f0 = (blockIdx.x * FBT_TILES + tile) * FBT_FRAMES;
   if (f0 >= n_frames) break;
   if (tile > 0) __syncthreads();   // the previous tile's fragments have been consumed
-  // frames: (t, n-pair) -> three bf16 split words.  Loads are issued in batches of 8 pairs per
+  // frames: (t, n-pair) -> two fp16 split words.  Loads are issued in batches of 8 pairs per
   // thread before any conversion so that their latency overlaps.
   constexpr int HALF = NFFT / 2;
   constexpr int kPairs = FBT_FRAMES * HALF / FBT_THREADS;   // pairs per thread
@@ -591,28 +585,27 @@ vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_
     for (int k = 0; k < kBatch; ++k) {
       const int i = threadIdx.x + (i0 + k) * FBT_THREADS;
       const int t = i / HALF, w = i - t * HALF;
-      uint32_t s1, s2, s3;
-      split3_pair(v[k].x, v[k].y, s1, s2, s3);
+      uint32_t s1, s2;
+      split2_pair(v[k].x, v[k].y, s1, s2);
       fr[(0 * FBT_FRAMES + t) * PW + w] = s1;
       fr[(1 * FBT_FRAMES + t) * PW + w] = s2;
-      fr[(2 * FBT_FRAMES + t) * PW + w] = s3;
     }
   }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tid = lane & 3;
-  float acc[3][4];
+  float da[3][4], db[3][4];
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    for (int i = 0; i < 4; ++i) { da[j][i] = 0.f; db[j][i] = 0.f; }
   const int row0 = warp * 16 + g;
 #pragma unroll
   for (int ks = 0; ks < NFFT / 16; ++ks) {
-    uint32_t a[3][4];
+    uint32_t a[2][4];
 #pragma unroll
-    for (int sp = 0; sp < 3; ++sp) {
+    for (int sp = 0; sp < 2; ++sp) {
       const uint32_t* base = fr + (sp * FBT_FRAMES + row0) * PW + ks * 8 + tid;
       a[sp][0] = base[0];
       a[sp][1] = base[8 * PW];
@@ -621,32 +614,29 @@ vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      uint32_t bb[3][2];
+      uint32_t bb[2][2];
 #pragma unroll
-      for (int sp = 0; sp < 3; ++sp) {
+      for (int sp = 0; sp < 2; ++sp) {
         const uint32_t* cb = cf + (sp * FBT_COLS + j * 8 + g) * PW + ks * 8 + tid;
         bb[sp][0] = cb[0];
         bb[sp][1] = cb[4];
       }
-      // smallest products first
-      mma_bf16_16816(acc[j], a[2], bb[0][0], bb[0][1]);  // x3 g1
-      mma_bf16_16816(acc[j], a[0], bb[2][0], bb[2][1]);  // x1 g3
-      mma_bf16_16816(acc[j], a[1], bb[1][0], bb[1][1]);  // x2 g2
-      mma_bf16_16816(acc[j], a[1], bb[0][0], bb[0][1]);  // x2 g1
-      mma_bf16_16816(acc[j], a[0], bb[1][0], bb[1][1]);  // x1 g2
-      mma_bf16_16816(acc[j], a[0], bb[0][0], bb[0][1]);  // x1 g1
+      mma_f16_16816(db[j], a[1], bb[0][0], bb[0][1]);  // x2 g1
+      mma_f16_16816(db[j], a[0], bb[1][0], bb[1][1]);  // x1 g2
+      mma_f16_16816(da[j], a[0], bb[0][0], bb[0][1]);  // x1 g1
     }
   }
   // epilogue: thread holds (re, im) of filter 4j + tid for frames row0 and row0 + 8
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int bin = bin0 + 4 * j + tid;
-    const float isl = __ldg(inv_sqrt_len + bin);
+    const float isl = __ldg(inv_sqrt_len + bin) * coef_inv_scale;
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int f = f0 + row0 + 8 * hrow;
       if (f < n_frames) {
-        const float re = acc[j][2 * hrow], im = acc[j][2 * hrow + 1];
+        const float re = da[j][2 * hrow] + db[j][2 * hrow] * (1.f / 2048.f);
+        const float im = da[j][2 * hrow + 1] + db[j][2 * hrow + 1] * (1.f / 2048.f);
         out[((size_t)b * n_bins + bin) * n_frames + f] = logf(sqrtf(re * re + im * im) * isl + 1e-9f);
       }
     }
@@ -657,7 +647,7 @@ vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_
 template <int NFFT, int FBT_FRAMES>
 static int fbt_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
                         int n_frames, float* out, cudaStream_t st) {
-  const size_t smem = (size_t)(3 * FBT_FRAMES + 3 * FBT_COLS) * ((NFFT + 8) / 2) * sizeof(uint32_t);
+  const size_t smem = (size_t)(2 * FBT_FRAMES + 2 * FBT_COLS) * ((NFFT + 8) / 2) * sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute((vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES>),
@@ -665,7 +655,7 @@ static int fbt_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, l
     attr_set = true;
   }
   dim3 grid((n_frames + FBT_FRAMES * FBT_TILES - 1) / (FBT_FRAMES * FBT_TILES), 1, batch);
-  vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES><<<grid, FBT_FRAMES * 2, smem, st>>>(sig, n_sig, stride, p->d_coef_bf[oct], hop_i,
+  vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES><<<grid, FBT_FRAMES * 2, smem, st>>>(sig, n_sig, stride, p->d_coef_bf[oct], p->coef_inv_scale[oct], hop_i,
                                                                     p->d_inv_sqrt_len, p->n_bins - p->bpo * (oct + 1),
                                                                     p->n_bins, n_frames, out);
   ZNS_CHECK_LAUNCH();
@@ -682,7 +672,7 @@ static int fb_launch(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long
       case 16: return fbt_launch_t<16, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
       case 32: return fbt_launch_t<32, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
       case 64: return fbt_launch_t<64, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
-      case 128: return fbt_launch_t<128, 64>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);  // 72 KB -> 3 CTAs/SM
+      case 128: return fbt_launch_t<128, 64>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);  // 48 KB -> 4 CTAs/SM
       default: break;
     }
   }
