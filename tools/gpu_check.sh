@@ -18,4 +18,7 @@ run full 900 tests/test_gpu_ops.py -k "conv_full"
 export ZNS_CONV_TRANSPOSED=1
 run convfwd_transposed 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full"
 unset ZNS_CONV_TRANSPOSED
+export ZNS_CONV_NO_STACK=1
+run convfwd_nostack 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full"
+unset ZNS_CONV_NO_STACK
 cat gpurun_out/summary.txt

@@ -550,6 +550,289 @@ conv_fwdT_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// C_out = 64 forward / data gradient with two output rows stacked on N.
+//   A 128 x 64 x 16 MMA is bound by its 4 KB A-tile read (48 clk instead of 32, measured), so the
+//   N = 64 kernel cannot pass 67 % of peak.  Here the weight tile is [W(r-1,s) ; W(r,s)] (N = 128):
+//   on input row hh one MMA feeds output row h+1 with tap row r-1 and output row h with tap row r,
+//   i.e. an accumulator holds two adjacent output rows and the tap-row loop has kh + 1 steps (tap
+//   rows -1 and kh are TMA out-of-bounds zero fill).  Three accumulators = six output rows per CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1)
+conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+                      const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                      const FwdTParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x_base = smem_base;
+  const uint32_t w_base = x_base + p.n_slots * p.slot_bytes;
+  constexpr uint32_t kWTile = 128 * 128;  // 2 stacked tap rows x 64 output channels x 64 input channels bf16
+  FwdTBarriers* bars = reinterpret_cast<FwdTBarriers*>(smem_raw + (w_base + p.n_wstages * kWTile - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int br = blockIdx.z;
+  const CUtensorMap* tm_in = br ? &tm_in1 : &tm_in0;
+  const CUtensorMap* tm_w = br ? &tm_w1 : &tm_w0;
+
+  int t = blockIdx.x;
+  const int wt = t % p.n_wtiles; t /= p.n_wtiles;
+  const int htile = t % p.n_htiles; t /= p.n_htiles;
+  const int g = t;
+  const int rows_per_cta = p.n_acc * p.stack;
+  const int w0 = wt * WT, h0 = htile * rows_per_cta;
+  const int acc_eff = min(p.n_acc, (p.H - h0 + p.stack - 1) / p.stack);
+  const int n_iter = p.kh + p.stack - 1;                     // tap-row steps r' = 0 .. kh + stack - 2
+  // relative input rows rr: hh = h0 - ph + rr; accumulator a needs row r' + a*stack at step r'
+  const int rr_lo = max(0, p.ph - h0);
+  const int rr_hi = min(acc_eff * p.stack + p.kh - 1, p.H + p.ph - h0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_slots; ++i) { mbar_init(smem_u32(&bars->x_full[i]), 1); mbar_init(smem_u32(&bars->x_empty[i]), 1); }
+    for (int i = 0; i < p.n_wstages; ++i) { mbar_init(smem_u32(&bars->w_full[i]), 1); mbar_init(smem_u32(&bars->w_empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tm_in);
+    tma_prefetch_desc(tm_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  // does step r' touch a valid input row for some accumulator?
+  auto step_active = [&](int rp) {
+    for (int a = 0; a < acc_eff; ++a) {
+      const int rr = rp + a * p.stack;
+      if (rr >= rr_lo && rr < rr_hi) return true;
+    }
+    return false;
+  };
+
+  const uint32_t bar_x_full = smem_u32(&bars->x_full[0]), bar_x_empty = smem_u32(&bars->x_empty[0]);
+  const uint32_t bar_w_full = smem_u32(&bars->w_full[0]), bar_w_empty = smem_u32(&bars->w_empty[0]);
+  const uint32_t n_slots = p.n_slots, n_wst = p.n_wstages;
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===== TMA producer (one elected thread, no div/mod) =====
+      uint32_t x_slot = 0, x_par = 1, w_st = 0, w_par = 1;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo;
+        for (int rp = 0; rp < n_iter; ++rp) {
+          const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
+          while (next_row < need_hi) {
+            mbar_wait(bar_x_empty + 8 * x_slot, x_par);
+            mbar_expect_tx(bar_x_full + 8 * x_slot, p.slot_bytes);
+            tma_load_5d(x_base + x_slot * p.slot_bytes, tm_in, bar_x_full + 8 * x_slot, c * 64, 0, w0 - p.pw,
+                        h0 - p.ph + next_row, g);
+            if (++x_slot == n_slots) { x_slot = 0; x_par ^= 1; }
+            ++next_row;
+          }
+          if (!step_active(rp)) continue;
+          for (int s = 0; s < p.kw; ++s) {
+            mbar_wait(bar_w_empty + 8 * w_st, w_par);
+            mbar_expect_tx(bar_w_full + 8 * w_st, kWTile);
+            for (int j = 0; j < p.stack; ++j) {
+              const int r = rp - (p.stack - 1) + j;      // weight tap row of M block j (out of range -> TMA zero fill)
+              const int tap = (r < 0 || r >= p.kh) ? -1 : r * p.kw + s;
+              tma_load_3d(w_base + w_st * kWTile + j * p.cout * 128, tm_w, bar_w_full + 8 * w_st, c * 64, 0, tap);
+            }
+            if (++w_st == n_wst) { w_st = 0; w_par ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      uint32_t x_slot = 0, x_par = 0, w_st = 0, w_par = 0;
+      uint32_t rel_slot = 0;
+      uint32_t started = 0;
+      const uint32_t ring_bytes = n_slots * p.slot_bytes;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        int next_row = rr_lo, rel_row = rr_lo;
+        for (int rp = 0; rp < n_iter; ++rp) {
+          const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
+          while (next_row < need_hi) {
+            mbar_wait(bar_x_full + 8 * x_slot, x_par);
+            if (++x_slot == n_slots) { x_slot = 0; x_par ^= 1; }
+            ++next_row;
+          }
+          if (step_active(rp)) {
+            // live rows are >= rel_row and fewer than n_slots: address of row rr by offset from rel_slot
+            uint32_t row_off[3];
+            uint32_t use = 0;
+            for (int a = 0; a < acc_eff; ++a) {
+              const int rr = rp + a * p.stack;
+              if (rr >= rr_lo && rr < rr_hi) {
+                uint32_t off = (rel_slot + (uint32_t)(rr - rel_row)) * p.slot_bytes;
+                if (off >= ring_bytes) off -= ring_bytes;
+                row_off[a] = off;
+                use |= 1u << a;
+              }
+            }
+            for (int s = 0; s < p.kw; ++s) {
+              mbar_wait(bar_w_full + 8 * w_st, w_par);
+              tc_fence_after();
+              const uint32_t b_lo = ((w_base + w_st * kWTile) >> 4) | (1u << 16);
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                if ((use >> a) & 1) {
+                  const uint32_t a_lo = ((x_base + row_off[a] + s * 1024) >> 4) | (1u << 16);
+                  const uint32_t acc = ((started >> a) & 1) | (s > 0);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    umma_bf16(tmem + a * 128, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
+                              idesc, acc | (k > 0));
+                  }
+                }
+              }
+              umma_commit(bar_w_empty + 8 * w_st);
+              if (++w_st == n_wst) { w_st = 0; w_par ^= 1; }
+            }
+            started |= use;
+          }
+          while (rel_row <= rp && rel_row < rr_hi) {   // row rp has had its last use (accumulator 0)
+            umma_commit(bar_x_empty + 8 * rel_slot);
+            if (++rel_slot == n_slots) rel_slot = 0;
+            ++rel_row;
+          }
+        }
+        while (rel_row < rr_hi) {
+          umma_commit(bar_x_empty + 8 * rel_slot);
+          if (++rel_slot == n_slots) rel_slot = 0;
+          ++rel_row;
+        }
+      }
+      umma_commit(smem_u32(&bars->acc_full));
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: thread = position row; accumulator a holds rows (h0+2a+1 | h0+2a) x 64 channels =====
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int w = w0 + (m >> 3), b8 = m & 7;
+    const bool valid = (w < p.W);
+    const float* bias = p.bias[br];
+    const bf16* mask = p.mask[br];
+    bf16* out = p.out[br];
+    uint32_t seed = p.seed;
+    if (p.seed_dev) seed ^= __ldg(p.seed_dev) * 0x9E3779B9u;
+    const bool do_drop = p.drop_p > 0.f;
+    const double thr_d = (double)p.drop_p * 4294967296.0;
+    const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
+    const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int a = 0; a < acc_eff; ++a) {
+#pragma unroll 1
+      for (int nb = 0; nb < 4; ++nb) {
+        const int j = nb >> 1;                              // stacked block: 0 -> upper row, 1 -> lower row
+        const int h = h0 + 2 * a + (1 - j);
+        const int c0 = (nb & 1) * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + a * 128 + nb * 32, v);
+        tmem_ld_wait();
+        if (valid && h < p.H) {
+          const size_t e0 = zns_act_index(g, h, w, b8, c0, p.H, p.W, 64);
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]);
+            if (bias) x += __ldg(bias + c0 + i);
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (do_drop) x = (zns_hash32(e0 + i, seed, p.stream_id + br) >= thr) ? x * keep : 0.f;
+            f[i] = x;
+          }
+          if (mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(mask + e0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 mv = __ldg(mp + q);
+              const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 mf = __bfloat1622float2(m2[i]);
+                if (!(mf.x > 0.f)) f[q * 8 + 2 * i] = 0.f;
+                if (!(mf.y > 0.f)) f[q * 8 + 2 * i + 1] = 0.f;
+              }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + e0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_bf16x2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale),
+                                pack_bf16x2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale),
+                                pack_bf16x2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale),
+                                pack_bf16x2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+
+static bool fwd_stack_config(const zns_conv_desc* d, FwdTParams* p) {
+  if (d->c_out != 64 || (d->H & 1)) return false;
+  const uint32_t slot = (uint32_t)(WT + d->kw - 1) * 1024u;
+  const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdTBarriers) - 64;
+  int n_acc = std::min(3, d->H / 2);
+  int slots = (n_acc - 1) * 2 + 2;
+  if ((uint64_t)slots * slot + 2ull * 16384 > budget) return false;
+  int wst = 2;
+  while (wst < MAX_RING && (uint64_t)slots * slot + (uint64_t)(wst + 1) * 16384 <= budget) ++wst;
+  p->cout = 64; p->stack = 2; p->n_acc = n_acc; p->n_slots = slots; p->n_wstages = wst; p->slot_bytes = slot;
+  return true;
+}
+
+static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, const void* const* in,
+                            const void* const* wpk, const float* const* bias, const void* const* mask, void* const* out,
+                            cudaStream_t st) {
+  const int G = zns_groups(d->batch);
+  FwdTParams p = cfg;
+  p.G = G; p.H = d->H; p.W = d->W; p.batch = d->batch;
+  p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
+  p.n_chunks = d->c_in / 64;
+  p.n_wtiles = (d->W + WT - 1) / WT;
+  const int rows_per_cta = p.n_acc * p.stack;
+  p.n_htiles = (d->H + rows_per_cta - 1) / rows_per_cta;
+  p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
+  const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * 16384 + sizeof(FwdTBarriers) + 64;
+  CUtensorMap tm_in[2], tm_w[2];
+  for (int b = 0; b < 2; ++b) {
+    const int s = b < n_br ? b : 0;
+    int rc = make_act_map(&tm_in[b], in[s], G, d->H, d->W, d->c_in, WT + d->kw - 1);
+    if (rc) return rc;
+    rc = make_w_map(&tm_w[b], wpk[s], d->kh * d->kw, d->c_out, d->c_in, d->c_out);
+    if (rc) return rc;
+    p.bias[b] = bias ? bias[s] : nullptr;
+    p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
+    p.out[b] = (bf16*)out[s];
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_stack_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    attr_set = true;
+  }
+  dim3 grid(p.n_wtiles * p.n_htiles * G, 1, n_br);
+  conv_fwd_stack_umma_kernel<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
 static bool fwdT_config(const zns_conv_desc* d, FwdTParams* p) {
   if (d->c_out != 64 && d->c_out != 128) return false;
   const int stack = 128 / d->c_out;
@@ -672,6 +955,12 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
     if (use_t && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
+  }
+  {
+    static const bool no_stack = getenv("ZNS_CONV_NO_STACK") != nullptr;   // A/B switch
+    FwdTParams cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    if (!no_stack && fwd_stack_config(d, &cfg)) return launch_fwd_stack(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
   switch (d->c_out) {
     case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);

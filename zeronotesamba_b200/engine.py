@@ -43,6 +43,8 @@ def _fwd_tag(c_out: int, H: int) -> str:
     import os
     if os.environ.get("ZNS_CONV_TRANSPOSED") and (c_out == 128 or (c_out == 64 and H % 2 == 0)):
         return f"conv_fwdT_umma(c_out={c_out})"
+    if c_out == 64 and H % 2 == 0 and not os.environ.get("ZNS_CONV_NO_STACK"):
+        return "conv_fwd_stack_umma(c_out=64, 2 rows on N)"
     return f"conv_fwd_umma<{c_out}>"
 
 
