@@ -332,3 +332,36 @@ def test_vqt_bank_and_index_only_crops():
             assert torch.equal(batch[j], bank[i, :, :, s0:s0 + 313])
         n += 1
     assert n == 3
+
+
+def test_prefetch_pipeline_equals_sequential(sd):
+    """prefetch_audio / step_prefetched (front-end of clip i+1 on a side stream under step i) gives the
+    same losses and weights as calling step_from_audio clip by clip."""
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import PretextTrainer, sample_crop_starts
+    clips = []
+    for i in range(3):
+        drums, other = synth.stem_pair(30 + i, 10.0)
+        st = torch.tensor(sample_crop_starts(16, random.Random(i)), dtype=torch.int32, device=DEV)
+        clips.append((torch.from_numpy(other).to(DEV), torch.from_numpy(drums).to(DEV), st))
+    outs = []
+    for mode in ("sequential", "prefetch"):
+        model = Pretext_CNN().to(DEV)
+        model.load_state_dict(sd)
+        tr = PretextTrainer(model, batch_len=16, dropout_p=0.0, use_graph=True, lr=1e-4)
+        losses = []
+        if mode == "sequential":
+            for c in clips:
+                losses.append(tr.step_from_audio(*c).cpu().numpy().copy())
+        else:
+            tr.prefetch_audio(*clips[0])
+            for i in range(3):
+                r = tr.step_prefetched()
+                if i + 1 < 3:
+                    tr.prefetch_audio(*clips[i + 1])
+                losses.append(r.cpu().numpy().copy())
+        torch.cuda.synchronize()
+        outs.append((np.stack(losses), tr.flat_p.clone()))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-3, atol=1e-4), (outs[0][0], outs[1][0])
+    assert float((outs[0][1] - outs[1][1]).abs().max()) <= 3e-4      # 3 Adam steps of 1e-4, fp32 atomics order

@@ -132,6 +132,13 @@ class PretextTrainer:
         self._vqt_buf: Optional[torch.Tensor] = None
         self._starts_buf = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self._graph_front: Optional[torch.cuda.CUDAGraph] = None
+        # the front-end writes a staging batch so that the NEXT clip's VQT + crops can run on a side
+        # stream while the current step's encoders are busy (prefetch_audio / step_prefetched)
+        self._stage_buf = torch.zeros_like(self.batch_buf)
+        self._side = torch.cuda.Stream(device=dev)
+        self._ev_ready = torch.cuda.Event()
+        self._ev_consumed = torch.cuda.Event()
+        self._ev_consumed.record(torch.cuda.current_stream())
 
     # ---- pieces ------------------------------------------------------------------------------
     def _forward_backward(self):
@@ -217,19 +224,17 @@ class PretextTrainer:
     # ---- VQT in the loop ---------------------------------------------------------------------------
     def _front(self):
         self._vqt_plan.forward(self._audio_buf, out=self._vqt_buf)
-        crop_batch(self._vqt_buf, self._starts_buf, out=self.batch_buf, crop=self.T)
+        crop_batch(self._vqt_buf, self._starts_buf, out=self._stage_buf, crop=self.T)
 
-    def step_from_audio(self, anchor_audio: torch.Tensor, positive_audio: torch.Tensor, starts: torch.Tensor,
-                        sample_rate: int = 16000, mode: str = "vqt", run_step: bool = True) -> torch.Tensor:
-        """Whole in-loop path on the device: two 16 kHz stems of one source clip (anchor = other stems,
-        positive = drums; pretext.py:83-84,144) -> VQT (2, 96, F) -> B crops at ``starts`` -> training step."""
+    def _ensure_front(self, n: int, sample_rate: int, mode: str):
         from .processing.input_rep import VQTPlan
-        n = anchor_audio.numel()
         if self._vqt_plan is None or self._audio_buf is None or self._audio_buf.shape[1] != n:
             self._vqt_plan = VQTPlan(sample_rate, mode, 2, n)
             self._audio_buf = torch.zeros(2, n, device=self.device)
             self._vqt_buf = torch.zeros(2, 96, self._vqt_plan.frames(n), device=self.device)
             self._graph_front = None
+
+    def _run_front(self, anchor_audio, positive_audio, starts):
         self._audio_buf[0].copy_(anchor_audio, non_blocking=True)
         self._audio_buf[1].copy_(positive_audio, non_blocking=True)
         self._starts_buf.copy_(starts, non_blocking=True)
@@ -239,6 +244,37 @@ class PretextTrainer:
             self._graph_front.replay()
         else:
             self._front()
+
+    def prefetch_audio(self, anchor_audio: torch.Tensor, positive_audio: torch.Tensor, starts: torch.Tensor,
+                       sample_rate: int = 16000, mode: str = "vqt") -> None:
+        """Start the front-end (H2D/D2D copies, VQT, crops) of the NEXT source clip on a side stream; it
+        overlaps whatever the current stream is doing (typically the previous clip's training step).
+        Consume it with ``step_prefetched()``."""
+        self._ensure_front(anchor_audio.numel(), sample_rate, mode)
+        if self.use_graph and self._graph_front is None:
+            self._run_front(anchor_audio, positive_audio, starts)      # first call captures on the current stream
+            self._ev_ready.record(torch.cuda.current_stream())
+            return
+        self._side.wait_event(self._ev_consumed)       # the staging batch of the previous prefetch has been taken
+        with torch.cuda.stream(self._side):
+            self._run_front(anchor_audio, positive_audio, starts)
+            self._ev_ready.record(self._side)
+
+    def step_prefetched(self) -> torch.Tensor:
+        """Training step on the clip handed to the last ``prefetch_audio``."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ev_ready)
+        self.batch_buf.copy_(self._stage_buf, non_blocking=True)
+        self._ev_consumed.record(cur)
+        return self.step()
+
+    def step_from_audio(self, anchor_audio: torch.Tensor, positive_audio: torch.Tensor, starts: torch.Tensor,
+                        sample_rate: int = 16000, mode: str = "vqt", run_step: bool = True) -> torch.Tensor:
+        """Whole in-loop path on the device: two 16 kHz stems of one source clip (anchor = other stems,
+        positive = drums; pretext.py:83-84,144) -> VQT (2, 96, F) -> B crops at ``starts`` -> training step."""
+        self._ensure_front(anchor_audio.numel(), sample_rate, mode)
+        self._run_front(anchor_audio, positive_audio, starts)
+        self.batch_buf.copy_(self._stage_buf, non_blocking=True)
         return self.step() if run_step else self.result
 
 
