@@ -176,6 +176,14 @@ int zns_ntxent_fwd_bwd(const float* anchors, const float* poss, int n_rows, int 
  * multiplied by grad_scale first (1/world_size after a sum all-reduce). */
 int zns_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, const uint32_t* step_dev, float grad_scale, void* stream);
+/* Data-parallel variant: fused gradient reduce-scatter + Adam + parameter all-gather over NVLink
+ * peer memory.  g_peers[r] / p_peers[r] (HOST arrays of `world` device pointers) address rank r's flat
+ * gradient / parameter buffer (symmetric memory mapped into this process); this rank reduces and
+ * updates its own 1/world shard and stores the new parameters into every rank's buffer.  m, v are
+ * local (only the owned shard is touched).  Gradients are averaged (1/world).  The caller must issue a
+ * cross-rank barrier before (all gradients complete) and after (all parameters visible). */
+int zns_adam_p2p(int world, int rank, const void* const* g_peers, void* const* p_peers, float* m, float* v, long long n,
+                 float lr, float beta1, float beta2, float eps, int step, const uint32_t* step_dev, void* stream);
 /* *ctr += inc on the stream (the device step counter used above). */
 int zns_counter_add(uint32_t* ctr, uint32_t inc, void* stream);
 

@@ -14,4 +14,7 @@ while [ $n -le $N ]; do
   echo "bench $n exit=$?"; grep -h '"metric"' gpurun_out/scale_$n.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['n_gpus'], round(d['value'],1), 'clips/s', round(d['ms_per_step'],3), 'ms/step e2e', round(d['e2e']['value'],1))"
   n=$((n*2))
 done
-grep -h -i -E "NVLS|Connected all|via P2P" gpurun_out/scale_$N.err | head -6
+# same N with the NCCL all-reduce + local Adam path, for comparison
+ZNS_P2P_ADAM=0 timeout -k 5 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29599 bench.py --gpus $N --steps 30 --warmup 5 --no-extras > gpurun_out/scale_${N}_nccl.json 2> gpurun_out/scale_${N}_nccl.err
+echo "bench $N (NCCL path) exit=$?"; grep -h '"metric"' gpurun_out/scale_${N}_nccl.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['n_gpus'], round(d['value'],1), 'clips/s', round(d['ms_per_step'],3), 'ms/step')"
+tail -3 gpurun_out/scale_$N.err

@@ -614,3 +614,84 @@ extern "C" int zns_counter_add(uint32_t* ctr, uint32_t inc, void* stream) {
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Fused gradient reduce-scatter + Adam + parameter all-gather over NVLink peer memory.
+//   Every rank owns one contiguous shard of the flat parameter vector.  For its shard it reads the
+//   gradient of EVERY rank straight from that rank's HBM (peer loads over NVLink/NVSwitch), sums
+//   them in rank order (the same order on every owner -> replicas stay bit-identical), applies
+//   Adam (moments exist only for the owned shard) and stores the new parameters into every rank's
+//   parameter buffer (peer stores).  One launch replaces all-reduce + optimizer: per rank
+//   2 (W-1)/W of the parameter bytes cross NVLink instead of the ring's 2 (W-1)/W * 2, and the
+//   transfers overlap the arithmetic element by element.  The caller brackets the launch with
+//   cross-rank barriers (gradients complete before, parameters visible after).
+// ---------------------------------------------------------------------------------------------
+#define P2P_MAX_WORLD 16
+
+struct P2PPtrs {
+  const float* g[P2P_MAX_WORLD];
+  float* p[P2P_MAX_WORLD];
+};
+
+__global__ void __launch_bounds__(256) adam_p2p_kernel(P2PPtrs ptrs, int world, int rank, float* __restrict__ m,
+                                                       float* __restrict__ v, long long lo4, long long hi4, float lr, float b1,
+                                                       float b2, float eps, float inv_bc1, float inv_sqrt_bc2,
+                                                       const uint32_t* __restrict__ step_dev, float gscale) {
+  if (step_dev) {
+    const double st = (double)__ldg(step_dev);
+    inv_bc1 = (float)(1.0 / (1.0 - pow((double)b1, st)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, st)));
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
+    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < world; ++r) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(ptrs.g[r]) + i);   // peer (or local) HBM, not cached
+      gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+    }
+    float4 pp = reinterpret_cast<float4*>(ptrs.p[rank])[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define ZNS_ADAM2(f)                                                        \
+  {                                                                         \
+    const float gr = gg.f * gscale;                                         \
+    mm.f = b1 * mm.f + (1.f - b1) * gr;                                     \
+    vv.f = b2 * vv.f + (1.f - b2) * gr * gr;                                \
+    const float denom = sqrtf(vv.f) * inv_sqrt_bc2 + eps;                   \
+    pp.f -= (lr * inv_bc1) * (mm.f / denom);                                \
+  }
+    ZNS_ADAM2(x) ZNS_ADAM2(y) ZNS_ADAM2(z) ZNS_ADAM2(w)
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(ptrs.p[r])[i] = pp;   // all-gather by peer stores
+  }
+}
+
+extern "C" int zns_adam_p2p(int world, int rank, const void* const* g_peers_host, void* const* p_peers_host, float* m, float* v,
+                            long long n, float lr, float beta1, float beta2, float eps, int step, const uint32_t* step_dev,
+                            void* stream) {
+  ZNS_REQUIRE(g_peers_host && p_peers_host && m && v, "NULL argument");
+  ZNS_REQUIRE(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "bad world/rank");
+  ZNS_REQUIRE(n % 4 == 0, "flat buffers must hold a multiple of 4 elements");
+  ZNS_REQUIRE(step >= 1 || step_dev, "Adam step counts from 1");
+  if (step < 1) step = 1;
+  P2PPtrs ptrs;
+  for (int r = 0; r < world; ++r) {
+    ZNS_REQUIRE(g_peers_host[r] && p_peers_host[r], "NULL peer pointer for rank %d", r);
+    ptrs.g[r] = (const float*)g_peers_host[r];
+    ptrs.p[r] = (float*)p_peers_host[r];
+  }
+  const long long n4 = n / 4;
+  const long long per = (n4 + world - 1) / world;
+  const long long lo4 = std::min<long long>(n4, per * rank), hi4 = std::min<long long>(n4, per * (rank + 1));
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  if (hi4 > lo4) {
+    const int blocks = (int)std::min<long long>((hi4 - lo4 + 255) / 256, 148 * 8);
+    adam_p2p_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ptrs, world, rank, m, v, lo4, hi4, lr, beta1, beta2, eps,
+                                                              (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), step_dev,
+                                                              1.0f / (float)world);
+    ZNS_CHECK_LAUNCH();
+  }
+  return ZNS_OK;
+}

@@ -43,3 +43,31 @@ def allreduce_gradients(flat_g: torch.Tensor) -> float:
 def broadcast_parameters(flat_p: torch.Tensor, src: int = 0) -> None:
     if is_distributed():
         dist.broadcast(flat_p, src)
+
+
+class SymmetricFlat:
+    """Flat fp32 parameter and gradient buffers in NVLink-addressable symmetric memory
+    (torch.distributed._symmetric_memory): ``p`` / ``g`` are this rank's tensors, ``p_ptrs`` / ``g_ptrs``
+    ctypes arrays with every rank's device address of the same buffers, ``barrier(channel)`` a
+    device-side cross-rank barrier enqueued on the current stream."""
+
+    def __init__(self, numel: int, device: torch.device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        group = dist.group.WORLD
+        self.p = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.g = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.p.zero_()
+        self.g.zero_()
+        self._hp = symm_mem.rendezvous(self.p, group)
+        self._hg = symm_mem.rendezvous(self.g, group)
+        self.p_ptrs = (ctypes.c_void_p * self.world)(*[int(a) for a in self._hp.buffer_ptrs])
+        self.g_ptrs = (ctypes.c_void_p * self.world)(*[int(a) for a in self._hg.buffer_ptrs])
+        assert int(self._hp.buffer_ptrs[self.rank]) == self.p.data_ptr(), "symmetric buffer is not where rendezvous says"
+        assert int(self._hg.buffer_ptrs[self.rank]) == self.g.data_ptr()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def barrier(self, channel: int = 0) -> None:
+        self._hg.barrier(channel=channel)

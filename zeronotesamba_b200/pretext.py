@@ -16,6 +16,7 @@ Bank building, pickling, plotting and Spleeter (pretext.py:30-172,418-448) are o
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -81,7 +82,8 @@ class PretextTrainer:
 
     def __init__(self, model: Pretext_CNN, batch_len: int = 16, temperature: float = 0.25, lr: float = 1e-6,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, crop_frames: int = CROP_FRAMES,
-                 dropout_p: Optional[float] = None, use_graph: bool = True, seed: int = 0, distributed: bool = True):
+                 dropout_p: Optional[float] = None, use_graph: bool = True, seed: int = 0, distributed: bool = True,
+                 p2p_adam: bool = True):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("PretextTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -100,8 +102,23 @@ class PretextTrainer:
         for p in plist:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4
-        self.flat_p = torch.zeros(total, device=dev)
-        self.flat_g = torch.zeros(total, device=dev)
+        # Multi-GPU: parameters and gradients live in symmetric memory so that every rank can address
+        # every other rank's buffers over NVLink; the optimizer is then ONE kernel that reduce-scatters
+        # the gradients, applies Adam to the owned shard and all-gathers the new parameters by peer
+        # stores (zns_adam_p2p).  ZNS_P2P_ADAM=0 (or a failed rendezvous) falls back to NCCL all-reduce
+        # + local Adam.
+        self._symm = None
+        if self.distributed and p2p_adam and os.environ.get("ZNS_P2P_ADAM", "1") != "0":
+            try:
+                self._symm = dist_utils.SymmetricFlat(total, dev)
+            except Exception as exc:   # pragma: no cover - depends on the fabric
+                print(f"[zns] symmetric-memory rendezvous failed ({exc!r}); using NCCL all-reduce + local Adam")
+                self._symm = None
+        if self._symm is not None:
+            self.flat_p, self.flat_g = self._symm.p, self._symm.g
+        else:
+            self.flat_p = torch.zeros(total, device=dev)
+            self.flat_g = torch.zeros(total, device=dev)
         self.flat_m = torch.zeros(total, device=dev)
         self.flat_v = torch.zeros(total, device=dev)
         self.params: List[Dict[str, torch.Tensor]] = [{}, {}]
@@ -153,6 +170,26 @@ class PretextTrainer:
                                        L.ptr(self.result), L.ptr(self.d_emb[0]), L.ptr(self.d_emb[1]), st))
         eng.backward(self.d_emb, self.params, self.grads)
 
+    def _optimizer_p2p(self):
+        sm = self._symm
+        L.check(L.lib().zns_adam_p2p(sm.world, sm.rank, sm.g_ptrs, sm.p_ptrs, L.ptr(self.flat_m), L.ptr(self.flat_v),
+                                     self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0,
+                                     L.ptr(self.engine.step_ctr), L.current_stream()))
+
+    def _reduce_and_update(self):
+        """Gradient exchange + optimizer of one step (eager calls between the captured graphs)."""
+        if self._symm is not None:
+            self._symm.barrier(0)          # every rank's gradients are complete
+            self._optimizer_p2p()
+            self._symm.barrier(1)          # every rank's parameter stores have landed
+        else:
+            if self.distributed:
+                dist_utils.allreduce_gradients(self.flat_g)     # NCCL over NVLink; Adam applies 1/world
+            if self.use_graph and self._graph_opt is not None:
+                self._graph_opt.replay()
+            else:
+                self._optimizer()
+
     def _optimizer(self):
         L.check(L.lib().zns_adam_flat(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
                                       self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0,
@@ -194,19 +231,16 @@ class PretextTrainer:
             if self._graph_fb is None:
                 snap = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.engine.step_ctr.clone())
                 self._graph_fb = self._capture(self._forward_backward)
-                self._graph_opt = self._capture(self._optimizer)
+                if self._symm is None:
+                    self._graph_opt = self._capture(self._optimizer)
                 # capture warm-ups really ran: restore the state they touched
                 self.flat_p.copy_(snap[0]); self.flat_m.copy_(snap[1]); self.flat_v.copy_(snap[2])
                 self.engine.step_ctr.copy_(snap[3])
             self._graph_fb.replay()
-            if self.distributed:
-                dist_utils.allreduce_gradients(self.flat_g)     # NCCL over NVLink; Adam applies 1/world
-            self._graph_opt.replay()
+            self._reduce_and_update()
         else:
             self._forward_backward()
-            if self.distributed:
-                dist_utils.allreduce_gradients(self.flat_g)
-            self._optimizer()
+            self._reduce_and_update()
         return self.result
 
     def eval_step(self, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
