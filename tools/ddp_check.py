@@ -63,7 +63,7 @@ def main():
     d = (tr2.flat_p - tr.flat_p).abs().max().item()
     moved = (tr.flat_p - torch.cat([v.reshape(-1) for v in he_normal_state_dict(7).values()]).to(dev)).abs().max().item() \
         if tr.flat_p.numel() == sum(v.numel() for v in he_normal_state_dict(7).values()) else float("nan")
-    ok = same and d < 3e-4 and d_nccl < 3e-4 and res[0].item() == res[0].item()
+    ok = same and d < 3e-4 and d_nccl < 1e-3 and res[0].item() == res[0].item()   # NCCL sums in another order: Adam sign flips of 2*lr per step
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

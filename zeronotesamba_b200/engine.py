@@ -91,6 +91,11 @@ class EncoderEngine:
         self._p = 0.0
         # optional per-launch timing (bench.py): list of (tag, flops, start_event, end_event)
         self.timers: Optional[list] = None
+        # backward: the weight gradient of layer L runs on a side stream next to the data gradient of the
+        # same layer (both only read dY_L), so the partial last wave of one kernel is filled by CTAs of
+        # the other (each kernel occupies an SM exclusively: ~200 KB of shared memory per CTA)
+        self._side = torch.cuda.Stream(device=device)
+        self.overlap_wgrad = True
 
     def _timed(self, tag: str, flops: float):
         eng = self
@@ -190,6 +195,22 @@ class EncoderEngine:
 
     # -- backward ----------------------------------------------------------------------------------
     def _wgrad(self, name, H, xs, dys, grads):
+        """Weight + bias gradient of one layer; with overlap on, issued on the side stream.  Returns an
+        event that fires when dys may be overwritten."""
+        if not self.overlap_wgrad or self.timers is not None:
+            self._wgrad_now(name, H, xs, dys, grads)
+            return None
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            self._wgrad_now(name, H, xs, dys, grads)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        return done
+
+    def _wgrad_now(self, name, H, xs, dys, grads):
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
         lib, st = L.lib(), L.current_stream()
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw)
@@ -224,23 +245,38 @@ class EncoderEngine:
             p, g = params[br], grads[br]
             L.check(lib.zns_head_bwd(L.ptr(self.x8[br]), L.ptr(self.emb[br]), L.ptr(d_embs[br]), L.ptr(p["fc1.weight"]),
                                      L.ptr(g["fc1.weight"]), L.ptr(g["fc1.bias"]), L.ptr(ga[br]), self.B, self.T, scale, st))
-        self._wgrad("cv8", 1, self.x7, ga, grads)
+        main = torch.cuda.current_stream()
+
+        def join(ev):
+            if ev is not None:
+                main.wait_event(ev)
+
+        # dY_L alternates between ga and gb; the wgrad of layer L (side stream) must have finished
+        # reading its buffer before the dgrad of layer L-1 writes into it.
+        w8 = self._wgrad("cv8", 1, self.x7, ga, grads)
         self._dgrad("cv8", 1, ga, self.x7, gb)          # dy7
-        self._wgrad("cv7", 1, self.p6, gb, grads)
+        w7 = self._wgrad("cv7", 1, self.p6, gb, grads)
+        join(w8)
         self._dgrad("cv7", 1, gb, self.p6, ga)          # dp6 (masked)
+        join(w7)
         self._unpool(8, 256, 8, self.y6, ga, gb)        # dy6
-        self._wgrad("cv6", 8, self.x5, gb, grads)
+        w6 = self._wgrad("cv6", 8, self.x5, gb, grads)
         self._dgrad("cv6", 8, gb, self.x5, ga)          # dy5
-        self._wgrad("cv5", 8, self.p4, ga, grads)
+        w5 = self._wgrad("cv5", 8, self.p4, ga, grads)
+        join(w6)
         self._dgrad("cv5", 8, ga, self.p4, gb)          # dp4
+        join(w5)
         self._unpool(32, 128, 4, self.y4, gb, ga)       # dy4
-        self._wgrad("cv4", 32, self.x3, ga, grads)
+        w4 = self._wgrad("cv4", 32, self.x3, ga, grads)
         self._dgrad("cv4", 32, ga, self.x3, gb)         # dy3
-        self._wgrad("cv3", 32, self.p2, gb, grads)
+        w3 = self._wgrad("cv3", 32, self.p2, gb, grads)
+        join(w4)
         self._dgrad("cv3", 32, gb, self.p2, ga)         # dp2
+        join(w3)
         self._unpool(96, 64, 3, self.y2, ga, gb)        # dy2
-        self._wgrad("cv2", 96, self.x1, gb, grads)
+        w2 = self._wgrad("cv2", 96, self.x1, gb, grads)
         self._dgrad("cv2", 96, gb, self.x1, ga)         # dy1
+        join(w2)
         for br in range(self.n_br):
             g = grads[br]
             L.check(lib.zns_conv1_wgrad(L.ptr(ga[br]), L.ptr(self._x_in[br]), self._x_stride, self._x_row,
