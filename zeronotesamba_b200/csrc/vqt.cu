@@ -206,6 +206,7 @@ struct zns_vqt_plan {
   float* d_coef[ZNS_VQT_MAX_OCT];  // [n_fft][2][bpo/2][2] interleaved (SIMT filterbank kernel)
   uint16_t* d_coef_bf[ZNS_VQT_MAX_OCT];  // [2 terms][2*bpo columns][n_fft] fp16 (tensor-core filterbank)
   float coef_inv_scale[ZNS_VQT_MAX_OCT]; // 1 / (power-of-two scale applied to the fp16 coefficients)
+  uint16_t* d_coef_umma[ZNS_VQT_MAX_OCT]; // shared-memory image of the stacked B operand [k-block][48 rows][64] fp16, 128B-swizzled
   float* d_inv_sqrt_len;           // [n_bins]
   float* d_scratch[ZNS_VQT_MAX_OCT];  // decimated signals, octave >= 1
   float* d_stage_in;               // for *_host: [max_batch][max_samples]
@@ -296,6 +297,21 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
           }
       ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef_bf[i], sp.size() * sizeof(uint16_t)));
       ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef_bf[i], sp.data(), sp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      // UMMA B operand: rows 0..23 = g1, rows 24..47 = g2 (K-major, canonical 128-byte-swizzle layout:
+      // 8-row atoms of 1024 B, 16-byte chunk c of row r stored at chunk c ^ (r % 8))
+      const int kblocks = (nf + 63) / 64;
+      std::vector<uint16_t> img((size_t)kblocks * 48 * 64, 0);
+      for (int row = 0; row < 48; ++row)
+        for (int n = 0; n < nf; ++n) {
+          const int term = row / 24, col = row % 24;
+          const uint16_t hv = sp[((size_t)term * ncol + col) * nf + n];
+          const int kb = n / 64, kl = n % 64;
+          const size_t byte = (size_t)kb * (48 * 128) + (size_t)(row / 8) * 1024 + (size_t)(row % 8) * 128 +
+                              (size_t)(((kl / 8) ^ (row % 8)) * 16) + (size_t)(kl % 8) * 2;
+          img[byte / 2] = hv;
+        }
+      ZNS_CHECK_CUDA(cudaMalloc(&p->d_coef_umma[i], img.size() * sizeof(uint16_t)));
+      ZNS_CHECK_CUDA(cudaMemcpy(p->d_coef_umma[i], img.data(), img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
   }
   std::vector<double> lens;
@@ -319,6 +335,7 @@ extern "C" int zns_vqt_plan_destroy(zns_vqt_plan* p) {
   for (int i = 0; i < ZNS_VQT_MAX_OCT; ++i) {
     if (p->d_coef[i]) cudaFree(p->d_coef[i]);
     if (p->d_coef_bf[i]) cudaFree(p->d_coef_bf[i]);
+    if (p->d_coef_umma[i]) cudaFree(p->d_coef_umma[i]);
     if (p->d_scratch[i]) cudaFree(p->d_scratch[i]);
   }
   if (p->d_inv_sqrt_len) cudaFree(p->d_inv_sqrt_len);
@@ -644,6 +661,161 @@ vqt_filterbank_mma_kernel(const float* __restrict__ y, int n_sig, long long sig_
   }  // tile loop
 }
 
+// ---------------------------------------------------------------------------------------------
+// device: tcgen05 filterbank.  Same two-term fp16 split as above, but the products run on the
+// 5th-generation tensor cores: the 128-frame tile [128 x n_fft] (x1 and x2) is written to shared
+// memory in the canonical K-major 128-byte-swizzle layout by plain stores (it is a Toeplitz view of
+// the signal, so TMA cannot stage it), the stacked coefficient operand [g1 ; g2] (48 rows) is a
+// precomputed shared-memory image, and per 16 taps two MMAs are issued:
+//   D_a[128 x 48] += x1 . [g1 ; g2]^T        D_b[128 x 32] += x2 . [g1 ; ...]^T
+// C = D_a[:, 0:24] + (D_a[:, 24:48] + D_b[:, 0:24]) / 2048 in the epilogue (TMEM -> registers), then
+// |.|, 1/sqrt(len), log(. + 1e-9); a thread owns one frame, so stores are coalesced along time.
+// ---------------------------------------------------------------------------------------------
+#define FBU_TILES 4
+
+template <int NFFT>
+__global__ void __launch_bounds__(256)
+vqt_filterbank_umma_kernel(const float* __restrict__ y, int n_sig, long long sig_stride,
+                           const uint16_t* __restrict__ coef_img, float coef_inv_scale, int hop,
+                           const float* __restrict__ inv_sqrt_len, int bin0, int n_bins, int n_frames,
+                           float* __restrict__ out) {
+  constexpr int KB = (NFFT + 63) / 64;           // 64-element k-blocks
+  constexpr int HALF = NFFT / 2;
+  constexpr uint32_t kATile = 128 * 128;          // one k-block of one split term: 128 rows x 128 B
+  constexpr uint32_t kBTile = 48 * 128;
+  extern __shared__ uint8_t fsm_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(fsm_raw) + 1023u) & ~1023u;
+  uint8_t* sm = fsm_raw + (base - smem_u32(fsm_raw));
+  uint8_t* sA1 = sm;                              // [KB][128][128 B]
+  uint8_t* sA2 = sm + KB * kATile;
+  uint8_t* sB = sm + 2 * KB * kATile;             // [KB][48][128 B]
+  const int b = blockIdx.z;
+  const float* yb = y + (size_t)b * sig_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 128); tmem_relinquish(); }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(coef_img);
+    for (int i = threadIdx.x; i < KB * (int)kBTile / 16; i += 256) reinterpret_cast<uint4*>(sB)[i] = __ldg(src + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  uint32_t parity = 0;
+
+  for (int tile = 0; tile < FBU_TILES; ++tile) {
+    const int f0 = (blockIdx.x * FBU_TILES + tile) * 128;
+    if (f0 >= n_frames) break;
+    // ---- fill: (frame t, tap pair w) -> x1 / x2 halves at the swizzled position ----
+    constexpr int kPairs = 128 * HALF / 256;
+    constexpr int kBatch = kPairs < 8 ? kPairs : 8;
+    const long span_lo = (long)f0 * hop - HALF;
+    const long span_hi = (long)(min(f0 + 128, n_frames) - 1) * hop + HALF;
+    const bool interior = span_lo >= 0 && span_hi <= (long)n_sig && f0 + 128 <= n_frames &&
+                          ((reinterpret_cast<uintptr_t>(yb) & 7) == 0);
+#pragma unroll 1
+    for (int i0 = 0; i0 < kPairs; i0 += kBatch) {
+      float2 v[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int i = threadIdx.x + (i0 + k) * 256;
+        const int t = i / HALF, w = i - t * HALF;
+        const int f = f0 + t;
+        const long q = (long)f * hop + 2 * w - HALF;
+        if (interior) {
+          v[k] = __ldg(reinterpret_cast<const float2*>(yb + q));
+        } else if (f < n_frames) {
+          v[k].x = __ldg(yb + reflect_index(q, n_sig));
+          v[k].y = __ldg(yb + reflect_index(q + 1, n_sig));
+        } else {
+          v[k] = make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int i = threadIdx.x + (i0 + k) * 256;
+        const int t = i / HALF, w = i - t * HALF;
+        const int n = 2 * w, kb = n >> 6, kl = n & 63;
+        const uint32_t off = kb * kATile + (t >> 3) * 1024 + (t & 7) * 128 + ((((kl >> 3) ^ (t & 7))) << 4) + (kl & 7) * 2;
+        uint32_t s1, s2;
+        split2_pair(v[k].x, v[k].y, s1, s2);
+        *reinterpret_cast<uint32_t*>(sA1 + off) = s1;
+        *reinterpret_cast<uint32_t*>(sA2 + off) = s2;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA (async proxy) reads
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // ---- MMAs: one elected thread ----
+    if (warp == 0) {
+      if (elect_one()) {
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t idesc_a = umma_idesc_f16(128, 48), idesc_b = umma_idesc_f16(128, 32);
+        const uint32_t a1 = (base >> 4) | (1u << 16), a2 = ((base + KB * kATile) >> 4) | (1u << 16);
+        const uint32_t bb = ((base + 2 * KB * kATile) >> 4) | (1u << 16);
+#pragma unroll
+        for (int ks = 0; ks < NFFT / 16; ++ks) {
+          const uint32_t ao = (ks >> 2) * (kATile >> 4) + (ks & 3) * 2, bo = (ks >> 2) * (kBTile >> 4) + (ks & 3) * 2;
+          umma_f16(tmem, ((uint64_t)kDescHi << 32) | (a1 + ao), ((uint64_t)kDescHi << 32) | (bb + bo), idesc_a, ks > 0);
+          umma_f16(tmem + 64, ((uint64_t)kDescHi << 32) | (a2 + ao), ((uint64_t)kDescHi << 32) | (bb + bo), idesc_b, ks > 0);
+        }
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), parity);
+    parity ^= 1;
+    tc_fence_after();
+    // ---- epilogue: warps 0..3, thread = frame ----
+    if (warp < 4) {
+      uint32_t da[48], db[32];
+      const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+      tmem_ld_32x32(tl, da);
+      tmem_ld_32x16(tl + 32, da + 32);
+      tmem_ld_32x32(tl + 64, db);
+      tmem_ld_wait();
+      const int f = f0 + warp * 32 + lane;
+      if (f < n_frames) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          const float re = __uint_as_float(da[2 * k]) + (__uint_as_float(da[24 + 2 * k]) + __uint_as_float(db[2 * k])) * (1.f / 2048.f);
+          const float im = __uint_as_float(da[2 * k + 1]) + (__uint_as_float(da[25 + 2 * k]) + __uint_as_float(db[2 * k + 1])) * (1.f / 2048.f);
+          const int bin = bin0 + k;
+          out[((size_t)b * n_bins + bin) * n_frames + f] =
+              logf(sqrtf(re * re + im * im) * (__ldg(inv_sqrt_len + bin) * coef_inv_scale) + 1e-9f);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();      // accumulators read, operand tiles free for the next fill
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int NFFT>
+static int fbu_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
+                        int n_frames, float* out, cudaStream_t st) {
+  constexpr int KB = (NFFT + 63) / 64;
+  const size_t smem = 1024 + (size_t)KB * (2 * 128 * 128 + 48 * 128);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_filterbank_umma_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((n_frames + 128 * FBU_TILES - 1) / (128 * FBU_TILES), 1, batch);
+  vqt_filterbank_umma_kernel<NFFT><<<grid, 256, smem, st>>>(sig, n_sig, stride, p->d_coef_umma[oct], p->coef_inv_scale[oct], hop_i,
+                                                            p->d_inv_sqrt_len, p->n_bins - p->bpo * (oct + 1), p->n_bins,
+                                                            n_frames, out);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
 template <int NFFT, int FBT_FRAMES>
 static int fbt_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
                         int n_frames, float* out, cudaStream_t st) {
@@ -667,6 +839,20 @@ static int fb_launch(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long
   const int nf = p->n_fft[oct];
   const int hb = p->bpo / 2;
   static const bool simt = getenv("ZNS_VQT_SIMT") != nullptr;   // A/B switch: the round-1 SIMT filterbank
+  // tcgen05 variant of the filterbank: parity-green, but measured slower than the mma.sync kernel
+  // (145 vs 110 us per 128-tap octave at cfg2, 100 vs 38 us at 32 taps): its per-tile chain
+  // fill -> fence -> MMA -> commit -> TMEM load -> stores is exposed with 1-2 CTAs per SM.  Opt-in until it
+  // is software-pipelined across tiles.
+  static const bool use_umma = getenv("ZNS_VQT_UMMA") != nullptr;
+  if (!simt && use_umma && p->bpo == 12) {
+    switch (nf) {
+      case 16: return fbu_launch_t<16>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      case 32: return fbu_launch_t<32>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      case 64: return fbu_launch_t<64>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      case 128: return fbu_launch_t<128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
+      default: break;
+    }
+  }
   if (!simt && p->bpo == 12) {
     switch (nf) {
       case 16: return fbt_launch_t<16, 128>(p, oct, sig, n_sig, stride, hop_i, batch, n_frames, out, st);
