@@ -333,9 +333,11 @@ def kernel_roofline(tr, dev_audio, starts_dev, peaks, args, ms_step):
                         "ms_per_step": 1e3 * t / n_rep, "share_of_step": (1e3 * t / n_rep) / ms_step}
         tot_f += fl; tot_t += t
     dom = max(fam.items(), key=lambda kv: kv[1][1])[0]
+    traffic, traffic_src = _ncu_traffic(dom)
     return {
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                     "frac": kernels[dom]["frac"], "traffic": None,
+                     "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_flops_per_launch": fam[dom][0] / fam[dom][2],
                      "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                      "algorithmic": "2*M*N*K per conv launch (M=B*H*T, N=C_out, K=C_in*kh*kw, both branches), "
                                     "CUDA events around each launch on the launching stream, eager (non-graph) pass"},
@@ -344,6 +346,22 @@ def kernel_roofline(tr, dev_audio, starts_dev, peaks, args, ms_step):
                               "ms_per_step": 1e3 * tot_t / n_rep,
                               "step_model_tflops": 6 * BATCH * FWD_GFLOP_PER_SAMPLE_BRANCH / 1e3 / (ms_step * 1e-3)},
     }
+
+
+def _ncu_traffic(tag: str):
+    """DRAM bytes per launch (read + write) of the dominant kernel family from the committed ncu capture
+    (profiles/r01_ncu_conv_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over every
+    tensor-core launch of one step); None when the family is not in the capture."""
+    names = {"conv_fwd_umma<128>": "conv_fwd_umma_kernel<128, 4>", "conv_fwd_umma<256>": "conv_fwd_umma_kernel<256, 2>",
+             "conv_fwd_umma<64>": "conv_fwd_umma_kernel<64, 4>", "conv_wgrad_umma<128>": "conv_wgrad_umma_kernel<128>",
+             "conv_wgrad_umma<64>": "conv_wgrad_umma_kernel<64>",
+             "conv_fwd_stack_umma(c_out=64, 2 rows on N)": "conv_fwd_stack_umma_kernel"}
+    path = os.path.join(ROOT, "profiles", "r01_ncu_conv_traffic.json")
+    try:
+        table = json.load(open(path))
+        return float(table[names[tag]]["dram_bytes_per_launch"]), "profiles/r01_ncu_conv_traffic.json (ncu, per launch)"
+    except Exception:
+        return None, None
 
 
 def vqt_cfg2(dev, peaks):
