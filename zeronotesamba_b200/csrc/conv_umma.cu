@@ -984,7 +984,8 @@ struct WgParams {
   int fold;                 // 1: c_in == 64, M = 2 taps x 64 channels
   int n_acc;                // accumulators (TMEM) per CTA
   int taps_per_cta;         // n_acc * (fold ? 2 : 1)
-  int n_sgroups;            // ceil(kw / taps_per_cta)
+  int n_sgroups;            // tap groups per filter row
+  int grp_base, grp_rem;    // group i covers grp_base + (i < grp_rem) accumulators (balanced split of the row)
   int n_cin_blocks;         // fold ? 1 : Cin / 128
   int n_cout_blocks;        // Cout / NB
   int n_slices;             // position slices
@@ -1020,12 +1021,14 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   const int cib = t % p.n_cin_blocks; t /= p.n_cin_blocks;
   const int sg = t % p.n_sgroups; t /= p.n_sgroups;
   const int r = t;
-  const int s0 = sg * p.taps_per_cta;
+  const int unit = p.fold ? 2 : 1;                       // taps per accumulator
+  const int acc0 = sg * p.grp_base + min(sg, p.grp_rem); // first accumulator (in row order) of this group
+  const int s0 = acc0 * unit;
   const int n_xchunks = p.fold ? 1 : 2;
   const int n_steps_total = p.G * p.H * p.n_wtiles;
   const int q0 = (int)((long long)n_steps_total * slice / p.n_slices);
   const int q1 = (int)((long long)n_steps_total * (slice + 1) / p.n_slices);
-  const int n_acc_eff = min(p.n_acc, (p.kw - s0 + (p.fold ? 1 : 0)) / (p.fold ? 2 : 1));
+  const int n_acc_eff = p.grp_base + (sg < p.grp_rem ? 1 : 0);
   constexpr uint32_t kDyChunk = WT * 1024;  // 128 positions x 64 channels
 
   if (threadIdx.x == 0) {
@@ -1160,15 +1163,17 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   p.n_acc = 512 / NB;
   if (p.fold) p.n_acc = std::min(p.n_acc, (d->kw + 1) / 2);
   else p.n_acc = std::min(p.n_acc, d->kw);
-  // balance the taps over the s-groups (e.g. 17 taps, 4 accumulators -> 5 groups of 4,4,3,3,3 become 5 x <=4)
+  // balanced split of a filter row over tap groups: e.g. 17 taps with 4 accumulators -> 5 groups of
+  // 4,4,3,3,3 accumulators (a 4,4,4,4,1 split leaves one CTA with a quarter of the MMAs per loaded byte)
   {
-    const int tpc = p.n_acc * (p.fold ? 2 : 1);
-    const int groups = (d->kw + tpc - 1) / tpc;
-    int per = (d->kw + groups - 1) / groups;
-    if (p.fold) per = (per + 1) & ~1;
-    p.n_acc = p.fold ? per / 2 : per;
-    p.taps_per_cta = p.n_acc * (p.fold ? 2 : 1);
-    p.n_sgroups = (d->kw + p.taps_per_cta - 1) / p.taps_per_cta;
+    const int unit = p.fold ? 2 : 1;
+    const int row_acc = (d->kw + unit - 1) / unit;           // accumulators needed for one filter row
+    const int groups = (row_acc + p.n_acc - 1) / p.n_acc;
+    p.n_sgroups = groups;
+    p.grp_base = row_acc / groups;
+    p.grp_rem = row_acc % groups;
+    p.n_acc = p.grp_base + (p.grp_rem ? 1 : 0);
+    p.taps_per_cta = p.n_acc * unit;
   }
   p.n_cin_blocks = p.fold ? 1 : d->c_in / 128;
   p.n_cout_blocks = d->c_out / NB;
