@@ -19,6 +19,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <tuple>
+#include <vector>
 
 #include "common.cuh"
 
@@ -76,6 +81,96 @@ static int make_w_map(CUtensorMap* m, const void* base, int taps, int rows, int 
 #define ZNS_SMEM_LIMIT 232448  // 227 KB opt-in maximum per CTA
 #define WT 16                  // frames per M tile (x 8 clips = 128 rows)
 #define MAX_RING 8
+#define ZNS_NUM_SMS 148
+
+// ---------------------------------------------------------------------------------------------
+// Tile plan.  Every conv CTA owns an SM (its shared memory does not leave room for a second), and the
+// layers offer only a few hundred equal tiles, so with one tile size the last wave is mostly empty
+// (640 tiles on 148 SMs = 4.3 waves).  A column (group, frame tile, branch) of `units` output rows is
+// therefore cut into `nb` big tiles of `hb` rows followed by `ns` small tiles of `hs` rows; big tiles
+// come first in block order, so the hardware's in-order dispatch behaves like longest-first list
+// scheduling.  plan_tiles() picks (hb, nb, hs, ns) by simulating that schedule.
+// ---------------------------------------------------------------------------------------------
+struct TilePlan {
+  int n_cols;   // G * n_wtiles * n_br
+  int hb, nb, hs, ns;
+  int n_big;    // n_cols * nb
+  int n_total;  // n_cols * (nb + ns)
+};
+
+__device__ __forceinline__ void tile_decode(const TilePlan& tp, int n_wtiles, int G, int t, int& br, int& g, int& wt,
+                                            int& u0, int& un) {
+  int j, col;
+  if (t < tp.n_big) {
+    j = t / tp.n_cols; col = t - j * tp.n_cols; u0 = j * tp.hb; un = tp.hb;
+  } else {
+    t -= tp.n_big;
+    j = t / tp.n_cols; col = t - j * tp.n_cols; u0 = tp.nb * tp.hb + j * tp.hs; un = tp.hs;
+  }
+  wt = col % n_wtiles; col /= n_wtiles;
+  g = col % G;
+  br = col / G;
+}
+
+// units: output rows (or stacked row pairs) per column; u_max: accumulators that fit TMEM / shared memory;
+// ovh: per-CTA prologue + epilogue cost in units of one row's MMA time.
+static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh) {
+  // plans are pure functions of their arguments: cache them (the simulation costs ~1 ms of host time)
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int, long>, TilePlan> cache;
+  const auto key = std::make_tuple(units, n_cols, u_max, lround(ovh * 4096.0));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  auto cost = [&](int h) {
+    // weight-tile bytes per MMA clock fall as 64/h B/clk; below ~1.7 rows per tile L2 cannot keep up
+    const double mult = std::max(1.0, (64.0 / h) / 38.0);
+    return h * mult + ovh;
+  };
+  auto simulate = [&](int hb, int nb, int hs, int ns) {
+    std::priority_queue<double, std::vector<double>, std::greater<double>> sm;   // SM finish times, earliest first
+    for (int i = 0; i < ZNS_NUM_SMS; ++i) sm.push(0.0);
+    double last = 0.0;
+    auto push = [&](double d) {
+      const double t = sm.top() + d;
+      sm.pop();
+      sm.push(t);
+      last = std::max(last, t);
+    };
+    for (long i = 0; i < (long)n_cols * nb; ++i) push(cost(hb));
+    for (long i = 0; i < (long)n_cols * ns; ++i) push(cost(hs));
+    return last;
+  };
+  TilePlan best;
+  memset(&best, 0, sizeof(best));
+  double best_t = 1e30;
+  u_max = std::max(1, std::min(u_max, units));
+  for (int hb = u_max; hb >= 1; --hb)
+    for (int nb = units / hb; nb >= 0; --nb) {
+      const int rem = units - nb * hb;
+      for (int hs = std::min(hb, std::max(rem, 1)); hs >= 1; --hs) {
+        if (rem == 0 && hs != hb) continue;
+        if (rem > 0 && rem % hs != 0) continue;
+        if (nb == 0 && hs != hb) continue;      // all-small plans are covered by a smaller hb
+        const int ns = rem / hs;
+        const double t = simulate(hb, nb, hs, ns);
+        if (t < best_t * 0.995) {
+          best_t = t;
+          best.hb = hb; best.nb = nb; best.hs = hs; best.ns = ns;
+        }
+      }
+    }
+  best.n_cols = n_cols;
+  best.n_big = n_cols * best.nb;
+  best.n_total = n_cols * (best.nb + best.ns);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = best;
+  }
+  return best;
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward / data-gradient kernel
@@ -84,7 +179,8 @@ struct FwdParams {
   int G, H, W, batch;
   int kh, kw, ph, pw;
   int n_chunks;             // input channels / 64
-  int n_wtiles, n_htiles;
+  int n_wtiles;
+  TilePlan tiles;           // rows per CTA (units = output rows)
   int n_slots, n_bstages;   // A row ring, B tile ring
   uint32_t slot_bytes;      // (WT + kw - 1) * 1024
   int relu;
@@ -114,17 +210,12 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem_raw + (b_base + p.n_bstages * kBTile - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int br = blockIdx.z;
+  // tile coordinates
+  int br, g, wt, h0, ht_eff;
+  tile_decode(p.tiles, p.n_wtiles, p.G, blockIdx.x, br, g, wt, h0, ht_eff);
   const CUtensorMap* tm_in = br ? &tm_in1 : &tm_in0;
   const CUtensorMap* tm_w = br ? &tm_w1 : &tm_w0;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int wt = t % p.n_wtiles; t /= p.n_wtiles;
-  const int htile = t % p.n_htiles; t /= p.n_htiles;
-  const int g = t;
-  const int w0 = wt * WT, h0 = htile * HT;
-  const int ht_eff = min(HT, p.H - h0);
+  const int w0 = wt * WT;
   // input rows rr (relative): hh = h0 - ph + rr, valid when 0 <= hh < H
   const int rr_lo = max(0, p.ph - h0);
   const int rr_hi = min(ht_eff + p.kh - 1, p.H + p.ph - h0);
@@ -326,6 +417,7 @@ struct FwdTParams {
   int kh, kw, ph, pw;
   int n_chunks;
   int n_wtiles, n_htiles;
+  TilePlan tiles;    // stacked kernel only: accumulators (row pairs) per CTA
   int cout;          // 64 or 128
   int stack;         // output rows stacked on M: 128 / cout
   int n_acc;         // accumulators (of 256 TMEM columns) per CTA
@@ -570,17 +662,11 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
   FwdTBarriers* bars = reinterpret_cast<FwdTBarriers*>(smem_raw + (w_base + p.n_wstages * kWTile - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int br = blockIdx.z;
+  int br, g, wt, u0, acc_eff;                       // tile = acc_eff stacked row pairs starting at pair u0
+  tile_decode(p.tiles, p.n_wtiles, p.G, blockIdx.x, br, g, wt, u0, acc_eff);
   const CUtensorMap* tm_in = br ? &tm_in1 : &tm_in0;
   const CUtensorMap* tm_w = br ? &tm_w1 : &tm_w0;
-
-  int t = blockIdx.x;
-  const int wt = t % p.n_wtiles; t /= p.n_wtiles;
-  const int htile = t % p.n_htiles; t /= p.n_htiles;
-  const int g = t;
-  const int rows_per_cta = p.n_acc * p.stack;
-  const int w0 = wt * WT, h0 = htile * rows_per_cta;
-  const int acc_eff = min(p.n_acc, (p.H - h0 + p.stack - 1) / p.stack);
+  const int w0 = wt * WT, h0 = u0 * p.stack;
   const int n_iter = p.kh + p.stack - 1;                     // tap-row steps r' = 0 .. kh + stack - 2
   // relative input rows rr: hh = h0 - ph + rr; accumulator a needs row r' + a*stack at step r'
   const int rr_lo = max(0, p.ph - h0);
@@ -789,6 +875,7 @@ static bool fwd_stack_config(const zns_conv_desc* d, FwdTParams* p) {
   const uint32_t slot = (uint32_t)(WT + d->kw - 1) * 1024u;
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdTBarriers) - 64;
   int n_acc = std::min(3, d->H / 2);
+  while (n_acc > 1 && (uint64_t)((n_acc - 1) * 2 + 2) * slot + 2ull * 16384 > budget) --n_acc;
   int slots = (n_acc - 1) * 2 + 2;
   if ((uint64_t)slots * slot + 2ull * 16384 > budget) return false;
   int wst = 2;
@@ -806,8 +893,12 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
   p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
   p.n_chunks = d->c_in / 64;
   p.n_wtiles = (d->W + WT - 1) / WT;
-  const int rows_per_cta = p.n_acc * p.stack;
-  p.n_htiles = (d->H + rows_per_cta - 1) / rows_per_cta;
+  {
+    const double pair_clk = (double)p.n_chunks * (d->kh + 1) * d->kw * 4.0 * 64.0;   // N = 128 MMAs per stacked pair
+    p.tiles = plan_tiles(d->H / 2, G * p.n_wtiles * n_br, p.n_acc, 8000.0 / pair_clk);
+    p.n_acc = p.tiles.hb;
+    p.n_slots = std::min(p.n_slots, (p.n_acc - 1) * 2 + 3);
+  }
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
   const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * 16384 + sizeof(FwdTBarriers) + 64;
@@ -827,7 +918,7 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_stack_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
     attr_set = true;
   }
-  dim3 grid(p.n_wtiles * p.n_htiles * G, 1, n_br);
+  dim3 grid(p.tiles.n_total, 1, 1);
   conv_fwd_stack_umma_kernel<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
@@ -897,13 +988,18 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
   p.n_chunks = d->c_in / 64;
   p.n_wtiles = (d->W + WT - 1) / WT;
-  p.n_htiles = (d->H + HT - 1) / HT;
   p.slot_bytes = (uint32_t)(WT + d->kw - 1) * 1024u;
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
-  const int ht_max = std::min(HT, d->H);
   const uint32_t btile = N * 128;
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdBarriers) - 64;
+  int u_max = std::min(HT, d->H);
+  while (u_max > 1 && (uint64_t)(u_max + 1) * p.slot_bytes + 2ull * btile > budget) --u_max;
+  {
+    const double row_clk = (double)p.n_chunks * d->kh * d->kw * 4.0 * (N / 2);
+    p.tiles = plan_tiles(d->H, G * p.n_wtiles * n_br, u_max, 8000.0 / row_clk);
+  }
+  const int ht_max = p.tiles.hb;
   int slots = ht_max + 1, bst = 2;
   ZNS_REQUIRE((uint64_t)slots * p.slot_bytes + (uint64_t)bst * btile <= budget,
               "conv tile does not fit shared memory (kw %d, c_out %d)", d->kw, N);
@@ -932,7 +1028,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
     attr_set = true;
   }
-  dim3 grid(p.n_wtiles * p.n_htiles * G, 1, n_br);
+  dim3 grid(p.tiles.n_total, 1, 1);
   kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
