@@ -1112,11 +1112,13 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
 
   // work item: (tap row r, s-group, cin block, cout block) x position slice
   int t = blockIdx.x;
+  // the tap group is the slowest index: groups with one more accumulator (sg < grp_rem) are dispatched
+  // first, so the in-order block scheduler behaves like longest-first list scheduling
   const int slice = t % p.n_slices; t /= p.n_slices;
   const int cob = t % p.n_cout_blocks; t /= p.n_cout_blocks;
   const int cib = t % p.n_cin_blocks; t /= p.n_cin_blocks;
-  const int sg = t % p.n_sgroups; t /= p.n_sgroups;
-  const int r = t;
+  const int r = t % p.kh; t /= p.kh;
+  const int sg = t;
   const int unit = p.fold ? 2 : 1;                       // taps per accumulator
   const int acc0 = sg * p.grp_base + min(sg, p.grp_rem); // first accumulator (in row order) of this group
   const int s0 = acc0 * unit;
@@ -1280,15 +1282,27 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   ZNS_REQUIRE(p.n_stages >= 2, "wgrad stage does not fit shared memory twice");
   const int items = d->kh * p.n_sgroups * p.n_cin_blocks * p.n_cout_blocks;
   const int n_steps_total = G * d->H * p.n_wtiles;
-  // position slices: fill the 148 SMs a whole number of times while keeping >= 24 steps per CTA
+  // position slices: simulate the in-order dispatch of the two CTA classes (groups with grp_base + 1 and
+  // with grp_base accumulators) for every slice count and keep the shortest makespan; more slices also
+  // mean more atomics in the epilogue, hence the small per-CTA overhead term
   int best = 1;
-  double best_eff = 0.0;
-  for (int s = 1; s <= 64; ++s) {
-    if (n_steps_total / s < 24 && s > 1) break;
-    const long long ctas = (long long)items * n_br * s;
-    const double waves = (double)ctas / 148.0;
-    const double eff = waves / ceil(waves);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  {
+    const long per_group = (long)d->kh * p.n_cin_blocks * p.n_cout_blocks * n_br;   // CTAs per tap group and slice
+    const int acc_big = p.grp_base + (p.grp_rem ? 1 : 0), acc_small = p.grp_base;
+    const int n_big_groups = p.grp_rem ? p.grp_rem : p.n_sgroups, n_small_groups = p.grp_rem ? p.n_sgroups - p.grp_rem : 0;
+    double best_t = 1e30;
+    for (int sl = 1; sl <= 64; ++sl) {
+      const double steps = (double)n_steps_total / sl;
+      if (steps < 16 && sl > 1) break;
+      const double ovh = 24.0;   // prologue + TMEM drain + atomics, in units of one accumulator-step (8 MMAs)
+      std::priority_queue<double, std::vector<double>, std::greater<double>> sm;
+      for (int i = 0; i < ZNS_NUM_SMS; ++i) sm.push(0.0);
+      double last = 0.0;
+      auto push = [&](double dur) { const double t = sm.top() + dur; sm.pop(); sm.push(t); last = std::max(last, t); };
+      for (long i = 0; i < per_group * n_big_groups * sl; ++i) push(steps * acc_big + ovh);
+      for (long i = 0; i < per_group * n_small_groups * sl; ++i) push(steps * acc_small + ovh);
+      if (last < best_t * 0.99) { best_t = last; best = sl; }
+    }
   }
   p.n_slices = best;
   const size_t smem = 1024 + (size_t)p.n_stages * p.stage_bytes + sizeof(WgBarriers) + 64;
