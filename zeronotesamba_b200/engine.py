@@ -138,6 +138,17 @@ class EncoderEngine:
         self._grad_ws_ready = True
 
     # -- weights -----------------------------------------------------------------------------------
+    def pack_weights_async(self, params: Sequence[Dict[str, torch.Tensor]], need_dgrad: bool):
+        """pack_weights on the side stream; forward() joins it right before cv2, so the packs overlap cv1."""
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            self.pack_weights(params, need_dgrad)
+            self._pack_event = torch.cuda.Event()
+            self._pack_event.record(self._side)
+
     def pack_weights(self, params: Sequence[Dict[str, torch.Tensor]], need_dgrad: bool):
         """fp32 state_dict-layout weights -> bf16 packs (forward, and flipped/transposed for dgrad)."""
         lib, st = L.lib(), L.current_stream()
@@ -177,6 +188,9 @@ class EncoderEngine:
             L.check(lib.zns_conv1_fwd(L.ptr(xs[br]), x_clip_stride, self._x_row, L.ptr(p["pretrained.cv1.weight"]),
                                       L.ptr(p["pretrained.cv1.bias"]), L.ptr(self.x1[br]), self.B, N_BINS, self.T,
                                       self._p, self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, 100 + br, st))
+        if getattr(self, "_pack_event", None) is not None:      # packs issued by pack_weights_async
+            torch.cuda.current_stream().wait_event(self._pack_event)
+            self._pack_event = None
         self._conv("cv2", 96, self.x1, self.y2, params, relu=0, drop=False, layer_id=2)
         self._pool(96, 64, 3, self.y2, self.p2, 2)
         self._conv("cv3", 32, self.p2, self.x3, params, relu=1, drop=True, layer_id=3)
@@ -218,6 +232,9 @@ class EncoderEngine:
             L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xs), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
         for br in range(self.n_br):
             L.check(lib.zns_bias_grad(L.ptr(dys[br]), self.B, H, self.T, co, L.ptr(grads[br][f"pretrained.{name}.bias"]), st))
+            # packed [tap][c_out][c_in] -> state_dict layout, on the same (side) stream: overlaps later layers
+            L.check(lib.zns_unpack_grads(L.ptr(self.gp[name][br]), co, ci, kh, kw, 1.0, 1,
+                                         L.ptr(grads[br][f"pretrained.{name}.weight"]), st))
 
     def _dgrad(self, name, H, dys, masks, outs):
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
@@ -282,6 +299,3 @@ class EncoderEngine:
             L.check(lib.zns_conv1_wgrad(L.ptr(ga[br]), L.ptr(self._x_in[br]), self._x_stride, self._x_row,
                                         L.ptr(g["pretrained.cv1.weight"]), L.ptr(g["pretrained.cv1.bias"]), self.B, N_BINS,
                                         self.T, st))
-            for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
-                L.check(lib.zns_unpack_grads(L.ptr(self.gp[name][br]), co, ci, kh, kw, 1.0, 1,
-                                             L.ptr(g[f"pretrained.{name}.weight"]), st))

@@ -162,7 +162,7 @@ class PretextTrainer:
         lib, st = L.lib(), L.current_stream()
         eng = self.engine
         L.check(lib.zns_counter_add(L.ptr(eng.step_ctr), 1, st))
-        eng.pack_weights(self.params, need_dgrad=True)
+        eng.pack_weights_async(self.params, need_dgrad=True)      # side stream, joined before cv2
         self.flat_g.zero_()
         eng.forward([self.batch_buf[:, 0], self.batch_buf[:, 1]], 2 * 96 * self.T, self.params, train=True,
                     dropout_p=self.dropout_p)
