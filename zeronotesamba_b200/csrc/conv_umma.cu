@@ -118,15 +118,19 @@ static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh) {
   // plans are pure functions of their arguments: cache them (the simulation costs ~1 ms of host time)
   static std::mutex mu;
   static std::map<std::tuple<int, int, int, long>, TilePlan> cache;
-  const auto key = std::make_tuple(units, n_cols, u_max, lround(ovh * 4096.0));
+  const auto key = std::make_tuple(units, n_cols, u_max, lround(ovh * 4096.0));   // (before env scaling: env is process-wide)
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
   }
+  // weight-tile bytes per MMA clock fall as 64/h B/clk; ZNS_PLAN_L2 (default 38 B/clk per SM) is what L2 is
+  // assumed to deliver, ZNS_PLAN_OVH scales the per-CTA overhead (both only for tuning experiments)
+  static const double l2_rate = getenv("ZNS_PLAN_L2") ? atof(getenv("ZNS_PLAN_L2")) : 38.0;
+  static const double ovh_scale = getenv("ZNS_PLAN_OVH") ? atof(getenv("ZNS_PLAN_OVH")) : 1.0;
+  ovh *= ovh_scale;
   auto cost = [&](int h) {
-    // weight-tile bytes per MMA clock fall as 64/h B/clk; below ~1.7 rows per tile L2 cannot keep up
-    const double mult = std::max(1.0, (64.0 / h) / 38.0);
+    const double mult = std::max(1.0, (64.0 / h) / l2_rate);
     return h * mult + ovh;
   };
   auto simulate = [&](int hb, int nb, int hs, int ns) {
