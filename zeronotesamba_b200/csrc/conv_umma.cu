@@ -201,7 +201,14 @@ struct FwdBarriers {
   uint32_t tmem_base;
 };
 
-template <int N, int HT>
+// CTAS = 2: two CTAs of a cluster (one TPC) work on adjacent frame tiles of the same rows as ONE
+// M = 256 MMA (tcgen05 cta_group::2).  Each CTA stages its own input rows and HALF of every weight
+// tile, so the operand reads per SM fall from 8 KB to 6 KB per 64-clock MMA at N = 128 -- below the
+// 128 B/clk shared-memory limit that the single-CTA kernel sits on -- and the weight traffic from L2
+// halves.  The even CTA (leader) issues the MMAs and owns the "full" barriers, which count the bytes
+// of both CTAs' TMA loads; the "empty" and accumulator barriers are signalled in both CTAs by
+// multicast commits.
+template <int N, int HT, int CTAS>
 __global__ void __launch_bounds__(192, 1)
 conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                      const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
@@ -210,7 +217,9 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + p.n_slots * p.slot_bytes;
-  constexpr uint32_t kBTile = N * 128;
+  constexpr uint32_t kBTile = N * 128 / CTAS;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem_raw + (b_base + p.n_bstages * kBTile - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,11 +242,12 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     tma_prefetch_desc(tm_w);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
@@ -258,9 +268,13 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
           const int need_hi = min(r + ht_eff, rr_hi);
           while (next_row < need_hi) {
             mbar_wait(bar_a_empty + 8 * a_slot, a_par);
-            mbar_expect_tx(bar_a_full + 8 * a_slot, p.slot_bytes);
-            tma_load_5d(a_base + a_slot * p.slot_bytes, tm_in, bar_a_full + 8 * a_slot, c * 64, 0, w0 - p.pw,
-                        h0 - p.ph + next_row, g);
+            if (leader) mbar_expect_tx(bar_a_full + 8 * a_slot, CTAS * p.slot_bytes);
+            if (CTAS == 2)
+              tma_load_5d_pair(a_base + a_slot * p.slot_bytes, tm_in, (bar_a_full + 8 * a_slot) & ZNS_PEER_MASK, c * 64, 0,
+                               w0 - p.pw, h0 - p.ph + next_row, g);
+            else
+              tma_load_5d(a_base + a_slot * p.slot_bytes, tm_in, bar_a_full + 8 * a_slot, c * 64, 0, w0 - p.pw,
+                          h0 - p.ph + next_row, g);
             if (++a_slot == n_slots) { a_slot = 0; a_par ^= 1; }
             ++next_row;
           }
@@ -268,8 +282,12 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
           const int tap0 = r * p.kw;
           for (int s = 0; s < p.kw; ++s) {
             mbar_wait(bar_b_empty + 8 * b_st, b_par);
-            mbar_expect_tx(bar_b_full + 8 * b_st, kBTile);
-            tma_load_3d(b_base + b_st * kBTile, tm_w, bar_b_full + 8 * b_st, c * 64, 0, tap0 + s);
+            if (leader) mbar_expect_tx(bar_b_full + 8 * b_st, CTAS * kBTile);
+            if (CTAS == 2)
+              tma_load_3d_pair(b_base + b_st * kBTile, tm_w, (bar_b_full + 8 * b_st) & ZNS_PEER_MASK, c * 64,
+                               (int)cta_rank * (N / 2), tap0 + s);
+            else
+              tma_load_3d(b_base + b_st * kBTile, tm_w, bar_b_full + 8 * b_st, c * 64, 0, tap0 + s);
             if (++b_st == n_bst) { b_st = 0; b_par ^= 1; }
           }
         }
@@ -277,9 +295,10 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (leader && elect_one()) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+      const uint32_t idesc = umma_idesc_bf16(128 * CTAS, N, 0, 0);
+      auto commit = [](uint32_t bar) { if (CTAS == 2) umma_commit_pair(bar); else umma_commit(bar); };
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
       uint32_t a_slot = 0, a_par = 0, b_st = 0, b_par = 0;
       uint32_t rel_slot = 0;      // slot of the oldest unreleased row (rel_row)
@@ -298,12 +317,13 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
             // rows lo..hi-1 are live, rel_row <= lo: slot(lo) = rel_slot + (lo - rel_row) (mod n_slots)
             uint32_t lo_slot = rel_slot + (uint32_t)(lo - rel_row);
             if (lo_slot >= n_slots) lo_slot -= n_slots;
-            const uint32_t lo_addr = a_base + lo_slot * p.slot_bytes;
-            const uint32_t wrap_addr = a_base + n_slots * p.slot_bytes;
+            // descriptors carry the 18-bit offset inside the CTA's shared window (the same in both CTAs of a pair)
+            const uint32_t lo_addr = (a_base & 0x3FFFFu) + lo_slot * p.slot_bytes;
+            const uint32_t wrap_addr = (a_base & 0x3FFFFu) + n_slots * p.slot_bytes;
             for (int s = 0; s < p.kw; ++s) {
               mbar_wait(bar_b_full + 8 * b_st, b_par);
               tc_fence_after();
-              const uint32_t b_lo = ((b_base + b_st * kBTile) >> 4) | (1u << 16);
+              const uint32_t b_lo = ((((b_base & 0x3FFFFu) + b_st * kBTile)) >> 4) | (1u << 16);
               uint32_t row_addr = lo_addr + s * 1024;
               for (int rr = lo; rr < hi; ++rr) {
                 const int h = rr - r;
@@ -311,30 +331,34 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
                 const uint32_t acc = ((started >> h) & 1) | (s > 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_bf16(tmem + h * N, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
-                            idesc, acc | (k > 0));
+                  if (CTAS == 2)
+                    umma_bf16_pair(tmem + h * N, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k),
+                                   ((uint64_t)kDescHi << 32) | (b_lo + 2 * k), idesc, acc | (k > 0));
+                  else
+                    umma_bf16(tmem + h * N, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k),
+                              ((uint64_t)kDescHi << 32) | (b_lo + 2 * k), idesc, acc | (k > 0));
                 }
                 row_addr += p.slot_bytes;
                 if (row_addr >= wrap_addr) row_addr -= n_slots * p.slot_bytes;
               }
-              umma_commit(bar_b_empty + 8 * b_st);
+              commit(bar_b_empty + 8 * b_st);
               if (++b_st == n_bst) { b_st = 0; b_par ^= 1; }
             }
             started |= ((1u << (hi - lo)) - 1u) << (lo - r);
           }
           while (rel_row <= r && rel_row < rr_hi) {   // row r has had its last use
-            umma_commit(bar_a_empty + 8 * rel_slot);
+            commit(bar_a_empty + 8 * rel_slot);
             if (++rel_slot == n_slots) rel_slot = 0;
             ++rel_row;
           }
         }
         while (rel_row < rr_hi) {
-          umma_commit(bar_a_empty + 8 * rel_slot);
+          commit(bar_a_empty + 8 * rel_slot);
           if (++rel_slot == n_slots) rel_slot = 0;
           ++rel_row;
         }
       }
-      umma_commit(smem_u32(&bars->acc_full));
+      commit(smem_u32(&bars->acc_full));
     }
     __syncwarp();
   } else {
@@ -398,9 +422,10 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair's MMAs / signals are in flight
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (CTAS == 2) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512);
   }
 }
 
@@ -982,7 +1007,7 @@ static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, 
   return ZNS_OK;
 }
 
-template <int N, int HT>
+template <int N, int HT, int CTAS = 1>
 static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
                       const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st) {
   const int G = zns_groups(d->batch);
@@ -995,7 +1020,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   p.slot_bytes = (uint32_t)(WT + d->kw - 1) * 1024u;
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
-  const uint32_t btile = N * 128;
+  const uint32_t btile = N * 128 / CTAS;   // a CTA of a pair stages half of each weight tile
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdBarriers) - 64;
   int u_max = std::min(HT, d->H);
   while (u_max > 1 && (uint64_t)(u_max + 1) * p.slot_bytes + 2ull * btile > budget) --u_max;
@@ -1020,20 +1045,32 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
     const int s = b < n_br ? b : 0;
     int rc = make_act_map(&tm_in[b], in[s], G, d->H, d->W, d->c_in, WT + d->kw - 1);
     if (rc) return rc;
-    rc = make_w_map(&tm_w[b], wpk[s], d->kh * d->kw, d->c_out, d->c_in, N);
+    rc = make_w_map(&tm_w[b], wpk[s], d->kh * d->kw, d->c_out, d->c_in, N / CTAS);
     if (rc) return rc;
     p.bias[b] = bias ? bias[s] : nullptr;
     p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
     p.out[b] = (bf16*)out[s];
   }
-  auto kern = conv_fwd_umma_kernel<N, HT>;
+  auto kern = conv_fwd_umma_kernel<N, HT, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
     attr_set = true;
   }
   dim3 grid(p.tiles.n_total, 1, 1);
-  kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  if (CTAS == 2) {
+    // blocks (2i, 2i+1) form a cluster: same rows and branch, adjacent frame tiles (the caller checked
+    // that the columns per branch are even, so a pair never straddles a row block or a branch)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_in[0], tm_in[1], tm_w[0], tm_w[1], p));
+  } else {
+    kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  }
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -1062,9 +1099,14 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
     memset(&cfg, 0, sizeof(cfg));
     if (!no_stack && fwd_stack_config(d, &cfg)) return launch_fwd_stack(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
+  // CTA-pair (cta_group::2) variant of the N = 128 kernel; needs an even number of frame-tile columns per branch
+  static const bool use_pair = getenv("ZNS_CONV_PAIR") != nullptr;
+  const bool can_pair = ((zns_groups(d->batch) * ((d->W + WT - 1) / WT)) % 2) == 0;
   switch (d->c_out) {
     case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);
-    case 128: return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st);
+    case 128:
+      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, st);
+      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st);
     case 256: return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st);
     default: return zns_set_error(ZNS_ERR_INVALID, "c_out must be 64, 128 or 256 (got %d)", d->c_out);
   }
