@@ -1,13 +1,13 @@
 #!/bin/bash
-# CTA-pair (cta_group::2) conv kernel: parity tests, then step time with and without it
+# CTA-pair (cta_group::2) conv kernels: parity tests, then step time per mode
 set -o pipefail
-export ZNS_CONV_PAIR=1
-timeout 300 python -m pytest tests/test_gpu_ops.py -x -q -k "conv_fwd_umma or full_size or dgrad or two_branches" 2>&1 | tail -15
+ZNS_CONV_PAIR=2 timeout 300 python -m pytest tests/test_gpu_ops.py -x -q -k "conv_fwd_umma or full_size or dgrad or two_branches" 2>&1 | tail -15
 rc=$?
 echo "tests rc=$rc"
 if [ $rc -eq 0 ]; then
   for i in 1 2; do
-    ZNS_CONV_PAIR=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-extras 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('pair', round(d['value'],1), round(d['ms_per_step'],3))"
-    env -u ZNS_CONV_PAIR timeout 200 python bench.py --steps 20 --warmup 5 --no-extras 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('base', round(d['value'],1), round(d['ms_per_step'],3))"
+    for m in 0 1 2; do
+      ZNS_CONV_PAIR=$m timeout 200 python bench.py --steps 20 --warmup 5 --no-extras 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('mode $m', round(d['value'],1), round(d['ms_per_step'],3))"
+    done
   done
 fi

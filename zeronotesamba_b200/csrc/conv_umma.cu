@@ -176,6 +176,19 @@ static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh) {
   return best;
 }
 
+// Launch with clusters of two CTAs: blocks (2i, 2i+1) form a pair -- same rows and branch, adjacent frame
+// tiles (callers check that the columns per branch are even, so a pair never straddles a row block or a branch).
+template <typename Kern, typename... Args>
+static cudaError_t launch_pair(Kern kern, dim3 grid, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward / data-gradient kernel
 // ---------------------------------------------------------------------------------------------
@@ -679,6 +692,9 @@ conv_fwdT_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
 //   i.e. an accumulator holds two adjacent output rows and the tap-row loop has kh + 1 steps (tap
 //   rows -1 and kh are TMA out-of-bounds zero fill).  Three accumulators = six output rows per CTA.
 // ---------------------------------------------------------------------------------------------
+// CTAS = 2: CTA pair as in conv_fwd_umma_kernel; the leader stages the upper weight block (tap row r-1), its
+// peer the lower one (tap row r) -- together the N = 128 tile of one M = 256 MMA.
+template <int CTAS>
 __global__ void __launch_bounds__(192, 1)
 conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                       const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
@@ -687,7 +703,9 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base;
   const uint32_t w_base = x_base + p.n_slots * p.slot_bytes;
-  constexpr uint32_t kWTile = 128 * 128;  // 2 stacked tap rows x 64 output channels x 64 input channels bf16
+  constexpr uint32_t kWTile = 128 * 128 / CTAS;  // 2 stacked tap rows x 64 output channels x 64 input channels bf16 (one tap row per CTA of a pair)
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   FwdTBarriers* bars = reinterpret_cast<FwdTBarriers*>(smem_raw + (w_base + p.n_wstages * kWTile - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -710,11 +728,12 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
     tma_prefetch_desc(tm_w);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
@@ -740,20 +759,30 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
           const int need_hi = min(rp + (acc_eff - 1) * p.stack + 1, rr_hi);
           while (next_row < need_hi) {
             mbar_wait(bar_x_empty + 8 * x_slot, x_par);
-            mbar_expect_tx(bar_x_full + 8 * x_slot, p.slot_bytes);
-            tma_load_5d(x_base + x_slot * p.slot_bytes, tm_in, bar_x_full + 8 * x_slot, c * 64, 0, w0 - p.pw,
-                        h0 - p.ph + next_row, g);
+            if (leader) mbar_expect_tx(bar_x_full + 8 * x_slot, CTAS * p.slot_bytes);
+            if (CTAS == 2)
+              tma_load_5d_pair(x_base + x_slot * p.slot_bytes, tm_in, (bar_x_full + 8 * x_slot) & ZNS_PEER_MASK, c * 64, 0,
+                               w0 - p.pw, h0 - p.ph + next_row, g);
+            else
+              tma_load_5d(x_base + x_slot * p.slot_bytes, tm_in, bar_x_full + 8 * x_slot, c * 64, 0, w0 - p.pw,
+                          h0 - p.ph + next_row, g);
             if (++x_slot == n_slots) { x_slot = 0; x_par ^= 1; }
             ++next_row;
           }
           if (!step_active(rp)) continue;
           for (int s = 0; s < p.kw; ++s) {
             mbar_wait(bar_w_empty + 8 * w_st, w_par);
-            mbar_expect_tx(bar_w_full + 8 * w_st, kWTile);
-            for (int j = 0; j < p.stack; ++j) {
-              const int r = rp - (p.stack - 1) + j;      // weight tap row of M block j (out of range -> TMA zero fill)
+            if (leader) mbar_expect_tx(bar_w_full + 8 * w_st, CTAS * kWTile);
+            if (CTAS == 2) {
+              const int r = rp - 1 + (int)cta_rank;      // this CTA's half of the stacked tile
               const int tap = (r < 0 || r >= p.kh) ? -1 : r * p.kw + s;
-              tma_load_3d(w_base + w_st * kWTile + j * p.cout * 128, tm_w, bar_w_full + 8 * w_st, c * 64, 0, tap);
+              tma_load_3d_pair(w_base + w_st * kWTile, tm_w, (bar_w_full + 8 * w_st) & ZNS_PEER_MASK, c * 64, 0, tap);
+            } else {
+              for (int j = 0; j < p.stack; ++j) {
+                const int r = rp - (p.stack - 1) + j;      // weight tap row of M block j (out of range -> TMA zero fill)
+                const int tap = (r < 0 || r >= p.kh) ? -1 : r * p.kw + s;
+                tma_load_3d(w_base + w_st * kWTile + j * p.cout * 128, tm_w, bar_w_full + 8 * w_st, c * 64, 0, tap);
+              }
             }
             if (++w_st == n_wst) { w_st = 0; w_par ^= 1; }
           }
@@ -762,9 +791,11 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (leader && elect_one()) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc = umma_idesc_bf16(128 * CTAS, 128, 0, 0);
+      auto commit = [](uint32_t bar) { if (CTAS == 2) umma_commit_pair(bar); else umma_commit(bar); };
+      const uint32_t x_dbase = x_base & 0x3FFFFu, w_dbase = w_base & 0x3FFFFu;   // descriptor offsets (same in both CTAs)
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
       uint32_t x_slot = 0, x_par = 0, w_st = 0, w_par = 0;
       uint32_t rel_slot = 0;
@@ -781,7 +812,7 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
           }
           if (step_active(rp)) {
             // live rows are >= rel_row and fewer than n_slots: address of row rr by offset from rel_slot
-            uint32_t row_off[3];
+            uint32_t row_off[4];
             uint32_t use = 0;
             for (int a = 0; a < acc_eff; ++a) {
               const int rr = rp + a * p.stack;
@@ -795,37 +826,41 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
             for (int s = 0; s < p.kw; ++s) {
               mbar_wait(bar_w_full + 8 * w_st, w_par);
               tc_fence_after();
-              const uint32_t b_lo = ((w_base + w_st * kWTile) >> 4) | (1u << 16);
+              const uint32_t b_lo = ((w_dbase + w_st * kWTile) >> 4) | (1u << 16);
 #pragma unroll
-              for (int a = 0; a < 3; ++a) {
+              for (int a = 0; a < 4; ++a) {
                 if ((use >> a) & 1) {
-                  const uint32_t a_lo = ((x_base + row_off[a] + s * 1024) >> 4) | (1u << 16);
+                  const uint32_t a_lo = ((x_dbase + row_off[a] + s * 1024) >> 4) | (1u << 16);
                   const uint32_t acc = ((started >> a) & 1) | (s > 0);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    umma_bf16(tmem + a * 128, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k), ((uint64_t)kDescHi << 32) | (b_lo + 2 * k),
-                              idesc, acc | (k > 0));
+                    if (CTAS == 2)
+                      umma_bf16_pair(tmem + a * 128, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k),
+                                     ((uint64_t)kDescHi << 32) | (b_lo + 2 * k), idesc, acc | (k > 0));
+                    else
+                      umma_bf16(tmem + a * 128, ((uint64_t)kDescHi << 32) | (a_lo + 2 * k),
+                                ((uint64_t)kDescHi << 32) | (b_lo + 2 * k), idesc, acc | (k > 0));
                   }
                 }
               }
-              umma_commit(bar_w_empty + 8 * w_st);
+              commit(bar_w_empty + 8 * w_st);
               if (++w_st == n_wst) { w_st = 0; w_par ^= 1; }
             }
             started |= use;
           }
           while (rel_row <= rp && rel_row < rr_hi) {   // row rp has had its last use (accumulator 0)
-            umma_commit(bar_x_empty + 8 * rel_slot);
+            commit(bar_x_empty + 8 * rel_slot);
             if (++rel_slot == n_slots) rel_slot = 0;
             ++rel_row;
           }
         }
         while (rel_row < rr_hi) {
-          umma_commit(bar_x_empty + 8 * rel_slot);
+          commit(bar_x_empty + 8 * rel_slot);
           if (++rel_slot == n_slots) rel_slot = 0;
           ++rel_row;
         }
       }
-      umma_commit(smem_u32(&bars->acc_full));
+      commit(smem_u32(&bars->acc_full));
     }
     __syncwarp();
   } else {
@@ -892,27 +927,31 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (CTAS == 2) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512);
   }
 }
 
 
-static bool fwd_stack_config(const zns_conv_desc* d, FwdTParams* p) {
+// ctas = 2: CTA-pair variant (half a weight tile per CTA, up to four accumulators)
+static bool fwd_stack_config(const zns_conv_desc* d, FwdTParams* p, int ctas) {
   if (d->c_out != 64 || (d->H & 1)) return false;
   const uint32_t slot = (uint32_t)(WT + d->kw - 1) * 1024u;
+  const uint32_t wtile = 16384u / ctas;
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdTBarriers) - 64;
-  int n_acc = std::min(3, d->H / 2);
-  while (n_acc > 1 && (uint64_t)((n_acc - 1) * 2 + 2) * slot + 2ull * 16384 > budget) --n_acc;
+  int n_acc = std::min(ctas == 2 ? 4 : 3, d->H / 2);
+  while (n_acc > 1 && (uint64_t)((n_acc - 1) * 2 + 2) * slot + 2ull * wtile > budget) --n_acc;
   int slots = (n_acc - 1) * 2 + 2;
-  if ((uint64_t)slots * slot + 2ull * 16384 > budget) return false;
+  if (slots > MAX_RING || (uint64_t)slots * slot + 2ull * wtile > budget) return false;
   int wst = 2;
-  while (wst < MAX_RING && (uint64_t)slots * slot + (uint64_t)(wst + 1) * 16384 <= budget) ++wst;
+  while (wst < MAX_RING && (uint64_t)slots * slot + (uint64_t)(wst + 1) * wtile <= budget) ++wst;
   p->cout = 64; p->stack = 2; p->n_acc = n_acc; p->n_slots = slots; p->n_wstages = wst; p->slot_bytes = slot;
   return true;
 }
 
+template <int CTAS>
 static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, const void* const* in,
                             const void* const* wpk, const float* const* bias, const void* const* mask, void* const* out,
                             cudaStream_t st) {
@@ -926,11 +965,11 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
     const double pair_clk = (double)p.n_chunks * (d->kh + 1) * d->kw * 4.0 * 64.0;   // N = 128 MMAs per stacked pair
     p.tiles = plan_tiles(d->H / 2, G * p.n_wtiles * n_br, p.n_acc, 8000.0 / pair_clk);
     p.n_acc = p.tiles.hb;
-    p.n_slots = std::min(p.n_slots, (p.n_acc - 1) * 2 + 3);
+    p.n_slots = std::min(p.n_slots, std::min(MAX_RING, (p.n_acc - 1) * 2 + 3));
   }
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
-  const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * 16384 + sizeof(FwdTBarriers) + 64;
+  const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * (16384 / CTAS) + sizeof(FwdTBarriers) + 64;
   CUtensorMap tm_in[2], tm_w[2];
   for (int b = 0; b < 2; ++b) {
     const int s = b < n_br ? b : 0;
@@ -942,13 +981,18 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
     p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
     p.out[b] = (bf16*)out[s];
   }
+  auto kern = conv_fwd_stack_umma_kernel<CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_stack_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
     attr_set = true;
   }
   dim3 grid(p.tiles.n_total, 1, 1);
-  conv_fwd_stack_umma_kernel<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  if (CTAS == 2) {
+    ZNS_CHECK_CUDA(launch_pair(kern, grid, smem, st, tm_in[0], tm_in[1], tm_w[0], tm_w[1], p));
+  } else {
+    kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+  }
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -1059,15 +1103,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   }
   dim3 grid(p.tiles.n_total, 1, 1);
   if (CTAS == 2) {
-    // blocks (2i, 2i+1) form a cluster: same rows and branch, adjacent frame tiles (the caller checked
-    // that the columns per branch are even, so a pair never straddles a row block or a branch)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_in[0], tm_in[1], tm_w[0], tm_w[1], p));
+    ZNS_CHECK_CUDA(launch_pair(kern, grid, smem, st, tm_in[0], tm_in[1], tm_w[0], tm_w[1], p));
   } else {
     kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
   }
@@ -1085,6 +1121,10 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
   ZNS_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout_p out of range");
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
   cudaStream_t st = (cudaStream_t)stream;
+  // CTA-pair (cta_group::2) kernels need an even number of frame-tile columns per branch
+  static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 0;
+  const bool use_pair = pair_mode != 0;
+  const bool can_pair = ((zns_groups(d->batch) * ((d->W + WT - 1) / WT)) % 2) == 0;
   {
     // Experimental transposed kernel (weights on M, 256 positions on N) for C_out <= 128: measured
     // slower than the direct kernel once the issue loops were fixed (profiles/README.md); opt-in only.
@@ -1097,17 +1137,18 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
     static const bool no_stack = getenv("ZNS_CONV_NO_STACK") != nullptr;   // A/B switch
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    if (!no_stack && fwd_stack_config(d, &cfg)) return launch_fwd_stack(d, cfg, n_br, in, wpk, bias, mask, out, st);
+    if (!no_stack && use_pair && can_pair && fwd_stack_config(d, &cfg, 2))
+      return launch_fwd_stack<2>(d, cfg, n_br, in, wpk, bias, mask, out, st);
+    if (!no_stack && fwd_stack_config(d, &cfg, 1)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
-  // CTA-pair (cta_group::2) variant of the N = 128 kernel; needs an even number of frame-tile columns per branch
-  static const bool use_pair = getenv("ZNS_CONV_PAIR") != nullptr;
-  const bool can_pair = ((zns_groups(d->batch) * ((d->W + WT - 1) / WT)) % 2) == 0;
   switch (d->c_out) {
     case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);
     case 128:
       if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, st);
       return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st);
-    case 256: return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st);
+    case 256:
+      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, st);
+      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st);
     default: return zns_set_error(ZNS_ERR_INVALID, "c_out must be 64, 128 or 256 (got %d)", d->c_out);
   }
 }
