@@ -1159,6 +1159,7 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
 //   A (M side) = x halo row, MN-major; M = 128 = two 64-channel chunks (LBO = chunk stride) or, for
 //   c_in == 64, two adjacent taps (LBO = one atom).  B (N side) = dy tile, MN-major, N = NB.
 // ---------------------------------------------------------------------------------------------
+#define WG_MAX_ITEMS 192
 struct WgParams {
   int G, H, W;
   int Cin, Cout;
@@ -1176,6 +1177,9 @@ struct WgParams {
   uint32_t x_chunk_bytes;   // (WT + taps_per_cta - 1) * 1024
   uint32_t stage_bytes;
   float* dw[2];
+  // CTA-pair kernel only: (tap row, tap group, cin block) work items, two consecutive entries per pair
+  int n_item_pairs;
+  uint32_t items[WG_MAX_ITEMS];   // r | s0 << 4 | n_acc << 10 | cib << 14 | valid << 18
 };
 
 struct WgBarriers {
@@ -1184,7 +1188,12 @@ struct WgBarriers {
   uint32_t any_step;
 };
 
-template <int NB>
+// CTAS = 2 (NB = 128): a CTA pair shares one dy tile -- each CTA stages 64 of its 128 channels -- and each CTA
+// brings the x rows of its own work item (tap row, tap group, cin block) as its half of an M = 256 MMA, so the
+// operand reads per SM fall from 8 KB to 6 KB per 64-clock MMA and the dy traffic halves.  Both items of a pair
+// have the same accumulator count; a step runs when either item's input row is inside the image (the other's
+// TMA load is then zero-filled), a dummy item (odd class size) repeats its partner and skips the epilogue.
+template <int NB, int CTAS>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                        const __grid_constant__ CUtensorMap tm_dy0, const __grid_constant__ CUtensorMap tm_dy1,
@@ -1198,23 +1207,39 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   const CUtensorMap* tm_dy = br ? &tm_dy1 : &tm_dy0;
 
   // work item: (tap row r, s-group, cin block, cout block) x position slice
-  int t = blockIdx.x;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  int t = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   // the tap group is the slowest index: groups with one more accumulator (sg < grp_rem) are dispatched
   // first, so the in-order block scheduler behaves like longest-first list scheduling
   const int slice = t % p.n_slices; t /= p.n_slices;
   const int cob = t % p.n_cout_blocks; t /= p.n_cout_blocks;
-  const int cib = t % p.n_cin_blocks; t /= p.n_cin_blocks;
-  const int r = t % p.kh; t /= p.kh;
-  const int sg = t;
   const int unit = p.fold ? 2 : 1;                       // taps per accumulator
-  const int acc0 = sg * p.grp_base + min(sg, p.grp_rem); // first accumulator (in row order) of this group
-  const int s0 = acc0 * unit;
+  int cib, r, r_peer, s0, n_acc_eff;
+  bool item_valid = true;
+  if (CTAS == 2) {
+    const uint32_t me = p.items[2 * t + cta_rank], peer = p.items[2 * t + (cta_rank ^ 1u)];
+    r = me & 15; s0 = (me >> 4) & 63; n_acc_eff = (me >> 10) & 15; cib = (me >> 14) & 15; item_valid = (me >> 18) & 1;
+    r_peer = peer & 15;
+  } else {
+    cib = t % p.n_cin_blocks; t /= p.n_cin_blocks;
+    r = t % p.kh; t /= p.kh;
+    const int sg = t;
+    const int acc0 = sg * p.grp_base + min(sg, p.grp_rem); // first accumulator (in row order) of this group
+    s0 = acc0 * unit;
+    n_acc_eff = p.grp_base + (sg < p.grp_rem ? 1 : 0);
+    r_peer = r;
+  }
   const int n_xchunks = p.fold ? 1 : 2;
   const int n_steps_total = p.G * p.H * p.n_wtiles;
   const int q0 = (int)((long long)n_steps_total * slice / p.n_slices);
   const int q1 = (int)((long long)n_steps_total * (slice + 1) / p.n_slices);
-  const int n_acc_eff = p.grp_base + (sg < p.grp_rem ? 1 : 0);
   constexpr uint32_t kDyChunk = WT * 1024;  // 128 positions x 64 channels
+  // a step (output row h) is live when the input row of this item or of its pair partner exists
+  auto live = [&](int h) {
+    const int hh = h + r - p.ph, hp = h + r_peer - p.ph;
+    return (hh >= 0 && hh < p.H) || (hp >= 0 && hp < p.H);
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
@@ -1225,11 +1250,12 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     tma_prefetch_desc(tm_dy);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const uint32_t dy_off = n_xchunks * p.x_chunk_bytes;  // dy tiles follow the x chunks inside a stage
@@ -1245,15 +1271,23 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
       int wt = wt_0, h = h_0, g = g_0;
       for (int q = q0; q < q1; ++q) {
         const int hh = h + r - p.ph;
-        if (hh >= 0 && hh < p.H) {
+        if (live(h)) {
           mbar_wait(bar_empty + 8 * st, par);
           const uint32_t base = smem_base + st * p.stage_bytes;
-          mbar_expect_tx(bar_full + 8 * st, p.stage_bytes);
-          for (int xc = 0; xc < n_xchunks; ++xc)
-            tma_load_5d(base + xc * p.x_chunk_bytes, tm_x, bar_full + 8 * st, (cib * n_xchunks + xc) * 64, 0,
-                        wt * WT - p.pw + s0, hh, g);
-          for (int j = 0; j < NB / 64; ++j)
-            tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, bar_full + 8 * st, cob * NB + j * 64, 0, wt * WT, h, g);
+          if (leader) mbar_expect_tx(bar_full + 8 * st, CTAS * p.stage_bytes);
+          if (CTAS == 2) {
+            const uint32_t bar = (bar_full + 8 * st) & ZNS_PEER_MASK;
+            for (int xc = 0; xc < n_xchunks; ++xc)      // a row outside the image is zero-filled by TMA
+              tma_load_5d_pair(base + xc * p.x_chunk_bytes, tm_x, bar, (cib * n_xchunks + xc) * 64, 0,
+                               wt * WT - p.pw + s0, hh, g);
+            tma_load_5d_pair(base + dy_off, tm_dy, bar, cob * NB + (int)cta_rank * 64, 0, wt * WT, h, g);
+          } else {
+            for (int xc = 0; xc < n_xchunks; ++xc)
+              tma_load_5d(base + xc * p.x_chunk_bytes, tm_x, bar_full + 8 * st, (cib * n_xchunks + xc) * 64, 0,
+                          wt * WT - p.pw + s0, hh, g);
+            for (int j = 0; j < NB / 64; ++j)
+              tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, bar_full + 8 * st, cob * NB + j * 64, 0, wt * WT, h, g);
+          }
           if (++st == n_st) { st = 0; par ^= 1; }
         }
         if (++wt == p.n_wtiles) { wt = 0; if (++h == p.H) { h = 0; ++g; } }
@@ -1261,8 +1295,9 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, NB, 1, 1);
+    if (leader && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128 * CTAS, NB, 1, 1);
+      const uint32_t dbase = smem_base & 0x3FFFFu;   // descriptor offsets (the same in both CTAs of a pair)
       const uint32_t a_lbo = p.fold ? 1024u : p.x_chunk_bytes;
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
       const uint32_t a_hi16 = ((a_lbo >> 4) & 0x3FFF) << 16, b_hi16 = (kDyChunk >> 4) << 16;
@@ -1270,29 +1305,34 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
       uint32_t st = 0, par = 0, any = 0;
       int wt = wt_0, h = h_0;
       for (int q = q0; q < q1; ++q) {
-        const int hh = h + r - p.ph;
-        if (hh >= 0 && hh < p.H) {
+        if (live(h)) {
           mbar_wait(bar_full + 8 * st, par);
           tc_fence_after();
-          const uint32_t base = smem_base + st * p.stage_bytes;
+          const uint32_t base = dbase + st * p.stage_bytes;
           const uint32_t b_lo = ((base + dy_off) >> 4) | b_hi16;
           uint32_t xa = base;
           for (int a = 0; a < n_acc_eff; ++a) {
             const uint32_t a_lo = (xa >> 4) | a_hi16;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              umma_bf16(tmem + a * NB, ((uint64_t)kDescHi << 32) | (a_lo + 128 * k), ((uint64_t)kDescHi << 32) | (b_lo + 128 * k),
-                        idesc, any | (k > 0));
+              if (CTAS == 2)
+                umma_bf16_pair(tmem + a * NB, ((uint64_t)kDescHi << 32) | (a_lo + 128 * k),
+                               ((uint64_t)kDescHi << 32) | (b_lo + 128 * k), idesc, any | (k > 0));
+              else
+                umma_bf16(tmem + a * NB, ((uint64_t)kDescHi << 32) | (a_lo + 128 * k),
+                          ((uint64_t)kDescHi << 32) | (b_lo + 128 * k), idesc, any | (k > 0));
             }
             xa += a_step;
           }
-          umma_commit(bar_empty + 8 * st);
+          if (CTAS == 2) umma_commit_pair(bar_empty + 8 * st); else umma_commit(bar_empty + 8 * st);
           if (++st == n_st) { st = 0; par ^= 1; }
           any = 1;
         }
         if (++wt == p.n_wtiles) { wt = 0; if (++h == p.H) h = 0; }
       }
-      if (any) {
+      if (CTAS == 2) {
+        if (any) umma_commit_pair(smem_u32(&bars->acc_full));   // (no live step: the epilogues of both CTAs do not wait)
+      } else if (any) {
         *reinterpret_cast<volatile uint32_t*>(&bars->any_step) = 1;
         umma_commit(smem_u32(&bars->acc_full));
       } else {
@@ -1301,10 +1341,22 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     }
     __syncwarp();
   } else {
-    mbar_wait(smem_u32(&bars->acc_full), 0);
-    tc_fence_after();
-    const bool any = *reinterpret_cast<volatile uint32_t*>(&bars->any_step) != 0;
-    if (any) {
+    bool any;
+    if (CTAS == 2) {
+      // both CTAs decide locally whether the slice has a live step (at most H rows to look at)
+      any = false;
+      const int gh1 = (q1 - 1) / p.n_wtiles;
+      if (q1 > q0) {
+        const int gh_end = min(gh1, gh_0 + p.H - 1);   // every output row is covered after H of them
+        for (int gh = gh_0; gh <= gh_end; ++gh) any = any || live(gh % p.H);
+      }
+      if (any) { mbar_wait(smem_u32(&bars->acc_full), 0); tc_fence_after(); }
+    } else {
+      mbar_wait(smem_u32(&bars->acc_full), 0);
+      tc_fence_after();
+      any = *reinterpret_cast<volatile uint32_t*>(&bars->any_step) != 0;
+    }
+    if (any && item_valid) {
       const int quad = warp & 3;
       const int m = quad * 32 + lane;
       float* dw = p.dw[br];
@@ -1329,15 +1381,17 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (CTAS == 2) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512);
   }
 }
 
-template <int NB>
+template <int NB, int CTAS = 1>
 static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy, float* const* dwpk,
                         cudaStream_t st) {
+  static_assert(CTAS == 1 || NB == 128, "the CTA-pair weight-gradient kernel splits a 128-channel dy tile");
   const int G = zns_groups(d->batch);
   WgParams p;
   memset(&p, 0, sizeof(p));
@@ -1363,20 +1417,46 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   p.n_cin_blocks = p.fold ? 1 : d->c_in / 128;
   p.n_cout_blocks = d->c_out / NB;
   p.x_chunk_bytes = (uint32_t)(WT + p.taps_per_cta - 1) * 1024u;
-  p.stage_bytes = (p.fold ? 1 : 2) * p.x_chunk_bytes + (NB / 64) * WT * 1024u;
+  p.stage_bytes = (p.fold ? 1 : 2) * p.x_chunk_bytes + (NB / 64 / CTAS) * WT * 1024u;   // per CTA
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(WgBarriers) - 64;
   p.n_stages = std::min<int>(MAX_RING, budget / p.stage_bytes);
   ZNS_REQUIRE(p.n_stages >= 2, "wgrad stage does not fit shared memory twice");
-  const int items = d->kh * p.n_sgroups * p.n_cin_blocks * p.n_cout_blocks;
+  int items = d->kh * p.n_sgroups * p.n_cin_blocks * p.n_cout_blocks;
+  int n_big_items = 0, n_small_items = 0;   // pair kernel: CTAs (dummies included) per class, cout block and slice
+  if (CTAS == 2) {
+    // work items by class (accumulator count), bigger class first; an odd class is padded with a dummy
+    // that repeats its partner (valid bit clear)
+    const int unit = p.fold ? 2 : 1;
+    int n = 0;
+    for (int cls = 0; cls < 2; ++cls) {
+      const int first = n;
+      for (int sg = 0; sg < p.n_sgroups; ++sg) {
+        const bool big = p.grp_rem == 0 || sg < p.grp_rem;
+        if (big != (cls == 0)) continue;
+        const int acc0 = sg * p.grp_base + std::min(sg, p.grp_rem);
+        const int n_acc = p.grp_base + (sg < p.grp_rem ? 1 : 0);
+        for (int r = 0; r < d->kh; ++r)
+          for (int cib = 0; cib < p.n_cin_blocks; ++cib) {
+            ZNS_REQUIRE(n < WG_MAX_ITEMS - 1, "too many weight-gradient work items for the pair kernel");
+            p.items[n++] = (uint32_t)r | ((uint32_t)(acc0 * unit) << 4) | ((uint32_t)n_acc << 10) | ((uint32_t)cib << 14) | (1u << 18);
+          }
+      }
+      if ((n - first) & 1) { p.items[n] = p.items[n - 1] & ~(1u << 18); ++n; }
+      (cls == 0 ? n_big_items : n_small_items) = n - first;
+    }
+    p.n_item_pairs = n / 2;
+    items = n * p.n_cout_blocks;   // CTAs per slice and branch
+  }
   const int n_steps_total = G * d->H * p.n_wtiles;
   // position slices: simulate the in-order dispatch of the two CTA classes (groups with grp_base + 1 and
   // with grp_base accumulators) for every slice count and keep the shortest makespan; more slices also
   // mean more atomics in the epilogue, hence the small per-CTA overhead term
   int best = 1;
   {
-    const long per_group = (long)d->kh * p.n_cin_blocks * p.n_cout_blocks * n_br;   // CTAs per tap group and slice
+    long per_group = (long)d->kh * p.n_cin_blocks * p.n_cout_blocks * n_br;   // CTAs per tap group and slice
     const int acc_big = p.grp_base + (p.grp_rem ? 1 : 0), acc_small = p.grp_base;
-    const int n_big_groups = p.grp_rem ? p.grp_rem : p.n_sgroups, n_small_groups = p.grp_rem ? p.n_sgroups - p.grp_rem : 0;
+    int n_big_groups = p.grp_rem ? p.grp_rem : p.n_sgroups, n_small_groups = p.grp_rem ? p.n_sgroups - p.grp_rem : 0;
+    if (CTAS == 2) { per_group = (long)p.n_cout_blocks * n_br; n_big_groups = n_big_items; n_small_groups = n_small_items; }
     double best_t = 1e30;
     for (int sl = 1; sl <= 64; ++sl) {
       const double steps = (double)n_steps_total / sl;
@@ -1403,14 +1483,18 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
     if (rc) return rc;
     p.dw[b] = dwpk[s];
   }
-  auto kern = conv_wgrad_umma_kernel<NB>;
+  auto kern = conv_wgrad_umma_kernel<NB, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
     attr_set = true;
   }
   dim3 grid(items * p.n_slices, 1, n_br);
-  kern<<<grid, 192, smem, st>>>(tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p);
+  if (CTAS == 2) {
+    ZNS_CHECK_CUDA(launch_pair(kern, grid, smem, st, tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p));
+  } else {
+    kern<<<grid, 192, smem, st>>>(tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p);
+  }
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -1425,6 +1509,15 @@ extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* cons
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(x[b] && dy[b] && dwpk[b], "NULL tensor for branch %d", b);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->c_out == 64) return launch_wgrad<64>(d, n_br, x, dy, dwpk, st);
+  {
+    // CTA-pair kernel when the (tap row, tap group, cin block) items fit its table
+    static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 0;
+    const int unit = d->c_in == 64 ? 2 : 1;
+    const int row_acc = (d->kw + unit - 1) / unit;
+    const int n_items = d->kh * ((row_acc + 3) / 4) * (d->c_in == 64 ? 1 : d->c_in / 128);
+    if (pair_mode >= 3 && n_items + 2 <= WG_MAX_ITEMS && d->c_in / 128 <= 15)
+      return launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st);
+  }
   return launch_wgrad<128>(d, n_br, x, dy, dwpk, st);
 }
 
