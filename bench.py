@@ -352,14 +352,23 @@ def _ncu_traffic(tag: str):
     """DRAM bytes per launch (read + write) of the dominant kernel family from the committed ncu capture
     (profiles/r01_ncu_conv_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over every
     tensor-core launch of one step); None when the family is not in the capture."""
-    names = {"conv_fwd_umma<128>": "conv_fwd_umma_kernel<128, 4>", "conv_fwd_umma<256>": "conv_fwd_umma_kernel<256, 2>",
-             "conv_fwd_umma<64>": "conv_fwd_umma_kernel<64, 4>", "conv_wgrad_umma<128>": "conv_wgrad_umma_kernel<128>",
-             "conv_wgrad_umma<64>": "conv_wgrad_umma_kernel<64>",
-             "conv_fwd_stack_umma(c_out=64, 2 rows on N)": "conv_fwd_stack_umma_kernel"}
+    names = {"conv_fwd_umma<128>": ("conv_fwd_umma_kernel", "128"), "conv_fwd_umma<256>": ("conv_fwd_umma_kernel", "256"),
+             "conv_fwd_umma<64>": ("conv_fwd_umma_kernel", "64"), "conv_wgrad_umma<128>": ("conv_wgrad_umma_kernel", "128"),
+             "conv_wgrad_umma<64>": ("conv_wgrad_umma_kernel", "64"),
+             "conv_fwd_stack_umma(c_out=64, 2 rows on N)": ("conv_fwd_stack_umma_kernel", None)}
     path = os.path.join(ROOT, "profiles", "r01_ncu_conv_traffic.json")
     try:
         table = json.load(open(path))
-        return float(table[names[tag]]["dram_bytes_per_launch"]), "profiles/r01_ncu_conv_traffic.json (ncu, per launch)"
+        base, arg = names[tag]
+        # template instantiations of one family (single-CTA and CTA-pair variants) are pooled by launch count
+        rows = [v for k, v in table.items()
+                if k.startswith(base) and (arg is None or k[len(base):].replace(" ", "").startswith("<" + arg + ",")
+                                           or k[len(base):].replace(" ", "") == "<" + arg + ">")]
+        n = sum(r["launches"] for r in rows)
+        if not n:
+            return None, None
+        return (sum(r["dram_bytes_per_launch"] * r["launches"] for r in rows) / n,
+                "profiles/r01_ncu_conv_traffic.json (ncu, per launch)")
     except Exception:
         return None, None
 

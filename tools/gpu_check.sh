@@ -21,4 +21,7 @@ unset ZNS_CONV_TRANSPOSED
 export ZNS_CONV_NO_STACK=1
 run convfwd_nostack 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full"
 unset ZNS_CONV_NO_STACK
+export ZNS_CONV_PAIR=0
+run conv_single_cta 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full or conv_wgrad_umma"
+unset ZNS_CONV_PAIR
 cat gpurun_out/summary.txt

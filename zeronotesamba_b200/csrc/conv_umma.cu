@@ -82,6 +82,9 @@ static int make_w_map(CUtensorMap* m, const void* base, int taps, int rows, int 
 #define WT 16                  // frames per M tile (x 8 clips = 128 rows)
 #define MAX_RING 8
 #define ZNS_NUM_SMS 148
+// Tensor-core conv kernels: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue.  A warp can read
+// only the TMEM lane quadrant (warp % 4), so two epilogue warps share a quadrant and split its column blocks.
+#define ZNS_CONV_THREADS 320
 
 // ---------------------------------------------------------------------------------------------
 // Tile plan.  Every conv CTA owns an SM (its shared memory does not leave room for a second), and the
@@ -181,7 +184,7 @@ static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh) {
 template <typename Kern, typename... Args>
 static cudaError_t launch_pair(Kern kern, dim3 grid, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = dim3(ZNS_CONV_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -222,7 +225,7 @@ struct FwdBarriers {
 // of both CTAs' TMA loads; the "empty" and accumulator barriers are signalled in both CTAs by
 // multicast commits.
 template <int N, int HT, int CTAS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ZNS_CONV_THREADS, 1)
 conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                      const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
                      const FwdParams p) {
@@ -378,7 +381,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     // ===== epilogue: TMEM -> registers -> bias / ReLU / dropout / mask -> bf16 act =====
     mbar_wait(smem_u32(&bars->acc_full), 0);
     tc_fence_after();
-    const int quad = warp & 3;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int w = w0 + (m >> 3), b8 = m & 7;
     const bool valid = (w < p.W);
@@ -394,7 +397,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     for (int h = 0; h < ht_eff; ++h) {
       const size_t e0 = zns_act_index(g, h0 + h, valid ? w : 0, b8, 0, p.H, p.W, N);
 #pragma unroll 1
-      for (int nb = 0; nb < N / 32; ++nb) {
+      for (int nb = half; nb < N / 32; nb += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + h * N + nb * 32, v);
         tmem_ld_wait();
@@ -695,7 +698,7 @@ conv_fwdT_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
 // CTAS = 2: CTA pair as in conv_fwd_umma_kernel; the leader stages the upper weight block (tap row r-1), its
 // peer the lower one (tap row r) -- together the N = 128 tile of one M = 256 MMA.
 template <int CTAS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ZNS_CONV_THREADS, 1)
 conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                       const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
                       const FwdTParams p) {
@@ -867,7 +870,7 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
     // ===== epilogue: thread = position row; accumulator a holds rows (h0+2a+1 | h0+2a) x 64 channels =====
     mbar_wait(smem_u32(&bars->acc_full), 0);
     tc_fence_after();
-    const int quad = warp & 3;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int w = w0 + (m >> 3), b8 = m & 7;
     const bool valid = (w < p.W);
@@ -882,7 +885,7 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
     const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
     for (int a = 0; a < acc_eff; ++a) {
 #pragma unroll 1
-      for (int nb = 0; nb < 4; ++nb) {
+      for (int nb = half; nb < 4; nb += 2) {
         const int j = nb >> 1;                              // stacked block: 0 -> upper row, 1 -> lower row
         const int h = h0 + 2 * a + (1 - j);
         const int c0 = (nb & 1) * 32;
@@ -991,7 +994,7 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
   if (CTAS == 2) {
     ZNS_CHECK_CUDA(launch_pair(kern, grid, smem, st, tm_in[0], tm_in[1], tm_w[0], tm_w[1], p));
   } else {
-    kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+    kern<<<grid, ZNS_CONV_THREADS, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
   }
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
@@ -1105,7 +1108,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   if (CTAS == 2) {
     ZNS_CHECK_CUDA(launch_pair(kern, grid, smem, st, tm_in[0], tm_in[1], tm_w[0], tm_w[1], p));
   } else {
-    kern<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
+    kern<<<grid, ZNS_CONV_THREADS, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
   }
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
@@ -1121,8 +1124,10 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
   ZNS_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout_p out of range");
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
   cudaStream_t st = (cudaStream_t)stream;
-  // CTA-pair (cta_group::2) kernels need an even number of frame-tile columns per branch
-  static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 0;
+  // CTA-pair (cta_group::2) kernels need an even number of frame-tile columns per branch.
+  // ZNS_CONV_PAIR (A/B switch): 0 = single-CTA kernels, 1 = pairs for N = 128 and the stacked kernel,
+  // 2 = also N = 256, 3 (default) = also the weight gradient
+  static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 3;
   const bool use_pair = pair_mode != 0;
   const bool can_pair = ((zns_groups(d->batch) * ((d->W + WT - 1) / WT)) % 2) == 0;
   {
@@ -1194,7 +1199,7 @@ struct WgBarriers {
 // have the same accumulator count; a step runs when either item's input row is inside the image (the other's
 // TMA load is then zero-filled), a dummy item (odd class size) repeats its partner and skips the epilogue.
 template <int NB, int CTAS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ZNS_CONV_THREADS, 1)
 conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                        const __grid_constant__ CUtensorMap tm_dy0, const __grid_constant__ CUtensorMap tm_dy1,
                        const WgParams p) {
@@ -1357,7 +1362,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
       any = *reinterpret_cast<volatile uint32_t*>(&bars->any_step) != 0;
     }
     if (any && item_valid) {
-      const int quad = warp & 3;
+      const int quad = warp & 3, half = (warp - 2) >> 2;
       const int m = quad * 32 + lane;
       float* dw = p.dw[br];
       for (int a = 0; a < n_acc_eff; ++a) {
@@ -1367,7 +1372,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
         const bool valid = tap_s < p.kw;
         const size_t o0 = ((size_t)(r * p.kw + (valid ? tap_s : 0)) * p.Cout + cob * NB) * p.Cin + cin;
 #pragma unroll 1
-        for (int nb = 0; nb < NB / 32; ++nb) {
+        for (int nb = half; nb < NB / 32; nb += 2) {
           uint32_t v[32];
           tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + a * NB + nb * 32, v);
           tmem_ld_wait();
@@ -1493,7 +1498,7 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   if (CTAS == 2) {
     ZNS_CHECK_CUDA(launch_pair(kern, grid, smem, st, tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p));
   } else {
-    kern<<<grid, 192, smem, st>>>(tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p);
+    kern<<<grid, ZNS_CONV_THREADS, smem, st>>>(tm_x[0], tm_x[1], tm_dy[0], tm_dy[1], p);
   }
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
@@ -1511,7 +1516,7 @@ extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* cons
   if (d->c_out == 64) return launch_wgrad<64>(d, n_br, x, dy, dwpk, st);
   {
     // CTA-pair kernel when the (tap row, tap group, cin block) items fit its table
-    static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 0;
+    static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 3;
     const int unit = d->c_in == 64 ? 2 : 1;
     const int row_acc = (d->kw + unit - 1) / unit;
     const int n_items = d->kh * ((row_acc + 3) / 4) * (d->c_in == 64 ? 1 : d->c_in / 128);
