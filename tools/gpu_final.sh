@@ -17,6 +17,7 @@ echo "ncu-launches exit=$?" >> gpurun_out/summary_ops.txt
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_ -s 42 -c 42 --csv \
    --log-file gpurun_out/conv_traffic.csv python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_traffic.log 2>&1
 echo "ncu-traffic exit=$?" >> gpurun_out/summary_ops.txt
+python tools/ncu_traffic_json.py gpurun_out/conv_traffic.csv > gpurun_out/conv_traffic.json 2>/dev/null
 timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:conv_fwd_umma_kernel -s 16 -c 3 -o gpurun_out/prof_convfwd \
    python bench.py --steps 1 --warmup 3 --no-extras > gpurun_out/ncu_full.log 2>&1
 echo "ncu-full exit=$?" >> gpurun_out/summary_ops.txt

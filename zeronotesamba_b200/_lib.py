@@ -7,7 +7,8 @@ import os
 from typing import Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzns_sm100.so")
+# ZNS_LIB_PATH: load another build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("ZNS_LIB_PATH") or os.path.join(_HERE, "libzns_sm100.so")
 
 c_void_p, c_int, c_float, c_double, c_ll, c_u32 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong, C.c_uint32
 

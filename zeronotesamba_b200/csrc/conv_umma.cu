@@ -82,9 +82,13 @@ static int make_w_map(CUtensorMap* m, const void* base, int taps, int rows, int 
 #define WT 16                  // frames per M tile (x 8 clips = 128 rows)
 #define MAX_RING 8
 #define ZNS_NUM_SMS 148
-// Tensor-core conv kernels: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue.  A warp can read
-// only the TMEM lane quadrant (warp % 4), so two epilogue warps share a quadrant and split its column blocks.
-#define ZNS_CONV_THREADS 320
+// Tensor-core conv kernels: warp 0 = TMA producer, warp 1 = MMA issuer, the rest = epilogue.  A warp can read
+// only the TMEM lane quadrant (warp % 4), so ZNS_EPI epilogue warps share a quadrant and take its 32-column
+// blocks round-robin (nothing else runs on the SM while the accumulators drain, so this time is not hidden).
+#ifndef ZNS_EPI
+#define ZNS_EPI 4   // measured on the training step: 1 -> 2 warps per quadrant +4.7 %, 2 -> 4 another +1.4 % (profiles/r01_epilogue_warps.txt)
+#endif
+#define ZNS_CONV_THREADS (64 + 128 * ZNS_EPI)
 
 // ---------------------------------------------------------------------------------------------
 // Tile plan.  Every conv CTA owns an SM (its shared memory does not leave room for a second), and the
@@ -394,10 +398,11 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     const double thr_d = (double)p.drop_p * 4294967296.0;
     const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
     const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
-    for (int h = 0; h < ht_eff; ++h) {
+    int nb = half;   // blocks of all rows are dealt round-robin: (h, nb) -> warp (h * N/32 + nb) % ZNS_EPI of the quadrant
+    for (int h = 0; h < ht_eff; ++h, nb -= N / 32) {
       const size_t e0 = zns_act_index(g, h0 + h, valid ? w : 0, b8, 0, p.H, p.W, N);
 #pragma unroll 1
-      for (int nb = half; nb < N / 32; nb += 2) {
+      for (; nb < N / 32; nb += ZNS_EPI) {
         uint32_t v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + h * N + nb * 32, v);
         tmem_ld_wait();
@@ -883,9 +888,10 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
     const double thr_d = (double)p.drop_p * 4294967296.0;
     const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
     const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
-    for (int a = 0; a < acc_eff; ++a) {
+    int nb = half;
+    for (int a = 0; a < acc_eff; ++a, nb -= 4) {
 #pragma unroll 1
-      for (int nb = half; nb < 4; nb += 2) {
+      for (; nb < 4; nb += ZNS_EPI) {
         const int j = nb >> 1;                              // stacked block: 0 -> upper row, 1 -> lower row
         const int h = h0 + 2 * a + (1 - j);
         const int c0 = (nb & 1) * 32;
@@ -1365,14 +1371,15 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
       const int quad = warp & 3, half = (warp - 2) >> 2;
       const int m = quad * 32 + lane;
       float* dw = p.dw[br];
-      for (int a = 0; a < n_acc_eff; ++a) {
+      int nb = half;
+      for (int a = 0; a < n_acc_eff; ++a, nb -= NB / 32) {
         int tap_s, cin;
         if (p.fold) { tap_s = s0 + 2 * a + (m >> 6); cin = m & 63; }
         else        { tap_s = s0 + a; cin = cib * 128 + m; }
         const bool valid = tap_s < p.kw;
         const size_t o0 = ((size_t)(r * p.kw + (valid ? tap_s : 0)) * p.Cout + cob * NB) * p.Cin + cin;
 #pragma unroll 1
-        for (int nb = half; nb < NB / 32; nb += 2) {
+        for (; nb < NB / 32; nb += ZNS_EPI) {
           uint32_t v[32];
           tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + a * NB + nb * 32, v);
           tmem_ld_wait();
