@@ -61,9 +61,10 @@ def main():
                                       1.0 / world, L.current_stream()))
     torch.cuda.synchronize()
     d = (tr2.flat_p - tr.flat_p).abs().max().item()
-    moved = (tr.flat_p - torch.cat([v.reshape(-1) for v in he_normal_state_dict(7).values()]).to(dev)).abs().max().item() \
-        if tr.flat_p.numel() == sum(v.numel() for v in he_normal_state_dict(7).values()) else float("nan")
-    ok = same and d < 3e-4 and d_nccl < 1e-3 and res[0].item() == res[0].item()   # NCCL sums in another order: Adam sign flips of 2*lr per step
+    p0 = torch.cat([v.reshape(-1) for v in he_normal_state_dict(7).values()]).to(dev)
+    moved = (tr.flat_p[:p0.numel()] - p0).abs().max().item()      # (the flat buffer is padded to a multiple of the world size)
+    # fp32 atomics / NCCL sum in another order: where a gradient is ~0 Adam's first steps flip sign, 2*lr per step
+    ok = same and d < 3 * 2e-4 * 1.05 and d_nccl < 1e-3 and moved > 1e-5 and res[0].item() == res[0].item()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
