@@ -121,19 +121,21 @@ __device__ __forceinline__ void tile_decode(const TilePlan& tp, int n_wtiles, in
 
 // units: output rows (or stacked row pairs) per column; u_max: accumulators that fit TMEM / shared memory;
 // ovh: per-CTA prologue + epilogue cost in units of one row's MMA time.
-static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh) {
+// ctas: CTAs sharing one weight tile (a pair loads half a tile each, so L2 feeds it twice as many tile rows).
+static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh, int ctas) {
   // plans are pure functions of their arguments: cache them (the simulation costs ~1 ms of host time)
   static std::mutex mu;
-  static std::map<std::tuple<int, int, int, long>, TilePlan> cache;
-  const auto key = std::make_tuple(units, n_cols, u_max, lround(ovh * 4096.0));   // (before env scaling: env is process-wide)
+  static std::map<std::tuple<int, int, int, long, int>, TilePlan> cache;
+  const auto key = std::make_tuple(units, n_cols, u_max, lround(ovh * 4096.0), ctas);   // (before env scaling: env is process-wide)
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
   }
-  // weight-tile bytes per MMA clock fall as 64/h B/clk; ZNS_PLAN_L2 (default 38 B/clk per SM) is what L2 is
+  // weight-tile bytes per MMA clock fall as 64/h B/clk; ZNS_PLAN_L2 (default 38 B/clk per SM, per CTA of a pair) is what L2 is
   // assumed to deliver, ZNS_PLAN_OVH scales the per-CTA overhead (both only for tuning experiments)
-  static const double l2_rate = getenv("ZNS_PLAN_L2") ? atof(getenv("ZNS_PLAN_L2")) : 38.0;
+  static const double l2_env = getenv("ZNS_PLAN_L2") ? atof(getenv("ZNS_PLAN_L2")) : 0.0;
+  const double l2_rate = l2_env > 0.0 ? l2_env : 38.0 * ctas;
   static const double ovh_scale = getenv("ZNS_PLAN_OVH") ? atof(getenv("ZNS_PLAN_OVH")) : 1.0;
   ovh *= ovh_scale;
   auto cost = [&](int h) {
@@ -972,7 +974,7 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
   p.n_wtiles = (d->W + WT - 1) / WT;
   {
     const double pair_clk = (double)p.n_chunks * (d->kh + 1) * d->kw * 4.0 * 64.0;   // N = 128 MMAs per stacked pair
-    p.tiles = plan_tiles(d->H / 2, G * p.n_wtiles * n_br, p.n_acc, 8000.0 / pair_clk);
+    p.tiles = plan_tiles(d->H / 2, G * p.n_wtiles * n_br, p.n_acc, 8000.0 / pair_clk, CTAS);
     p.n_acc = p.tiles.hb;
     p.n_slots = std::min(p.n_slots, std::min(MAX_RING, (p.n_acc - 1) * 2 + 3));
   }
@@ -1079,7 +1081,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   while (u_max > 1 && (uint64_t)(u_max + 1) * p.slot_bytes + 2ull * btile > budget) --u_max;
   {
     const double row_clk = (double)p.n_chunks * d->kh * d->kw * 4.0 * (N / 2);
-    p.tiles = plan_tiles(d->H, G * p.n_wtiles * n_br, u_max, 8000.0 / row_clk);
+    p.tiles = plan_tiles(d->H, G * p.n_wtiles * n_br, u_max, 8000.0 / row_clk, CTAS);
   }
   const int ht_max = p.tiles.hb;
   int slots = ht_max + 1, bst = 2;
