@@ -1178,6 +1178,8 @@ struct WgParams {
   int Cin, Cout;
   int kh, kw, ph, pw;
   int n_wtiles;
+  int stack_dy;             // 1: c_out == 64, N = 128 = dy rows (h, h + 1); row items 0..kh, every second row is a step
+  int n_rows;               // row items: kh (+ 1 with stack_dy)
   int fold;                 // 1: c_in == 64, M = 2 taps x 64 channels
   int n_acc;                // accumulators (TMEM) per CTA
   int taps_per_cta;         // n_acc * (fold ? 2 : 1)
@@ -1236,7 +1238,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     r_peer = peer & 15;
   } else {
     cib = t % p.n_cin_blocks; t /= p.n_cin_blocks;
-    r = t % p.kh; t /= p.kh;
+    r = t % p.n_rows; t /= p.n_rows;
     const int sg = t;
     const int acc0 = sg * p.grp_base + min(sg, p.grp_rem); // first accumulator (in row order) of this group
     s0 = acc0 * unit;
@@ -1244,7 +1246,10 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     r_peer = r;
   }
   const int n_xchunks = p.fold ? 1 : 2;
-  const int n_steps_total = p.G * p.H * p.n_wtiles;
+  // stack_dy: only every second output row is a step (its dy tile carries rows h and h + 1)
+  const int hmul = p.stack_dy ? 2 : 1;
+  const int Hs = (p.H + hmul - 1) / hmul;
+  const int n_steps_total = p.G * Hs * p.n_wtiles;
   const int q0 = (int)((long long)n_steps_total * slice / p.n_slices);
   const int q1 = (int)((long long)n_steps_total * (slice + 1) / p.n_slices);
   constexpr uint32_t kDyChunk = WT * 1024;  // 128 positions x 64 channels
@@ -1277,7 +1282,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   const uint32_t n_st = p.n_stages;
   // position-step cursor (wt, h, g) of step q0, advanced incrementally (no div/mod in the loops)
   const int wt_0 = q0 % p.n_wtiles, gh_0 = q0 / p.n_wtiles;
-  const int h_0 = gh_0 % p.H, g_0 = gh_0 / p.H;
+  const int h_0 = (gh_0 % Hs) * hmul, g_0 = gh_0 / Hs;
   if (warp == 0) {
     if (elect_one()) {
       uint32_t st = 0, par = 1;
@@ -1293,17 +1298,20 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
             for (int xc = 0; xc < n_xchunks; ++xc)      // a row outside the image is zero-filled by TMA
               tma_load_5d_pair(base + xc * p.x_chunk_bytes, tm_x, bar, (cib * n_xchunks + xc) * 64, 0,
                                wt * WT - p.pw + s0, hh, g);
-            tma_load_5d_pair(base + dy_off, tm_dy, bar, cob * NB + (int)cta_rank * 64, 0, wt * WT, h, g);
+            if (p.stack_dy) tma_load_5d_pair(base + dy_off, tm_dy, bar, 0, 0, wt * WT, h + (int)cta_rank, g);
+            else tma_load_5d_pair(base + dy_off, tm_dy, bar, cob * NB + (int)cta_rank * 64, 0, wt * WT, h, g);
           } else {
             for (int xc = 0; xc < n_xchunks; ++xc)
               tma_load_5d(base + xc * p.x_chunk_bytes, tm_x, bar_full + 8 * st, (cib * n_xchunks + xc) * 64, 0,
                           wt * WT - p.pw + s0, hh, g);
-            for (int j = 0; j < NB / 64; ++j)
-              tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, bar_full + 8 * st, cob * NB + j * 64, 0, wt * WT, h, g);
+            for (int j = 0; j < NB / 64; ++j) {
+              if (p.stack_dy) tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, bar_full + 8 * st, 0, 0, wt * WT, h + j, g);
+              else tma_load_5d(base + dy_off + j * kDyChunk, tm_dy, bar_full + 8 * st, cob * NB + j * 64, 0, wt * WT, h, g);
+            }
           }
           if (++st == n_st) { st = 0; par ^= 1; }
         }
-        if (++wt == p.n_wtiles) { wt = 0; if (++h == p.H) { h = 0; ++g; } }
+        if (++wt == p.n_wtiles) { wt = 0; h += hmul; if (h >= p.H) { h = 0; ++g; } }
       }
     }
     __syncwarp();
@@ -1341,7 +1349,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
           if (++st == n_st) { st = 0; par ^= 1; }
           any = 1;
         }
-        if (++wt == p.n_wtiles) { wt = 0; if (++h == p.H) h = 0; }
+        if (++wt == p.n_wtiles) { wt = 0; h += hmul; if (h >= p.H) h = 0; }
       }
       if (CTAS == 2) {
         if (any) umma_commit_pair(smem_u32(&bars->acc_full));   // (no live step: the epilogues of both CTAs do not wait)
@@ -1360,8 +1368,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
       any = false;
       const int gh1 = (q1 - 1) / p.n_wtiles;
       if (q1 > q0) {
-        const int gh_end = min(gh1, gh_0 + p.H - 1);   // every output row is covered after H of them
-        for (int gh = gh_0; gh <= gh_end; ++gh) any = any || live(gh % p.H);
+        const int gh_end = min(gh1, gh_0 + Hs - 1);   // every row step is covered after Hs of them
+        for (int gh = gh_0; gh <= gh_end; ++gh) any = any || live((gh % Hs) * hmul);
       }
       if (any) { mbar_wait(smem_u32(&bars->acc_full), 0); tc_fence_after(); }
     } else {
@@ -1379,15 +1387,18 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
         if (p.fold) { tap_s = s0 + 2 * a + (m >> 6); cin = m & 63; }
         else        { tap_s = s0 + a; cin = cib * 128 + m; }
         const bool valid = tap_s < p.kw;
-        const size_t o0 = ((size_t)(r * p.kw + (valid ? tap_s : 0)) * p.Cout + cob * NB) * p.Cin + cin;
 #pragma unroll 1
         for (; nb < NB / 32; nb += ZNS_EPI) {
           uint32_t v[32];
           tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + a * NB + nb * 32, v);
           tmem_ld_wait();
-          if (valid) {
+          // stack_dy: columns 0-63 pair x row hh with dy row h (tap row r), columns 64-127 with dy row h + 1 (tap row r - 1)
+          const int tap_r = p.stack_dy ? r - (nb >> 1) : r;
+          const int cout0 = p.stack_dy ? (nb & 1) * 32 : cob * NB + nb * 32;
+          if (valid && tap_r >= 0 && tap_r < p.kh) {
+            const size_t o0 = ((size_t)(tap_r * p.kw + tap_s) * p.Cout + cout0) * p.Cin + cin;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dw + o0 + (size_t)(nb * 32 + j) * p.Cin, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(dw + o0 + (size_t)j * p.Cin, __uint_as_float(v[j]));
           }
         }
       }
@@ -1402,10 +1413,15 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   }
 }
 
+// stack_dy (c_out == 64 with NB = 128): a 128 x 64 x 16 MMA is bound by its A-tile read (48 clk instead of 32), so the
+// dy tiles of output rows h and h + 1 are stacked on N.  On input row hh = h + rho - ph the first 64 columns then
+// accumulate tap row rho and the last 64 tap row rho - 1; with steps on even h only, tap row r gets its even rows from
+// item rho = r and its odd rows from item rho = r + 1: kh + 1 row items of H/2 steps each, every MMA at N = 128.
 template <int NB, int CTAS = 1>
 static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy, float* const* dwpk,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool stack_dy = false) {
   static_assert(CTAS == 1 || NB == 128, "the CTA-pair weight-gradient kernel splits a 128-channel dy tile");
+  if (stack_dy && (NB != 128 || d->c_out != 64)) return zns_set_error(ZNS_ERR_INVALID, "stack_dy needs c_out == 64 and NB == 128");
   const int G = zns_groups(d->batch);
   WgParams p;
   memset(&p, 0, sizeof(p));
@@ -1413,6 +1429,8 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
   p.n_wtiles = (d->W + WT - 1) / WT;
   p.fold = d->c_in == 64;
+  p.stack_dy = stack_dy ? 1 : 0;
+  p.n_rows = d->kh + p.stack_dy;
   p.n_acc = 512 / NB;
   if (p.fold) p.n_acc = std::min(p.n_acc, (d->kw + 1) / 2);
   else p.n_acc = std::min(p.n_acc, d->kw);
@@ -1429,13 +1447,13 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
     p.taps_per_cta = p.n_acc * unit;
   }
   p.n_cin_blocks = p.fold ? 1 : d->c_in / 128;
-  p.n_cout_blocks = d->c_out / NB;
+  p.n_cout_blocks = stack_dy ? 1 : d->c_out / NB;
   p.x_chunk_bytes = (uint32_t)(WT + p.taps_per_cta - 1) * 1024u;
   p.stage_bytes = (p.fold ? 1 : 2) * p.x_chunk_bytes + (NB / 64 / CTAS) * WT * 1024u;   // per CTA
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(WgBarriers) - 64;
   p.n_stages = std::min<int>(MAX_RING, budget / p.stage_bytes);
   ZNS_REQUIRE(p.n_stages >= 2, "wgrad stage does not fit shared memory twice");
-  int items = d->kh * p.n_sgroups * p.n_cin_blocks * p.n_cout_blocks;
+  int items = p.n_rows * p.n_sgroups * p.n_cin_blocks * p.n_cout_blocks;
   int n_big_items = 0, n_small_items = 0;   // pair kernel: CTAs (dummies included) per class, cout block and slice
   if (CTAS == 2) {
     // work items by class (accumulator count), bigger class first; an odd class is padded with a dummy
@@ -1449,7 +1467,7 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
         if (big != (cls == 0)) continue;
         const int acc0 = sg * p.grp_base + std::min(sg, p.grp_rem);
         const int n_acc = p.grp_base + (sg < p.grp_rem ? 1 : 0);
-        for (int r = 0; r < d->kh; ++r)
+        for (int r = 0; r < p.n_rows; ++r)
           for (int cib = 0; cib < p.n_cin_blocks; ++cib) {
             ZNS_REQUIRE(n < WG_MAX_ITEMS - 1, "too many weight-gradient work items for the pair kernel");
             p.items[n++] = (uint32_t)r | ((uint32_t)(acc0 * unit) << 4) | ((uint32_t)n_acc << 10) | ((uint32_t)cib << 14) | (1u << 18);
@@ -1461,13 +1479,13 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
     p.n_item_pairs = n / 2;
     items = n * p.n_cout_blocks;   // CTAs per slice and branch
   }
-  const int n_steps_total = G * d->H * p.n_wtiles;
+  const int n_steps_total = G * (stack_dy ? (d->H + 1) / 2 : d->H) * p.n_wtiles;
   // position slices: simulate the in-order dispatch of the two CTA classes (groups with grp_base + 1 and
   // with grp_base accumulators) for every slice count and keep the shortest makespan; more slices also
   // mean more atomics in the epilogue, hence the small per-CTA overhead term
   int best = 1;
   {
-    long per_group = (long)d->kh * p.n_cin_blocks * p.n_cout_blocks * n_br;   // CTAs per tap group and slice
+    long per_group = (long)p.n_rows * p.n_cin_blocks * p.n_cout_blocks * n_br;   // CTAs per tap group and slice
     const int acc_big = p.grp_base + (p.grp_rem ? 1 : 0), acc_small = p.grp_base;
     int n_big_groups = p.grp_rem ? p.grp_rem : p.n_sgroups, n_small_groups = p.grp_rem ? p.n_sgroups - p.grp_rem : 0;
     if (CTAS == 2) { per_group = (long)p.n_cout_blocks * n_br; n_big_groups = n_big_items; n_small_groups = n_small_items; }
@@ -1522,16 +1540,20 @@ extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* cons
   ZNS_REQUIRE((d->kh & 1) && (d->kw & 1) && d->kw <= 41 && d->kh <= 15, "filter %dx%d not supported", d->kh, d->kw);
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(x[b] && dy[b] && dwpk[b], "NULL tensor for branch %d", b);
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->c_out == 64) return launch_wgrad<64>(d, n_br, x, dy, dwpk, st);
-  {
-    // CTA-pair kernel when the (tap row, tap group, cin block) items fit its table
-    static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 3;
-    const int unit = d->c_in == 64 ? 2 : 1;
-    const int row_acc = (d->kw + unit - 1) / unit;
-    const int n_items = d->kh * ((row_acc + 3) / 4) * (d->c_in == 64 ? 1 : d->c_in / 128);
-    if (pair_mode >= 3 && n_items + 2 <= WG_MAX_ITEMS && d->c_in / 128 <= 15)
-      return launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st);
+  // CTA-pair kernel when the (tap row, tap group, cin block) items fit its table
+  static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 3;
+  const int unit = d->c_in == 64 ? 2 : 1;
+  const int row_acc = (d->kw + unit - 1) / unit;
+  const int n_items = (d->kh + 1) * ((row_acc + 3) / 4) * (d->c_in == 64 ? 1 : d->c_in / 128);
+  const bool pair_ok = pair_mode >= 3 && n_items + 2 <= WG_MAX_ITEMS && d->c_in / 128 <= 15;
+  if (d->c_out == 64) {
+    // ZNS_WGRAD_STACK=1 (experimental, opt-in): dy rows (h, h + 1) stacked on N instead of the N = 64 kernel
+    static const bool stack = getenv("ZNS_WGRAD_STACK") != nullptr && atoi(getenv("ZNS_WGRAD_STACK")) != 0;
+    if (stack && d->kh < 15)
+      return pair_ok ? launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st, true) : launch_wgrad<128, 1>(d, n_br, x, dy, dwpk, st, true);
+    return launch_wgrad<64>(d, n_br, x, dy, dwpk, st);
   }
+  if (pair_ok) return launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st);
   return launch_wgrad<128>(d, n_br, x, dy, dwpk, st);
 }
 
