@@ -200,6 +200,16 @@ int zns_dbg_umma_probe(int variant, const void* a, const void* b, float* d, int 
 /* tcgen05 issue/throughput microbenchmark (diagnostic): cycles[n_ctas] per CTA. */
 int zns_dbg_umma_rate(int n, int iters, int per_group, int mode, int n_ctas, long long* cycles, void* stream);
 
+/* Host-only (no CUDA call): the launch geometry zns_conv_fwd / zns_conv_wgrad would choose for a layer, so that tile
+ * plans and the CTA-pair work-item table can be checked on a machine without a GPU (tests/test_lib_host.py).
+ *   fwd  out[14]: kernel (0 direct, 1 stacked), N, CTAs per cluster, hb, nb, hs, ns, n_cols, n_total, A-row slots,
+ *                 weight stages, grid x, dynamic shared memory bytes, units per column
+ *   wgrad out[16]: NB, CTAs per cluster, position slices, accumulators per CTA, tap groups per row, grp_base, grp_rem,
+ *                 row items, stack_dy, fold, cin blocks, cout blocks, item pairs, stages, grid x, dynamic smem bytes;
+ *         items[2 * item pairs] (may be NULL): r | s0 << 4 | n_acc << 10 | cin block << 14 | valid << 18 */
+int zns_dbg_conv_fwd_plan(const zns_conv_desc* d, int n_br, int* out);
+int zns_dbg_conv_wgrad_plan(const zns_conv_desc* d, int n_br, int* out, unsigned int* items);
+
 #ifdef __cplusplus
 }
 #endif

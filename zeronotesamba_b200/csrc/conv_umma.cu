@@ -15,6 +15,11 @@
 //   * wgrad: the reduction runs over positions; both operands are MN-major views of the same
 //     kind of tile (x halo row shifted by the tap, dy tile), accumulators are per-tap
 //     [c_in x c_out] blocks in TMEM, reduced across position slices with fp32 atomics.
+//   * CTA pairs: the default kernels run as clusters of two CTAs on one TPC issuing M = 256
+//     tcgen05.mma.cta_group::2 -- each CTA stages its own M half (input rows / x rows) and half of the
+//     shared N operand (weight tile / dy tile), which takes the operand reads per SM below the
+//     128 B/clk shared-memory limit of a single-CTA N = 128 MMA and halves the shared operand's L2 traffic.
+//     ZNS_CONV_PAIR=0..3 selects how many kernel families use pairs (A/B switch, default 3 = all).
 #include <stdlib.h>
 #include <string.h>
 
@@ -184,6 +189,20 @@ static TilePlan plan_tiles(int units, int n_cols, int u_max, double ovh, int cta
   }
   return best;
 }
+
+// Host-side launch geometry, reported instead of launching when a launcher is given a non-NULL `dry`
+// (zns_dbg_conv_*_plan: lets the CPU tests check tile plans and work-item tables without a GPU).
+struct PlanDump {
+  int kernel;               // 0 = conv_fwd_umma, 1 = conv_fwd_stack_umma, 2 = conv_fwdT_umma, 3 = conv_wgrad_umma
+  int n, ctas;              // MMA N (NB for the weight gradient), CTAs per cluster
+  TilePlan tiles;           // forward kernels
+  int n_slots, n_stages;    // forward: A-row ring / weight ring; weight gradient: -, stage ring
+  int grid_x, grid_z;
+  size_t smem;
+  // weight gradient
+  int n_slices, n_acc, n_sgroups, grp_base, grp_rem, n_rows, stack_dy, fold, n_cin_blocks, n_cout_blocks, n_item_pairs;
+  uint32_t items[256];
+};
 
 // Launch with clusters of two CTAs: blocks (2i, 2i+1) form a pair -- same rows and branch, adjacent frame
 // tiles (callers check that the columns per branch are even, so a pair never straddles a row block or a branch).
@@ -965,7 +984,7 @@ static bool fwd_stack_config(const zns_conv_desc* d, FwdTParams* p, int ctas) {
 template <int CTAS>
 static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, const void* const* in,
                             const void* const* wpk, const float* const* bias, const void* const* mask, void* const* out,
-                            cudaStream_t st) {
+                            cudaStream_t st, PlanDump* dry = nullptr) {
   const int G = zns_groups(d->batch);
   FwdTParams p = cfg;
   p.G = G; p.H = d->H; p.W = d->W; p.batch = d->batch;
@@ -981,6 +1000,11 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
   const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * (16384 / CTAS) + sizeof(FwdTBarriers) + 64;
+  if (dry) {
+    dry->kernel = 1; dry->n = 128; dry->ctas = CTAS; dry->tiles = p.tiles; dry->n_slots = p.n_slots; dry->n_stages = p.n_wstages;
+    dry->grid_x = p.tiles.n_total; dry->grid_z = 1; dry->smem = smem;
+    return ZNS_OK;
+  }
   CUtensorMap tm_in[2], tm_w[2];
   for (int b = 0; b < 2; ++b) {
     const int s = b < n_br ? b : 0;
@@ -1064,7 +1088,8 @@ static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, 
 
 template <int N, int HT, int CTAS = 1>
 static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                      const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st) {
+                      const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st,
+                      PlanDump* dry = nullptr) {
   const int G = zns_groups(d->batch);
   FwdParams p;
   memset(&p, 0, sizeof(p));
@@ -1094,6 +1119,11 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   while (bst < MAX_RING && (uint64_t)slots * p.slot_bytes + (uint64_t)(bst + 1) * btile <= budget) ++bst;
   p.n_slots = slots; p.n_bstages = bst;
   const size_t smem = 1024 + (size_t)slots * p.slot_bytes + (size_t)bst * btile + sizeof(FwdBarriers) + 64;
+  if (dry) {
+    dry->kernel = 0; dry->n = N; dry->ctas = CTAS; dry->tiles = p.tiles; dry->n_slots = slots; dry->n_stages = bst;
+    dry->grid_x = p.tiles.n_total; dry->grid_z = 1; dry->smem = smem;
+    return ZNS_OK;
+  }
 
   CUtensorMap tm_in[2], tm_w[2];
   for (int b = 0; b < 2; ++b) {
@@ -1122,16 +1152,16 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   return ZNS_OK;
 }
 
-extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                            const float* const* bias, const void* const* mask, void* const* out, void* stream) {
-  ZNS_REQUIRE(d && in && wpk && out, "NULL argument");
+// Kernel choice and launch of the forward / data-gradient convolution; with `dry` only the geometry is reported.
+static int conv_fwd_dispatch(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
+                             const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st,
+                             PlanDump* dry) {
+  ZNS_REQUIRE(d != nullptr, "NULL argument");
   ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(d->c_in % 64 == 0 && d->c_in >= 64, "c_in must be a multiple of 64 (got %d)", d->c_in);
   ZNS_REQUIRE((d->kh & 1) && (d->kw & 1) && d->kw <= 41 && d->kh <= 15, "filter %dx%d not supported", d->kh, d->kw);
   ZNS_REQUIRE(d->batch > 0 && d->H > 0 && d->W > 0, "bad geometry");
   ZNS_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout_p out of range");
-  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
-  cudaStream_t st = (cudaStream_t)stream;
   // CTA-pair (cta_group::2) kernels need an even number of frame-tile columns per branch.
   // ZNS_CONV_PAIR (A/B switch): 0 = single-CTA kernels, 1 = pairs for N = 128 and the stacked kernel,
   // 2 = also N = 256, 3 (default) = also the weight gradient
@@ -1144,26 +1174,49 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
     static const bool use_t = getenv("ZNS_CONV_TRANSPOSED") != nullptr;
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    if (use_t && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
+    if (use_t && !dry && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
   {
     static const bool no_stack = getenv("ZNS_CONV_NO_STACK") != nullptr;   // A/B switch
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
     if (!no_stack && use_pair && can_pair && fwd_stack_config(d, &cfg, 2))
-      return launch_fwd_stack<2>(d, cfg, n_br, in, wpk, bias, mask, out, st);
-    if (!no_stack && fwd_stack_config(d, &cfg, 1)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, st);
+      return launch_fwd_stack<2>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
+    if (!no_stack && fwd_stack_config(d, &cfg, 1)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
   }
   switch (d->c_out) {
-    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st);
+    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st, dry);
     case 128:
-      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, st);
-      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st);
+      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, st, dry);
+      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st, dry);
     case 256:
-      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, st);
-      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st);
+      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, st, dry);
+      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st, dry);
     default: return zns_set_error(ZNS_ERR_INVALID, "c_out must be 64, 128 or 256 (got %d)", d->c_out);
   }
+}
+
+extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
+                            const float* const* bias, const void* const* mask, void* const* out, void* stream) {
+  ZNS_REQUIRE(d && in && wpk && out, "NULL argument");
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
+  return conv_fwd_dispatch(d, n_br, in, wpk, bias, mask, out, (cudaStream_t)stream, nullptr);
+}
+
+// Host-only: the launch geometry zns_conv_fwd would use for this layer (no CUDA call is made).
+//   out[0..13] = kernel (0 direct, 1 stacked), N, CTAs per cluster, hb, nb, hs, ns, n_cols, n_total, A-row slots,
+//                weight stages, grid x, dynamic shared memory bytes, units per column (rows, or row pairs when stacked)
+extern "C" int zns_dbg_conv_fwd_plan(const zns_conv_desc* d, int n_br, int* out) {
+  ZNS_REQUIRE(d && out, "NULL argument");
+  PlanDump pd;
+  memset(&pd, 0, sizeof(pd));
+  int rc = conv_fwd_dispatch(d, n_br, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &pd);
+  if (rc) return rc;
+  const int vals[14] = {pd.kernel, pd.n, pd.ctas, pd.tiles.hb, pd.tiles.nb, pd.tiles.hs, pd.tiles.ns, pd.tiles.n_cols,
+                        pd.tiles.n_total, pd.n_slots, pd.n_stages, pd.grid_x, (int)pd.smem, pd.kernel == 1 ? d->H / 2 : d->H};
+  for (int i = 0; i < 14; ++i) out[i] = vals[i];
+  return ZNS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1419,7 +1472,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
 // item rho = r and its odd rows from item rho = r + 1: kh + 1 row items of H/2 steps each, every MMA at N = 128.
 template <int NB, int CTAS = 1>
 static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy, float* const* dwpk,
-                        cudaStream_t st, bool stack_dy = false) {
+                        cudaStream_t st, bool stack_dy = false, PlanDump* dry = nullptr) {
   static_assert(CTAS == 1 || NB == 128, "the CTA-pair weight-gradient kernel splits a 128-channel dy tile");
   if (stack_dy && (NB != 128 || d->c_out != 64)) return zns_set_error(ZNS_ERR_INVALID, "stack_dy needs c_out == 64 and NB == 128");
   const int G = zns_groups(d->batch);
@@ -1505,6 +1558,16 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   }
   p.n_slices = best;
   const size_t smem = 1024 + (size_t)p.n_stages * p.stage_bytes + sizeof(WgBarriers) + 64;
+  if (dry) {
+    dry->kernel = 3; dry->n = NB; dry->ctas = CTAS; dry->n_stages = p.n_stages; dry->smem = smem;
+    dry->grid_x = items * p.n_slices; dry->grid_z = n_br;
+    dry->n_slices = p.n_slices; dry->n_acc = p.n_acc; dry->n_sgroups = p.n_sgroups; dry->grp_base = p.grp_base;
+    dry->grp_rem = p.grp_rem; dry->n_rows = p.n_rows; dry->stack_dy = p.stack_dy; dry->fold = p.fold;
+    dry->n_cin_blocks = p.n_cin_blocks; dry->n_cout_blocks = p.n_cout_blocks; dry->n_item_pairs = p.n_item_pairs;
+    static_assert(sizeof(dry->items) >= sizeof(p.items), "PlanDump::items too small");
+    memcpy(dry->items, p.items, sizeof(p.items));
+    return ZNS_OK;
+  }
 
   CUtensorMap tm_x[2], tm_dy[2];
   for (int b = 0; b < 2; ++b) {
@@ -1531,15 +1594,15 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
   return ZNS_OK;
 }
 
-extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy,
-                              float* const* dwpk, void* stream) {
-  ZNS_REQUIRE(d && x && dy && dwpk, "NULL argument");
+// Kernel choice and launch of the weight gradient; with `dry` only the geometry is reported.
+static int conv_wgrad_dispatch(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy,
+                               float* const* dwpk, cudaStream_t st, PlanDump* dry) {
+  ZNS_REQUIRE(d != nullptr, "NULL argument");
   ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(d->c_in == 64 || d->c_in % 128 == 0, "wgrad needs c_in == 64 or a multiple of 128 (got %d)", d->c_in);
   ZNS_REQUIRE(d->c_out % 64 == 0, "c_out must be a multiple of 64");
   ZNS_REQUIRE((d->kh & 1) && (d->kw & 1) && d->kw <= 41 && d->kh <= 15, "filter %dx%d not supported", d->kh, d->kw);
-  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(x[b] && dy[b] && dwpk[b], "NULL tensor for branch %d", b);
-  cudaStream_t st = (cudaStream_t)stream;
+  ZNS_REQUIRE(d->batch > 0 && d->H > 0 && d->W > 0, "bad geometry");
   // CTA-pair kernel when the (tap row, tap group, cin block) items fit its table
   static const int pair_mode = getenv("ZNS_CONV_PAIR") ? atoi(getenv("ZNS_CONV_PAIR")) : 3;
   const int unit = d->c_in == 64 ? 2 : 1;
@@ -1550,11 +1613,36 @@ extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* cons
     // ZNS_WGRAD_STACK=1 (experimental, opt-in): dy rows (h, h + 1) stacked on N instead of the N = 64 kernel
     static const bool stack = getenv("ZNS_WGRAD_STACK") != nullptr && atoi(getenv("ZNS_WGRAD_STACK")) != 0;
     if (stack && d->kh < 15)
-      return pair_ok ? launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st, true) : launch_wgrad<128, 1>(d, n_br, x, dy, dwpk, st, true);
-    return launch_wgrad<64>(d, n_br, x, dy, dwpk, st);
+      return pair_ok ? launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st, true, dry) : launch_wgrad<128, 1>(d, n_br, x, dy, dwpk, st, true, dry);
+    return launch_wgrad<64>(d, n_br, x, dy, dwpk, st, false, dry);
   }
-  if (pair_ok) return launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st);
-  return launch_wgrad<128>(d, n_br, x, dy, dwpk, st);
+  if (pair_ok) return launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st, false, dry);
+  return launch_wgrad<128>(d, n_br, x, dy, dwpk, st, false, dry);
+}
+
+extern "C" int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const void* const* dy,
+                              float* const* dwpk, void* stream) {
+  ZNS_REQUIRE(d && x && dy && dwpk, "NULL argument");
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(x[b] && dy[b] && dwpk[b], "NULL tensor for branch %d", b);
+  return conv_wgrad_dispatch(d, n_br, x, dy, dwpk, (cudaStream_t)stream, nullptr);
+}
+
+// Host-only: the launch geometry zns_conv_wgrad would use for this layer (no CUDA call is made).
+//   out[0..15] = NB, CTAs per cluster, position slices, accumulators per CTA, tap groups per row, grp_base, grp_rem,
+//                row items, stack_dy, fold, cin blocks, cout blocks, item pairs, stages, grid x, dynamic smem bytes
+//   items[0..2*out[12]) = the CTA-pair work-item table (r | s0 << 4 | n_acc << 10 | cib << 14 | valid << 18); may be NULL
+extern "C" int zns_dbg_conv_wgrad_plan(const zns_conv_desc* d, int n_br, int* out, unsigned int* items) {
+  ZNS_REQUIRE(d && out, "NULL argument");
+  PlanDump pd;
+  memset(&pd, 0, sizeof(pd));
+  int rc = conv_wgrad_dispatch(d, n_br, nullptr, nullptr, nullptr, nullptr, &pd);
+  if (rc) return rc;
+  const int vals[16] = {pd.n, pd.ctas, pd.n_slices, pd.n_acc, pd.n_sgroups, pd.grp_base, pd.grp_rem, pd.n_rows, pd.stack_dy,
+                        pd.fold, pd.n_cin_blocks, pd.n_cout_blocks, pd.n_item_pairs, pd.n_stages, pd.grid_x, (int)pd.smem};
+  for (int i = 0; i < 16; ++i) out[i] = vals[i];
+  if (items) for (int i = 0; i < 2 * pd.n_item_pairs; ++i) items[i] = pd.items[i];
+  return ZNS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
