@@ -218,6 +218,9 @@ static bool g_taps_uploaded = false;
 
 extern "C" int zns_vqt_num_frames(int n_samples, int hop) { return 1 + n_samples / hop; }
 
+static int vqt_plan_fill(zns_vqt_plan* p, int sr, int n_bins, int bpo, double fmin, double gamma_in, double gamma,
+                         int n_oct, int max_batch, int max_samples);
+
 extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double fmin, double gamma_in, int max_batch,
                                    int max_samples, zns_vqt_plan** out) {
   ZNS_REQUIRE(out != nullptr, "plan out pointer is NULL");
@@ -250,7 +253,19 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
   if (!p) return zns_set_error(ZNS_ERR_ALLOC, "out of host memory");
   p->sr = sr; p->hop = hop; p->n_bins = n_bins; p->bpo = bpo; p->n_oct = n_oct;
   p->max_batch = max_batch; p->max_samples = max_samples;
+  rc = vqt_plan_fill(p, sr, n_bins, bpo, fmin, gamma_in, gamma, n_oct, max_batch, max_samples);
+  if (rc) {                       // a failed upload / allocation releases what was built so far
+    zns_vqt_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return ZNS_OK;
+}
 
+// Filter kernels, their fp16 split images, per-bin scales and the decimation scratch of a plan (device uploads).
+static int vqt_plan_fill(zns_vqt_plan* p, int sr, int n_bins, int bpo, double fmin, double gamma_in, double gamma,
+                         int n_oct, int max_batch, int max_samples) {
+  int rc = ZNS_OK;
   if (!g_taps_uploaded) {
     double t64[32];
     float t32[32];
@@ -264,7 +279,7 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
   for (int i = 0; i < n_oct; ++i) {
     int nf = 0;
     rc = zns_vqt_basis_host(sr, n_bins, bpo, fmin, gamma_in, i, re.data(), im.data(), &nf);
-    if (rc) { free(p); return rc; }
+    if (rc) return rc;
     p->n_fft[i] = nf;
     // device layout: coef[n][half][kk][2], kk < bpo/2, filter k = half*(bpo/2) + kk
     const int hb = bpo / 2;
@@ -326,7 +341,6 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
     n = (n + 1) / 2;
     ZNS_CHECK_CUDA(cudaMalloc(&p->d_scratch[i], (size_t)max_batch * n * sizeof(float)));
   }
-  *out = p;
   return ZNS_OK;
 }
 
