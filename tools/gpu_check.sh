@@ -24,4 +24,7 @@ unset ZNS_CONV_NO_STACK
 export ZNS_CONV_PAIR=0
 run conv_single_cta 600 tests/test_gpu_ops.py -k "conv_fwd_umma or two_branches or dgrad or conv_full or conv_wgrad_umma"
 unset ZNS_CONV_PAIR
+export ZNS_WGRAD_STACK=1
+run wgrad_stacked_dy 600 tests/test_gpu_ops.py -k "conv_wgrad_umma or conv_full"
+unset ZNS_WGRAD_STACK
 cat gpurun_out/summary.txt
