@@ -195,7 +195,12 @@ int zns_counter_add(uint32_t* ctr, uint32_t inc, void* stream);
 int zns_dbg_conv_fwd_simt(const zns_conv_desc* d, const void* in, const void* wpk, const float* bias,
                           const void* mask, void* out, void* stream);
 int zns_dbg_conv_wgrad_simt(const zns_conv_desc* d, const void* x, const void* dy, float* dwpk, void* stream);
-/* Raw tcgen05 GEMM probe (descriptor self-test); see csrc/umma_probe.cu. */
+/* Raw tcgen05 probe (csrc/dbg_probe.cu): a verbatim shared-memory image plus host-built matrix descriptors; returns the
+ * accumulator columns (reps == 1) and the cycles the MMA list took.  tools/umma_view_probe.py drives it. */
+int zns_dbg_umma_raw(const void* image, int image_bytes, const uint64_t* a_desc, const uint64_t* b_desc,
+                     const uint32_t* d_col, const uint32_t* acc, const uint32_t* idescs, int n_mma, int n_cols_out,
+                     float* d_out, int reps, long long* cycles, void* stream);
+/* tcgen05 GEMM probe with hand-swizzled operands (descriptor self-test); csrc/conv_umma.cu. */
 int zns_dbg_umma_probe(int variant, const void* a, const void* b, float* d, int n, int k, void* stream);
 /* tcgen05 issue/throughput microbenchmark (diagnostic): cycles[n_ctas] per CTA. */
 int zns_dbg_umma_rate(int n, int iters, int per_group, int mode, int n_ctas, long long* cycles, void* stream);

@@ -69,6 +69,8 @@ _PROTOS = {
     "zns_dbg_conv_wgrad_simt": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "zns_dbg_umma_probe": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "zns_dbg_umma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "zns_dbg_umma_raw": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                 c_int, c_void_p, c_void_p]),
     "zns_dbg_conv_fwd_plan": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_int)]),
     "zns_dbg_conv_wgrad_plan": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_int), C.POINTER(c_u32)]),
 }
@@ -81,7 +83,7 @@ KERNELS_PER_CALL = {
     "zns_conv_fwd": 1, "zns_conv_wgrad": 1, "zns_bias_grad": 1, "zns_pack_weights": 2, "zns_unpack_grads": 1,
     "zns_pool_fwd": 1, "zns_pool_bwd": 1, "zns_head_fwd": 1, "zns_head_bwd": 1, "zns_merge": 1, "zns_act_from_nchw": 1,
     "zns_act_to_nchw": 1, "zns_ntxent_fwd_bwd": 1, "zns_adam_flat": 1, "zns_adam_p2p": 1, "zns_counter_add": 1, "zns_dbg_conv_fwd_simt": 1,
-    "zns_dbg_conv_wgrad_simt": 1, "zns_dbg_umma_probe": 1, "zns_dbg_umma_rate": 1,
+    "zns_dbg_conv_wgrad_simt": 1, "zns_dbg_umma_probe": 1, "zns_dbg_umma_rate": 1, "zns_dbg_umma_raw": 1,
 }
 CALL_COUNTS: dict = {}
 
