@@ -200,6 +200,11 @@ int zns_dbg_conv_wgrad_simt(const zns_conv_desc* d, const void* x, const void* d
 int zns_dbg_umma_raw(const void* image, int image_bytes, const uint64_t* a_desc, const uint64_t* b_desc,
                      const uint32_t* d_col, const uint32_t* acc, const uint32_t* idescs, int n_mma, int n_cols_out,
                      float* d_out, int reps, long long* cycles, void* stream);
+/* Host-only (no CUDA call): the tcgen05 level plan of one VQT pyramid level (struct VqtLevelDev of csrc/vqt_plan.h, raw
+ * bytes) and its fp16 coefficient image, so that the MMA list can be replayed in numpy against the oracle
+ * (tests/test_vqt_level_plan.py). */
+int zns_dbg_vqt_level_plan(int sr, int hop, int n_bins, int bins_per_octave, double fmin, double gamma, int level,
+                           void* level_struct, int struct_bytes, uint16_t* coef_image, int coef_halfwords);
 /* tcgen05 GEMM probe with hand-swizzled operands (descriptor self-test); csrc/conv_umma.cu. */
 int zns_dbg_umma_probe(int variant, const void* a, const void* b, float* d, int n, int k, void* stream);
 /* tcgen05 issue/throughput microbenchmark (diagnostic): cycles[n_ctas] per CTA. */

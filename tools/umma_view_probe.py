@@ -151,31 +151,59 @@ def timing(mode, N, n_mma, reps, a_stride_bytes):
     _, cyc = run(img, mmas, 32, reps=reps)
     return cyc / (reps * n_mma)
 
+def zero_block_test(rng):
+    """accumulate = 0 with an all-zero 128-byte block as BOTH operands (LBO = SBO = 0: every row and chunk aliases it)
+    must clear an accumulator window of any N without touching its neighbours."""
+    img = np.zeros(IMG, dtype=np.uint8)
+    h = img.view(np.float16)
+    S = rng.integers(-3, 4, size=4096).astype(np.float16)
+    h[: S.size] = S                                   # chunk-major q = 1 signal: row r at 16 r
+    Bm = rng.integers(-3, 4, size=(256, 16)).astype(np.float16)
+    b_starts = put_b(img, np.concatenate([Bm] * 4, axis=1))   # K = 64 canonical tiles
+    zoff = A_BYTES - 1024                              # zero block (image is zero there)
+    fill = (s64(desc(0, 16, 128, 0)), s64(desc(b_starts[0], 16, 1024, 2)), 0, 0, idesc_f16(128, 256))
+    res = {}
+    for n in (16, 48, 128, 256):
+        zero = (s64(desc(zoff, 0, 0, 0)), s64(desc(zoff, 0, 0, 0)), 64, 0, idesc_f16(128, n))
+        D, _ = run(img, [fill, zero], 512 if n > 192 else 256)
+        r = np.arange(128)[:, None]
+        A = S[8 * r + np.arange(16)[None, :]].astype(np.float32)
+        want = A @ Bm.astype(np.float32).T
+        want[:, 64:min(256, 64 + n)] = 0
+        got = D[:, :256]
+        if n + 64 > 256:
+            assert np.abs(D[:, 256:64 + n]).max() == 0
+        res[n] = float(np.abs(got - want).max())
+    return res
+
 
 if __name__ == "__main__":
-    rng = np.random.default_rng(0)
-    print("== Toeplitz views through swizzled K-major descriptors: max|D - prediction| (abs-address rule, row-relative rule)")
-    for mode, hop in (("sw128", 64), ("sw64", 32), ("sw32", 16)):
-        for start in (0, 8, hop, hop + 24, 3 * hop + 8, 5 * hop):
-            for rule in (0, 1):
-                try:
-                    ea, er = toeplitz_test(mode, hop, start, 128, 32, rule, rng)
-                    print(f"{mode} hop={hop} start={start:4d} base_offset_field={'(start>>7)&7' if rule else '0':12s}: abs {ea:8.1f}  rel {er:8.1f}")
-                except Exception as e:  # noqa: BLE001
-                    print(f"{mode} start={start} rule={rule}: FAILED {e}")
-    print("== no-swizzle K-major, SBO=128 (rows at 16-byte pitch), LBO = 16*R: max|D - prediction|")
-    for hop_chunks, R, start_row, K in ((1, 2048, 0, 64), (1, 2048, 5, 96), (4, 256, 0, 96), (4, 256, 3, 96), (8, 200, 1, 128), (2, 515, 2, 64)):
-        try:
-            e = chunk_major_test(hop_chunks, R, start_row, K, 48, rng)
-            print(f"hop={8*hop_chunks:3d} R={R} start_row={start_row} K={K}: {e:8.1f}")
-        except Exception as ex:  # noqa: BLE001
-            print(f"hop_chunks={hop_chunks}: FAILED {ex}")
-    print("== cycles per MMA (128 x N x 16, fp16), one CTA, 64 MMAs per commit, 50 reps")
-    for mode in ("sw128", "sw64", "sw32", "none"):
-        for N in (16, 32, 48, 64, 96, 128, 256):
-            for stride in (0, 32, 2048):
-                try:
-                    c = timing(mode, N, 64, 50, stride)
-                    print(f"{mode:6s} N={N:3d} a_stride={stride:5d}: {c:7.1f} clk/MMA")
-                except Exception as ex:  # noqa: BLE001
-                    print(f"{mode} N={N}: FAILED {ex}")
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("== zeroing MMA with an aliased zero block (LBO = SBO = 0): max|D - expected| per N:", zero_block_test(np.random.default_rng(1)))
+    if only == "all":
+        rng = np.random.default_rng(0)
+        print("== Toeplitz views through swizzled K-major descriptors: max|D - prediction| (abs-address rule, row-relative rule)")
+        for mode, hop in (("sw128", 64), ("sw64", 32), ("sw32", 16)):
+            for start in (0, 8, hop, hop + 24, 3 * hop + 8, 5 * hop):
+                for rule in (0, 1):
+                    try:
+                        ea, er = toeplitz_test(mode, hop, start, 128, 32, rule, rng)
+                        print(f"{mode} hop={hop} start={start:4d} base_offset_field={'(start>>7)&7' if rule else '0':12s}: abs {ea:8.1f}  rel {er:8.1f}")
+                    except Exception as e:  # noqa: BLE001
+                        print(f"{mode} start={start} rule={rule}: FAILED {e}")
+        print("== no-swizzle K-major, SBO=128 (rows at 16-byte pitch), LBO = 16*R: max|D - prediction|")
+        for hop_chunks, R, start_row, K in ((1, 2048, 0, 64), (1, 2048, 5, 96), (4, 256, 0, 96), (4, 256, 3, 96), (8, 200, 1, 128), (2, 515, 2, 64)):
+            try:
+                e = chunk_major_test(hop_chunks, R, start_row, K, 48, rng)
+                print(f"hop={8*hop_chunks:3d} R={R} start_row={start_row} K={K}: {e:8.1f}")
+            except Exception as ex:  # noqa: BLE001
+                print(f"hop_chunks={hop_chunks}: FAILED {ex}")
+        print("== cycles per MMA (128 x N x 16, fp16), one CTA, 64 MMAs per commit, 50 reps")
+        for mode in ("sw128", "sw64", "sw32", "none"):
+            for N in (16, 32, 48, 64, 96, 128, 256):
+                for stride in (0, 32, 2048):
+                    try:
+                        c = timing(mode, N, 64, 50, stride)
+                        print(f"{mode:6s} N={N:3d} a_stride={stride:5d}: {c:7.1f} clk/MMA")
+                    except Exception as ex:  # noqa: BLE001
+                        print(f"{mode} N={N}: FAILED {ex}")

@@ -197,21 +197,7 @@ extern "C" int zns_vqt_basis_host(int sr, int n_bins, int bpo, double fmin, doub
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
-#define ZNS_VQT_MAX_OCT 10
-
-struct zns_vqt_plan {
-  int sr, hop, n_bins, bpo, n_oct;
-  int max_batch, max_samples;
-  int n_fft[ZNS_VQT_MAX_OCT];
-  float* d_coef[ZNS_VQT_MAX_OCT];  // [n_fft][2][bpo/2][2] interleaved (SIMT filterbank kernel)
-  uint16_t* d_coef_bf[ZNS_VQT_MAX_OCT];  // [2 terms][2*bpo columns][n_fft] fp16 (tensor-core filterbank)
-  float coef_inv_scale[ZNS_VQT_MAX_OCT]; // 1 / (power-of-two scale applied to the fp16 coefficients)
-  uint16_t* d_coef_umma[ZNS_VQT_MAX_OCT]; // shared-memory image of the stacked B operand [k-block][48 rows][64] fp16, 128B-swizzled
-  float* d_inv_sqrt_len;           // [n_bins]
-  float* d_scratch[ZNS_VQT_MAX_OCT];  // decimated signals, octave >= 1
-  float* d_stage_in;               // for *_host: [max_batch][max_samples]
-  float* d_stage_out;              // [max_batch][n_bins][frames]
-};
+#include "vqt_plan.h"
 
 __constant__ float c_dec_taps[32];
 static bool g_taps_uploaded = false;
@@ -254,6 +240,7 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
   p->sr = sr; p->hop = hop; p->n_bins = n_bins; p->bpo = bpo; p->n_oct = n_oct;
   p->max_batch = max_batch; p->max_samples = max_samples;
   rc = vqt_plan_fill(p, sr, n_bins, bpo, fmin, gamma_in, gamma, n_oct, max_batch, max_samples);
+  if (!rc) rc = vqt_umma_build(p, fmin, gamma_in);
   if (rc) {                       // a failed upload / allocation releases what was built so far
     zns_vqt_plan_destroy(p);
     return rc;
@@ -296,9 +283,7 @@ static int vqt_plan_fill(zns_vqt_plan* p, int sr, int n_bins, int bpo, double fm
     // column = 2*filter + {re, im}
     {
       const int ncol = 2 * bpo;
-      float gmax = 0.f;
-      for (int k = 0; k < bpo * nf; ++k) gmax = std::max(gmax, std::max(fabsf(re[k]), fabsf(im[k])));
-      const float gs = gmax > 0.f ? exp2f(-1.f - floorf(log2f(gmax))) : 1.f;
+      const float gs = vqt_coef_scale(re.data(), im.data(), bpo * nf);
       p->coef_inv_scale[i] = 1.f / gs;
       std::vector<uint16_t> sp((size_t)2 * ncol * nf);
       for (int k = 0; k < bpo; ++k)
@@ -346,6 +331,7 @@ static int vqt_plan_fill(zns_vqt_plan* p, int sr, int n_bins, int bpo, double fm
 
 extern "C" int zns_vqt_plan_destroy(zns_vqt_plan* p) {
   if (!p) return ZNS_OK;
+  vqt_umma_free(p);
   for (int i = 0; i < ZNS_VQT_MAX_OCT; ++i) {
     if (p->d_coef[i]) cudaFree(p->d_coef[i]);
     if (p->d_coef_bf[i]) cudaFree(p->d_coef_bf[i]);
@@ -902,6 +888,10 @@ extern "C" int zns_vqt_forward(zns_vqt_plan* p, const float* y, int batch, int n
   ZNS_REQUIRE(n_samples <= p->max_samples, "n_samples %d exceeds plan max_samples %d", n_samples, p->max_samples);
   ZNS_REQUIRE((n_samples >> (p->n_oct - 1)) >= 2, "signal too short: %d samples for %d octaves", n_samples, p->n_oct);
   cudaStream_t st = (cudaStream_t)stream;
+  // default: the tcgen05 pyramid (vqt_umma.cu); ZNS_VQT_LEGACY=1 keeps the round-1 SIMT decimator + mma.sync
+  // filterbank (A/B), which also serve geometries the level kernels do not cover
+  static const bool legacy = getenv("ZNS_VQT_LEGACY") != nullptr;
+  if (p->umma_ok && !legacy) return vqt_umma_forward(p, y, batch, n_samples, out, stream);
   const int n_frames = zns_vqt_num_frames(n_samples, p->hop);
   const float* cur = y;
   int n_cur = n_samples;
