@@ -205,6 +205,9 @@ int zns_dbg_umma_raw(const void* image, int image_bytes, const uint64_t* a_desc,
  * (tests/test_vqt_level_plan.py). */
 int zns_dbg_vqt_level_plan(int sr, int hop, int n_bins, int bins_per_octave, double fmin, double gamma, int level,
                            void* level_struct, int struct_bytes, uint16_t* coef_image, int coef_halfwords);
+/* Diagnostic: device buffer (16 int64 per pyramid level) that CTA 0 of every VQT level kernel fills with per-role cycle
+ * counters (issuer / epilogue / loader: total and waiting); NULL switches it off.  tools/vqt_bench.py --timing. */
+int zns_dbg_vqt_timing(long long* buf);
 /* tcgen05 GEMM probe with hand-swizzled operands (descriptor self-test); csrc/conv_umma.cu. */
 int zns_dbg_umma_probe(int variant, const void* a, const void* b, float* d, int n, int k, void* stream);
 /* tcgen05 issue/throughput microbenchmark (diagnostic): cycles[n_ctas] per CTA. */

@@ -49,3 +49,27 @@ def vqt_check(out: np.ndarray, ref: np.ndarray):
     rel = float((np.abs(v - r)[big] / r[big]).max())
     ab = float(np.abs(v - r).max() / mx)
     return rel, ab
+
+
+def check_adam_deltas(d_got, d_ref, g_ref, w0, lr, g_floor=1e-6, min_sign=0.99):
+    """Discriminating check of one Adam step (first step: delta = -lr * g / (|g| + eps), eps = 1e-8).
+
+    On entries whose reference gradient is well above eps and above the bf16 noise of the gradient (|g_ref| > g_floor)
+    the update must (a) be there -- the reference moved the weight by ~lr --, (b) have the reference's sign on at least
+    ``min_sign`` of the entries, and (c) where the sign agrees, match the reference's size to 1e-3 relative plus two ulps
+    of the fp32 weight (w + delta is rounded to the fp32 grid by both implementations).
+    Returns (entries checked, sign agreement)."""
+    d_got, d_ref, g_ref, w0 = (np.asarray(a, dtype=np.float64) for a in (d_got, d_ref, g_ref, w0))
+    sel = np.abs(g_ref) > g_floor
+    n = int(sel.sum())
+    if n == 0:
+        return 0, 1.0
+    assert np.all(np.abs(d_ref[sel]) > 0.5 * lr), "golden deltas are not ~lr where |g| >> eps"
+    same = np.sign(d_got[sel]) == np.sign(d_ref[sel])
+    ulp = np.spacing(np.abs(w0[sel]).astype(np.float32)).astype(np.float64)
+    tol = 1e-3 * np.abs(d_ref[sel]) + 2 * ulp
+    bad = (np.abs(d_got[sel] - d_ref[sel]) > tol) & same
+    assert not bad.any(), f"{int(bad.sum())} of {n} updates differ in size: worst {np.abs(d_got[sel] - d_ref[sel])[bad].max():.3e}"
+    frac = float(same.mean())
+    assert frac >= min_sign, f"update sign agreement {frac:.4f} < {min_sign} over {n} entries"
+    return n, frac

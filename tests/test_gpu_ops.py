@@ -56,6 +56,13 @@ def test_umma_probe(variant, n, k):
 # --------------------------------------------------------------------------------------------
 # VQT
 # --------------------------------------------------------------------------------------------
+# |V_gpu - V_oracle32| <= 2e-6 max|V|: the oracle's float32 arithmetic is itself up to 6e-7 max|V| away from the float64
+# evaluation (tests/test_oracle_vqt.py), the tensor-core pyramid up to 8e-7 (fp32 accumulation in TMEM truncates, seven
+# cascaded decimations), so two independent float32 evaluations differ by up to ~1.3e-6; each is checked against the
+# float64 truth at 1e-6 in test_vqt_vs_oracle.
+VQT_ABS_TOL = 2e-6
+
+
 def _plan(max_batch, max_samples, gamma=-1.0):
     h = C.c_void_p()
     fmin = 440.0 * 2.0 ** ((12 - 69) / 12.0)
@@ -79,7 +86,13 @@ def test_vqt_vs_oracle(mode, gamma):
         ref = vo.vqt_ref_f32(y[i], 16000, mode)
         assert ref.shape == (96, 626)
         rel, ab = vqt_check(out[i], ref)
-        assert rel < 1e-4 and ab < 1e-6, f"clip {i}: rel {rel} abs/max {ab}"
+        assert rel < 1e-4 and ab < VQT_ABS_TOL, f"clip {i}: rel {rel} abs/max {ab}"
+        # against the float64 evaluation of the same mathematics the GPU result is as close as the reference's own
+        # float32 arithmetic is: both sit within 1e-6 of full scale of the truth
+        tru = vo.vqt_truth_f64(y[i], 16000, mode)
+        rel_t, ab_t = vqt_check(out[i], tru)
+        rel_o, ab_o = vqt_check(ref, tru)
+        assert rel_t < 1e-4 and ab_t < 1e-6, f"clip {i} vs float64: rel {rel_t} abs/max {ab_t} (oracle f32: {rel_o} {ab_o})"
     L.check(L.lib().zns_vqt_plan_destroy(plan))
 
 
@@ -94,7 +107,7 @@ def test_vqt_ragged_lengths_host_path(n):
     L.check(L.lib().zns_vqt_forward_host(plan, y.ctypes.data, 1, n, out.ctypes.data, st()))
     ref = vo.vqt_ref_f32(y)
     rel, ab = vqt_check(out, ref)
-    assert rel < 1e-4 and ab < 1e-6, f"n={n}: rel {rel} abs/max {ab}"
+    assert rel < 1e-4 and ab < VQT_ABS_TOL, f"n={n}: rel {rel} abs/max {ab}"
     L.check(L.lib().zns_vqt_plan_destroy(plan))
 
 

@@ -15,19 +15,26 @@ import pytest
 from oracle import vqt_oracle as vo
 from zeronotesamba_b200 import _lib as L
 
-MAX_MMA = 112
+MAX_MMA = 120
 
 
 class VqtMma(C.Structure):
     _fields_ = [("a_off", C.c_uint32), ("b_off", C.c_uint32), ("n", C.c_uint16), ("d_col", C.c_uint16),
-                ("term", C.c_uint16), ("b_rows", C.c_uint16)]
+                ("term", C.c_uint8), ("job", C.c_uint8), ("flags", C.c_uint8), ("b_rows8", C.c_uint8)]
+
+
+class VqtSeg(C.Structure):
+    _fields_ = [("begin", C.c_uint16), ("count", C.c_uint16), ("job", C.c_uint8), ("flags", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
 class VqtLevel(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ("q", "hb", "ha", "rtot", "a_lbo", "fpr", "hop", "n_fft", "bin0", "dec_w", "wacc",
-                                       "dec_a_col", "dec_b_col", "fb_a_col", "fb_b_col", "fb_b_stride", "tmem_cols",
-                                       "n_mma", "b_bytes")] + \
-               [("dec_scale", C.c_float), ("fb_scale", C.c_float), ("mma", VqtMma * MAX_MMA)]
+    _fields_ = [(k, C.c_int) for k in ("q", "hb", "ha", "rtot", "a_lbo", "fpr", "hop", "n_fft", "bin0", "dec_w", "dec_wp",
+                                       "n_pass", "fb_n1", "fb_n2", "pg", "gpt", "n_slots", "slot_term_bytes")] + \
+               [("g_order", C.c_int * 8), ("g_mma_begin", C.c_int * 9), ("ring_base", C.c_int * 2),
+                ("ring_width", C.c_int * 2), ("ring_stages", C.c_int * 2), ("n_jobs", C.c_int), ("ep_job", C.c_int * 3),
+                ("n_mma", C.c_int), ("b_bytes", C.c_int), ("dec_scale", C.c_float), ("fb_scale", C.c_float),
+                ("mma", VqtMma * MAX_MMA), ("pk", C.c_uint32 * (4 * MAX_MMA)), ("g_seg_begin", C.c_int * 9),
+                ("seg", VqtSeg * 24)]
 
 
 def level_plan(level, mode="vqt"):
@@ -46,32 +53,76 @@ def split(x):
     return h1, h2
 
 
+def acc_base(lv, job):
+    """TMEM column of a job's accumulator stage for the first tile of a CTA."""
+    if job == 0:
+        return lv.ring_base[0]
+    return lv.ring_base[1] + ((job - 1) % lv.ring_stages[1]) * lv.ring_width[1]
+
+
 def replay(lv, bimg, sig, row0):
-    """Emulate one tile: returns the TMEM accumulator [128][512] (float64)."""
+    """Emulate one tile the way the kernel runs it (group by group): returns the TMEM accumulator [128][512]."""
     q, R = lv.q, 8 * lv.q
     n_rows = 128 + lv.hb + lv.ha
-    planes = [np.zeros(q * lv.rtot * 8 if q > 1 else lv.rtot * 8, dtype=np.float16) for _ in range(2)]
     first = (row0 - lv.hb) * R
     idx = first + np.arange(n_rows * R)
     x = np.where((idx >= 0) & (idx < sig.size), sig[np.clip(idx, 0, sig.size - 1)], 0.0).astype(np.float32)
     h1, h2 = split(x)
+    # slots: [group][term] -> halfword array of slot_term_bytes
+    slots = [[np.zeros(lv.slot_term_bytes // 2, dtype=np.float16) for _ in range(2)] for _ in range(lv.gpt)]
     for i in range(n_rows * q):
         r, c = divmod(i, q)
-        off = (16 * r if q == 1 else c * lv.a_lbo + 16 * r) // 2
-        planes[0][off:off + 8] = h1[8 * i:8 * i + 8]
-        planes[1][off:off + 8] = h2[8 * i:8 * i + 8]
-    D = np.zeros((128, 512))
+        g, cl = divmod(c, lv.pg)
+        off = (16 * r if q == 1 else cl * lv.a_lbo + 16 * r) // 2
+        slots[g][0][off:off + 8] = h1[8 * i:8 * i + 8]
+        slots[g][1][off:off + 8] = h2[8 * i:8 * i + 8]
+    D = np.full((128, 512), np.nan)            # garbage until a clearing MMA has run
     r = np.arange(128)[:, None]
     k = np.arange(16)[None, :]
-    for i in range(lv.n_mma):
-        m = lv.mma[i]
-        a_idx = (m.a_off + (k // 8) * lv.a_lbo + 16 * r) // 2 + (k % 8)
-        A = planes[m.term][a_idx].astype(np.float64)
-        n = np.arange(m.n)[:, None]
-        b_idx = (m.b_off + (k // 8) * 16 * m.b_rows + 16 * n) // 2 + (k % 8)
-        B = bimg[b_idx].astype(np.float64)
-        D[:, m.d_col:m.d_col + m.n] += A @ B.T
+    seen_first, seen_last, covered = set(), set(), set()
+    for pos in range(lv.gpt):
+        g = lv.g_order[pos]
+        for si in range(lv.g_seg_begin[pos], lv.g_seg_begin[pos + 1]):
+            sg = lv.seg[si]
+            base = acc_base(lv, sg.job)
+            if sg.flags & 1:                   # the issuer waits for the stage, then clears the job's whole ring width
+                assert sg.job not in seen_first
+                seen_first.add(sg.job)
+                D[:, base:base + lv.ring_width[1 if sg.job else 0]] = 0.0
+            assert sg.job in seen_first and sg.job not in seen_last
+            for i in range(sg.begin, sg.begin + sg.count):
+                m = lv.mma[i]
+                assert m.job == sg.job and m.term in (0, 1) and i not in covered
+                assert lv.g_mma_begin[pos] <= i < lv.g_mma_begin[pos + 1]
+                covered.add(i)
+                # the packed entry the issuer reads must describe the same MMA
+                a_lo, b_lo, idesc, col = (lv.pk[4 * i + j] for j in range(4))
+                assert a_lo == ((m.a_off + m.term * lv.slot_term_bytes) >> 4) | ((lv.a_lbo >> 4) << 16)
+                assert b_lo == (m.b_off >> 4) | (((128 * m.b_rows8) >> 4) << 16)
+                assert idesc == (1 << 4) | ((m.n >> 3) << 17) | (8 << 24)
+                assert col == lv.ring_base[1 if m.job else 0] + m.d_col
+                c0 = base + m.d_col
+                a_idx = (m.a_off + (k // 8) * lv.a_lbo + 16 * r) // 2 + (k % 8)
+                A = slots[g][m.term][a_idx].astype(np.float64)
+                n = np.arange(m.n)[:, None]
+                b_idx = (m.b_off + (k // 8) * 128 * m.b_rows8 + 16 * n) // 2 + (k % 8)
+                B = bimg[b_idx].astype(np.float64)
+                D[:, c0:c0 + m.n] += A @ B.T
+            if sg.flags & 2:
+                seen_last.add(sg.job)
+    assert covered == {i for i in range(lv.n_mma) if lv.mma[i].term != 2}
+    assert seen_first == seen_last == set(range(lv.n_jobs))
+    assert sorted(lv.ep_job[: lv.n_jobs]) == list(range(lv.n_jobs))
     return D
+
+
+def dec_outputs(lv, D):
+    cols = []
+    for p in range(lv.n_pass):
+        base = acc_base(lv, 1 + p)
+        w = min(64, lv.dec_w - 64 * p)
+        cols.append((D[:, base:base + w] + D[:, base + lv.dec_wp:base + lv.dec_wp + w] / 2048.0) * lv.dec_scale)
+    return np.concatenate(cols, axis=1)
 
 
 @pytest.mark.parametrize("level", range(8))
@@ -86,7 +137,7 @@ def test_level_plan_replay_matches_oracle(level):
     # ---- decimator ----
     if lv.dec_w:
         want = vo.resample_2to1_f64(sig)          # sqrt(2) sum h x, zero extended
-        got = (D[:, lv.dec_a_col:lv.dec_a_col + lv.dec_w] + D[:, lv.dec_b_col:lv.dec_b_col + lv.dec_w] / 2048.0) * lv.dec_scale
+        got = dec_outputs(lv, D)
         t = (row0 + np.arange(128))[:, None] * lv.dec_w + np.arange(lv.dec_w)[None, :]
         ref = want[t]
         assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
@@ -96,8 +147,9 @@ def test_level_plan_replay_matches_oracle(level):
     g, n_fft = vo.octave_time_kernels(level, 16000.0, vo.default_gamma())
     assert n_fft == lv.n_fft
     for j in range(lv.fpr):
-        a = D[:, lv.fb_a_col + 48 * j: lv.fb_a_col + 48 * j + 48]
-        b = D[:, lv.fb_b_col + 24 * j: lv.fb_b_col + 24 * j + 24]
+        fb0 = acc_base(lv, 0)
+        a = D[:, fb0 + 48 * j: fb0 + 48 * j + 48]
+        b = D[:, fb0 + lv.fb_n1 + 24 * j: fb0 + lv.fb_n1 + 24 * j + 24]
         c = (a[:, :24] + (a[:, 24:48] + b) / 2048.0) * lv.fb_scale
         got = c[:, 0::2] + 1j * c[:, 1::2]                        # [128 rows][12 bins]
         f = (row0 + np.arange(128)) * lv.fpr + j
@@ -114,7 +166,7 @@ def test_level_plan_edges_zero_extension():
     sig = (0.5 * rng.standard_normal(64 * 128 + 11)).astype(np.float32)
     D = replay(lv, bimg, sig, 0)
     want = vo.resample_2to1_f64(sig)
-    got = (D[:, :lv.dec_w] + D[:, lv.dec_b_col:lv.dec_b_col + lv.dec_w] / 2048.0) * lv.dec_scale
+    got = dec_outputs(lv, D)
     t = np.arange(128)[:, None] * lv.dec_w + np.arange(lv.dec_w)[None, :]
     n_valid = sig.size // 2
     ok = t < n_valid
@@ -126,8 +178,9 @@ def test_level_geometry_table():
     for level, (q, fpr) in rows.items():
         lv, _ = level_plan(level)
         assert (lv.q, lv.fpr) == (q, fpr)
-        assert lv.n_mma <= MAX_MMA and lv.tmem_cols in (128, 256, 512)
-        assert 2 * lv.q * lv.rtot * 16 + lv.b_bytes < 220 * 1024
+        assert lv.n_mma <= MAX_MMA and lv.q == lv.pg * lv.gpt and lv.n_slots % lv.gpt == 0
+        assert lv.ring_base[0] + lv.ring_stages[0] * lv.ring_width[0] <= 512
+        assert lv.n_slots * 2 * lv.slot_term_bytes + lv.b_bytes + 256 < 220 * 1024
 
 
 def test_cqt_geometry_falls_back():

@@ -151,6 +151,34 @@ def timing(mode, N, n_mma, reps, a_stride_bytes):
     _, cyc = run(img, mmas, 32, reps=reps)
     return cyc / (reps * n_mma)
 
+def window_timing(pattern, n_mma=60, reps=50, N=48):
+    """cycles per MMA for accumulator-window patterns (all operands no-swizzle chunk-major, as the VQT level kernels):
+    same: every MMA into columns [0, N); shift8: window start 8 * (i // 3) (the decimator's overlapping windows);
+    shift16 / shift48: start 16 / 48 * (i // 3); two: alternate two disjoint windows; fb: alternate N = 48 / 32 windows."""
+    img = np.zeros(IMG, dtype=np.uint8)
+    img.view(np.float16)[:] = np.float16(1.0)
+    mmas = []
+    for i in range(n_mma):
+        a = desc(16 * (i % 7), 2096, 128, 0)
+        b = desc(B_OFF + 16 * (i % 5), 1792, 128, 0)
+        n = N
+        if pattern == "same":
+            col = 0
+        elif pattern == "shift8":
+            col = 8 * (i // 3)
+        elif pattern == "shift16":
+            col = 16 * (i // 3)
+        elif pattern == "shift48":
+            col = 48 * ((i // 3) % 8)
+        elif pattern == "two":
+            col = 64 * (i % 2)
+        elif pattern == "fb":
+            col, n = (0, 48) if i % 2 == 0 else (48, 32)
+        mmas.append((s64(a), s64(b), col, 1, idesc_f16(128, n)))
+    _, cyc = run(img, mmas, 32, reps=reps)
+    return cyc / (reps * n_mma)
+
+
 def zero_block_test(rng):
     """accumulate = 0 with an all-zero 128-byte block as BOTH operands (LBO = SBO = 0: every row and chunk aliases it)
     must clear an accumulator window of any N without touching its neighbours."""
@@ -179,6 +207,9 @@ def zero_block_test(rng):
 
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("== cycles per MMA by accumulator-window pattern (N = 48, chunk-major operands):",
+          {p: round(window_timing(p), 1) for p in ("same", "shift8", "shift16", "shift48", "two", "fb")})
+    print("== same, by MMAs per commit:", {n: round(window_timing("shift8", n_mma=n), 1) for n in (3, 10, 30, 60, 120)})
     print("== zeroing MMA with an aliased zero block (LBO = SBO = 0): max|D - expected| per N:", zero_block_test(np.random.default_rng(1)))
     if only == "all":
         rng = np.random.default_rng(0)

@@ -72,6 +72,7 @@ _PROTOS = {
     "zns_dbg_umma_raw": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_int, c_void_p, c_void_p]),
     "zns_dbg_vqt_level_plan": (c_int, [c_int, c_int, c_int, c_int, c_double, c_double, c_int, c_void_p, c_int, c_void_p, c_int]),
+    "zns_dbg_vqt_timing": (c_int, [c_void_p]),
     "zns_dbg_conv_fwd_plan": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_int)]),
     "zns_dbg_conv_wgrad_plan": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_int), C.POINTER(c_u32)]),
 }

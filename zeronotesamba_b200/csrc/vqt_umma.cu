@@ -19,6 +19,11 @@
 //    decimator: banded Toeplitz, per 16-sample k-step one 48-output window of a shared tap tile.
 //  * epilogue: TMEM -> registers; filterbank rows -> log-magnitude -> out[b][bin][frame]; decimator rows ->
 //    the next level's signal, already split into its two fp16 terms.
+//  * one persistent CTA per SM, warp specialised: 8 loader warps (cp.async into a ring of plane-group slots, fp32 ->
+//    two-term fp16 conversion in place for level 0), 4 MMA-issuing warps (the tiles' MMAs are many and small -- N <= 48,
+//    ~55 clocks each -- so a single issuing thread, at ~190 clocks of scalar work per MMA, is the bottleneck; the
+//    accumulator units are dealt to four threads, each owning its units' TMEM columns), 8 epilogue warps; TMEM
+//    accumulator rings with two stages so that the epilogue of a tile overlaps the MMAs of the next.
 //  * frames whose window crosses a clip edge need reflect padding while the decimator needs zero extension:
 //    the level kernels zero-extend and a tiny SIMT kernel recomputes those (<= 4 per edge and octave) frames.
 #include <math.h>
@@ -62,6 +67,9 @@ static inline size_t tile_idx(size_t tile_off_bytes, int rows, int n, int k) {
 #define DEC_T_ROWS 112   // decimator tap tile rows n = -32 .. 79
 #define DEC_T_N0 (-32)
 #define DEC_TAP_SCALE 2.0f
+#define VQT_ZERO_BYTES 128
+
+struct PendingMma { VqtMma m; int group; int issuer; };
 
 static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, const double* taps) {
   VqtLevelDev& L = p->level[lvl];
@@ -75,9 +83,13 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   const bool last = (lvl == p->n_oct - 1);
   L.q = q; L.fpr = fpr; L.hop = hop; L.n_fft = nf; L.bin0 = p->n_bins - p->bpo * (lvl + 1);
   L.dec_w = last ? 0 : R / 2;
-  L.wacc = last ? 0 : ((L.dec_w + 15) / 16) * 16;
+  L.n_pass = last ? 0 : (L.dec_w + 63) / 64;
+  L.dec_wp = last ? 0 : ((std::min(L.dec_w, 64) + 15) / 16) * 16;
   L.dec_scale = (float)(sqrt(2.0) / DEC_TAP_SCALE);
   L.fb_scale = p->coef_inv_scale[lvl];
+  L.pg = (q == 1) ? 1 : 4;
+  L.gpt = q / L.pg;
+  if (L.gpt > ZNS_VQT_MAX_GROUPS) return 1;
 
   // ---- k-steps (16 samples at offset X0 from the row start) ----
   std::vector<int> fb_x0, dec_x0;
@@ -97,21 +109,29 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   else if (q == 4) { while (rtot % 8 != 2) ++rtot; }
   L.rtot = rtot;
   L.a_lbo = (q == 1) ? 16 : 16 * rtot;
+  L.slot_term_bytes = L.pg * rtot * 16;
+  // group (slot) and byte offset inside the slot's term half of the k-step at x0
+  auto a_group = [&](int x0) -> int {
+    if (q == 1) return 0;
+    const int rs = floordiv(x0, R);
+    return ((x0 - rs * R) / 8) / L.pg;
+  };
   auto a_off = [&](int x0) -> uint32_t {
     if (q == 1) return (uint32_t)(16 * (floordiv(x0, 8) + L.hb));
     const int rs = floordiv(x0, R), p0 = (x0 - rs * R) / 8;
-    return (uint32_t)(p0 * L.a_lbo + 16 * (rs + L.hb));
+    return (uint32_t)((p0 % L.pg) * L.a_lbo + 16 * (rs + L.hb));
   };
 
-  // ---- TMEM columns ----
+  // ---- TMEM rings: [0] filterbank, [1] decimator ----
   const int n1 = fpr * 48, n2 = std::max(32, fpr * 24);
-  L.fb_b_stride = 24;
-  L.dec_a_col = 0; L.dec_b_col = L.wacc; L.fb_a_col = 2 * L.wacc; L.fb_b_col = L.fb_a_col + n1;
-  const int used = L.fb_b_col + n2;
-  int alloc = 32;
-  while (alloc < used) alloc *= 2;
-  if (alloc > 512) return 1;
-  L.tmem_cols = alloc;
+  L.fb_n1 = n1; L.fb_n2 = n2;
+  L.ring_width[0] = n1 + n2;
+  L.ring_width[1] = 2 * L.dec_wp;
+  L.ring_stages[1] = last ? 0 : 2;
+  L.ring_base[1] = 0;
+  L.ring_base[0] = L.ring_stages[1] * L.ring_width[1];
+  L.ring_stages[0] = (L.ring_base[0] + 2 * L.ring_width[0] <= 512) ? 2 : 1;
+  if (L.ring_base[0] + L.ring_stages[0] * L.ring_width[0] > 512) return 1;
 
   // ---- coefficient image ----
   std::vector<float> re((size_t)p->bpo * 1024), im((size_t)p->bpo * 1024);
@@ -153,35 +173,123 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   L.b_bytes = (int)total;
   p->h_bimg[lvl] = img;
 
-  // ---- MMA list ----
-  int m = 0;
-  auto push = [&](uint32_t ao, size_t bo, int n, int col, int term, int brows) -> bool {
-    if (m >= ZNS_VQT_MAX_MMA) return false;
-    L.mma[m++] = VqtMma{ao, (uint32_t)bo, (uint16_t)n, (uint16_t)col, (uint16_t)term, (uint16_t)brows};
-    return true;
+  // ---- MMAs, tagged with the plane group they read and their accumulator unit (job, part) ----
+  std::vector<PendingMma> pend;
+  auto push = [&](int x0, size_t bo, int n, int col, int term, int brows, int job, int part) {
+    PendingMma pm;
+    pm.m = VqtMma{a_off(x0), (uint32_t)bo, (uint16_t)n, (uint16_t)col, (uint8_t)term, (uint8_t)job, (uint8_t)part,
+                  (uint8_t)(brows / 8)};
+    pm.group = a_group(x0);
+    pm.issuer = 0;
+    pend.push_back(pm);
   };
   for (size_t s = 0; s < fb_x0.size(); ++s) {
     const size_t t1 = s * (fb_tile1 + fb_tile2), t2 = t1 + fb_tile1;
-    if (!push(a_off(fb_x0[s]), t1, n1, L.fb_a_col, 0, n1)) return 1;
-    if (!push(a_off(fb_x0[s]), t2, n2, L.fb_b_col, 1, n2)) return 1;
+    push(fb_x0[s], t1, n1, 0, 0, n1, 0, 0);
+    push(fb_x0[s], t2, n2, n1, 1, n2, 0, 1);
   }
-  for (int x0 : dec_x0) {
-    // outputs o = x0/2 - 16 + n; taps are non-zero for n in [1, 39]
-    const int o_lo = std::max(0, x0 / 2 - 15), o_hi = std::min(L.dec_w - 1, x0 / 2 + 23);
-    if (o_lo > o_hi) continue;
-    int o_start = (o_lo / 8) * 8;
-    int n = ((o_hi + 1 - o_start + 15) / 16) * 16;
-    if (o_start + n > L.wacc) o_start = L.wacc - n;
-    if (o_start < 0) { o_start = 0; n = L.wacc; }
-    const int n0 = o_start - x0 / 2 + 16;
-    if (n0 < DEC_T_N0 || n0 + n > DEC_T_N0 + DEC_T_ROWS) return 1;
-    const size_t row_off = (size_t)16 * (n0 - DEC_T_N0);
-    const size_t tt1 = dec_base + row_off, tt2 = dec_base + (size_t)DEC_T_ROWS * 32 + row_off;
-    if (!push(a_off(x0), tt1, n, L.dec_a_col + o_start, 0, DEC_T_ROWS)) return 1;
-    if (!push(a_off(x0), tt2, n, L.dec_b_col + o_start, 0, DEC_T_ROWS)) return 1;
-    if (!push(a_off(x0), tt1, n, L.dec_b_col + o_start, 1, DEC_T_ROWS)) return 1;
+  for (int pass = 0; pass < L.n_pass; ++pass) {
+    const int c0 = 64 * pass, c1 = std::min(L.dec_w, c0 + 64);   // output columns of this pass
+    for (int x0 : dec_x0) {
+      // outputs o = x0/2 - 16 + n; taps are non-zero for n in [1, 39]
+      const int o_lo = std::max(c0, x0 / 2 - 15), o_hi = std::min(c1 - 1, x0 / 2 + 23);
+      if (o_lo > o_hi) continue;
+      int o_start = c0 + ((o_lo - c0) / 8) * 8;
+      int n = ((o_hi + 1 - o_start + 15) / 16) * 16;
+      if (o_start + n > c0 + L.dec_wp) o_start = c0 + L.dec_wp - n;
+      if (o_start < c0) { o_start = c0; n = L.dec_wp; }
+      const int n0 = o_start - x0 / 2 + 16;
+      if (n0 < DEC_T_N0 || n0 + n > DEC_T_N0 + DEC_T_ROWS) return 1;
+      const size_t row_off = (size_t)16 * (n0 - DEC_T_N0);
+      const size_t tt1 = dec_base + row_off, tt2 = dec_base + (size_t)DEC_T_ROWS * 32 + row_off;
+      const int col = o_start - c0;
+      push(x0, tt1, n, col, 0, DEC_T_ROWS, 1 + pass, 0);
+      push(x0, tt2, n, L.dec_wp + col, 0, DEC_T_ROWS, 1 + pass, 1);
+      push(x0, tt1, n, L.dec_wp + col, 1, DEC_T_ROWS, 1 + pass, 1);
+    }
+  }
+  L.n_jobs = 1 + L.n_pass;
+
+  // ---- deal the accumulator units to the issuer warps (longest first) ----
+  const int n_units = 2 * L.n_jobs;
+  int weight[2 * ZNS_VQT_MAX_JOBS] = {0}, unit_issuer[2 * ZNS_VQT_MAX_JOBS] = {0}, load[ZNS_VQT_ISSUERS] = {0};
+  for (const PendingMma& pm : pend) weight[2 * pm.m.job + pm.m.part] += 1;
+  std::vector<int> by_w(n_units);
+  for (int u = 0; u < n_units; ++u) by_w[u] = u;
+  std::stable_sort(by_w.begin(), by_w.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+  for (int u : by_w) {
+    int best = 0;
+    for (int k = 1; k < ZNS_VQT_ISSUERS; ++k) if (load[k] < load[best]) best = k;
+    unit_issuer[u] = best;
+    load[best] += weight[u];
+  }
+  for (PendingMma& pm : pend) pm.issuer = unit_issuer[2 * pm.m.job + pm.m.part];
+
+  // ---- group order: start with the group the filterbank's first (row - 1) k-step reads ----
+  const int g_first = a_group(fb_x0[0]);
+  for (int i = 0; i < L.gpt; ++i) L.g_order[i] = (g_first + i) % L.gpt;
+
+  // ---- segments: (issuer, position, unit) runs ----
+  int m = 0, n_seg = 0;
+  int last_seg[2 * ZNS_VQT_MAX_JOBS], last_mma[ZNS_VQT_MAX_JOBS];
+  bool started[2 * ZNS_VQT_MAX_JOBS];
+  for (int u = 0; u < 2 * ZNS_VQT_MAX_JOBS; ++u) { last_seg[u] = -1; started[u] = false; }
+  for (int j = 0; j < ZNS_VQT_MAX_JOBS; ++j) last_mma[j] = -1;
+  for (int isr = 0; isr < ZNS_VQT_ISSUERS; ++isr) {
+    for (int pos = 0; pos < L.gpt; ++pos) {
+      L.seg_begin[isr][pos] = n_seg;
+      for (int u = 0; u < n_units; ++u) {
+        if (unit_issuer[u] != isr) continue;
+        int seg_first = -1, seg_count = 0;
+        for (const PendingMma& pm : pend) {
+          if (pm.group != L.g_order[pos] || 2 * pm.m.job + pm.m.part != u) continue;
+          if (m >= ZNS_VQT_MAX_MMA) return 1;
+          if (seg_first < 0) seg_first = m;
+          L.mma[m] = pm.m;
+          last_mma[pm.m.job] = std::max(last_mma[pm.m.job], pos);
+          ++m;
+          ++seg_count;
+        }
+        if (seg_count > 0) {
+          if (n_seg >= ZNS_VQT_MAX_SEGS) return 1;
+          L.seg[n_seg] = VqtSeg{(uint16_t)seg_first, (uint16_t)seg_count, (uint8_t)(u / 2), (uint8_t)(u % 2),
+                                (uint8_t)(started[u] ? 0 : 1), 0};
+          started[u] = true;
+          last_seg[u] = n_seg;
+          ++n_seg;
+        }
+      }
+    }
+    L.seg_begin[isr][L.gpt] = n_seg;
   }
   L.n_mma = m;
+  L.n_seg = n_seg;
+  for (int u = 0; u < n_units; ++u) {
+    if (last_seg[u] < 0) return 1;            // every unit must appear: the "full" barriers expect two commits per job
+    L.seg[last_seg[u]].flags |= 2;
+  }
+  // epilogue order = completion order (ties: filterbank first)
+  int order[ZNS_VQT_MAX_JOBS] = {0, 1, 2};
+  std::stable_sort(order, order + L.n_jobs, [&](int a, int b) { return last_mma[a] < last_mma[b]; });
+  for (int j = 0; j < L.n_jobs; ++j) L.ep_job[j] = order[j];
+
+  for (int i = 0; i < L.n_mma; ++i) {
+    const VqtMma& mm = L.mma[i];
+    VqtMmaPacked& pk = L.pk[i];
+    pk.a_lo = ((mm.a_off + (uint32_t)mm.term * (uint32_t)L.slot_term_bytes) >> 4) | (((uint32_t)L.a_lbo >> 4) << 16);
+    pk.b_lo = (mm.b_off >> 4) | (((128u * mm.b_rows8) >> 4) << 16);
+    pk.idesc = umma_idesc_f16(128, mm.n);
+    pk.col = (uint32_t)(L.ring_base[mm.job ? 1 : 0] + mm.d_col);
+  }
+
+  // ---- shared-memory ring ----
+  const size_t slot = 2 * (size_t)L.slot_term_bytes;
+  const size_t budget = 200 * 1024 - (size_t)L.b_bytes - VQT_ZERO_BYTES;
+  int n_slots = (int)(budget / slot);
+  n_slots = std::min(n_slots, 8);
+  n_slots = (n_slots / L.gpt) * L.gpt;      // whole tiles
+  if (n_slots < L.gpt) return 1;
+  L.n_slots = n_slots;
   return 0;
 }
 
@@ -195,7 +303,9 @@ void vqt_umma_free(zns_vqt_plan* p) {
   }
 }
 
-static size_t level_smem(const VqtLevelDev& L) { return (size_t)2 * L.q * L.rtot * 16 + (size_t)L.b_bytes + 16; }
+static size_t level_smem(const VqtLevelDev& L) {
+  return (size_t)L.n_slots * 2 * L.slot_term_bytes + (size_t)L.b_bytes + VQT_ZERO_BYTES + 128;
+}
 
 int vqt_umma_build(zns_vqt_plan* p, double fmin, double gamma_in) {
   p->umma_ok = false;
@@ -204,7 +314,7 @@ int vqt_umma_build(zns_vqt_plan* p, double fmin, double gamma_in) {
   for (int i = 0; i < p->n_oct; ++i) {
     if (build_level(p, i, fmin, gamma_in, taps) != 0 || level_smem(p->level[i]) > 220 * 1024) {
       vqt_umma_free(p);
-      return ZNS_OK;   // unsupported geometry: the legacy kernels stay in charge
+      return ZNS_OK;   // unsupported geometry: the round-1 kernels stay in charge
     }
   }
   size_t n = (size_t)p->max_samples;
@@ -221,6 +331,7 @@ int vqt_umma_build(zns_vqt_plan* p, double fmin, double gamma_in) {
       ZNS_CHECK_CUDA(cudaMemset(p->d_lo[i], 0, bytes));
     }
   }
+  p->umma_last_n = 0;
   p->umma_ok = true;
   return ZNS_OK;
 }
@@ -234,20 +345,19 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
-// zero 32 lanes x 16 columns
-__device__ __forceinline__ void tmem_zero_32x16(uint32_t taddr) {
-  const uint32_t z = 0;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-      ::"r"(taddr), "r"(z)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// no-swizzle K-major descriptor, rows at 16-byte pitch (SBO = 128), leading-dimension offset lbo
-__device__ __forceinline__ uint64_t desc_rows16(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+// 16-byte asynchronous global -> shared copy; bytes beyond src_bytes are zero filled
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // x = x1 + x2 / 2048 for eight values -> two 16-byte chunks
@@ -265,217 +375,376 @@ __device__ __forceinline__ void split8(const float* v, uint4& c1, uint4& c2) {
   c2 = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
-#define VQT_LEVEL_THREADS 256
+// Warp roles of the persistent level kernel: loaders = warps 0..7, epilogue = warps 8..15, MMA issuers = warps 16..19
+// (one per scheduler sub-partition).
+#define VQT_EPI_WARPS 8
+#define VQT_LOAD_WARPS 8
+#define VQT_ISSUE_WARP0 (VQT_LOAD_WARPS + VQT_EPI_WARPS)
+#define VQT_LEVEL_THREADS (32 * (VQT_ISSUE_WARP0 + ZNS_VQT_ISSUERS))
+
+struct VqtLevelArgs {
+  const float* y32;            // level 0 source [batch][src_stride]
+  const uint16_t* src_hi;      // level >= 1 source, two fp16 terms (zero beyond n_sig up to the stride)
+  const uint16_t* src_lo;
+  int n_sig;
+  long long src_stride;
+  const uint16_t* bimg;
+  const float* inv_sqrt_len;
+  float* out;                  // [batch][n_bins][n_frames]
+  int n_frames, n_bins;
+  uint16_t* dst_hi;            // next level
+  uint16_t* dst_lo;
+  int n_valid;
+  long long dst_stride;
+  int tiles_per_clip, n_tiles;
+  long long* dbg;              // optional per-role cycle counters of CTA 0 (zns_dbg_vqt_timing), else NULL
+};
 
 template <bool SRC_F32>
-__global__ void __launch_bounds__(VQT_LEVEL_THREADS)
-vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const float* __restrict__ y32,
-                 const uint16_t* __restrict__ src_hi, const uint16_t* __restrict__ src_lo, int n_sig,
-                 long long src_stride, const uint16_t* __restrict__ bimg, const float* __restrict__ inv_sqrt_len,
-                 float* __restrict__ out, int n_frames, int n_bins, uint16_t* __restrict__ dst_hi,
-                 uint16_t* __restrict__ dst_lo, int n_valid, long long dst_stride) {
-  extern __shared__ __align__(16) uint8_t sm[];
-  __shared__ uint64_t bar;
+__global__ void __launch_bounds__(VQT_LEVEL_THREADS, 1)
+vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ VqtLevelArgs A) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t bar_full[8], bar_empty[8], bar_acc_full[4], bar_acc_empty[4];   // acc barriers: [type * 2 + stage]
   __shared__ uint32_t tmem_slot;
   const int q = L.q, R = 8 * q;
-  const uint32_t plane_bytes = (uint32_t)q * L.rtot * 16;
-  uint8_t* sA1 = sm;
-  uint8_t* sA2 = sm + plane_bytes;
-  uint8_t* sB = sm + 2 * plane_bytes;
-  const int clip = blockIdx.z;
-  const int row0 = blockIdx.x * 128;
+  const uint32_t slot_bytes = 2u * (uint32_t)L.slot_term_bytes;
+  uint8_t* sZero = sm;                                   // 128 zero bytes (both operands of the clearing MMAs)
+  uint8_t* sB = sm + VQT_ZERO_BYTES;
+  uint8_t* sRing = sB + ((L.b_bytes + 127) / 128) * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
-  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), (uint32_t)L.tmem_cols); tmem_relinquish(); }
-
-  // coefficient image
-  for (int i = threadIdx.x; i < L.b_bytes / 16; i += VQT_LEVEL_THREADS)
-    reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(bimg) + i);
-
-  // signal rows row0 - hb .. row0 + 127 + ha, zero extended outside [0, n_sig)
-  {
-    const int n_rows = 128 + L.hb + L.ha;
-    const int n_chunks = n_rows * q;
-    const long long first = ((long long)row0 - L.hb) * R;     // sample index of chunk 0
-    const float* yb = SRC_F32 ? y32 + (size_t)clip * src_stride : nullptr;
-    const uint16_t* hb_ = SRC_F32 ? nullptr : src_hi + (size_t)clip * src_stride;
-    const uint16_t* lb_ = SRC_F32 ? nullptr : src_lo + (size_t)clip * src_stride;
-    const bool vec_ok = SRC_F32 ? ((reinterpret_cast<uintptr_t>(yb) & 15) == 0) : true;
-    for (int i = threadIdx.x; i < n_chunks; i += VQT_LEVEL_THREADS) {
-      const int r = i / q, c = i - r * q;
-      const long long s0 = first + 8LL * i;
-      uint4 c1 = make_uint4(0, 0, 0, 0), c2 = c1;
-      if (s0 + 8 > 0 && s0 < n_sig) {
-        if (SRC_F32) {
-          float v[8];
-          if (s0 >= 0 && s0 + 8 <= n_sig && vec_ok) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(yb + s0));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(yb + s0) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (s0 + e >= 0 && s0 + e < n_sig) ? __ldg(yb + s0 + e) : 0.f;
-          }
-          split8(v, c1, c2);
-        } else if (s0 >= 0) {
-          c1 = __ldg(reinterpret_cast<const uint4*>(hb_ + s0));
-          c2 = __ldg(reinterpret_cast<const uint4*>(lb_ + s0));
-          if (s0 + 8 > n_sig) {     // the tail of the buffer may hold a longer earlier signal
-            uint16_t* p1 = reinterpret_cast<uint16_t*>(&c1);
-            uint16_t* p2 = reinterpret_cast<uint16_t*>(&c2);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if (s0 + e >= n_sig) { p1[e] = 0; p2[e] = 0; }
-          }
-        }
-      }
-      const uint32_t off = (q == 1) ? (uint32_t)(16 * r) : (uint32_t)(c * L.a_lbo + 16 * r);
-      *reinterpret_cast<uint4*>(sA1 + off) = c1;
-      *reinterpret_cast<uint4*>(sA2 + off) = c2;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < L.n_slots; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), 32);                       // one loader warp fills a slot
+      mbar_init(smem_u32(&bar_empty[i]), ZNS_VQT_ISSUERS);          // every issuer commits once per group
     }
+    for (int t = 0; t < 4; ++t) {
+      mbar_init(smem_u32(&bar_acc_full[t]), 2);                    // two accumulator units (parts) per job
+      mbar_init(smem_u32(&bar_acc_empty[t]), 32 * VQT_EPI_WARPS);
+    }
+    mbar_fence_init();
   }
+  if (warp == VQT_ISSUE_WARP0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  if (threadIdx.x < VQT_ZERO_BYTES / 4) reinterpret_cast<uint32_t*>(sZero)[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < L.b_bytes / 16; i += VQT_LEVEL_THREADS)
+    reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(A.bimg) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const int used_cols = L.fb_b_col + max(32, L.fpr * 24);
+  const int n_my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int sh0 = L.ring_stages[0] == 2 ? 1 : 0, sh1 = L.ring_stages[1] == 2 ? 1 : 0;   // log2(stages)
 
-  // zero the accumulators (every MMA accumulates: the decimator windows overlap)
-  if (warp < 4) {
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c = 0; c < used_cols; c += 16) tmem_zero_32x16(tl + c);
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-
-  if (warp == 0) {
+  if (warp >= VQT_ISSUE_WARP0) {
+    // =================================== MMA issuers: one elected thread each, O(1) bookkeeping ===================================
+    const int isr = warp - VQT_ISSUE_WARP0;
     if (elect_one()) {
-      const uint32_t a_base[2] = {smem_u32(sA1), smem_u32(sA2)};
-      const uint32_t b_base = smem_u32(sB);
+      const uint32_t ring16 = smem_u32(sRing) >> 4, b16 = smem_u32(sB) >> 4, z16 = smem_u32(sZero) >> 4;
+      const uint32_t slot16 = slot_bytes >> 4;
+      const uint64_t hi_norm = (uint64_t)((128u >> 4) | (1u << 14)) << 32, hi_zero = (uint64_t)(1u << 14) << 32;
+      const uint64_t zdesc = hi_zero | z16;
+      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      const uint32_t accf0 = smem_u32(&bar_acc_full[0]), acce0 = smem_u32(&bar_acc_empty[0]);
+      int slot = 0;
+      uint32_t full_par = 0;
+      uint32_t dec_inst0 = 0;
+      long long t_wait_full = 0, t_wait_acc = 0, n_mma_issued = 0;
+      const long long t_begin = clock64();
 #pragma unroll 1
-      for (int i = 0; i < L.n_mma; ++i) {
-        const VqtMma m = L.mma[i];
-        umma_f16(tmem + m.d_col, desc_rows16(a_base[m.term] + m.a_off, (uint32_t)L.a_lbo),
-                 desc_rows16(b_base + m.b_off, 16u * m.b_rows), umma_idesc_f16(128, m.n), 1u);
+      for (int ts = 0; ts < n_my_tiles; ++ts, dec_inst0 += (uint32_t)L.n_pass) {
+#pragma unroll 1
+        for (int pos = 0; pos < L.gpt; ++pos) {
+          const int s_begin = L.seg_begin[isr][pos], s_end = L.seg_begin[isr][pos + 1];
+          if (s_begin < s_end) {
+            const long long t0 = clock64();
+            mbar_wait(full0 + 8 * slot, full_par);
+            t_wait_full += clock64() - t0;
+            tc_fence_after();
+          }
+          const uint32_t a16 = ring16 + (uint32_t)slot * slot16;
+#pragma unroll 1
+          for (int si = s_begin; si < s_end; ++si) {
+            const VqtSeg sg = L.seg[si];
+            // accumulator stage of this job instance: ring slot, its barrier, the parity of its "drained" phase
+            const int type = sg.job ? 1 : 0;
+            const uint32_t inst = type ? dec_inst0 + (uint32_t)(sg.job - 1) : (uint32_t)ts;
+            const int sh = type ? sh1 : sh0;
+            const uint32_t stage = inst & (uint32_t)sh;
+            const uint32_t bidx = (uint32_t)(2 * type) + stage;
+            const uint32_t cb = tmem + stage * (uint32_t)L.ring_width[type];
+            if (sg.flags & 1) {
+              const long long t0 = clock64();
+              mbar_wait(acce0 + 8 * bidx, ((inst >> sh) & 1) ^ 1);
+              t_wait_acc += clock64() - t0;
+              tc_fence_after();
+              // clear this unit's columns: accumulate = 0 with the zero block as both operands
+              const int w0 = type ? L.dec_wp : L.fb_n1, w1 = type ? L.dec_wp : L.fb_n2;
+              const int c_lo = sg.part ? w0 : 0, c_hi = sg.part ? w0 + w1 : w0;
+              for (int c = c_lo; c < c_hi; c += 256)
+                umma_f16(cb + (uint32_t)(L.ring_base[type] + c), zdesc, zdesc, umma_idesc_f16(128, min(256, c_hi - c)), 0u);
+            }
+            const int i_end = sg.begin + sg.count;
+#pragma unroll 4
+            for (int i = sg.begin; i < i_end; ++i) {
+              const VqtMmaPacked m = L.pk[i];
+              umma_f16(cb + m.col, hi_norm | (uint64_t)(m.a_lo + a16), hi_norm | (uint64_t)(m.b_lo + b16), m.idesc, 1u);
+            }
+            n_mma_issued += sg.count;
+            if (sg.flags & 2) umma_commit(accf0 + 8 * bidx);
+          }
+          umma_commit(empty0 + 8 * slot);       // this issuer no longer reads the slot (immediate when it had no MMAs)
+          if (++slot == L.n_slots) { slot = 0; full_par ^= 1; }
+        }
       }
-      umma_commit(smem_u32(&bar));
+      if (A.dbg && blockIdx.x == 0) {
+        long long* d = A.dbg + 4 * isr;
+        d[0] = clock64() - t_begin; d[1] = t_wait_full; d[2] = t_wait_acc; d[3] = n_mma_issued;
+      }
     }
     __syncwarp();
-  }
-  mbar_wait(smem_u32(&bar), 0);
-  tc_fence_after();
-
-  // ---- epilogue: warp -> TMEM lane quadrant (warp & 3), column share (warp >> 2) ----
-  const int quad = warp & 3, half = warp >> 2;
-  const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-  const long long g = (long long)row0 + quad * 32 + lane;      // global row
-  if (L.dec_w > 0) {
-    uint16_t* dh = dst_hi + (size_t)clip * dst_stride;
-    uint16_t* dl = dst_lo + (size_t)clip * dst_stride;
-    const int n_blk = (L.dec_w + 15) / 16;
-    for (int kb = half; kb < n_blk; kb += 2) {
-      uint32_t a[16], b[16];
-      tmem_ld_32x16(tl + L.dec_a_col + 16 * kb, a);
-      tmem_ld_32x16(tl + L.dec_b_col + 16 * kb, b);
-      tmem_ld_wait();
-      const long long t0 = g * L.dec_w + 16 * kb;
-      float yv[16];
+  } else if (warp >= VQT_LOAD_WARPS) {
+    // =================================== epilogue ===================================
+    const int quad = warp & 3, half = (warp - VQT_LOAD_WARPS) >> 2;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    long long t_wait_ep = 0;
+    const long long t_begin_ep = clock64();
+    float isl[12];                                          // 1 / sqrt(L_k) / (coefficient scale) of this octave's bins
 #pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        const float v = (__uint_as_float(a[o]) + __uint_as_float(b[o]) * (1.f / 2048.f)) * L.dec_scale;
-        yv[o] = (t0 + o < n_valid) ? v : 0.f;
-      }
-      uint4 h1a, h2a, h1b, h2b;
-      split8(yv, h1a, h2a);
-      split8(yv + 8, h1b, h2b);
-      if (L.dec_w >= 16) {
-        if (t0 + 16 <= dst_stride) {
-          reinterpret_cast<uint4*>(dh + t0)[0] = h1a; reinterpret_cast<uint4*>(dh + t0)[1] = h1b;
-          reinterpret_cast<uint4*>(dl + t0)[0] = h2a; reinterpret_cast<uint4*>(dl + t0)[1] = h2b;
-        } else if (t0 + 8 <= dst_stride) {
-          reinterpret_cast<uint4*>(dh + t0)[0] = h1a;
-          reinterpret_cast<uint4*>(dl + t0)[0] = h2a;
+    for (int k = 0; k < 12; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + k) * L.fb_scale;
+#pragma unroll 1
+    for (int ts = 0; ts < n_my_tiles; ++ts) {
+      const int tau = (int)blockIdx.x + ts * (int)gridDim.x;
+      const int clip = tau / A.tiles_per_clip;
+      const long long row_first = (long long)(tau - clip * A.tiles_per_clip) * 128;
+      const long long g = row_first + quad * 32 + lane;   // global row
+      // every decimator output of the tile lies inside the signal: no per-element masking (all but the last tile of a clip)
+      const bool tile_valid = (row_first + 128) * L.dec_w <= A.n_valid;
+#pragma unroll 1
+      for (int jj = 0; jj < L.n_jobs; ++jj) {
+        const int job = L.ep_job[jj];
+        const int type = job ? 1 : 0;
+        const uint32_t inst = type ? (uint32_t)(ts * L.n_pass + (job - 1)) : (uint32_t)ts;
+        const int sh = type ? sh1 : sh0;
+        const uint32_t stage = inst & (uint32_t)sh;
+        {
+          const long long t0 = clock64();
+          if (lane == 0) mbar_wait(smem_u32(&bar_acc_full[type * 2 + stage]), (inst >> sh) & 1);
+          __syncwarp();
+          t_wait_ep += clock64() - t0;
         }
-      } else if (t0 + 4 <= dst_stride) {      // dec_w == 4: four outputs per row
-        *reinterpret_cast<uint2*>(dh + t0) = make_uint2(h1a.x, h1a.y);
-        *reinterpret_cast<uint2*>(dl + t0) = make_uint2(h2a.x, h2a.y);
+        tc_fence_after();
+        const uint32_t acc = tl + (uint32_t)(L.ring_base[type] + (int)stage * L.ring_width[type]);
+        if (type == 1) {
+          const int c0 = 64 * (job - 1);
+          const int w = min(64, L.dec_w - c0);
+          uint16_t* dh = A.dst_hi + (size_t)clip * A.dst_stride;
+          uint16_t* dl = A.dst_lo + (size_t)clip * A.dst_stride;
+          const int n_blk = (w + 15) / 16;
+          for (int kb = half; kb < n_blk; kb += 2) {
+            uint32_t a[16], b[16];
+            tmem_ld_32x16(acc + 16 * kb, a);
+            tmem_ld_32x16(acc + L.dec_wp + 16 * kb, b);
+            tmem_ld_wait();
+            const long long t0 = g * L.dec_w + c0 + 16 * kb;
+            float yv[16];
+            const float s_b = L.dec_scale * (1.f / 2048.f);
+#pragma unroll
+            for (int o = 0; o < 16; ++o) yv[o] = fmaf(__uint_as_float(b[o]), s_b, __uint_as_float(a[o]) * L.dec_scale);
+            if (!tile_valid) {
+#pragma unroll
+              for (int o = 0; o < 16; ++o) if (t0 + o >= A.n_valid) yv[o] = 0.f;
+            }
+            uint4 h1a, h2a, h1b, h2b;
+            split8(yv, h1a, h2a);
+            split8(yv + 8, h1b, h2b);
+            if (L.dec_w >= 16) {
+              if (t0 + 16 <= A.dst_stride) {
+                reinterpret_cast<uint4*>(dh + t0)[0] = h1a; reinterpret_cast<uint4*>(dh + t0)[1] = h1b;
+                reinterpret_cast<uint4*>(dl + t0)[0] = h2a; reinterpret_cast<uint4*>(dl + t0)[1] = h2b;
+              } else if (t0 + 8 <= A.dst_stride) {
+                reinterpret_cast<uint4*>(dh + t0)[0] = h1a;
+                reinterpret_cast<uint4*>(dl + t0)[0] = h2a;
+              }
+            } else if (t0 + 4 <= A.dst_stride) {      // dec_w == 4: four outputs per row
+              *reinterpret_cast<uint2*>(dh + t0) = make_uint2(h1a.x, h1a.y);
+              *reinterpret_cast<uint2*>(dl + t0) = make_uint2(h2a.x, h2a.y);
+            }
+          }
+        } else {
+          for (int j = half; j < L.fpr; j += 2) {
+            const long long f = g * L.fpr + j;
+            uint32_t fa[48], fb[24];
+            tmem_ld_32x32(acc + 48 * j, fa);
+            tmem_ld_32x16(acc + 48 * j + 32, fa + 32);
+            tmem_ld_32x16(acc + L.fb_n1 + 24 * j, fb);
+            tmem_ld_32x8(acc + L.fb_n1 + 24 * j + 16, fb + 16);
+            tmem_ld_wait();
+            if (f < A.n_frames) {
+              float* op = A.out + ((size_t)clip * A.n_bins + L.bin0) * A.n_frames + f;
+#pragma unroll
+              for (int k = 0; k < 12; ++k) {
+                const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fa[24 + 2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
+                const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fa[25 + 2 * k]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
+                op[(size_t)k * A.n_frames] = logf(sqrtf(re * re + im * im) * isl[k] + 1e-9f);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_acc_empty[type * 2 + stage]));
       }
     }
-  }
-  for (int j = half; j < L.fpr; j += 2) {
-    const long long f = g * L.fpr + j;
-    uint32_t fa[48], fb[24];
-    tmem_ld_32x32(tl + L.fb_a_col + 48 * j, fa);
-    tmem_ld_32x16(tl + L.fb_a_col + 48 * j + 32, fa + 32);
-    tmem_ld_32x16(tl + L.fb_b_col + 24 * j, fb);
-    tmem_ld_32x8(tl + L.fb_b_col + 24 * j + 16, fb + 16);
-    tmem_ld_wait();
-    if (f < n_frames) {
+    if (A.dbg && blockIdx.x == 0 && (warp == VQT_LOAD_WARPS || warp == VQT_LOAD_WARPS + 4) && lane == 0) {
+      A.dbg[16 + 2 * half] = clock64() - t_begin_ep; A.dbg[17 + 2 * half] = t_wait_ep;
+    }
+  } else {
+    // =================================== loader: warp w owns ring slot w ===================================
+    const int lw = warp;
+    const int n_rows = 128 + L.hb + L.ha;
+    const int n_chunks = n_rows * L.pg;
+    const int n_groups = n_my_tiles * L.gpt;
+    if (lw < L.n_slots) {
+      const uint32_t s1 = smem_u32(sRing) + (uint32_t)lw * slot_bytes;
+      const uint32_t s2 = s1 + (uint32_t)L.slot_term_bytes;
+      const uint32_t bfull = smem_u32(&bar_full[lw]), bempty = smem_u32(&bar_empty[lw]);
+      uint32_t par = 1;                           // first use of a slot passes immediately
+      long long t_wait_ld = 0;
+      const long long t_begin_ld = clock64();
+#pragma unroll 1
+      for (int gi = lw; gi < n_groups; gi += L.n_slots, par ^= 1) {
+        const int ts = gi / L.gpt, pos = gi - ts * L.gpt;
+        const int tau = (int)blockIdx.x + ts * (int)gridDim.x;
+        const int clip = tau / A.tiles_per_clip;
+        const long long row0 = (long long)(tau - clip * A.tiles_per_clip) * 128;
+        const float* yb = SRC_F32 ? A.y32 + (size_t)clip * A.src_stride : nullptr;
+        const uint16_t* hsrc = SRC_F32 ? nullptr : A.src_hi + (size_t)clip * A.src_stride;
+        const uint16_t* lsrc = SRC_F32 ? nullptr : A.src_lo + (size_t)clip * A.src_stride;
+        const bool vec_ok = SRC_F32 ? ((reinterpret_cast<uintptr_t>(yb) & 15) == 0) : true;
+        const int plane0 = L.g_order[pos] * L.pg;
+        const long long base_s = (row0 - L.hb) * R + 8LL * plane0;     // sample of chunk (row 0, plane 0 of the group)
+        {
+          const long long t0 = clock64();
+          if (lane == 0) mbar_wait(bempty, par);
+          __syncwarp();
+          t_wait_ld += clock64() - t0;
+        }
+        if (vec_ok) {
+          // phase 1: asynchronous 16-byte copies, every chunk of the group in flight at once (one DRAM latency per group).
+          // fp32 source: the chunk's two 16-byte halves are parked where its x1 / x2 chunks will live.
+#pragma unroll 2
+          for (int i = lane; i < n_chunks; i += 32) {
+            const int r = (L.pg == 4) ? (i >> 2) : i, c = (L.pg == 4) ? (i & 3) : 0;
+            const long long s0 = base_s + (long long)r * R + 8 * c;
+            const uint32_t off = (uint32_t)(c * L.a_lbo + 16 * r);
+            const long long left = (long long)A.n_sig - s0;              // samples of this chunk inside the signal
+            const bool in = s0 >= 0 && left > 0;
+            if (SRC_F32) {
+              const int n1 = in ? (int)min(4LL, left) * 4 : 0, n2 = in ? (int)max(0LL, min(4LL, left - 4)) * 4 : 0;
+              const float* src = yb + (in ? s0 : 0);
+              cp_async16(s1 + off, src, n1);
+              cp_async16(s2 + off, src + 4, n2);
+            } else {
+              const int nb = in ? 16 : 0;                                 // the buffers hold zeros beyond n_sig
+              cp_async16(s1 + off, hsrc + (in ? s0 : 0), nb);
+              cp_async16(s2 + off, lsrc + (in ? s0 : 0), nb);
+            }
+          }
+          cp_async_wait_all();
+          if (SRC_F32) {
+            // phase 2: in place, every lane converts the chunks it fetched itself
+#pragma unroll 2
+            for (int i = lane; i < n_chunks; i += 32) {
+              const int r = (L.pg == 4) ? (i >> 2) : i, c = (L.pg == 4) ? (i & 3) : 0;
+              const uint32_t off = (uint32_t)(c * L.a_lbo + 16 * r);
+              const uint4 ra = lds128(s1 + off), rb = lds128(s2 + off);
+              const float v[8] = {__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z), __uint_as_float(ra.w),
+                                  __uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), __uint_as_float(rb.w)};
+              uint4 c1, c2;
+              split8(v, c1, c2);
+              sts128(s1 + off, c1);
+              sts128(s2 + off, c2);
+            }
+          }
+        } else {
+          // unaligned fp32 clips (n_samples not a multiple of 4): element-wise loads
+          for (int i = lane; i < n_chunks; i += 32) {
+            const int r = (L.pg == 4) ? (i >> 2) : i, c = (L.pg == 4) ? (i & 3) : 0;
+            const long long s0 = base_s + (long long)r * R + 8 * c;
+            float v[8];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fa[24 + 2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
-        const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fa[25 + 2 * k]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-        const int bin = L.bin0 + k;
-        out[((size_t)clip * n_bins + bin) * n_frames + f] =
-            logf(sqrtf(re * re + im * im) * (__ldg(inv_sqrt_len + bin) * L.fb_scale) + 1e-9f);
+            for (int e = 0; e < 8; ++e) v[e] = (s0 + e >= 0 && s0 + e < A.n_sig) ? __ldg(yb + s0 + e) : 0.f;
+            uint4 c1, c2;
+            split8(v, c1, c2);
+            const uint32_t off = (uint32_t)(c * L.a_lbo + 16 * r);
+            sts128(s1 + off, c1);
+            sts128(s2 + off, c2);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bfull);
       }
+      if (A.dbg && blockIdx.x == 0 && lw == 0 && lane == 0) { A.dbg[20] = clock64() - t_begin_ld; A.dbg[21] = t_wait_ld; }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, (uint32_t)L.tmem_cols); }
+  if (warp == VQT_ISSUE_WARP0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ---- frames whose window crosses a clip edge: reflect padding, direct fp32 evaluation -------------
 struct VqtEdgeParams {
   int n_oct, bpo, n_bins, n_frames;
   int n_fft[ZNS_VQT_MAX_OCT], hop[ZNS_VQT_MAX_OCT], n_sig[ZNS_VQT_MAX_OCT];
+  int item0[ZNS_VQT_MAX_OCT + 1];          // first (frame, filter) item of each octave
+  int n_left[ZNS_VQT_MAX_OCT], t_right[ZNS_VQT_MAX_OCT];
   long long stride[ZNS_VQT_MAX_OCT];
   const float* coef[ZNS_VQT_MAX_OCT];      // [n][2][bpo/2][2]
   const uint16_t* hi[ZNS_VQT_MAX_OCT];
   const uint16_t* lo[ZNS_VQT_MAX_OCT];
-  float scale[ZNS_VQT_MAX_OCT];
 };
 
-__device__ __forceinline__ int reflect_idx(long long qq, int n) {
+__device__ __forceinline__ int reflect_idx32(int qq, int n) {
   if (n == 1) return 0;
-  const long long period = 2LL * (n - 1);
+  const int period = 2 * (n - 1);
   qq %= period;
   if (qq < 0) qq += period;
-  return (int)(qq < n ? qq : period - qq);
+  return qq < n ? qq : period - qq;
 }
 
-__global__ void __launch_bounds__(192)
+// one warp per (edge frame, filter): lanes stride over the taps
+__global__ void __launch_bounds__(256)
 vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict__ y32, long long y_stride,
                 const float* __restrict__ inv_sqrt_len, float* __restrict__ out) {
-  const int oct = blockIdx.x, clip = blockIdx.z;
+  const int clip = blockIdx.z;
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (item >= P.item0[P.n_oct]) return;
+  int oct = 0;
+  while (item >= P.item0[oct + 1]) ++oct;
+  const int w = item - P.item0[oct];
+  const int e = w / P.bpo, k = w - e * P.bpo;
   const int nf = P.n_fft[oct], hop = P.hop[oct], n = P.n_sig[oct], F = P.n_frames;
-  // left: frames t with t*hop < nf/2 ; right: frames with t*hop + nf/2 > n
-  const int n_left = min(F, (nf / 2 + hop - 1) / hop);
-  int t_right = (n >= nf / 2) ? (n - nf / 2) / hop + 1 : 0;
-  t_right = max(t_right, n_left);
-  const int n_edge = n_left + max(0, F - t_right);
-  const int hb = P.bpo / 2;
-  for (int w = threadIdx.x; w < n_edge * P.bpo; w += blockDim.x) {
-    const int e = w / P.bpo, k = w - e * P.bpo;
-    const int t = e < n_left ? e : t_right + (e - n_left);
-    float re = 0.f, im = 0.f;
-    const float* cf = P.coef[oct] + ((size_t)(k / hb) * hb + k % hb) * 2;
-    for (int i = 0; i < nf; ++i) {
-      const int idx = reflect_idx((long long)t * hop + i - nf / 2, n);
-      float s;
-      if (oct == 0) s = __ldg(y32 + (size_t)clip * y_stride + idx);
-      else {
-        const size_t o = (size_t)clip * P.stride[oct] + idx;
-        s = __half2float(__ushort_as_half(P.hi[oct][o])) + __half2float(__ushort_as_half(P.lo[oct][o])) * (1.f / 2048.f);
-      }
-      const float* cn = cf + (size_t)i * P.bpo * 2;
-      re = fmaf(cn[0], s, re);
-      im = fmaf(cn[1], s, im);
+  const int t = e < P.n_left[oct] ? e : P.t_right[oct] + (e - P.n_left[oct]);
+  float re = 0.f, im = 0.f;
+  const float* cf = P.coef[oct] + (size_t)k * 2;
+  for (int i = lane; i < nf; i += 32) {
+    const int idx = reflect_idx32(t * hop + i - nf / 2, n);
+    float s;
+    if (oct == 0) s = __ldg(y32 + (size_t)clip * y_stride + idx);
+    else {
+      const size_t o = (size_t)clip * P.stride[oct] + idx;
+      s = __half2float(__ushort_as_half(P.hi[oct][o])) + __half2float(__ushort_as_half(P.lo[oct][o])) * (1.f / 2048.f);
     }
+    const float* cn = cf + (size_t)i * P.bpo * 2;
+    re = fmaf(__ldg(cn), s, re);
+    im = fmaf(__ldg(cn + 1), s, im);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) {
     const int bin = P.n_bins - P.bpo * (oct + 1) + k;
     out[((size_t)clip * P.n_bins + bin) * F + t] = logf(sqrtf(re * re + im * im) * __ldg(inv_sqrt_len + bin) + 1e-9f);
   }
@@ -484,17 +753,35 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // host: forward
 // ---------------------------------------------------------------------------------------------
+static long long* g_vqt_dbg = nullptr;
+// Diagnostic: device buffer of 32 int64 per level that CTA 0 of every level kernel fills with cycle counters:
+// [4 i + 0..3] issuer i: total, waiting for operands, waiting for an accumulator stage, MMAs issued;
+// [16],[17] epilogue (first half) total / waiting, [18],[19] second half, [20],[21] loader warp 0 total / waiting for its slot
+extern "C" int zns_dbg_vqt_timing(long long* buf) { g_vqt_dbg = buf; return ZNS_OK; }
+
 int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int n_frames = zns_vqt_num_frames(n_samples, p->hop);
   static bool attr_set[64] = {};
+  static int n_sm[64] = {};
   int dev = 0;
   ZNS_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
+  ZNS_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
+  if (n_samples < p->umma_last_n) {
+    // a shorter signal than last time: the level buffers must read as zero beyond its end
+    for (int i = 1; i < p->n_oct; ++i) {
+      const size_t bytes = (size_t)p->max_batch * p->sig_stride[i] * sizeof(uint16_t);
+      ZNS_CHECK_CUDA(cudaMemsetAsync(p->d_hi[i], 0, bytes, st));
+      ZNS_CHECK_CUDA(cudaMemsetAsync(p->d_lo[i], 0, bytes, st));
+    }
+  }
+  p->umma_last_n = n_samples;
   VqtEdgeParams E;
   memset(&E, 0, sizeof(E));
   E.n_oct = p->n_oct; E.bpo = p->bpo; E.n_bins = p->n_bins; E.n_frames = n_frames;
@@ -502,28 +789,46 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
   for (int i = 0; i < p->n_oct; ++i) {
     const VqtLevelDev& L = p->level[i];
     const int R = 8 * L.q;
-    const int n_valid = n_cur / 2, n_next = (n_cur + 1) / 2;
+    const int n_next = (n_cur + 1) / 2;
     int rows = (n_frames + L.fpr - 1) / L.fpr;
     if (L.dec_w > 0) rows = std::max(rows, (n_cur + R - 1) / R);
-    dim3 grid((rows + 127) / 128, 1, batch);
-    const size_t smem = level_smem(L);
     const bool last = (i == p->n_oct - 1);
-    if (i == 0)
-      vqt_level_kernel<true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(
-          L, y, nullptr, nullptr, n_cur, (long long)n_samples, p->d_bimg[i], p->d_inv_sqrt_len, out, n_frames, p->n_bins,
-          last ? nullptr : p->d_hi[i + 1], last ? nullptr : p->d_lo[i + 1], n_valid, last ? 0 : p->sig_stride[i + 1]);
-    else
-      vqt_level_kernel<false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(
-          L, nullptr, p->d_hi[i], p->d_lo[i], n_cur, p->sig_stride[i], p->d_bimg[i], p->d_inv_sqrt_len, out, n_frames,
-          p->n_bins, last ? nullptr : p->d_hi[i + 1], last ? nullptr : p->d_lo[i + 1], n_valid,
-          last ? 0 : p->sig_stride[i + 1]);
+    VqtLevelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.y32 = (i == 0) ? y : nullptr;
+    a.src_hi = p->d_hi[i]; a.src_lo = p->d_lo[i];
+    a.n_sig = n_cur;
+    a.src_stride = (i == 0) ? (long long)n_samples : p->sig_stride[i];
+    a.bimg = p->d_bimg[i];
+    a.inv_sqrt_len = p->d_inv_sqrt_len;
+    a.out = out; a.n_frames = n_frames; a.n_bins = p->n_bins;
+    a.dst_hi = last ? nullptr : p->d_hi[i + 1];
+    a.dst_lo = last ? nullptr : p->d_lo[i + 1];
+    a.n_valid = n_cur / 2;
+    a.dst_stride = last ? 0 : p->sig_stride[i + 1];
+    a.tiles_per_clip = (rows + 127) / 128;
+    a.n_tiles = a.tiles_per_clip * batch;
+    a.dbg = g_vqt_dbg ? g_vqt_dbg + 32 * i : nullptr;
+    const int grid = std::min(a.n_tiles, n_sm[dev]);
+    const size_t smem = level_smem(L);
+    if (i == 0) vqt_level_kernel<true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
+    else vqt_level_kernel<false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
     ZNS_CHECK_LAUNCH();
+    // edge frames: left t*hop < nf/2 ; right t*hop + nf/2 > n
+    const int nl = std::min(n_frames, (L.n_fft / 2 + L.hop - 1) / L.hop);
+    int tr = (n_cur >= L.n_fft / 2) ? (n_cur - L.n_fft / 2) / L.hop + 1 : 0;
+    tr = std::max(tr, nl);
     E.n_fft[i] = L.n_fft; E.hop[i] = L.hop; E.n_sig[i] = n_cur; E.stride[i] = p->sig_stride[i];
     E.coef[i] = p->d_coef[i]; E.hi[i] = p->d_hi[i]; E.lo[i] = p->d_lo[i];
+    E.n_left[i] = nl; E.t_right[i] = tr;
+    E.item0[i + 1] = E.item0[i] + (nl + std::max(0, n_frames - tr)) * p->bpo;
     n_cur = n_next;
   }
-  vqt_edge_kernel<<<dim3(p->n_oct, 1, batch), 192, 0, st>>>(E, y, (long long)n_samples, p->d_inv_sqrt_len, out);
-  ZNS_CHECK_LAUNCH();
+  const int n_items = E.item0[p->n_oct];
+  if (n_items > 0) {
+    vqt_edge_kernel<<<dim3((n_items + 7) / 8, 1, batch), 256, 0, st>>>(E, y, (long long)n_samples, p->d_inv_sqrt_len, out);
+    ZNS_CHECK_LAUNCH();
+  }
   return ZNS_OK;
 }
 

@@ -33,7 +33,7 @@ class _EngineCache:
         self._engines: Dict[Tuple[int, int, int], EncoderEngine] = {}
 
     def get(self, batch: int, T: int, n_br: int, device) -> EncoderEngine:
-        key = (batch, T, n_br)
+        key = (batch, T, n_br, device.index if device.index is not None else torch.cuda.current_device())
         eng = self._engines.get(key)
         if eng is None:
             if len(self._engines) >= 4:   # bounded: variable-length inference would otherwise pile up workspaces
@@ -109,6 +109,10 @@ class _EncoderFunction(torch.autograd.Function):
         else:
             eng = cache.get(B, T, n_br, xs[0].device)
         eng.pack_weights(params, need_dgrad=True)
+        if train and dropout_p > 0:
+            # the keep masks are hash(element, seed ^ step counter, layer): a new counter value per training forward
+            # gives a fresh mask (reference: nn.Dropout draws from the global generator, models.py:30)
+            L.check(L.lib().zns_counter_add(L.ptr(eng.step_ctr), 1, L.current_stream()))
         if plan is not None:
             embs = eng.forward(xs, plan[1], params, train=train, dropout_p=dropout_p, x_row_stride=T)
             out = tuple(_unfold(e, plan, T) for e in embs)

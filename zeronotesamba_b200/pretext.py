@@ -134,7 +134,9 @@ class PretextTrainer:
             self.grads[br][names[n]] = gseg
         if self.distributed:
             dist_utils.broadcast_parameters(self.flat_p, 0)   # replicas start from rank 0's weights
-        self.engine = EncoderEngine(self.B, self.T, 2, dev, seed=seed)
+        # every data-parallel rank draws its own dropout masks
+        rank = torch.distributed.get_rank() if self.distributed else 0
+        self.engine = EncoderEngine(self.B, self.T, 2, dev, seed=(int(seed) + 0x9E3779B1 * rank) & 0xFFFFFFFF)
         self.engine._ensure_grad_ws()
         self.batch_buf = torch.zeros(self.B, 2, 96, self.T, device=dev)
         self.result = torch.zeros(3, device=dev)

@@ -73,3 +73,17 @@ def stem_batch(first_clip: int, count: int, seconds: float = 10.0, seed: int = 1
     """``(drums[count, N], other[count, N])`` for clips ``first_clip .. first_clip + count - 1``."""
     pairs = [stem_pair(first_clip + i, seconds, seed) for i in range(count)]
     return np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+
+
+def cfg2_batch(device, n_clips: int = 256, seconds: float = 30.0, n_base: int = 8):
+    """BASELINE.json configs[1] input: ``n_clips`` distinct ``seconds``-long 16 kHz clips as a CUDA fp32 tensor.
+
+    ``n_base`` synthetic stems (drums / other alternating) are tiled and made distinct by seeded -80 dBFS device noise
+    (torch.Generator(device).manual_seed(1234)), so bench.py and the parity test see the same batch."""
+    import torch
+    base = np.stack([stem_pair(i, seconds)[i % 2] for i in range(n_base)])
+    y = torch.from_numpy(base).to(device).repeat((n_clips + n_base - 1) // n_base, 1)[:n_clips].contiguous()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234)
+    y += 1e-4 * torch.randn(y.shape, device=device, generator=gen)
+    return y
