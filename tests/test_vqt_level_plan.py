@@ -20,21 +20,25 @@ MAX_MMA = 120
 
 class VqtMma(C.Structure):
     _fields_ = [("a_off", C.c_uint32), ("b_off", C.c_uint32), ("n", C.c_uint16), ("d_col", C.c_uint16),
-                ("term", C.c_uint8), ("job", C.c_uint8), ("flags", C.c_uint8), ("b_rows8", C.c_uint8)]
+                ("term", C.c_uint8), ("job", C.c_uint8), ("part", C.c_uint8), ("b_rows8", C.c_uint8)]
 
 
 class VqtSeg(C.Structure):
-    _fields_ = [("begin", C.c_uint16), ("count", C.c_uint16), ("job", C.c_uint8), ("flags", C.c_uint8), ("pad", C.c_uint8 * 2)]
+    _fields_ = [("begin", C.c_uint16), ("count", C.c_uint16), ("job", C.c_uint8), ("part", C.c_uint8), ("flags", C.c_uint8),
+                ("pad", C.c_uint8)]
+
+
+N_ISSUERS = 4
 
 
 class VqtLevel(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("q", "hb", "ha", "rtot", "a_lbo", "fpr", "hop", "n_fft", "bin0", "dec_w", "dec_wp",
                                        "n_pass", "fb_n1", "fb_n2", "pg", "gpt", "n_slots", "slot_term_bytes")] + \
-               [("g_order", C.c_int * 8), ("g_mma_begin", C.c_int * 9), ("ring_base", C.c_int * 2),
-                ("ring_width", C.c_int * 2), ("ring_stages", C.c_int * 2), ("n_jobs", C.c_int), ("ep_job", C.c_int * 3),
-                ("n_mma", C.c_int), ("b_bytes", C.c_int), ("dec_scale", C.c_float), ("fb_scale", C.c_float),
-                ("mma", VqtMma * MAX_MMA), ("pk", C.c_uint32 * (4 * MAX_MMA)), ("g_seg_begin", C.c_int * 9),
-                ("seg", VqtSeg * 24)]
+               [("g_order", C.c_int * 8), ("ring_base", C.c_int * 2), ("ring_width", C.c_int * 2), ("ring_stages", C.c_int * 2),
+                ("n_jobs", C.c_int), ("ep_job", C.c_int * 3), ("n_mma", C.c_int), ("b_bytes", C.c_int),
+                ("dec_scale", C.c_float), ("fb_scale", C.c_float), ("n_seg", C.c_int),
+                ("seg_begin", (C.c_int * 9) * N_ISSUERS), ("seg", VqtSeg * 64), ("mma", VqtMma * MAX_MMA),
+                ("pk", C.c_uint32 * (4 * MAX_MMA))]
 
 
 def level_plan(level, mode="vqt"):
@@ -79,39 +83,44 @@ def replay(lv, bimg, sig, row0):
     D = np.full((128, 512), np.nan)            # garbage until a clearing MMA has run
     r = np.arange(128)[:, None]
     k = np.arange(16)[None, :]
-    seen_first, seen_last, covered = set(), set(), set()
-    for pos in range(lv.gpt):
-        g = lv.g_order[pos]
-        for si in range(lv.g_seg_begin[pos], lv.g_seg_begin[pos + 1]):
-            sg = lv.seg[si]
-            base = acc_base(lv, sg.job)
-            if sg.flags & 1:                   # the issuer waits for the stage, then clears the job's whole ring width
-                assert sg.job not in seen_first
-                seen_first.add(sg.job)
-                D[:, base:base + lv.ring_width[1 if sg.job else 0]] = 0.0
-            assert sg.job in seen_first and sg.job not in seen_last
-            for i in range(sg.begin, sg.begin + sg.count):
-                m = lv.mma[i]
-                assert m.job == sg.job and m.term in (0, 1) and i not in covered
-                assert lv.g_mma_begin[pos] <= i < lv.g_mma_begin[pos + 1]
-                covered.add(i)
-                # the packed entry the issuer reads must describe the same MMA
-                a_lo, b_lo, idesc, col = (lv.pk[4 * i + j] for j in range(4))
-                assert a_lo == ((m.a_off + m.term * lv.slot_term_bytes) >> 4) | ((lv.a_lbo >> 4) << 16)
-                assert b_lo == (m.b_off >> 4) | (((128 * m.b_rows8) >> 4) << 16)
-                assert idesc == (1 << 4) | ((m.n >> 3) << 17) | (8 << 24)
-                assert col == lv.ring_base[1 if m.job else 0] + m.d_col
-                c0 = base + m.d_col
-                a_idx = (m.a_off + (k // 8) * lv.a_lbo + 16 * r) // 2 + (k % 8)
-                A = slots[g][m.term][a_idx].astype(np.float64)
-                n = np.arange(m.n)[:, None]
-                b_idx = (m.b_off + (k // 8) * 128 * m.b_rows8 + 16 * n) // 2 + (k % 8)
-                B = bimg[b_idx].astype(np.float64)
-                D[:, c0:c0 + m.n] += A @ B.T
-            if sg.flags & 2:
-                seen_last.add(sg.job)
-    assert covered == {i for i in range(lv.n_mma) if lv.mma[i].term != 2}
-    assert seen_first == seen_last == set(range(lv.n_jobs))
+    started, finished, covered = set(), set(), set()
+    # the four issuers run concurrently; their accumulator units are disjoint, so any interleaving gives the same result
+    for isr in range(N_ISSUERS):
+        for pos in range(lv.gpt):
+            g = lv.g_order[pos]
+            for si in range(lv.seg_begin[isr][pos], lv.seg_begin[isr][pos + 1]):
+                sg = lv.seg[si]
+                unit = (sg.job, sg.part)
+                base = acc_base(lv, sg.job)
+                w0, w1 = (lv.dec_wp, lv.dec_wp) if sg.job else (lv.fb_n1, lv.fb_n2)
+                lo, hi = (w0, w0 + w1) if sg.part else (0, w0)
+                if sg.flags & 1:               # the issuer waits for the stage, then clears the unit's columns
+                    assert unit not in started
+                    started.add(unit)
+                    D[:, base + lo:base + hi] = 0.0
+                assert unit in started and unit not in finished
+                for i in range(sg.begin, sg.begin + sg.count):
+                    m = lv.mma[i]
+                    assert (m.job, m.part) == unit and m.term in (0, 1) and i not in covered
+                    assert lo <= m.d_col and m.d_col + m.n <= hi     # an issuer only touches its own unit's columns
+                    covered.add(i)
+                    # the packed entry the issuer reads must describe the same MMA
+                    a_lo, b_lo, idesc, col = (lv.pk[4 * i + j] for j in range(4))
+                    assert a_lo == ((m.a_off + m.term * lv.slot_term_bytes) >> 4) | ((lv.a_lbo >> 4) << 16)
+                    assert b_lo == (m.b_off >> 4) | (((128 * m.b_rows8) >> 4) << 16)
+                    assert idesc == (1 << 4) | ((m.n >> 3) << 17) | (8 << 24)
+                    assert col == lv.ring_base[1 if m.job else 0] + m.d_col
+                    c0 = base + m.d_col
+                    a_idx = (m.a_off + (k // 8) * lv.a_lbo + 16 * r) // 2 + (k % 8)
+                    A = slots[g][m.term][a_idx].astype(np.float64)
+                    n = np.arange(m.n)[:, None]
+                    b_idx = (m.b_off + (k // 8) * 128 * m.b_rows8 + 16 * n) // 2 + (k % 8)
+                    B = bimg[b_idx].astype(np.float64)
+                    D[:, c0:c0 + m.n] += A @ B.T
+                if sg.flags & 2:
+                    finished.add(unit)
+    assert covered == set(range(lv.n_mma))
+    assert started == finished == {(j, p) for j in range(lv.n_jobs) for p in (0, 1)}   # two commits per job
     assert sorted(lv.ep_job[: lv.n_jobs]) == list(range(lv.n_jobs))
     return D
 
@@ -178,7 +187,7 @@ def test_level_geometry_table():
     for level, (q, fpr) in rows.items():
         lv, _ = level_plan(level)
         assert (lv.q, lv.fpr) == (q, fpr)
-        assert lv.n_mma <= MAX_MMA and lv.q == lv.pg * lv.gpt and lv.n_slots % lv.gpt == 0
+        assert lv.n_mma <= MAX_MMA and lv.n_seg <= 64 and lv.q == lv.pg * lv.gpt and lv.n_slots % lv.gpt == 0
         assert lv.ring_base[0] + lv.ring_stages[0] * lv.ring_width[0] <= 512
         assert lv.n_slots * 2 * lv.slot_term_bytes + lv.b_bytes + 256 < 220 * 1024
 

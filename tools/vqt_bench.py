@@ -15,7 +15,7 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 timing = len(sys.argv) > 2 and sys.argv[2] == "--timing"
 if timing:
     from zeronotesamba_b200 import _lib as L
-    dbg = torch.zeros(8, 16, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(8 * 32 + 64, dtype=torch.int64, device="cuda")
     L.check(L.lib().zns_dbg_vqt_timing(L.ptr(dbg)))
 for _ in range(2):
     plan.forward(y, out=out)
@@ -30,8 +30,11 @@ ms = e0.elapsed_time(e1) / reps
 print(f"cfg2 VQT: {ms:.3f} ms  ({B*30/(ms*1e-3):.3e} audio-s/s, {B*(4*N+4*96*1876)/(ms*1e-3)/1e9:.1f} GB/s algorithmic)")
 
 if timing:
-    d = dbg.cpu().numpy()
-    print("level: issuer total / wait operands / wait accumulator  [tiles] | epilogue A total / wait | epilogue B total / wait | loader total / wait slot   (cycles, CTA 0)")
+    d = dbg.cpu().numpy()[:256].reshape(8, 32)
+    print('L0 loader 0 timestamps (loop top, after wait, issue start, issue end, wait_all end, convert end, fence end, arrive end):')
+    print(dbg.cpu().numpy()[256:304].reshape(6, 8))
+    print("per level (cycles, CTA 0): issuers [total / wait operands / wait accumulator / MMAs] x4 | epilogue A total/wait | B total/wait | loader 0 total/wait slot")
     for lv in range(8):
         r = d[lv]
-        print(f"  L{lv}: {r[0]:9d} {r[1]:9d} {r[2]:9d} [{r[3]}] | {r[4]:9d} {r[5]:9d} | {r[6]:9d} {r[7]:9d} | {r[8]:9d} {r[9]:9d}  || in umma {r[10]} in commit {r[11]} mmas {r[12]}")
+        iss = "  ".join(f"{r[4*i]}/{r[4*i+1]}/{r[4*i+2]}/{r[4*i+3]}" for i in range(4))
+        print(f"  L{lv}: {iss} | {r[16]}/{r[17]} | {r[18]}/{r[19]} | {r[20]}/{r[21]} (issue {r[22]} wait_all {r[23]} convert {r[24]} fence {r[25]} arrive {r[26]})")

@@ -98,6 +98,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Waiting without burning issue slots or instruction cache: poll once, then back off with nanosleep (20 -> 80 ns), which
+// really parks the warp (a try_wait loop re-issues a dozen instructions every few tens of clocks; with ~20 waiting warps per
+// SM that was 60 % of all issued instructions of the VQT level kernels).  Deliberately NOT inlined and not unrolled: the
+// persistent warp-specialised kernels run three instruction streams per scheduler, and code size is what keeps them out
+// of instruction-fetch stalls.
+static __device__ __noinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t ns = 20;
+#pragma unroll 1
+  for (int it = 0; it < 20000000; ++it) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if (ns < 80) ns *= 2;
+  }
+  printf("libzns_sm100: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+
 // ---- TMA (cp.async.bulk.tensor) ---------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -94,7 +94,8 @@ struct zns_vqt_plan {
   uint16_t* d_bimg[ZNS_VQT_MAX_OCT];
   uint16_t* d_hi[ZNS_VQT_MAX_OCT];  // level >= 1 signal, leading fp16 term  [max_batch][stride]
   uint16_t* d_lo[ZNS_VQT_MAX_OCT];  // residual * 2048
-  long long sig_stride[ZNS_VQT_MAX_OCT];
+  long long sig_stride[ZNS_VQT_MAX_OCT];   // halfwords per clip of a level buffer (tiled layout incl. the two zero pad tiles)
+  long long sig_cap[ZNS_VQT_MAX_OCT];      // samples per clip a level buffer holds
   int umma_last_n;                 // n_samples of the previous forward (a shorter signal needs the buffer tails cleared)
 };
 

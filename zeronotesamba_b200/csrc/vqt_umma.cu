@@ -87,7 +87,7 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   L.dec_wp = last ? 0 : ((std::min(L.dec_w, 64) + 15) / 16) * 16;
   L.dec_scale = (float)(sqrt(2.0) / DEC_TAP_SCALE);
   L.fb_scale = p->coef_inv_scale[lvl];
-  L.pg = (q == 1) ? 1 : 4;
+  L.pg = (q == 1) ? 1 : (q >= 8 ? 8 : 4);     // bigger groups = fewer pipeline hand-offs per tile
   L.gpt = q / L.pg;
   if (L.gpt > ZNS_VQT_MAX_GROUPS) return 1;
 
@@ -286,9 +286,8 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   const size_t slot = 2 * (size_t)L.slot_term_bytes;
   const size_t budget = 200 * 1024 - (size_t)L.b_bytes - VQT_ZERO_BYTES;
   int n_slots = (int)(budget / slot);
-  n_slots = std::min(n_slots, 8);
-  n_slots = (n_slots / L.gpt) * L.gpt;      // whole tiles
-  if (n_slots < L.gpt) return 1;
+  n_slots = n_slots >= 8 ? 8 : (n_slots >= 4 ? 4 : (n_slots >= 2 ? 2 : n_slots));     // 8 loader warps share the slots evenly
+  if (n_slots < L.gpt || n_slots % L.gpt != 0) return 1;                            // whole tiles
   L.n_slots = n_slots;
   return 0;
 }
@@ -318,12 +317,18 @@ int vqt_umma_build(zns_vqt_plan* p, double fmin, double gamma_in) {
     }
   }
   size_t n = (size_t)p->max_samples;
+  const size_t f_max = 1 + (size_t)p->max_samples / p->hop;
   for (int i = 0; i < p->n_oct; ++i) {
     ZNS_CHECK_CUDA(cudaMalloc(&p->d_bimg[i], p->level[i].b_bytes));
     ZNS_CHECK_CUDA(cudaMemcpy(p->d_bimg[i], p->h_bimg[i]->data(), p->level[i].b_bytes, cudaMemcpyHostToDevice));
     if (i > 0) {
       n = (n + 1) / 2;
-      p->sig_stride[i] = (long long)((n + 63) / 64) * 64;
+      const VqtLevelDev& L = p->level[i];
+      const size_t R = 8 * (size_t)L.q;
+      const size_t rows = std::max((f_max + L.fpr - 1) / L.fpr, (n + R - 1) / R);
+      const size_t tiles = (rows + 127) / 128;
+      p->sig_cap[i] = (long long)(tiles * 128 * R);
+      p->sig_stride[i] = (long long)((tiles + 2) * L.q * 1024);       // one zero pad tile before and after
       const size_t bytes = (size_t)p->max_batch * p->sig_stride[i] * sizeof(uint16_t);
       ZNS_CHECK_CUDA(cudaMalloc(&p->d_hi[i], bytes));
       ZNS_CHECK_CUDA(cudaMalloc(&p->d_lo[i], bytes));
@@ -360,6 +365,36 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Global layout of a level signal (levels >= 1; written by the previous level's epilogue, read by this level's
+// loader as a handful of bulk copies per plane group).  q >= 4 ("tiled"): the 16-byte chunk c of row r of tile t lives at
+//   (((t + 1) q + c) 128 + r) chunks   -- i.e. per tile the shared-memory plane order; tile -1 and the tile after the
+// last one are zero padding, so halo rows never need a special case.  q == 1: linear, one 1024-sample zero pad in front.
+__host__ __device__ __forceinline__ long long level_index(long long p, int q) {
+  if (q == 1) return 1024 + p;
+  const int R = 8 * q;
+  const long long row = p / R;
+  const int c = (int)(p - row * R) >> 3, e = (int)(p & 7);
+  const long long t = row >> 7;
+  const int r = (int)(row & 127);
+  return (((t + 1) * q + c) * 128 + r) * 8 + e;
+}
+
+// the same for a power-of-two row length 8 q = 1 << shift (device epilogue: no 64-bit division)
+__device__ __forceinline__ long long level_index_pow2(long long p, int q, int shift) {
+  if (q == 1) return 1024 + p;
+  const long long row = p >> shift;
+  const int c = (int)(p & ((1 << shift) - 1)) >> 3, e = (int)(p & 7);
+  const long long t = row >> 7;
+  const int r = (int)(row & 127);
+  return (((t + 1) * q + c) * 128 + r) * 8 + e;
+}
+
+// bulk asynchronous copy global -> shared (TMA, no tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // x = x1 + x2 / 2048 for eight values -> two 16-byte chunks
 __device__ __forceinline__ void split8(const float* v, uint4& c1, uint4& c2) {
   uint32_t a[4], b[4];
@@ -375,16 +410,17 @@ __device__ __forceinline__ void split8(const float* v, uint4& c1, uint4& c2) {
   c2 = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
-// Warp roles of the persistent level kernel: loaders = warps 0..7, epilogue = warps 8..15, MMA issuers = warps 16..19
-// (one per scheduler sub-partition).
+// Warp roles of the persistent level kernel: epilogue = warps 0..7, MMA issuers = warps 8..11 (one per scheduler
+// sub-partition), loaders = warps 12..19.
 #define VQT_EPI_WARPS 8
 #define VQT_LOAD_WARPS 8
-#define VQT_ISSUE_WARP0 (VQT_LOAD_WARPS + VQT_EPI_WARPS)
-#define VQT_LEVEL_THREADS (32 * (VQT_ISSUE_WARP0 + ZNS_VQT_ISSUERS))
+#define VQT_ISSUE_WARP0 VQT_EPI_WARPS
+#define VQT_LOAD_WARP0 (VQT_EPI_WARPS + ZNS_VQT_ISSUERS)
+#define VQT_LEVEL_THREADS (32 * (VQT_LOAD_WARP0 + VQT_LOAD_WARPS))
 
 struct VqtLevelArgs {
   const float* y32;            // level 0 source [batch][src_stride]
-  const uint16_t* src_hi;      // level >= 1 source, two fp16 terms (zero beyond n_sig up to the stride)
+  const uint16_t* src_hi;      // level >= 1 source, two fp16 terms, tiled chunk-major layout (zero beyond n_sig)
   const uint16_t* src_lo;
   int n_sig;
   long long src_stride;
@@ -392,13 +428,25 @@ struct VqtLevelArgs {
   const float* inv_sqrt_len;
   float* out;                  // [batch][n_bins][n_frames]
   int n_frames, n_bins;
-  uint16_t* dst_hi;            // next level
+  uint16_t* dst_hi;            // next level (tiled chunk-major layout, see level_index)
   uint16_t* dst_lo;
   int n_valid;
   long long dst_stride;
+  int dst_q;                   // planes per row of the next level (1: linear layout)
+  long long dst_cap;           // samples the next level's buffer holds per clip
   int tiles_per_clip, n_tiles;
   long long* dbg;              // optional per-role cycle counters of CTA 0 (zns_dbg_vqt_timing), else NULL
 };
+
+// Cycle counters of the roles (zns_dbg_vqt_timing) exist only in builds with -DZNS_VQT_TIMING: the product kernels carry
+// no diagnostic code (instruction-cache footprint).
+#ifdef ZNS_VQT_TIMING
+#define VQT_CLOCK() clock64()
+#define VQT_TIMING_ON true
+#else
+#define VQT_CLOCK() 0LL
+#define VQT_TIMING_ON false
+#endif
 
 template <bool SRC_F32>
 __global__ void __launch_bounds__(VQT_LEVEL_THREADS, 1)
@@ -415,7 +463,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.n_slots; ++i) {
-      mbar_init(smem_u32(&bar_full[i]), 32);                       // one loader warp fills a slot
+      // VQT_LOAD_WARPS / n_slots loader warps fill a slot: all their lanes arrive (fp32 source) or one per warp (bulk copies)
+      mbar_init(smem_u32(&bar_full[i]), (SRC_F32 ? 32 : 1) * (VQT_LOAD_WARPS / L.n_slots));
       mbar_init(smem_u32(&bar_empty[i]), ZNS_VQT_ISSUERS);          // every issuer commits once per group
     }
     for (int t = 0; t < 4; ++t) {
@@ -436,7 +485,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
   const int n_my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int sh0 = L.ring_stages[0] == 2 ? 1 : 0, sh1 = L.ring_stages[1] == 2 ? 1 : 0;   // log2(stages)
 
-  if (warp >= VQT_ISSUE_WARP0) {
+  if (warp >= VQT_ISSUE_WARP0 && warp < VQT_LOAD_WARP0) {
     // =================================== MMA issuers: one elected thread each, O(1) bookkeeping ===================================
     const int isr = warp - VQT_ISSUE_WARP0;
     if (elect_one()) {
@@ -450,16 +499,16 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
       uint32_t full_par = 0;
       uint32_t dec_inst0 = 0;
       long long t_wait_full = 0, t_wait_acc = 0, n_mma_issued = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = VQT_CLOCK();
 #pragma unroll 1
       for (int ts = 0; ts < n_my_tiles; ++ts, dec_inst0 += (uint32_t)L.n_pass) {
 #pragma unroll 1
         for (int pos = 0; pos < L.gpt; ++pos) {
           const int s_begin = L.seg_begin[isr][pos], s_end = L.seg_begin[isr][pos + 1];
           if (s_begin < s_end) {
-            const long long t0 = clock64();
-            mbar_wait(full0 + 8 * slot, full_par);
-            t_wait_full += clock64() - t0;
+            const long long t0 = VQT_CLOCK();
+            mbar_wait_parked(full0 + 8 * slot, full_par);
+            t_wait_full += VQT_CLOCK() - t0;
             tc_fence_after();
           }
           const uint32_t a16 = ring16 + (uint32_t)slot * slot16;
@@ -474,9 +523,9 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             const uint32_t bidx = (uint32_t)(2 * type) + stage;
             const uint32_t cb = tmem + stage * (uint32_t)L.ring_width[type];
             if (sg.flags & 1) {
-              const long long t0 = clock64();
-              mbar_wait(acce0 + 8 * bidx, ((inst >> sh) & 1) ^ 1);
-              t_wait_acc += clock64() - t0;
+              const long long t0 = VQT_CLOCK();
+              mbar_wait_parked(acce0 + 8 * bidx, ((inst >> sh) & 1) ^ 1);
+              t_wait_acc += VQT_CLOCK() - t0;
               tc_fence_after();
               // clear this unit's columns: accumulate = 0 with the zero block as both operands
               const int w0 = type ? L.dec_wp : L.fb_n1, w1 = type ? L.dec_wp : L.fb_n2;
@@ -497,18 +546,20 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           if (++slot == L.n_slots) { slot = 0; full_par ^= 1; }
         }
       }
-      if (A.dbg && blockIdx.x == 0) {
+      if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0) {
         long long* d = A.dbg + 4 * isr;
-        d[0] = clock64() - t_begin; d[1] = t_wait_full; d[2] = t_wait_acc; d[3] = n_mma_issued;
+        d[0] = VQT_CLOCK() - t_begin; d[1] = t_wait_full; d[2] = t_wait_acc; d[3] = n_mma_issued;
       }
     }
     __syncwarp();
-  } else if (warp >= VQT_LOAD_WARPS) {
+  } else if (warp < VQT_EPI_WARPS) {
     // =================================== epilogue ===================================
-    const int quad = warp & 3, half = (warp - VQT_LOAD_WARPS) >> 2;
+    const int quad = warp & 3, half = warp >> 2;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     long long t_wait_ep = 0;
-    const long long t_begin_ep = clock64();
+    const long long t_begin_ep = VQT_CLOCK();
+    int dst_shift = 3;                                      // log2(samples per row) of the next level
+    while ((8 << (dst_shift - 3)) < 8 * A.dst_q) ++dst_shift;
     float isl[12];                                          // 1 / sqrt(L_k) / (coefficient scale) of this octave's bins
 #pragma unroll
     for (int k = 0; k < 12; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + k) * L.fb_scale;
@@ -528,10 +579,10 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const int sh = type ? sh1 : sh0;
         const uint32_t stage = inst & (uint32_t)sh;
         {
-          const long long t0 = clock64();
-          if (lane == 0) mbar_wait(smem_u32(&bar_acc_full[type * 2 + stage]), (inst >> sh) & 1);
+          const long long t0 = VQT_CLOCK();
+          if (lane == 0) mbar_wait_parked(smem_u32(&bar_acc_full[type * 2 + stage]), (inst >> sh) & 1);
           __syncwarp();
-          t_wait_ep += clock64() - t0;
+          t_wait_ep += VQT_CLOCK() - t0;
         }
         tc_fence_after();
         const uint32_t acc = tl + (uint32_t)(L.ring_base[type] + (int)stage * L.ring_width[type]);
@@ -541,16 +592,19 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           uint16_t* dh = A.dst_hi + (size_t)clip * A.dst_stride;
           uint16_t* dl = A.dst_lo + (size_t)clip * A.dst_stride;
           const int n_blk = (w + 15) / 16;
+          const long long t_row = g * L.dec_w + c0;                      // first output of this row in this pass
+          const long long o_row = level_index_pow2(t_row, A.dst_q, dst_shift);
+          const long long o_blk = A.dst_q == 1 ? 16 : 2048;               // 16 outputs further: two planes (tiled) / 16 samples
+          const float s_a = L.dec_scale, s_b = L.dec_scale * (1.f / 2048.f);
           for (int kb = half; kb < n_blk; kb += 2) {
             uint32_t a[16], b[16];
             tmem_ld_32x16(acc + 16 * kb, a);
             tmem_ld_32x16(acc + L.dec_wp + 16 * kb, b);
             tmem_ld_wait();
-            const long long t0 = g * L.dec_w + c0 + 16 * kb;
+            const long long t0 = t_row + 16 * kb;
             float yv[16];
-            const float s_b = L.dec_scale * (1.f / 2048.f);
 #pragma unroll
-            for (int o = 0; o < 16; ++o) yv[o] = fmaf(__uint_as_float(b[o]), s_b, __uint_as_float(a[o]) * L.dec_scale);
+            for (int o = 0; o < 16; ++o) yv[o] = fmaf(__uint_as_float(b[o]), s_b, __uint_as_float(a[o]) * s_a);
             if (!tile_valid) {
 #pragma unroll
               for (int o = 0; o < 16; ++o) if (t0 + o >= A.n_valid) yv[o] = 0.f;
@@ -558,17 +612,34 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             uint4 h1a, h2a, h1b, h2b;
             split8(yv, h1a, h2a);
             split8(yv + 8, h1b, h2b);
-            if (L.dec_w >= 16) {
-              if (t0 + 16 <= A.dst_stride) {
-                reinterpret_cast<uint4*>(dh + t0)[0] = h1a; reinterpret_cast<uint4*>(dh + t0)[1] = h1b;
-                reinterpret_cast<uint4*>(dl + t0)[0] = h2a; reinterpret_cast<uint4*>(dl + t0)[1] = h2b;
-              } else if (t0 + 8 <= A.dst_stride) {
-                reinterpret_cast<uint4*>(dh + t0)[0] = h1a;
-                reinterpret_cast<uint4*>(dl + t0)[0] = h2a;
+            if (t0 < A.dst_cap) {
+              const long long o = o_row + kb * o_blk;
+              if (L.dec_w >= 16) {           // 16 outputs = two chunks of one row (tiled: 2 KB apart; linear: adjacent)
+                const long long o2 = A.dst_q == 1 ? o + 8 : o + 1024;
+                *reinterpret_cast<uint4*>(dh + o) = h1a; *reinterpret_cast<uint4*>(dh + o2) = h1b;
+                *reinterpret_cast<uint4*>(dl + o) = h2a; *reinterpret_cast<uint4*>(dl + o2) = h2b;
+              } else {                       // dec_w == 4: four outputs per row
+                *reinterpret_cast<uint2*>(dh + o) = make_uint2(h1a.x, h1a.y);
+                *reinterpret_cast<uint2*>(dl + o) = make_uint2(h2a.x, h2a.y);
               }
-            } else if (t0 + 4 <= A.dst_stride) {      // dec_w == 4: four outputs per row
-              *reinterpret_cast<uint2*>(dh + t0) = make_uint2(h1a.x, h1a.y);
-              *reinterpret_cast<uint2*>(dl + t0) = make_uint2(h2a.x, h2a.y);
+            }
+          }
+        } else if (L.fpr == 1) {
+          // one frame per row: the two warps of a lane quadrant take six bins each
+          const long long f = g;
+          uint32_t fa[12], fg[12], fb[12];
+          const int k0 = 6 * half;
+          tmem_ld_32x8(acc + 2 * k0, fa); tmem_ld_32x8(acc + 2 * k0 + 8, fa + 8);          // x1 . g1 (12 of the 16 loaded columns used)
+          tmem_ld_32x8(acc + 24 + 2 * k0, fg); tmem_ld_32x8(acc + 24 + 2 * k0 + 8, fg + 8); // x1 . g2
+          tmem_ld_32x8(acc + L.fb_n1 + 2 * k0, fb); tmem_ld_32x8(acc + L.fb_n1 + 2 * k0 + 8, fb + 8);   // x2 . g1
+          tmem_ld_wait();
+          if (f < A.n_frames) {
+            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * A.n_frames + f;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
+              const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
+              op[(size_t)k * A.n_frames] = __logf(fmaf(__fsqrt_rn(fmaf(re, re, im * im)), half ? isl[6 + k] : isl[k], 1e-9f));
             }
           }
         } else {
@@ -586,7 +657,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
               for (int k = 0; k < 12; ++k) {
                 const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fa[24 + 2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
                 const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fa[25 + 2 * k]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-                op[(size_t)k * A.n_frames] = logf(sqrtf(re * re + im * im) * isl[k] + 1e-9f);
+                op[(size_t)k * A.n_frames] = __logf(fmaf(__fsqrt_rn(fmaf(re, re, im * im)), isl[k], 1e-9f));
               }
             }
           }
@@ -595,24 +666,33 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         mbar_arrive(smem_u32(&bar_acc_empty[type * 2 + stage]));
       }
     }
-    if (A.dbg && blockIdx.x == 0 && (warp == VQT_LOAD_WARPS || warp == VQT_LOAD_WARPS + 4) && lane == 0) {
-      A.dbg[16 + 2 * half] = clock64() - t_begin_ep; A.dbg[17 + 2 * half] = t_wait_ep;
+    if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && (warp == 0 || warp == 4) && lane == 0) {
+      A.dbg[16 + 2 * half] = VQT_CLOCK() - t_begin_ep; A.dbg[17 + 2 * half] = t_wait_ep;
     }
   } else {
-    // =================================== loader: warp w owns ring slot w ===================================
-    const int lw = warp;
+    // =================================== loaders: VQT_LOAD_WARPS / n_slots warps per ring slot ===================================
+    const int lw = warp - VQT_LOAD_WARP0;
+    const int wps = VQT_LOAD_WARPS / L.n_slots;              // warps per slot
+    const int my_slot = lw % L.n_slots, sub = lw / L.n_slots; // this warp takes every wps-th block of 32 chunks of its slot's groups
+    const int pg_shift = L.pg == 8 ? 3 : (L.pg == 4 ? 2 : 0);
     const int n_rows = 128 + L.hb + L.ha;
     const int n_chunks = n_rows * L.pg;
     const int n_groups = n_my_tiles * L.gpt;
-    if (lw < L.n_slots) {
-      const uint32_t s1 = smem_u32(sRing) + (uint32_t)lw * slot_bytes;
+    {
+      const uint32_t s1 = smem_u32(sRing) + (uint32_t)my_slot * slot_bytes;
       const uint32_t s2 = s1 + (uint32_t)L.slot_term_bytes;
-      const uint32_t bfull = smem_u32(&bar_full[lw]), bempty = smem_u32(&bar_empty[lw]);
+      const uint32_t bfull = smem_u32(&bar_full[my_slot]), bempty = smem_u32(&bar_empty[my_slot]);
       uint32_t par = 1;                           // first use of a slot passes immediately
-      long long t_wait_ld = 0;
-      const long long t_begin_ld = clock64();
+      long long t_wait_ld = 0, t_p1 = 0, t_cpw = 0, t_p2 = 0;
+      const long long t_begin_ld = VQT_CLOCK();
+      // lane -> (row, plane) of its first chunk; each further chunk of this warp is (32 / pg) * wps rows down
+      const int i_first = lane + 32 * sub;
+      const int r_first = i_first >> pg_shift, c_lane = i_first & (L.pg - 1);
+      const int r_step = (32 >> pg_shift) * wps;
+      const uint32_t off0 = (uint32_t)(c_lane * L.a_lbo + 16 * r_first), off_step = 16u * (uint32_t)r_step;
+      const int n_it = (n_chunks > i_first ? (n_chunks - i_first + 32 * wps - 1) / (32 * wps) : 0);
 #pragma unroll 1
-      for (int gi = lw; gi < n_groups; gi += L.n_slots, par ^= 1) {
+      for (int gi = my_slot; gi < n_groups; gi += L.n_slots, par ^= 1) {
         const int ts = gi / L.gpt, pos = gi - ts * L.gpt;
         const int tau = (int)blockIdx.x + ts * (int)gridDim.x;
         const int clip = tau / A.tiles_per_clip;
@@ -620,63 +700,107 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const float* yb = SRC_F32 ? A.y32 + (size_t)clip * A.src_stride : nullptr;
         const uint16_t* hsrc = SRC_F32 ? nullptr : A.src_hi + (size_t)clip * A.src_stride;
         const uint16_t* lsrc = SRC_F32 ? nullptr : A.src_lo + (size_t)clip * A.src_stride;
-        const bool vec_ok = SRC_F32 ? ((reinterpret_cast<uintptr_t>(yb) & 15) == 0) : true;
+        const bool vec_ok = SRC_F32 && ((reinterpret_cast<uintptr_t>(yb) & 15) == 0);
         const int plane0 = L.g_order[pos] * L.pg;
         const long long base_s = (row0 - L.hb) * R + 8LL * plane0;     // sample of chunk (row 0, plane 0 of the group)
         {
-          const long long t0 = clock64();
-          if (lane == 0) mbar_wait(bempty, par);
+          const long long t0 = VQT_CLOCK();
+          if (lane == 0) mbar_wait_parked(bempty, par);
           __syncwarp();
-          t_wait_ld += clock64() - t0;
+          t_wait_ld += VQT_CLOCK() - t0;
+        }
+        if (!SRC_F32) {
+          // levels >= 1: the source is stored tile by tile in plane order: per plane and term one 2 KB bulk copy for the
+          // 128 tile rows plus two small ones for the halo rows out of the neighbouring tiles (zero pad tiles at the ends)
+          const long long t = row0 >> 7;
+          if (L.pg > 1) {
+            const int n_cp = 6 * L.pg;                    // (term, plane, part) copies of the group
+            uint32_t tx = 0;
+            for (int k = sub; k < n_cp; k += wps) { const int part = k % 3; tx += part == 1 ? 2048u : 16u * (part == 0 ? L.hb : L.ha); }
+            if (lane == 0) mbar_expect_tx(bfull, tx);
+            __syncwarp();
+            for (int k = sub + wps * lane; k < n_cp; k += 32 * wps) {
+              const int term = k / (3 * L.pg), c = (k % (3 * L.pg)) / 3, part = k % 3;     // part: 0 halo before, 1 main, 2 halo after
+              const uint16_t* src = (term ? lsrc : hsrc);
+              const uint32_t dst = (term ? s2 : s1) + (uint32_t)(c * L.a_lbo);
+              const long long plane = (long long)(plane0 + c);
+              if (part == 1) bulk_g2s(dst + 16u * L.hb, src + (((t + 1) * q + plane) * 128) * 8, 2048u, bfull);
+              else if (part == 0) { if (L.hb > 0) bulk_g2s(dst, src + ((t * q + plane) * 128 + (128 - L.hb)) * 8, 16u * L.hb, bfull); }
+              else if (L.ha > 0) bulk_g2s(dst + 16u * (L.hb + 128), src + (((t + 2) * q + plane) * 128) * 8, 16u * L.ha, bfull);
+            }
+          } else {                             // q == 1: rows are consecutive chunks of the linear signal; warp `sub` moves term `sub` (wps >= 2)
+            const uint32_t bytes = (uint32_t)(n_rows * 16);
+            const int n_mine = (wps >= 2) ? (sub < 2 ? 1 : 0) : 2;
+            if (lane == 0) mbar_expect_tx(bfull, bytes * (uint32_t)n_mine);
+            __syncwarp();
+            if (lane < 2 && (wps < 2 || lane == 0) && n_mine > 0) {
+              const int term = (wps >= 2) ? sub : lane;
+              bulk_g2s(term ? s2 : s1, (term ? lsrc : hsrc) + 1024 + (row0 - L.hb) * 8, bytes, bfull);
+            }
+          }
+          continue;
         }
         if (vec_ok) {
           // phase 1: asynchronous 16-byte copies, every chunk of the group in flight at once (one DRAM latency per group).
-          // fp32 source: the chunk's two 16-byte halves are parked where its x1 / x2 chunks will live.
-#pragma unroll 2
-          for (int i = lane; i < n_chunks; i += 32) {
-            const int r = (L.pg == 4) ? (i >> 2) : i, c = (L.pg == 4) ? (i & 3) : 0;
-            const long long s0 = base_s + (long long)r * R + 8 * c;
-            const uint32_t off = (uint32_t)(c * L.a_lbo + 16 * r);
-            const long long left = (long long)A.n_sig - s0;              // samples of this chunk inside the signal
-            const bool in = s0 >= 0 && left > 0;
-            if (SRC_F32) {
+          // The chunk's two 16-byte halves are parked where its x1 / x2 chunks will live.
+          const long long tp0 = VQT_CLOCK();
+          const bool interior = base_s >= 0 && base_s + (long long)(n_rows - 1) * R + 8 * L.pg <= (long long)A.n_sig;
+          if (interior) {
+            const float* src = yb + base_s + (long long)r_first * R + 8 * c_lane;
+            const long long src_step = (long long)r_step * R;
+            uint32_t d1 = s1 + off0, d2 = s2 + off0;
+#pragma unroll 4
+            for (int it = 0; it < n_it; ++it) {
+              cp_async16(d1, src, 16);
+              cp_async16(d2, src + 4, 16);
+              src += src_step; d1 += off_step; d2 += off_step;
+            }
+          } else {
+#pragma unroll 1
+            for (int it = 0; it < n_it; ++it) {
+              const int r = r_first + it * r_step;
+              const long long s0 = base_s + (long long)r * R + 8 * c_lane;
+              const uint32_t off = off0 + (uint32_t)it * off_step;
+              const long long left = (long long)A.n_sig - s0;              // samples of this chunk inside the signal
+              const bool in = s0 >= 0 && left > 0;
               const int n1 = in ? (int)min(4LL, left) * 4 : 0, n2 = in ? (int)max(0LL, min(4LL, left - 4)) * 4 : 0;
               const float* src = yb + (in ? s0 : 0);
               cp_async16(s1 + off, src, n1);
               cp_async16(s2 + off, src + 4, n2);
-            } else {
-              const int nb = in ? 16 : 0;                                 // the buffers hold zeros beyond n_sig
-              cp_async16(s1 + off, hsrc + (in ? s0 : 0), nb);
-              cp_async16(s2 + off, lsrc + (in ? s0 : 0), nb);
             }
           }
+          const long long tp1 = VQT_CLOCK();
           cp_async_wait_all();
-          if (SRC_F32) {
+          const long long tp2 = VQT_CLOCK();
+          t_p1 += tp1 - tp0; t_cpw += tp2 - tp1;
+          {
             // phase 2: in place, every lane converts the chunks it fetched itself
+            uint32_t d1 = s1 + off0, d2 = s2 + off0;
+            const int n_cv = n_it;
 #pragma unroll 2
-            for (int i = lane; i < n_chunks; i += 32) {
-              const int r = (L.pg == 4) ? (i >> 2) : i, c = (L.pg == 4) ? (i & 3) : 0;
-              const uint32_t off = (uint32_t)(c * L.a_lbo + 16 * r);
-              const uint4 ra = lds128(s1 + off), rb = lds128(s2 + off);
+            for (int it = 0; it < n_cv; ++it) {
+              const uint4 ra = lds128(d1), rb = lds128(d2);
               const float v[8] = {__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z), __uint_as_float(ra.w),
                                   __uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), __uint_as_float(rb.w)};
               uint4 c1, c2;
               split8(v, c1, c2);
-              sts128(s1 + off, c1);
-              sts128(s2 + off, c2);
+              sts128(d1, c1);
+              sts128(d2, c2);
+              d1 += off_step; d2 += off_step;
             }
           }
+          t_p2 += VQT_CLOCK() - tp2;
         } else {
           // unaligned fp32 clips (n_samples not a multiple of 4): element-wise loads
-          for (int i = lane; i < n_chunks; i += 32) {
-            const int r = (L.pg == 4) ? (i >> 2) : i, c = (L.pg == 4) ? (i & 3) : 0;
-            const long long s0 = base_s + (long long)r * R + 8 * c;
+          for (int it = 0; it < n_it; ++it) {
+            const int r = r_first + it * r_step;
+            const long long s0 = base_s + (long long)r * R + 8 * c_lane;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = (s0 + e >= 0 && s0 + e < A.n_sig) ? __ldg(yb + s0 + e) : 0.f;
             uint4 c1, c2;
             split8(v, c1, c2);
-            const uint32_t off = (uint32_t)(c * L.a_lbo + 16 * r);
+            const uint32_t off = off0 + (uint32_t)it * off_step;
             sts128(s1 + off, c1);
             sts128(s2 + off, c2);
           }
@@ -684,7 +808,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(bfull);
       }
-      if (A.dbg && blockIdx.x == 0 && lw == 0 && lane == 0) { A.dbg[20] = clock64() - t_begin_ld; A.dbg[21] = t_wait_ld; }
+      if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && lw == 0 && lane == 0) { A.dbg[20] = VQT_CLOCK() - t_begin_ld; A.dbg[21] = t_wait_ld;
+                                                              A.dbg[22] = t_p1; A.dbg[23] = t_cpw; A.dbg[24] = t_p2; }
     }
   }
   tc_fence_before();
@@ -699,6 +824,7 @@ struct VqtEdgeParams {
   int item0[ZNS_VQT_MAX_OCT + 1];          // first (frame, filter) item of each octave
   int n_left[ZNS_VQT_MAX_OCT], t_right[ZNS_VQT_MAX_OCT];
   long long stride[ZNS_VQT_MAX_OCT];
+  int q[ZNS_VQT_MAX_OCT];                  // layout of the level buffers (level_index)
   const float* coef[ZNS_VQT_MAX_OCT];      // [n][2][bpo/2][2]
   const uint16_t* hi[ZNS_VQT_MAX_OCT];
   const uint16_t* lo[ZNS_VQT_MAX_OCT];
@@ -732,7 +858,7 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
     float s;
     if (oct == 0) s = __ldg(y32 + (size_t)clip * y_stride + idx);
     else {
-      const size_t o = (size_t)clip * P.stride[oct] + idx;
+      const size_t o = (size_t)clip * P.stride[oct] + (size_t)level_index(idx, P.q[oct]);
       s = __half2float(__ushort_as_half(P.hi[oct][o])) + __half2float(__ushort_as_half(P.lo[oct][o])) * (1.f / 2048.f);
     }
     const float* cn = cf + (size_t)i * P.bpo * 2;
@@ -806,6 +932,8 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     a.dst_lo = last ? nullptr : p->d_lo[i + 1];
     a.n_valid = n_cur / 2;
     a.dst_stride = last ? 0 : p->sig_stride[i + 1];
+    a.dst_q = last ? 1 : p->level[i + 1].q;
+    a.dst_cap = last ? 0 : p->sig_cap[i + 1];
     a.tiles_per_clip = (rows + 127) / 128;
     a.n_tiles = a.tiles_per_clip * batch;
     a.dbg = g_vqt_dbg ? g_vqt_dbg + 32 * i : nullptr;
@@ -818,7 +946,7 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     const int nl = std::min(n_frames, (L.n_fft / 2 + L.hop - 1) / L.hop);
     int tr = (n_cur >= L.n_fft / 2) ? (n_cur - L.n_fft / 2) / L.hop + 1 : 0;
     tr = std::max(tr, nl);
-    E.n_fft[i] = L.n_fft; E.hop[i] = L.hop; E.n_sig[i] = n_cur; E.stride[i] = p->sig_stride[i];
+    E.n_fft[i] = L.n_fft; E.hop[i] = L.hop; E.n_sig[i] = n_cur; E.stride[i] = p->sig_stride[i]; E.q[i] = L.q;
     E.coef[i] = p->d_coef[i]; E.hi[i] = p->d_hi[i]; E.lo[i] = p->d_lo[i];
     E.n_left[i] = nl; E.t_right[i] = tr;
     E.item0[i + 1] = E.item0[i] + (nl + std::max(0, n_frames - tr)) * p->bpo;
