@@ -14,8 +14,11 @@
  * except where stated (plans own their scratch; *_host helpers copy and synchronise).
  * One process per GPU.  There is no CPU fallback: without a CUDA device calls fail with ZNS_ERR_CUDA.
  *
- * Activation layout used between encoder layers ("act"): bf16 [G][H][W][8][C], G = ceil(B/8);
- * clip b lives at group b/8, slot b%8; slots >= B hold zeros.
+ * Activation layout used between encoder layers ("act"): 16-bit [G][H][W][8][C], G = ceil(B/8);
+ * clip b lives at group b/8, slot b%8; slots >= B hold zeros.  Element type: the FORWARD activations and the
+ * forward weight pack are fp16 or bf16 (the caller says which: `*_f16` arguments, zns_conv_desc.fmt; the product path
+ * uses fp16 -- 11 significant bits instead of 8 at the same tensor-core rate, values are far inside its range),
+ * GRADIENT activations and the data-gradient weight pack are always bf16 (range).
  */
 #ifndef ZNS_H_
 #define ZNS_H_
@@ -85,11 +88,12 @@ int zns_rms_gate(const float* stem, const float* ros, int batch, int n_samples, 
  * (the (B,1,96,T) NCHW input; the strides let channel 0 / 1 of a (B,2,96,T) crop batch be read in
  * place, pretext.py:476-477, and let overlapping time segments of ONE long clip act as the "clips" of a
  * group: x_clip_stride = segment hop, x_row_stride = T)
- * -> act bf16 [G][H][W][8][64] = dropout(relu(conv + bias)). */
+ * -> act [G][H][W][8][64] = dropout(relu(conv + bias)), fp16 if out_f16 else bf16; out_act_bf16 (may be NULL)
+ * receives the same values as bf16 (the x operand of cv2's weight gradient, whose two operands must share a type). */
 int zns_conv1_fwd(const float* x, long long x_clip_stride, long long x_row_stride, const float* weight, const float* bias,
                   void* out_act,
                   int batch, int H, int W, float dropout_p, uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream,
-                  void* stream);
+                  int out_f16, void* out_act_bf16, void* stream);
 /* cv1 weight/bias gradient: dy act bf16 [G][H][W][8][64]; dw fp32 [64][1][3][11] and db [64] are
  * accumulated into (+=). */
 int zns_conv1_wgrad(const void* dy_act, const float* x, long long x_clip_stride, long long x_row_stride, float* dw,
@@ -107,7 +111,14 @@ typedef struct {
   const uint32_t* seed_dev; /* optional device word XORed into seed (a step counter: lets a captured
                                CUDA graph draw a fresh mask on every replay); NULL = unused */
   float out_scale;/* epilogue multiplies by this after masking (dgrad: 1/(1-p)) */
+  int fmt;        /* ZNS_FMT_* bits: which operands are fp16 (0 = all bf16) */
 } zns_conv_desc;
+#define ZNS_FMT_IN_F16 1  /* zns_conv_fwd: `in` is fp16 */
+#define ZNS_FMT_W_F16 2   /* zns_conv_fwd: `wpk` is fp16 */
+#define ZNS_FMT_OUT_F16 4 /* zns_conv_fwd: `out` is written as fp16 */
+/* forward convolution of the product path / its data gradient (dy bf16, flipped weights bf16, mask = fp16 forward act;
+ * the mask test "> 0" reads sign and magnitude bits and is the same for both types) */
+#define ZNS_FMT_FORWARD_F16 (ZNS_FMT_IN_F16 | ZNS_FMT_W_F16 | ZNS_FMT_OUT_F16)
 
 /* cv2..cv8 forward (models.py:17-23,41-70) and, with transposed/flipped packed weights, the data
  * gradient.  Implicit GEMM on tcgen05/TMEM, operands staged by TMA.  `n_br` (1 or 2) encoders of
@@ -117,9 +128,14 @@ typedef struct {
  *   bias[br]  fp32 [c_out] or NULL
  *   mask[br]  act bf16 [G][H][W][8][c_out] or NULL: output is zeroed where mask <= 0
  *             (dgrad through ReLU/dropout of the layer below)
- *   out[br]   act bf16 [G][H][W][8][c_out] = scale * mask(dropout(relu?(conv + bias))) */
+ *   out[br]   act bf16 [G][H][W][8][c_out] = scale * mask(dropout(relu?(conv + bias)))
+ *   out_bf16  NULL, or per branch a second act tensor that receives the same values as bf16 (used when `out` is
+ *             fp16: the weight gradient of the next layer needs its x operand in dy's type; tcgen05.mma kind::f16
+ *             with one fp16 and one bf16 operand is an illegal instruction on sm_100a)
+ * d->fmt says which of in / wpk / out are fp16. */
 int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                 const float* const* bias, const void* const* mask, void* const* out, void* stream);
+                 const float* const* bias, const void* const* mask, void* const* out, void* const* out_bf16,
+                 void* stream);
 
 /* Weight gradient of cv2..cv8: x act bf16 [G][H][W][8][c_in], dy act bf16 [G][H][W][8][c_out],
  * dwpk[br] fp32 [kh*kw][c_out][c_in] accumulated (+=, atomics).  Only d->batch,H,W,c_in,c_out,kh,kw
@@ -130,37 +146,39 @@ int zns_conv_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, const
 /* db[c] += sum over positions of dy act[...][c]. */
 int zns_bias_grad(const void* dy_act, int batch, int H, int W, int C, float* db, void* stream);
 
-/* fp32 [c_out][c_in][kh][kw] (state_dict layout, models.py:16-23) -> bf16 forward pack
- * wf [kh*kw][c_out][c_in] and data-gradient pack wd [kh*kw][c_in][c_out] with taps flipped.
- * Either output may be NULL. */
-int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, void* stream);
+/* fp32 [c_out][c_in][kh][kw] (state_dict layout, models.py:16-23) -> forward pack
+ * wf [kh*kw][c_out][c_in] (fp16 if wf_f16 else bf16) and bf16 data-gradient pack wd [kh*kw][c_in][c_out] with taps
+ * flipped.  Either output may be NULL. */
+int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, int wf_f16, void* stream);
 /* fp32 [kh*kw][c_out][c_in] -> g[c_out][c_in][kh][kw] (= or +=) scale * packed. */
 int zns_unpack_grads(const float* gpk, int c_out, int c_in, int kh, int kw, float scale, int accumulate, float* g,
                      void* stream);
 
 /* MaxPool2d((pool,1)) -> ReLU -> Dropout (models.py:41-44,50-53,59-62):
- * y act [G][H][W][8][C] -> out act [G][H/pool][W][8][C]. */
+ * y act [G][H][W][8][C] -> out act [G][H/pool][W][8][C] (both fp16 if act_f16 else bf16); out_act_bf16 (may be NULL)
+ * receives a bf16 copy of out. */
 int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, int W, int C, int pool, float dropout_p,
-                 uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, void* stream);
+                 uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int act_f16, void* out_act_bf16,
+                 void* stream);
 /* Backward of the above: dpool act [G][H/pool][W][8][C] (already masked and scaled by the dgrad
  * epilogue) is routed to the first arg-max row of each window of y; dy act [G][H][W][8][C]. */
 int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_act, int batch, int H, int W, int C, int pool,
-                 void* stream);
+                 int y_f16, void* stream);
 
 /* fc1 + sigmoid + flatten (models.py:99-101): x act [G][1][T][8][128] -> emb fp32 [B][T]. */
 int zns_head_fwd(const void* x_act, const float* w128, const float* bias1, float* emb, int batch, int T,
-                 void* stream);
+                 int x_f16, void* stream);
 /* Backward: d_emb [B][T] -> dw128 += , dbias1 +=, dy act [G][1][T][8][128] = gradient at cv8's
  * pre-activation (x is cv8's ReLU/dropout output, so dy = dz * w * (x > 0) * out_scale). */
 int zns_head_bwd(const void* x_act, const float* emb, const float* d_emb, const float* w128, float* dw128,
-                 float* dbias1, void* dy_act, int batch, int T, float out_scale, void* stream);
+                 float* dbias1, void* dy_act, int batch, int T, float out_scale, int x_f16, void* stream);
 
 /* Down_CNN merge (models.py:144-148): mode 0 = maximum, 1 = mean. */
 int zns_merge(const float* a, const float* b, float* out, long long n, int mode, void* stream);
 
-/* act bf16 [G][H][W][8][C] <-> fp32 NCHW [B][C][H][W] (module boundaries, tests). */
-int zns_act_from_nchw(const float* x, void* act, int batch, int C, int H, int W, void* stream);
-int zns_act_to_nchw(const void* act, float* x, int batch, int C, int H, int W, void* stream);
+/* act (fp16 if act_f16 else bf16) [G][H][W][8][C] <-> fp32 NCHW [B][C][H][W] (module boundaries, tests). */
+int zns_act_from_nchw(const float* x, void* act, int batch, int C, int H, int W, int act_f16, void* stream);
+int zns_act_to_nchw(const void* act, float* x, int batch, int C, int H, int W, int act_f16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * NT-Xent (loss_functions.py:24-55), forward and backward in one launch.

@@ -17,6 +17,8 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import check_adam_deltas
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -32,6 +34,21 @@ def sd(gold):
     return he_normal_state_dict(int(gold["ckpt_seed"]))
 
 
+# Embedding tolerance: north_star's 1e-2 relative (L2), plus a per-frame bound on the (0, 1) sigmoid outputs.  With bf16
+# forward activations cfg3 measured 1.09e-2 on the anchor branch (just over); the forward pass now keeps its activations and
+# weights in fp16 (11 significant bits, same tensor-core rate), which is what these bounds are for.
+EMB_REL = 1e-2
+EMB_ABS = 1e-2
+
+
+def _emb_ok(got, ref):
+    got, ref = torch.as_tensor(got).double().cpu(), torch.as_tensor(ref).double().cpu()
+    rel = float((got - ref).norm() / ref.norm())
+    ab = float((got - ref).abs().max())
+    print(f"embedding error: L2-relative {rel:.3e}, max abs {ab:.3e}")
+    return rel < EMB_REL and ab < EMB_ABS
+
+
 def _rel(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / b.norm())
@@ -45,14 +62,16 @@ def _tied(sd):
     return out
 
 
-def check_weight_update(gold, tag, model, w0_sd, min_sign=0.99, g_floor=1e-6):
-    """Discriminating one-step check on the sampled entries: sign of the update and its size."""
+def check_weight_update(gold, tag, model, w0_sd, min_sign=0.99, g_floor=1e-6, min_checked=1000):
+    """Discriminating one-step check on the sampled entries (helpers.check_adam_deltas): the update is Adam's step on this
+    implementation's gradient (every entry), and it has the reference's sign and size wherever the reference gradient
+    stands clear of eps and of the tensor's reduced-precision gradient noise."""
     keys = [str(k) for k in gold["layout_keys"]]
     off = gold["sample_off"]
     new_sd = model.state_dict()
+    named = dict(model.named_parameters())
     lr = float(gold[f"{tag}_lr"])
-    n_checked = agree = 0
-    worst = 0.0
+    n_checked = agree = 0.0
     for i, k in enumerate(keys):
         sl = slice(off[i], off[i + 1])
         idx = gold["sample_idx"][sl]
@@ -61,21 +80,13 @@ def check_weight_update(gold, tag, model, w0_sd, min_sign=0.99, g_floor=1e-6):
         d_ref = gold[f"{tag}_w1_samples"][sl].astype(np.float64) - w0
         d_got = new_sd[k].reshape(-1)[idx].double().cpu().numpy() - w0
         g_ref = gold[f"{tag}_grad_samples"][sl].astype(np.float64)
-        sel = np.abs(g_ref) > g_floor                      # >> eps = 1e-8 and above the bf16 noise of the gradient
-        if not sel.any():
-            continue
-        assert np.all(np.abs(d_ref[sel]) > 0.5 * lr), k     # the reference really moved these by ~lr
-        same = np.sign(d_got[sel]) == np.sign(d_ref[sel])
-        n_checked += int(sel.sum())
-        agree += int(same.sum())
-        ulp = np.spacing(np.abs(w0[sel]).astype(np.float32)).astype(np.float64)
-        err = np.abs(d_got[sel] - d_ref[sel])[same] - (1e-3 * np.abs(d_ref[sel]) + 2 * ulp)[same]
-        if err.size:
-            worst = max(worst, float(err.max()))
-    assert n_checked > 2000, n_checked
+        g_got = named[k].grad.reshape(-1)[idx].double().cpu().numpy()
+        n, frac = check_adam_deltas(d_got, d_ref, g_ref, w0, lr, g_got=g_got, g_floor=g_floor, min_sign=0.8)
+        n_checked += n
+        agree += n * frac
+    assert n_checked > min_checked, n_checked
     assert agree / n_checked >= min_sign, (agree, n_checked)
-    assert worst <= 0.0, worst
-    return agree / n_checked, n_checked
+    return agree / n_checked, int(n_checked)
 
 
 def grad_stats(gold, tag, model):
@@ -117,8 +128,8 @@ def test_cfg3_training_step_identical_inputs(gold, sd, use_graph):
     # the loss sits 7.5e-3 below ln 16 (a constant-output network gives exactly ln 16): resolve that gap to 25 %
     assert abs((np.log(16.0) - res[0]) - (np.log(16.0) - want[0])) <= 0.25 * (np.log(16.0) - want[0]), (res, want)
     assert abs(res[1] - want[1]) <= 2e-3 and abs(res[2] - want[2]) <= 2e-3, (res, want)
-    assert _rel(tr.engine.emb[0], gold["cfg3_anc_emb"]) < 1e-2
-    assert _rel(tr.engine.emb[1], gold["cfg3_pos_emb"]) < 1e-2
+    assert _emb_ok(tr.engine.emb[0], gold["cfg3_anc_emb"])
+    assert _emb_ok(tr.engine.emb[1], gold["cfg3_pos_emb"])
     frac, n = check_weight_update(gold, "cfg3", model, sd, min_sign=0.97)
     print(f"cfg3: update sign agreement {frac:.4f} over {n} sampled weights")
 
@@ -141,7 +152,7 @@ def test_cfg3_end_to_end_from_audio(gold, sd):
         assert rel < 1e-4 and ab < 2e-6, (c, rel, ab)
     want = gold["cfg3_train_loss_cos"]
     assert abs(res[0] - want[0]) <= 1e-2 * abs(want[0]) and abs(res[1] - want[1]) <= 2e-3 and abs(res[2] - want[2]) <= 2e-3
-    assert _rel(tr.engine.emb[0], gold["cfg3_anc_emb"]) < 1e-2
+    assert _emb_ok(tr.engine.emb[0], gold["cfg3_anc_emb"])
     check_weight_update(gold, "cfg3", model, sd, min_sign=0.97)
 
 
@@ -160,7 +171,7 @@ def test_conditioned_step_gradients_and_update(gold, sd):
     assert want[1] - want[2] > 0.05
     assert abs(res[0] - want[0]) <= 1e-2 * abs(want[0]) and abs(res[1] - want[1]) <= 2e-3 and abs(res[2] - want[2]) <= 2e-3
     assert abs((res[1] - res[2]) - (want[1] - want[2])) <= 0.05 * (want[1] - want[2])
-    assert _rel(tr.engine.emb[0], gold["cond_anc_emb"]) < 1e-2 and _rel(tr.engine.emb[1], gold["cond_pos_emb"]) < 1e-2
+    assert _emb_ok(tr.engine.emb[0], gold["cond_anc_emb"]) and _emb_ok(tr.engine.emb[1], gold["cond_pos_emb"])
     stats = grad_stats(gold, "cond", model)
     for k, ratio, cos in stats:
         print(f"cond grad {k}: |g|/|g_ref| {ratio:.4f} cos {cos:.4f}")
@@ -194,11 +205,9 @@ def test_cfg1_sample_script_path(gold, sd):
         anchor = model.pretext.anchor(vqt_anchor)
         both = model(vqt_anchor, vqt_postve)
     assert postve.shape == anchor.shape == both.shape == (1, 1876)
-    assert _rel(postve, gold["cfg1_postve"]) < 1e-2
-    assert _rel(anchor, gold["cfg1_anchor"]) < 1e-2
-    assert _rel(both, gold["cfg1_max"]) < 1e-2
-    # per-frame check as well: activations are in (0, 1)
-    assert float((both.cpu() - torch.from_numpy(gold["cfg1_max"])).abs().max()) < 1e-2
+    assert _emb_ok(postve, gold["cfg1_postve"])
+    assert _emb_ok(anchor, gold["cfg1_anchor"])
+    assert _emb_ok(both, gold["cfg1_max"])
 
 
 def test_cfg2_bench_batch_against_oracle():
@@ -220,6 +229,12 @@ def test_cfg2_bench_batch_against_oracle():
         worst = (max(worst[0], rel), max(worst[1], ab))
         assert rel < 1e-4 and ab < 2e-6, (i, rel, ab)
     print("cfg2 worst rel / abs-over-max:", worst)
-    # size-independent property over the whole batch: clips that share a base stem differ by -80 dBFS noise only
-    d = (out[0:8] - out[8:16]).abs().max()
-    assert float(d) < 1.0
+    # size-independent property over the whole batch: clips that share a base stem differ by -80 dBFS noise only.  The
+    # transform is linear before |.|, so in the magnitude domain (the log is ill-conditioned near silence) every replica is
+    # within the noise's own response of its base clip: |V_a - V_b| <= |V(noise_a - noise_b)|, a few 1e-4 sqrt(L_k)-normalised
+    v = torch.exp(out.double()) - 1e-9
+    vmax = float(v.max())
+    for r in range(1, 256 // 8):
+        d = float((v[0:8] - v[8 * r:8 * r + 8]).abs().max())
+        assert d < 2e-3 * vmax, (r, d, vmax)
+    assert float((v[0:8] - v[8:16]).abs().max()) > 0.0       # and they are distinct clips

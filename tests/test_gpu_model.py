@@ -100,16 +100,18 @@ def _check_step(gold, sd, model, res, lr=1e-6):
     keys = [str(k) for k in gold["layout_keys"]]
     off = gold["sample_off"]
     new_sd = model.state_dict()
+    named = dict(model.named_parameters())
     checked, agree = 0, 0.0
     for i, k in enumerate(keys):
         sl = slice(off[i], off[i + 1])
         idx = gold["sample_idx"][sl]
         w0 = sd[k].reshape(-1)[idx].double().numpy()
         d_got = new_sd[k].reshape(-1)[idx].double().cpu().numpy() - w0
-        n, frac = check_adam_deltas(d_got, gold["delta_samples"][sl], gold["grad_samples"][sl], w0, lr, min_sign=0.9)
+        g_got = named[k].grad.reshape(-1)[idx].double().cpu().numpy()
+        n, frac = check_adam_deltas(d_got, gold["delta_samples"][sl], gold["grad_samples"][sl], w0, lr, g_got=g_got, min_sign=0.8)
         checked += n
         agree += n * frac
-    assert checked > 800, checked                    # most sampled gradients are above the floor
+    assert checked > 400, checked                    # sampled gradients that stand clear of eps and of the gradient noise
     assert agree / checked >= 0.97, agree / checked  # this operating point (cos+ ~ cos-) is ill conditioned: see
     #                                                  tests/test_gpu_configs.py::test_conditioned_step_* for the tight check
 
@@ -413,3 +415,31 @@ def test_multi_gpu_ddp_check_if_available():
            "--master-port", "29533", os.path.join(root, "tools", "ddp_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert "DDP_CHECK_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_train_model_epoch_driver(tmp_path):
+    """train_model (pretext.py:175-415) on a small device bank: epoch structure, history, best-validation checkpoint in
+    the reference's file name and state_dict layout."""
+    from zeronotesamba_b200 import synth
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import train_model, vqt_bank
+    drums, other = synth.stem_batch(40, 6, 10.0)
+    bank = vqt_bank(torch.from_numpy(other).to(DEV), torch.from_numpy(drums).to(DEV))
+    assert bank.shape == (6, 2, 96, 626)
+    yml = dict(batch_size=4, num_epochs=2, temp=0.25, pt_task="zerons", lr=1e-4)
+    torch.manual_seed(0)
+    model, hist = train_model(yml, bank[:4], bank[4:], model_dir=str(tmp_path), chunks_per_epoch=2, val_chunks=2, seed=3,
+                              verbose=False)
+    assert isinstance(model, Pretext_CNN)
+    assert all(len(hist[k]) == 2 for k in hist) and hist["saved"][0] is True
+    assert all(np.isfinite(hist[k]).all() for k in ("train_loss", "val_loss", "train_an_pos", "val_an_neg"))
+    # NT-Xent over 4 rows starts near ln 4 and is bounded by the temperature-scaled cosine range
+    assert 0.0 < hist["train_loss"][0] < 2.0 * np.log(4.0)
+    path = tmp_path / "shift_pret_cnn_4.pth"
+    assert path.exists()
+    ckpt = torch.load(path)
+    ref = Pretext_CNN()
+    assert list(ckpt.keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(ckpt)                                    # the reference's loading call (sample_script.py:41-42)
+    with pytest.raises(ValueError, match="Which pretext task are we running"):
+        train_model(dict(yml, pt_task="other"), bank[:4], bank[4:], model_dir=str(tmp_path))

@@ -11,7 +11,9 @@ import torch.nn.functional as F
 
 from zeronotesamba_b200 import _lib as L
 from zeronotesamba_b200 import synth
-from helpers import bf16_round, from_act, pack_wd, pack_wf, rel_err, to_act, vqt_check
+from helpers import bf16_round, from_act, pack_wd, pack_wf, rel_err, round16, to_act, vqt_check
+
+F16, BF16 = torch.float16, torch.bfloat16
 
 pytestmark = pytest.mark.gpu
 
@@ -138,8 +140,9 @@ def test_crop_gather():
 # --------------------------------------------------------------------------------------------
 # bandwidth-bound encoder pieces
 # --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("adt", [BF16, F16])
 @pytest.mark.parametrize("B,H,W", [(8, 96, 48), (5, 12, 37), (16, 96, 313)])
-def test_conv1_fwd_wgrad(B, H, W):
+def test_conv1_fwd_wgrad(B, H, W, adt):
     g = torch.Generator().manual_seed(1)
     x2 = (torch.randn(B, 2, H, W, generator=g) * 3 - 4).to(DEV)
     w = (torch.randn(64, 1, 3, 11, generator=g) * 0.2).to(DEV)
@@ -147,12 +150,12 @@ def test_conv1_fwd_wgrad(B, H, W):
     G = (B + 7) // 8
     for ch in (0, 1):
         x = x2[:, ch]
-        out = torch.empty(G, H, W, 8, 64, dtype=torch.bfloat16, device=DEV)
+        out = torch.empty(G, H, W, 8, 64, dtype=adt, device=DEV)
         L.check(L.lib().zns_conv1_fwd(L.ptr(x2) + ch * H * W * 4, 2 * H * W, W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.0,
-                                      0, None, 0, st()))
+                                      0, None, 0, int(adt == F16), None, st()))
         ref = F.relu(F.conv2d(x.unsqueeze(1), w, b, padding=(1, 5)))
         got = from_act(out, B)
-        assert rel_err(got, ref) < 4e-3
+        assert rel_err(got, ref) < (5e-4 if adt == F16 else 4e-3)
         if B % 8:
             assert float(out.view(G, H, W, 8, 64)[-1, :, :, B % 8:, :].float().abs().max()) == 0.0
         # weight gradient against autograd on the same (bf16-rounded) dy
@@ -176,8 +179,8 @@ def test_conv1_dropout_statistics():
     b = torch.ones(64, device=DEV)
     out = torch.empty(1, H, W, 8, 64, dtype=torch.bfloat16, device=DEV)
     ref = torch.empty_like(out)
-    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(ref), B, H, W, 0.0, 7, None, 3, st()))
-    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.1, 7, None, 3, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(ref), B, H, W, 0.0, 7, None, 3, 0, None, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(out), B, H, W, 0.1, 7, None, 3, 0, None, st()))
     kept = out.float() != 0
     rate = float(kept.float().mean())
     assert abs(rate - 0.9) < 3e-3, rate
@@ -185,40 +188,42 @@ def test_conv1_dropout_statistics():
     assert float((ratio - 1 / 0.9).abs().max()) < 1e-2
     out2 = torch.empty_like(out)
     ctr = torch.tensor([5], dtype=torch.int32, device=DEV)
-    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(out2), B, H, W, 0.1, 7, L.ptr(ctr), 3, st()))
+    L.check(L.lib().zns_conv1_fwd(L.ptr(x), H * W, W, L.ptr(w), L.ptr(b), L.ptr(out2), B, H, W, 0.1, 7, L.ptr(ctr), 3, 0, None, st()))
     assert float(((out2.float() != 0) != kept).float().mean()) > 0.1  # a different mask with a device seed word
 
 
+@pytest.mark.parametrize("adt", [BF16, F16])
 @pytest.mark.parametrize("B,H,W,Cc,pool", [(8, 96, 20, 64, 3), (16, 32, 33, 128, 4), (3, 8, 50, 256, 8)])
-def test_pool_fwd_bwd(B, H, W, Cc, pool):
+def test_pool_fwd_bwd(B, H, W, Cc, pool, adt):
     g = torch.Generator().manual_seed(2)
     y = torch.randn(B, Cc, H, W, generator=g).to(DEV)
-    ya = to_act(y)
+    ya = to_act(y, adt)
     G = (B + 7) // 8
-    out = torch.empty(G, H // pool, W, 8, Cc, dtype=torch.bfloat16, device=DEV)
-    L.check(L.lib().zns_pool_fwd(L.ptr(ya), L.ptr(out), B, H, W, Cc, pool, 0.0, 0, None, 0, st()))
-    yr = bf16_round(y).requires_grad_(True)
+    out = torch.empty(G, H // pool, W, 8, Cc, dtype=adt, device=DEV)
+    L.check(L.lib().zns_pool_fwd(L.ptr(ya), L.ptr(out), B, H, W, Cc, pool, 0.0, 0, None, 0, int(adt == F16), None, st()))
+    yr = round16(y, adt).requires_grad_(True)
     ref = F.relu(F.max_pool2d(yr, (pool, 1)))
     assert torch.equal(from_act(out, B), ref.detach())
     dp = torch.randn(B, Cc, H // pool, W, generator=g).to(DEV)
     # the dgrad epilogue has already applied the ReLU mask to dp in the product path
     dp_masked = bf16_round(dp) * (ref.detach() > 0)
-    dy = torch.empty_like(ya)
-    L.check(L.lib().zns_pool_bwd(L.ptr(ya), L.ptr(to_act(dp_masked)), L.ptr(dy), B, H, W, Cc, pool, st()))
+    dy = torch.empty_like(ya, dtype=BF16)      # gradients are always bf16
+    L.check(L.lib().zns_pool_bwd(L.ptr(ya), L.ptr(to_act(dp_masked)), L.ptr(dy), B, H, W, Cc, pool, int(adt == F16), st()))
     ref.backward(bf16_round(dp))
     assert torch.equal(from_act(dy, B), yr.grad)
 
 
+@pytest.mark.parametrize("adt", [BF16, F16])
 @pytest.mark.parametrize("B,T", [(16, 313), (5, 40), (1, 1876)])
-def test_head_fwd_bwd(B, T):
+def test_head_fwd_bwd(B, T, adt):
     g = torch.Generator().manual_seed(3)
     x = F.relu(torch.randn(B, 128, 1, T, generator=g)).to(DEV)
     w = (torch.randn(1, 128, 1, generator=g) * 0.1).to(DEV)
     b = torch.tensor([0.05], device=DEV)
-    xa = to_act(x)
+    xa = to_act(x, adt)
     emb = torch.empty(B, T, device=DEV)
-    L.check(L.lib().zns_head_fwd(L.ptr(xa), L.ptr(w), L.ptr(b), L.ptr(emb), B, T, st()))
-    xr = bf16_round(x).squeeze(2).requires_grad_(True)
+    L.check(L.lib().zns_head_fwd(L.ptr(xa), L.ptr(w), L.ptr(b), L.ptr(emb), B, T, int(adt == F16), st()))
+    xr = round16(x, adt).squeeze(2).requires_grad_(True)
     wr = w.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True)
     ref = torch.sigmoid(F.conv1d(xr, wr, br)).reshape(B, T)
@@ -230,7 +235,7 @@ def test_head_fwd_bwd(B, T):
     G = (B + 7) // 8
     dy = torch.empty(G, 1, T, 8, 128, dtype=torch.bfloat16, device=DEV)
     L.check(L.lib().zns_head_bwd(L.ptr(xa), L.ptr(emb), L.ptr(de), L.ptr(w), L.ptr(dw), L.ptr(db), L.ptr(dy), B, T, 1.0,
-                                 st()))
+                                 int(adt == F16), st()))
     assert rel_err(dw, wr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
     want = (xr.grad * (xr.detach() > 0)).unsqueeze(2)
     assert rel_err(from_act(dy, B), want) < 4e-3
@@ -245,12 +250,13 @@ def test_merge_and_layout():
     L.check(L.lib().zns_merge(L.ptr(a), L.ptr(b), L.ptr(o), a.numel(), 1, st()))
     assert torch.allclose(o, (a + b) / 2)
     x = torch.randn(5, 64, 7, 9, device=DEV)
-    act = torch.empty(1, 7, 9, 8, 64, dtype=torch.bfloat16, device=DEV)
-    L.check(L.lib().zns_act_from_nchw(L.ptr(x), L.ptr(act), 5, 64, 7, 9, st()))
-    assert torch.equal(act, to_act(x))
-    back = torch.empty_like(x)
-    L.check(L.lib().zns_act_to_nchw(L.ptr(act), L.ptr(back), 5, 64, 7, 9, st()))
-    assert torch.equal(back, bf16_round(x))
+    for adt in (BF16, F16):
+        act = torch.empty(1, 7, 9, 8, 64, dtype=adt, device=DEV)
+        L.check(L.lib().zns_act_from_nchw(L.ptr(x), L.ptr(act), 5, 64, 7, 9, int(adt == F16), st()))
+        assert torch.equal(act, to_act(x, adt))
+        back = torch.empty_like(x)
+        L.check(L.lib().zns_act_to_nchw(L.ptr(act), L.ptr(back), 5, 64, 7, 9, int(adt == F16), st()))
+        assert torch.equal(back, round16(x, adt))
 
 
 @pytest.mark.parametrize("co,ci,kh,kw", [(64, 64, 7, 13), (128, 128, 9, 17), (256, 128, 3, 19), (128, 256, 1, 23)])
@@ -258,8 +264,11 @@ def test_pack_unpack(co, ci, kh, kw):
     w = torch.randn(co, ci, kh, kw, device=DEV)
     wf = torch.empty(kh * kw, co, ci, dtype=torch.bfloat16, device=DEV)
     wd = torch.empty(kh * kw, ci, co, dtype=torch.bfloat16, device=DEV)
-    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(wf), L.ptr(wd), st()))
+    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(wf), L.ptr(wd), 0, st()))
     assert torch.equal(wf, pack_wf(w)) and torch.equal(wd, pack_wd(w))
+    wf16 = torch.empty(kh * kw, co, ci, dtype=F16, device=DEV)
+    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(wf16), None, 1, st()))
+    assert torch.equal(wf16, pack_wf(w, F16))
     gp = torch.randn(kh * kw, co, ci, device=DEV)
     gout = torch.ones(co, ci, kh, kw, device=DEV)
     L.check(L.lib().zns_unpack_grads(L.ptr(gp), co, ci, kh, kw, 0.5, 0, L.ptr(gout), st()))
@@ -366,7 +375,7 @@ def test_conv_fwd_umma(B, H, W, ci, co, kh, kw):
     out = torch.full((G, H, W, 8, co), float("nan"), dtype=torch.bfloat16, device=DEV)
     d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=1)
     L.check(L.lib().zns_conv_fwd(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([wf]), L.ptr_array([b]), None,
-                                 L.ptr_array([out]), st()))
+                                 L.ptr_array([out]), None, st()))
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(bf16_round(x), bf16_round(w), b, padding=(kh // 2, kw // 2)))
     got = from_act(out, B)
@@ -391,7 +400,7 @@ def test_conv_fwd_two_branches_mask_scale():
         refs.append(ref * (bf16_round(m) > 0) * 1.25)
     d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=0, out_scale=1.25)
     L.check(L.lib().zns_conv_fwd(C.byref(d), 2, L.ptr_array(xs), L.ptr_array(ws), None, L.ptr_array(masks),
-                                 L.ptr_array(outs), st()))
+                                 L.ptr_array(outs), None, st()))
     for br in range(2):
         assert rel_err(from_act(outs[br], B), refs[br]) < 4e-3
 
@@ -403,11 +412,11 @@ def test_conv_dgrad_via_flipped_pack():
     xr = bf16_round(x).requires_grad_(True)
     F.conv2d(xr, bf16_round(w), None, padding=(kh // 2, kw // 2)).backward(bf16_round(dy))
     wd = torch.empty(kh * kw, ci, co, dtype=torch.bfloat16, device=DEV)
-    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, None, L.ptr(wd), st()))
+    L.check(L.lib().zns_pack_weights(L.ptr(w), co, ci, kh, kw, None, L.ptr(wd), 0, st()))
     dx = torch.empty(1, H, W, 8, ci, dtype=torch.bfloat16, device=DEV)
     d = L.conv_desc(B, H, W, co, ci, kh, kw)
     L.check(L.lib().zns_conv_fwd(C.byref(d), 1, L.ptr_array([to_act(dy)]), L.ptr_array([wd]), None, None,
-                                 L.ptr_array([dx]), st()))
+                                 L.ptr_array([dx]), None, st()))
     assert rel_err(from_act(dx, B), xr.grad) < 4e-3
 
 
@@ -445,25 +454,42 @@ FULL = [  # the reference's layers at B=16, T=313
 ]
 
 
+@pytest.mark.parametrize("adt", [BF16, F16])
 @pytest.mark.parametrize("B,H,W,ci,co,kh,kw", FULL)
-def test_conv_full_size_layers(B, H, W, ci, co, kh, kw):
+def test_conv_full_size_layers(B, H, W, ci, co, kh, kw, adt):
+    """adt = forward activation / forward weight type.  F16 is the product configuration: forward fp16 x fp16 -> fp16 plus
+    a bf16 copy of the output, weight gradient bf16 x bf16 (on that copy), data gradient bf16 dy times bf16 flipped weights
+    masked by the fp16 forward activation."""
+    f16 = adt == F16
     x, w, b = _conv_case(B, H, W, ci, co, kh, kw, seed=9)
     dy = torch.randn(B, co, H, W, device=DEV)
-    xa, wf, dya = to_act(x), pack_wf(w), to_act(dy)
-    out = torch.empty(2, H, W, 8, co, dtype=torch.bfloat16, device=DEV)
-    d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=0)
+    xa, wf, dya = to_act(x, adt), pack_wf(w, adt), to_act(dy)
+    out = torch.empty(2, H, W, 8, co, dtype=adt, device=DEV)
+    d = L.conv_desc(B, H, W, ci, co, kh, kw, relu=0, fmt=L.FMT_FORWARD_F16 if f16 else 0)
+    out_b = torch.empty_like(out, dtype=BF16)
     L.check(L.lib().zns_conv_fwd(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([wf]), L.ptr_array([b]), None,
-                                 L.ptr_array([out]), st()))
-    wr = bf16_round(w).requires_grad_(True)
-    xr = bf16_round(x).requires_grad_(True)
+                                 L.ptr_array([out]), L.ptr_array([out_b]), st()))
+    assert torch.equal(out_b, out.float().to(BF16)) or rel_err(out_b.float(), out.float()) < 3e-3   # double rounding at ties
+    wr = round16(w, adt).requires_grad_(True)
+    xr = round16(x, adt).requires_grad_(True)
     ref = F.conv2d(xr, wr, b, padding=(kh // 2, kw // 2))
-    assert rel_err(from_act(out, B), ref.detach()) < 4e-3
-    ref.backward(bf16_round(dy))
+    assert rel_err(from_act(out, B), ref.detach()) < (5e-4 if f16 else 4e-3)
+    simt = torch.empty_like(out)
+    L.check(L.lib().zns_dbg_conv_fwd_simt(C.byref(d), L.ptr(xa), L.ptr(wf), L.ptr(b), None, L.ptr(simt), st()))
+    assert rel_err(from_act(simt, B), ref.detach()) < (5e-4 if f16 else 4e-3)
+    # weight gradient: both operands bf16 (the engine hands it the bf16 copy of the fp16 activation)
+    xb = to_act(x)
     gp = torch.zeros(kh * kw, co, ci, device=DEV)
-    L.check(L.lib().zns_conv_wgrad(C.byref(d), 1, L.ptr_array([xa]), L.ptr_array([dya]), L.ptr_array([gp]), st()))
-    assert rel_err(gp, wr.grad.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)) < 2e-4
+    dw = L.conv_desc(B, H, W, ci, co, kh, kw)
+    L.check(L.lib().zns_conv_wgrad(C.byref(dw), 1, L.ptr_array([xb]), L.ptr_array([dya]), L.ptr_array([gp]), st()))
+    wb = w.clone().requires_grad_(True)
+    F.conv2d(bf16_round(x), wb, None, padding=(kh // 2, kw // 2)).backward(bf16_round(dy))
+    assert rel_err(gp, wb.grad.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)) < 2e-4
+    # data gradient: dy bf16, flipped weights bf16 (of the unrounded master weights), mask = the forward activation x
     wd = pack_wd(w)
     dx = torch.empty(2, H, W, 8, ci, dtype=torch.bfloat16, device=DEV)
     dd = L.conv_desc(B, H, W, co, ci, kh, kw)
-    L.check(L.lib().zns_conv_fwd(C.byref(dd), 1, L.ptr_array([dya]), L.ptr_array([wd]), None, None, L.ptr_array([dx]), st()))
-    assert rel_err(from_act(dx, B), xr.grad) < 4e-3
+    L.check(L.lib().zns_conv_fwd(C.byref(dd), 1, L.ptr_array([dya]), L.ptr_array([wd]), None, L.ptr_array([xa]),
+                                 L.ptr_array([dx]), None, st()))
+    xg = torch.autograd.grad(F.conv2d(xr, bf16_round(w), None, padding=(kh // 2, kw // 2)), xr, bf16_round(dy))[0]
+    assert rel_err(from_act(dx, B), xg * (xr.detach() > 0)) < 4e-3

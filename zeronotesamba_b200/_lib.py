@@ -22,8 +22,12 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("batch", c_int), ("H", c_int), ("W", c_int), ("c_in", c_int), ("c_out", c_int), ("kh", c_int), ("kw", c_int),
         ("relu", c_int), ("dropout_p", c_float), ("seed", c_u32), ("rng_stream", c_u32), ("seed_dev", c_void_p),
-        ("out_scale", c_float),
+        ("out_scale", c_float), ("fmt", c_int),
     ]
+
+
+FMT_IN_F16, FMT_W_F16, FMT_OUT_F16 = 1, 2, 4
+FMT_FORWARD_F16 = FMT_IN_F16 | FMT_W_F16 | FMT_OUT_F16
 
 
 _PROTOS = {
@@ -40,24 +44,24 @@ _PROTOS = {
     "zns_crop_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_rms_gate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "zns_conv1_fwd": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_u32,
-                              c_void_p, c_u32, c_void_p]),
+                              c_void_p, c_u32, c_int, c_void_p, c_void_p]),
     "zns_conv1_wgrad": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "zns_conv_fwd": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
-                             C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p]),
+                             C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p]),
     "zns_conv_wgrad": (c_int, [C.POINTER(ConvDesc), c_int, C.POINTER(c_void_p), C.POINTER(c_void_p),
                                C.POINTER(c_void_p), c_void_p]),
     "zns_bias_grad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "zns_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "zns_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "zns_unpack_grads": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "zns_pool_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_u32, c_void_p, c_u32,
-                             c_void_p]),
-    "zns_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "zns_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                             c_int, c_void_p, c_void_p]),
+    "zns_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "zns_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "zns_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                             c_float, c_void_p]),
+                             c_float, c_int, c_void_p]),
     "zns_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
-    "zns_act_from_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "zns_act_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "zns_act_from_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "zns_act_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "zns_ntxent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "zns_adam_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int,
@@ -163,6 +167,6 @@ def current_stream() -> int:
 
 
 def conv_desc(batch, H, W, c_in, c_out, kh, kw, relu=0, dropout_p=0.0, seed=0, rng_stream=0, seed_dev=None,
-              out_scale=1.0) -> ConvDesc:
+              out_scale=1.0, fmt=0) -> ConvDesc:
     return ConvDesc(batch, H, W, c_in, c_out, kh, kw, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFF,
-                    int(rng_stream), ptr(seed_dev), float(out_scale))
+                    int(rng_stream), ptr(seed_dev), float(out_scale), int(fmt))

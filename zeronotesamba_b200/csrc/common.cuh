@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -264,6 +265,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 __host__ __device__ inline uint32_t umma_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// 16-bit operands with the element type of each operand selectable (format code 0 = fp16, 1 = bf16)
+__host__ __device__ inline uint32_t umma_idesc_16(int m, int n, int a_mn_major, int b_mn_major, int a_f16, int b_f16) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -273,6 +279,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// two values -> one 32-bit word of the act tensor's element type (fp16 forward activations, bf16 gradients)
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+// "element > 0" on the raw 16 bits: the same test for fp16 and bf16 (sign clear, magnitude non-zero)
+__device__ __forceinline__ bool act_bits_positive(uint32_t h) { return (h & 0x8000u) == 0u && (h & 0x7FFFu) != 0u; }
 
 // Counter-based keep mask for dropout: murmur3-style finaliser of (element index, seed, stream).
 __host__ __device__ inline uint32_t zns_hash32(uint64_t idx, uint32_t seed, uint32_t stream) {

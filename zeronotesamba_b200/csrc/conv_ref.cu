@@ -7,11 +7,17 @@
 
 typedef __nv_bfloat16 bf16;
 
+// element i of a 16-bit tensor that is fp16 (f16 != 0) or bf16
+__device__ __forceinline__ float ld16(const bf16* p, size_t i, int f16) {
+  return f16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : __bfloat162float(p[i]);
+}
+
 __global__ void conv_fwd_simt_kernel(const bf16* __restrict__ in, const bf16* __restrict__ wpk,
                                      const float* __restrict__ bias, const bf16* __restrict__ mask,
                                      bf16* __restrict__ out, int G, int H, int W, int Cin, int Cout, int kh, int kw,
-                                     int relu, float scale, size_t total) {
+                                     int relu, float scale, size_t total, int fmt) {
   const int ph = kh / 2, pw = kw / 2;
+  const int in16 = fmt & ZNS_FMT_IN_F16, w16 = fmt & ZNS_FMT_W_F16, out16 = fmt & ZNS_FMT_OUT_F16;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int n = (int)(r % Cout); r /= Cout;
@@ -28,12 +34,13 @@ __global__ void conv_fwd_simt_kernel(const bf16* __restrict__ in, const bf16* __
         if (ww < 0 || ww >= W) continue;
         const bf16* xp = in + zns_act_index(g, hh, ww, b8, 0, H, W, Cin);
         const bf16* wp = wpk + ((size_t)(rr * kw + ss) * Cout + n) * Cin;
-        for (int c = 0; c < Cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+        for (int c = 0; c < Cin; ++c) acc = fmaf(ld16(xp, c, in16), ld16(wp, c, w16), acc);
       }
     }
     if (relu) acc = fmaxf(acc, 0.f);
-    if (mask && !(__bfloat162float(mask[i]) > 0.f)) acc = 0.f;
-    out[i] = __float2bfloat16(acc * scale);
+    if (mask && !act_bits_positive(reinterpret_cast<const uint16_t*>(mask)[i])) acc = 0.f;
+    if (out16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(acc * scale);
+    else out[i] = __float2bfloat16(acc * scale);
   }
 }
 
@@ -46,7 +53,7 @@ extern "C" int zns_dbg_conv_fwd_simt(const zns_conv_desc* d, const void* in, con
   conv_fwd_simt_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (const bf16*)wpk, bias,
                                                                  (const bf16*)mask, (bf16*)out, G, d->H, d->W, d->c_in,
                                                                  d->c_out, d->kh, d->kw, d->relu,
-                                                                 d->out_scale == 0.f ? 1.f : d->out_scale, total);
+                                                                 d->out_scale == 0.f ? 1.f : d->out_scale, total, d->fmt);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -76,8 +83,7 @@ __global__ void conv_wgrad_simt_kernel(const bf16* __restrict__ x, const bf16* _
       const int g = (int)q;
       const int hh = h + rr - ph, ww = w + ss - pw;
       if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      acc = fmaf(__bfloat162float(dy[p * Cout + n]), __bfloat162float(x[zns_act_index(g, hh, ww, b8, c, H, W, Cin)]),
-                 acc);
+      acc = fmaf(__bfloat162float(dy[p * Cout + n]), __bfloat162float(x[zns_act_index(g, hh, ww, b8, c, H, W, Cin)]), acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

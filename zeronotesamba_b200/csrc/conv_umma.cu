@@ -235,6 +235,8 @@ struct FwdParams {
   const float* bias[2];
   const bf16* mask[2];
   bf16* out[2];
+  bf16* out2[2];               // optional second copy of the output, always bf16 (x operand of the next weight gradient)
+  int a_f16, b_f16, out_f16;   // element types: input activations / weights / output (0 = bf16, 1 = fp16)
 };
 
 struct FwdBarriers {
@@ -338,7 +340,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
   } else if (warp == 1) {
     if (leader && elect_one()) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(128 * CTAS, N, 0, 0);
+      const uint32_t idesc = umma_idesc_16(128 * CTAS, N, 0, 0, p.a_f16, p.b_f16);
       auto commit = [](uint32_t bar) { if (CTAS == 2) umma_commit_pair(bar); else umma_commit(bar); };
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
       uint32_t a_slot = 0, a_par = 0, b_st = 0, b_par = 0;
@@ -413,6 +415,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     const float* bias = p.bias[br];
     const bf16* mask = p.mask[br];
     bf16* out = p.out[br];
+    bf16* out2 = p.out2[br];
     uint32_t seed = p.seed;
     if (p.seed_dev) seed ^= __ldg(p.seed_dev) * 0x9E3779B9u;
     const bool do_drop = p.drop_p > 0.f;
@@ -442,22 +445,30 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 mv = __ldg(mp + q);
-              const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mv);
+              const uint32_t* m2 = reinterpret_cast<const uint32_t*>(&mv);   // fp16 or bf16 forward activations: sign / zero test
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 mf = __bfloat1622float2(m2[j]);
-                if (!(mf.x > 0.f)) f[q * 8 + 2 * j] = 0.f;
-                if (!(mf.y > 0.f)) f[q * 8 + 2 * j + 1] = 0.f;
+                if (!act_bits_positive(m2[j] & 0xFFFFu)) f[q * 8 + 2 * j] = 0.f;
+                if (!act_bits_positive(m2[j] >> 16)) f[q * 8 + 2 * j + 1] = 0.f;
               }
             }
           }
           uint4* dst = reinterpret_cast<uint4*>(out + e0 + nb * 32);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(pack_bf16x2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale),
-                                pack_bf16x2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale),
-                                pack_bf16x2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale),
-                                pack_bf16x2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale));
+            dst[q] = make_uint4(pack_act2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale, p.out_f16),
+                                pack_act2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale, p.out_f16),
+                                pack_act2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale, p.out_f16),
+                                pack_act2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale, p.out_f16));
+          if (out2) {
+            uint4* dst2 = reinterpret_cast<uint4*>(out2 + e0 + nb * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              dst2[q] = make_uint4(pack_bf16x2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale),
+                                   pack_bf16x2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale),
+                                   pack_bf16x2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale),
+                                   pack_bf16x2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale));
+          }
         }
       }
     }
@@ -501,6 +512,7 @@ struct FwdTParams {
   const float* bias[2];
   const bf16* mask[2];
   bf16* out[2];
+  int a_f16, b_f16, out_f16;   // element types: input activations / weights / output (0 = bf16, 1 = fp16)
 };
 
 struct FwdTBarriers {
@@ -822,7 +834,7 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
   } else if (warp == 1) {
     if (leader && elect_one()) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(128 * CTAS, 128, 0, 0);
+      const uint32_t idesc = umma_idesc_16(128 * CTAS, 128, 0, 0, p.a_f16, p.b_f16);
       auto commit = [](uint32_t bar) { if (CTAS == 2) umma_commit_pair(bar); else umma_commit(bar); };
       const uint32_t x_dbase = x_base & 0x3FFFFu, w_dbase = w_base & 0x3FFFFu;   // descriptor offsets (same in both CTAs)
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -935,22 +947,21 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 mv = __ldg(mp + q);
-              const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mv);
+              const uint32_t* m2 = reinterpret_cast<const uint32_t*>(&mv);   // fp16 or bf16 forward activations: sign / zero test
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 mf = __bfloat1622float2(m2[i]);
-                if (!(mf.x > 0.f)) f[q * 8 + 2 * i] = 0.f;
-                if (!(mf.y > 0.f)) f[q * 8 + 2 * i + 1] = 0.f;
+                if (!act_bits_positive(m2[i] & 0xFFFFu)) f[q * 8 + 2 * i] = 0.f;
+                if (!act_bits_positive(m2[i] >> 16)) f[q * 8 + 2 * i + 1] = 0.f;
               }
             }
           }
           uint4* dst = reinterpret_cast<uint4*>(out + e0);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(pack_bf16x2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale),
-                                pack_bf16x2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale),
-                                pack_bf16x2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale),
-                                pack_bf16x2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale));
+            dst[q] = make_uint4(pack_act2(f[q * 8] * p.scale, f[q * 8 + 1] * p.scale, p.out_f16),
+                                pack_act2(f[q * 8 + 2] * p.scale, f[q * 8 + 3] * p.scale, p.out_f16),
+                                pack_act2(f[q * 8 + 4] * p.scale, f[q * 8 + 5] * p.scale, p.out_f16),
+                                pack_act2(f[q * 8 + 6] * p.scale, f[q * 8 + 7] * p.scale, p.out_f16));
         }
       }
     }
@@ -998,6 +1009,7 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
     p.n_slots = std::min(p.n_slots, std::min(MAX_RING, (p.n_acc - 1) * 2 + 3));
   }
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  p.a_f16 = (d->fmt & ZNS_FMT_IN_F16) ? 1 : 0; p.b_f16 = (d->fmt & ZNS_FMT_W_F16) ? 1 : 0; p.out_f16 = (d->fmt & ZNS_FMT_OUT_F16) ? 1 : 0;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
   const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * (16384 / CTAS) + sizeof(FwdTBarriers) + 64;
   if (dry) {
@@ -1062,6 +1074,7 @@ static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, 
   const int rows_per_cta = p.n_acc * p.stack;
   p.n_htiles = (d->H + rows_per_cta - 1) / rows_per_cta;
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  p.a_f16 = (d->fmt & ZNS_FMT_IN_F16) ? 1 : 0; p.b_f16 = (d->fmt & ZNS_FMT_W_F16) ? 1 : 0; p.out_f16 = (d->fmt & ZNS_FMT_OUT_F16) ? 1 : 0;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
   const size_t smem = 1024 + (size_t)p.n_slots * p.slot_bytes + (size_t)p.n_wstages * 16384 + sizeof(FwdTBarriers) + 64;
   CUtensorMap tm_in[2], tm_w[2];
@@ -1088,8 +1101,8 @@ static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, 
 
 template <int N, int HT, int CTAS = 1>
 static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                      const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st,
-                      PlanDump* dry = nullptr) {
+                      const float* const* bias, const void* const* mask, void* const* out, void* const* out2,
+                      cudaStream_t st, PlanDump* dry = nullptr) {
   const int G = zns_groups(d->batch);
   FwdParams p;
   memset(&p, 0, sizeof(p));
@@ -1099,6 +1112,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   p.n_wtiles = (d->W + WT - 1) / WT;
   p.slot_bytes = (uint32_t)(WT + d->kw - 1) * 1024u;
   p.relu = d->relu; p.drop_p = d->dropout_p; p.scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  p.a_f16 = (d->fmt & ZNS_FMT_IN_F16) ? 1 : 0; p.b_f16 = (d->fmt & ZNS_FMT_W_F16) ? 1 : 0; p.out_f16 = (d->fmt & ZNS_FMT_OUT_F16) ? 1 : 0;
   p.seed = d->seed; p.stream_id = d->rng_stream; p.seed_dev = d->seed_dev;
   const uint32_t btile = N * 128 / CTAS;   // a CTA of a pair stages half of each weight tile
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdBarriers) - 64;
@@ -1135,6 +1149,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
     p.bias[b] = bias ? bias[s] : nullptr;
     p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
     p.out[b] = (bf16*)out[s];
+    p.out2[b] = out2 ? (bf16*)out2[s] : nullptr;
   }
   auto kern = conv_fwd_umma_kernel<N, HT, CTAS>;
   static bool attr_set = false;
@@ -1154,8 +1169,8 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
 
 // Kernel choice and launch of the forward / data-gradient convolution; with `dry` only the geometry is reported.
 static int conv_fwd_dispatch(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                             const float* const* bias, const void* const* mask, void* const* out, cudaStream_t st,
-                             PlanDump* dry) {
+                             const float* const* bias, const void* const* mask, void* const* out, void* const* out2,
+                             cudaStream_t st, PlanDump* dry) {
   ZNS_REQUIRE(d != nullptr, "NULL argument");
   ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(d->c_in % 64 == 0 && d->c_in >= 64, "c_in must be a multiple of 64 (got %d)", d->c_in);
@@ -1174,34 +1189,36 @@ static int conv_fwd_dispatch(const zns_conv_desc* d, int n_br, const void* const
     static const bool use_t = getenv("ZNS_CONV_TRANSPOSED") != nullptr;
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    if (use_t && !dry && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
+    if (use_t && !dry && d->fmt == 0 && !out2 && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
   {
     static const bool no_stack = getenv("ZNS_CONV_NO_STACK") != nullptr;   // A/B switch
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    if (!no_stack && use_pair && can_pair && fwd_stack_config(d, &cfg, 2))
+    // (a second bf16 output is written by the direct kernels only)
+    if (!no_stack && !out2 && use_pair && can_pair && fwd_stack_config(d, &cfg, 2))
       return launch_fwd_stack<2>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
-    if (!no_stack && fwd_stack_config(d, &cfg, 1)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
+    if (!no_stack && !out2 && fwd_stack_config(d, &cfg, 1)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
   }
   switch (d->c_out) {
-    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, st, dry);
+    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
     case 128:
-      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, st, dry);
-      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, st, dry);
+      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
+      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
     case 256:
-      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, st, dry);
-      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, st, dry);
+      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
+      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
     default: return zns_set_error(ZNS_ERR_INVALID, "c_out must be 64, 128 or 256 (got %d)", d->c_out);
   }
 }
 
 extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                            const float* const* bias, const void* const* mask, void* const* out, void* stream) {
+                            const float* const* bias, const void* const* mask, void* const* out, void* const* out_bf16,
+                            void* stream) {
   ZNS_REQUIRE(d && in && wpk && out, "NULL argument");
   ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
-  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b], "NULL tensor for branch %d", b);
-  return conv_fwd_dispatch(d, n_br, in, wpk, bias, mask, out, (cudaStream_t)stream, nullptr);
+  for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b] && (!out_bf16 || out_bf16[b]), "NULL tensor for branch %d", b);
+  return conv_fwd_dispatch(d, n_br, in, wpk, bias, mask, out, out_bf16, (cudaStream_t)stream, nullptr);
 }
 
 // Host-only: the launch geometry zns_conv_fwd would use for this layer (no CUDA call is made).
@@ -1211,7 +1228,7 @@ extern "C" int zns_dbg_conv_fwd_plan(const zns_conv_desc* d, int n_br, int* out)
   ZNS_REQUIRE(d && out, "NULL argument");
   PlanDump pd;
   memset(&pd, 0, sizeof(pd));
-  int rc = conv_fwd_dispatch(d, n_br, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &pd);
+  int rc = conv_fwd_dispatch(d, n_br, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &pd);
   if (rc) return rc;
   const int vals[14] = {pd.kernel, pd.n, pd.ctas, pd.tiles.hb, pd.tiles.nb, pd.tiles.hs, pd.tiles.ns, pd.tiles.n_cols,
                         pd.tiles.n_total, pd.n_slots, pd.n_stages, pd.grid_x, (int)pd.smem, pd.kernel == 1 ? d->H / 2 : d->H};

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
                                                         long long row_stride, const float* __restrict__ weight,
                                                         const float* __restrict__ bias, bf16* __restrict__ out,
                                                         int B, int H, int W, float drop_p, uint32_t seed,
-                                                        const uint32_t* __restrict__ seed_dev, uint32_t stream_id) {
+                                                        const uint32_t* __restrict__ seed_dev, uint32_t stream_id, int f16,
+                                                        bf16* __restrict__ out2) {
   __shared__ __align__(16) float ws[C1_TAPS][C1_CO];
   if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
   __shared__ float bs[C1_CO];
@@ -81,19 +82,23 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       if (drop_p > 0.f) v = (zns_hash32(e0 + cb + i, seed, stream_id) >= thr) ? v * keep_scale : 0.f;
       acc[i] = v;
     }
-    dst[cb / 8] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                             pack_bf16x2(acc[6], acc[7]));
+    dst[cb / 8] = make_uint4(pack_act2(acc[0], acc[1], f16), pack_act2(acc[2], acc[3], f16), pack_act2(acc[4], acc[5], f16),
+                             pack_act2(acc[6], acc[7], f16));
+    if (out2)   // bf16 copy: the x operand of cv2's weight gradient
+      reinterpret_cast<uint4*>(out2 + e0)[cb / 8] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                               pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
   }
 }
 
 extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long row_stride, const float* weight,
                              const float* bias, void* out_act, int batch, int H, int W, float drop_p, uint32_t seed,
-                             const uint32_t* seed_dev, uint32_t rng_stream, void* stream) {
+                             const uint32_t* seed_dev, uint32_t rng_stream, int out_f16, void* out_act_bf16,
+                             void* stream) {
   ZNS_REQUIRE(x && weight && bias && out_act, "NULL argument");
   ZNS_REQUIRE(batch > 0 && H > 0 && W > 0 && drop_p >= 0.f && drop_p < 1.f, "bad conv1 geometry");
   dim3 grid((W + 31) / 32, H, zns_groups(batch));
   conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, clip_stride, row_stride, weight, bias, (bf16*)out_act, batch, H, W,
-                                                           drop_p, seed, seed_dev, rng_stream);
+                                                           drop_p, seed, seed_dev, rng_stream, out_f16, (bf16*)out_act_bf16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -178,7 +183,17 @@ extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long cli
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d((pool,1)) -> ReLU -> Dropout, and its backward (first arg-max routing)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+__device__ __forceinline__ void unpack8(const uint4& u, float* f, bool f16 = false) {
+  if (f16) {
+    const __half2* p = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 v = __half22float2(p[i]);
+      f[2 * i] = v.x;
+      f[2 * i + 1] = v.y;
+    }
+    return;
+  }
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -187,13 +202,13 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
     f[2 * i + 1] = v.y;
   }
 }
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+__device__ __forceinline__ uint4 pack8(const float* f, bool f16 = false) {
+  return make_uint4(pack_act2(f[0], f[1], f16), pack_act2(f[2], f[3], f16), pack_act2(f[4], f[5], f16), pack_act2(f[6], f[7], f16));
 }
 
 __global__ void pool_fwd_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, size_t n_vec, size_t row_vec,
                                 int Hp, int pool, float drop_p, uint32_t seed, const uint32_t* __restrict__ seed_dev,
-                                uint32_t stream_id) {
+                                uint32_t stream_id, int f16, uint4* __restrict__ out2) {
   if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
   // vec index = ((g*Hp + hp) * row_vec + r), row_vec = W*8*C/8
   const uint32_t thr = dropout_threshold(drop_p);
@@ -203,9 +218,9 @@ __global__ void pool_fwd_kernel(const uint4* __restrict__ y, uint4* __restrict__
     const size_t g = ghp / Hp, hp = ghp - g * Hp;
     const uint4* src = y + ((g * Hp + hp) * pool) * row_vec + r;
     float m[8], v[8];
-    unpack8(__ldg(src), m);
+    unpack8(__ldg(src), m, f16);
     for (int k = 1; k < pool; ++k) {
-      unpack8(__ldg(src + (size_t)k * row_vec), v);
+      unpack8(__ldg(src + (size_t)k * row_vec), v, f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
     }
@@ -215,12 +230,14 @@ __global__ void pool_fwd_kernel(const uint4* __restrict__ y, uint4* __restrict__
       if (drop_p > 0.f) t = (zns_hash32(i * 8 + j, seed, stream_id) >= thr) ? t * keep_scale : 0.f;
       m[j] = t;
     }
-    out[i] = pack8(m);
+    out[i] = pack8(m, f16);
+    if (out2) out2[i] = pack8(m, false);   // bf16 copy: the x operand of the next layer's weight gradient
   }
 }
 
 extern "C" int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, int W, int C, int pool, float drop_p,
-                            uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, void* stream) {
+                            uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int act_f16, void* out_act_bf16,
+                            void* stream) {
   ZNS_REQUIRE(y_act && out_act, "NULL argument");
   ZNS_REQUIRE(pool >= 1 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
   const int G = zns_groups(batch), Hp = H / pool;
@@ -228,24 +245,24 @@ extern "C" int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, 
   const size_t n_vec = (size_t)G * Hp * row_vec;
   const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
   pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_act, (uint4*)out_act, n_vec, row_vec, Hp,
-                                                            pool, drop_p, seed, seed_dev, rng_stream);
+                                                            pool, drop_p, seed, seed_dev, rng_stream, act_f16, (uint4*)out_act_bf16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
 
 __global__ void pool_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dp, uint4* __restrict__ dy,
-                                size_t n_vec, size_t row_vec, int Hp, int pool) {
+                                size_t n_vec, size_t row_vec, int Hp, int pool, int y_f16) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
     const size_t ghp = i / row_vec, r = i - ghp * row_vec;
     const size_t g = ghp / Hp, hp = ghp - g * Hp;
     const size_t base = ((g * Hp + hp) * pool) * row_vec + r;
     float m[8], v[8], d[8];
     int arg[8];
-    unpack8(__ldg(y + base), m);
+    unpack8(__ldg(y + base), m, y_f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) arg[j] = 0;
     for (int k = 1; k < pool; ++k) {
-      unpack8(__ldg(y + base + (size_t)k * row_vec), v);
+      unpack8(__ldg(y + base + (size_t)k * row_vec), v, y_f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (v[j] > m[j]) { m[j] = v[j]; arg[j] = k; }
@@ -260,7 +277,7 @@ __global__ void pool_bwd_kernel(const uint4* __restrict__ y, const uint4* __rest
 }
 
 extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_act, int batch, int H, int W, int C,
-                            int pool, void* stream) {
+                            int pool, int y_f16, void* stream) {
   ZNS_REQUIRE(y_act && dpool_act && dy_act, "NULL argument");
   ZNS_REQUIRE(pool >= 1 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
   const int G = zns_groups(batch), Hp = H / pool;
@@ -268,7 +285,7 @@ extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_a
   const size_t n_vec = (size_t)G * Hp * row_vec;
   const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
   pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_act, (const uint4*)dpool_act, (uint4*)dy_act,
-                                                            n_vec, row_vec, Hp, pool);
+                                                            n_vec, row_vec, Hp, pool, y_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -281,7 +298,7 @@ extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_a
 
 __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ emb, int B,
-                                                       int T, int n_pos) {
+                                                       int T, int n_pos, int f16) {
   const int part = threadIdx.x & 7;
   const int pos = blockIdx.x * 32 + (threadIdx.x >> 3);
   float acc = 0.f;
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ 
     float v[8];
 #pragma unroll
     for (int hlf = 0; hlf < 2; ++hlf) {
-      unpack8(__ldg(src + hlf), v);
+      unpack8(__ldg(src + hlf), v, f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc = fmaf(v[j], __ldg(w + part * 16 + hlf * 8 + j), acc);
     }
@@ -308,11 +325,11 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ 
 }
 
 extern "C" int zns_head_fwd(const void* x_act, const float* w128, const float* bias1, float* emb, int batch, int T,
-                            void* stream) {
+                            int x_f16, void* stream) {
   ZNS_REQUIRE(x_act && w128 && bias1 && emb, "NULL argument");
   const int n_pos = zns_groups(batch) * T * 8;
   head_fwd_kernel<<<(n_pos + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_act, w128, bias1, emb, batch, T,
-                                                                        n_pos);
+                                                                        n_pos, x_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -320,7 +337,7 @@ extern "C" int zns_head_fwd(const void* x_act, const float* w128, const float* b
 __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ emb,
                                                        const float* __restrict__ d_emb, const float* __restrict__ w,
                                                        float* __restrict__ dw, float* __restrict__ dbias,
-                                                       bf16* __restrict__ dy, int B, int T, int n_pos, float out_scale) {
+                                                       bf16* __restrict__ dy, int B, int T, int n_pos, float out_scale, int x_f16) {
   __shared__ float sdw[HD_C];
   __shared__ float sdb;
   if (threadIdx.x < HD_C) sdw[threadIdx.x] = 0.f;
@@ -342,7 +359,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ 
     float v[8], o[8];
 #pragma unroll
     for (int hlf = 0; hlf < 2; ++hlf) {
-      unpack8(__ldg(src + hlf), v);
+      unpack8(__ldg(src + hlf), v, x_f16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = part * 16 + hlf * 8 + j;
@@ -359,11 +376,11 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ 
 }
 
 extern "C" int zns_head_bwd(const void* x_act, const float* emb, const float* d_emb, const float* w128, float* dw128,
-                            float* dbias1, void* dy_act, int batch, int T, float out_scale, void* stream) {
+                            float* dbias1, void* dy_act, int batch, int T, float out_scale, int x_f16, void* stream) {
   ZNS_REQUIRE(x_act && emb && d_emb && w128 && dw128 && dbias1 && dy_act, "NULL argument");
   const int n_pos = zns_groups(batch) * T * 8;
   head_bwd_kernel<<<(n_pos + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_act, emb, d_emb, w128, dw128,
-                                                                        dbias1, (bf16*)dy_act, batch, T, n_pos, out_scale);
+                                                                        dbias1, (bf16*)dy_act, batch, T, n_pos, out_scale, x_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -389,7 +406,7 @@ extern "C" int zns_merge(const float* a, const float* b, float* out, long long n
 // layout converters
 // ---------------------------------------------------------------------------------------------
 __global__ void act_from_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ act, int B, int C, int H, int W,
-                                     size_t total) {
+                                     size_t total, int f16) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int c = (int)(r % C); r /= C;
@@ -397,34 +414,37 @@ __global__ void act_from_nchw_kernel(const float* __restrict__ x, bf16* __restri
     const int w = (int)(r % W); r /= W;
     const int h = (int)(r % H); r /= H;
     const int b = (int)r * 8 + b8;
-    act[i] = __float2bfloat16(b < B ? x[(((size_t)b * C + c) * H + h) * W + w] : 0.f);
+    const float v = b < B ? x[(((size_t)b * C + c) * H + h) * W + w] : 0.f;
+    if (f16) reinterpret_cast<__half*>(act)[i] = __float2half_rn(v);
+    else act[i] = __float2bfloat16(v);
   }
 }
 __global__ void act_to_nchw_kernel(const bf16* __restrict__ act, float* __restrict__ x, int B, int C, int H, int W,
-                                   size_t total) {
+                                   size_t total, int f16) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int w = (int)(r % W); r /= W;
     const int h = (int)(r % H); r /= H;
     const int c = (int)(r % C); r /= C;
     const int b = (int)r;
-    x[i] = __bfloat162float(act[zns_act_index(b / 8, h, w, b % 8, c, H, W, C)]);
+    const size_t e = zns_act_index(b / 8, h, w, b % 8, c, H, W, C);
+    x[i] = f16 ? __half2float(reinterpret_cast<const __half*>(act)[e]) : __bfloat162float(act[e]);
   }
 }
 
-extern "C" int zns_act_from_nchw(const float* x, void* act, int batch, int C, int H, int W, void* stream) {
+extern "C" int zns_act_from_nchw(const float* x, void* act, int batch, int C, int H, int W, int act_f16, void* stream) {
   ZNS_REQUIRE(x && act, "NULL argument");
   const size_t total = (size_t)zns_groups(batch) * H * W * 8 * C;
   act_from_nchw_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      x, (bf16*)act, batch, C, H, W, total);
+      x, (bf16*)act, batch, C, H, W, total, act_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
-extern "C" int zns_act_to_nchw(const void* act, float* x, int batch, int C, int H, int W, void* stream) {
+extern "C" int zns_act_to_nchw(const void* act, float* x, int batch, int C, int H, int W, int act_f16, void* stream) {
   ZNS_REQUIRE(x && act, "NULL argument");
   const size_t total = (size_t)batch * C * H * W;
   act_to_nchw_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)act, x, batch, C, H, W, total);
+      (const bf16*)act, x, batch, C, H, W, total, act_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
@@ -434,7 +454,7 @@ extern "C" int zns_act_to_nchw(const void* act, float* x, int batch, int C, int 
 // (each through a shared-memory tile so that both sides stay coalesced)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_wf_kernel(const float* __restrict__ w, bf16* __restrict__ wf, int c_out,
-                                                      int c_in, int ntaps) {
+                                                      int c_in, int ntaps, int f16) {
   extern __shared__ float tile[];  // [64 ci][ntaps]
   const int co = blockIdx.y, ci0 = blockIdx.x * 64;
   const float* src = w + ((size_t)co * c_in + ci0) * ntaps;
@@ -443,7 +463,9 @@ __global__ void __launch_bounds__(256) pack_wf_kernel(const float* __restrict__ 
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += 256) {
     const int t = i / 64, ci = i - t * 64;
-    wf[((size_t)t * c_out + co) * c_in + ci0 + ci] = __float2bfloat16(tile[ci * ntaps + t]);
+    const size_t o = ((size_t)t * c_out + co) * c_in + ci0 + ci;
+    if (f16) reinterpret_cast<__half*>(wf)[o] = __float2half_rn(tile[ci * ntaps + t]);
+    else wf[o] = __float2bfloat16(tile[ci * ntaps + t]);
   }
 }
 __global__ void __launch_bounds__(256) pack_wd_kernel(const float* __restrict__ w, bf16* __restrict__ wd, int c_out,
@@ -462,14 +484,15 @@ __global__ void __launch_bounds__(256) pack_wd_kernel(const float* __restrict__ 
   }
 }
 
-extern "C" int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, void* stream) {
+extern "C" int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, int wf_f16,
+                                void* stream) {
   ZNS_REQUIRE(w, "NULL weight");
   ZNS_REQUIRE(c_out % 64 == 0 && c_in % 64 == 0, "channels must be multiples of 64 (got %d, %d)", c_out, c_in);
   const int ntaps = kh * kw;
   const size_t smem = (size_t)64 * ntaps * sizeof(float);
   ZNS_REQUIRE(smem <= 48 * 1024, "filter with %d taps not supported", ntaps);
   if (wf) {
-    pack_wf_kernel<<<dim3(c_in / 64, c_out), 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wf, c_out, c_in, ntaps);
+    pack_wf_kernel<<<dim3(c_in / 64, c_out), 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wf, c_out, c_in, ntaps, wf_f16);
     ZNS_CHECK_LAUNCH();
   }
   if (wd) {

@@ -436,6 +436,7 @@ struct VqtLevelArgs {
   long long dst_cap;           // samples the next level's buffer holds per clip
   int tiles_per_clip, n_tiles;
   long long* dbg;              // optional per-role cycle counters of CTA 0 (zns_dbg_vqt_timing), else NULL
+  int mode;                    // timing build only (ZNS_VQT_DBG_MODE): knock-out bits, see VQT_KO
 };
 
 // Cycle counters of the roles (zns_dbg_vqt_timing) exist only in builds with -DZNS_VQT_TIMING: the product kernels carry
@@ -443,9 +444,14 @@ struct VqtLevelArgs {
 #ifdef ZNS_VQT_TIMING
 #define VQT_CLOCK() clock64()
 #define VQT_TIMING_ON true
+// knock-out experiments (results are garbage, only the time is of interest): 1 loader skips the fp32 -> fp16 split,
+// 2 epilogue skips everything but the handshakes, 4 issuers skip the MMAs, 8 loaders skip the copies, 16 epilogue skips
+// the global stores only
+#define VQT_KO(bit) ((A.mode & (bit)) != 0)
 #else
 #define VQT_CLOCK() 0LL
 #define VQT_TIMING_ON false
+#define VQT_KO(bit) false
 #endif
 
 template <bool SRC_F32>
@@ -536,6 +542,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             const int i_end = sg.begin + sg.count;
 #pragma unroll 4
             for (int i = sg.begin; i < i_end; ++i) {
+              if (VQT_KO(4)) break;
               const VqtMmaPacked m = L.pk[i];
               umma_f16(cb + m.col, hi_norm | (uint64_t)(m.a_lo + a16), hi_norm | (uint64_t)(m.b_lo + b16), m.idesc, 1u);
             }
@@ -586,7 +593,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         }
         tc_fence_after();
         const uint32_t acc = tl + (uint32_t)(L.ring_base[type] + (int)stage * L.ring_width[type]);
-        if (type == 1) {
+        if (VQT_KO(2)) {
+        } else if (type == 1) {
           const int c0 = 64 * (job - 1);
           const int w = min(64, L.dec_w - c0);
           uint16_t* dh = A.dst_hi + (size_t)clip * A.dst_stride;
@@ -612,7 +620,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             uint4 h1a, h2a, h1b, h2b;
             split8(yv, h1a, h2a);
             split8(yv + 8, h1b, h2b);
-            if (t0 < A.dst_cap) {
+            if (t0 < A.dst_cap && !VQT_KO(16)) {
               const long long o = o_row + kb * o_blk;
               if (L.dec_w >= 16) {           // 16 outputs = two chunks of one row (tiled: 2 KB apart; linear: adjacent)
                 const long long o2 = A.dst_q == 1 ? o + 8 : o + 1024;
@@ -633,7 +641,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           tmem_ld_32x8(acc + 24 + 2 * k0, fg); tmem_ld_32x8(acc + 24 + 2 * k0 + 8, fg + 8); // x1 . g2
           tmem_ld_32x8(acc + L.fb_n1 + 2 * k0, fb); tmem_ld_32x8(acc + L.fb_n1 + 2 * k0 + 8, fb + 8);   // x2 . g1
           tmem_ld_wait();
-          if (f < A.n_frames) {
+          if (f < A.n_frames && !VQT_KO(16)) {
             float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * A.n_frames + f;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
@@ -651,7 +659,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             tmem_ld_32x16(acc + L.fb_n1 + 24 * j, fb);
             tmem_ld_32x8(acc + L.fb_n1 + 24 * j + 16, fb + 16);
             tmem_ld_wait();
-            if (f < A.n_frames) {
+            if (f < A.n_frames && !VQT_KO(16)) {
               float* op = A.out + ((size_t)clip * A.n_bins + L.bin0) * A.n_frames + f;
 #pragma unroll
               for (int k = 0; k < 12; ++k) {
@@ -708,6 +716,10 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           if (lane == 0) mbar_wait_parked(bempty, par);
           __syncwarp();
           t_wait_ld += VQT_CLOCK() - t0;
+        }
+        if (VQT_KO(8)) {
+          if (SRC_F32 || lane == 0) mbar_arrive(bfull);     // fp32 source: every lane arrives; bulk copies: one per warp
+          continue;
         }
         if (!SRC_F32) {
           // levels >= 1: the source is stored tile by tile in plane order: per plane and term one 2 KB bulk copy for the
@@ -773,7 +785,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           cp_async_wait_all();
           const long long tp2 = VQT_CLOCK();
           t_p1 += tp1 - tp0; t_cpw += tp2 - tp1;
-          {
+          if (!VQT_KO(1)) {
             // phase 2: in place, every lane converts the chunks it fetched itself
             uint32_t d1 = s1 + off0, d2 = s2 + off0;
             const int n_cv = n_it;
@@ -937,6 +949,9 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     a.tiles_per_clip = (rows + 127) / 128;
     a.n_tiles = a.tiles_per_clip * batch;
     a.dbg = g_vqt_dbg ? g_vqt_dbg + 32 * i : nullptr;
+#ifdef ZNS_VQT_TIMING
+    a.mode = getenv("ZNS_VQT_DBG_MODE") ? atoi(getenv("ZNS_VQT_DBG_MODE")) : 0;
+#endif
     const int grid = std::min(a.n_tiles, n_sm[dev]);
     const size_t smem = level_smem(L);
     if (i == 0) vqt_level_kernel<true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);

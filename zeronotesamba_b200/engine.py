@@ -58,10 +58,13 @@ class EncoderEngine:
         self.G = (batch + 7) // 8
         self.seed = seed
         bf = torch.bfloat16
+        # forward activations and the forward weight pack are fp16 (11 significant bits; same tensor-core rate as bf16;
+        # log-magnitude inputs in [-21, 2] and O(1..100) activations are far inside its range), gradients stay bf16
+        fa = torch.float16
         G = self.G
 
         def act(H, Cc):
-            return [torch.zeros(G, H, T, 8, Cc, dtype=bf, device=device) for _ in range(n_br)]
+            return [torch.zeros(G, H, T, 8, Cc, dtype=fa, device=device) for _ in range(n_br)]
 
         # forward activations (kept for backward)
         self.x1 = act(96, 64)      # dropout(relu(cv1))
@@ -75,19 +78,29 @@ class EncoderEngine:
         self.p6 = act(1, 256)
         self.x7 = act(1, 128)
         self.x8 = act(1, 128)
+        # bf16 shadows of the activations that are the x operand of a weight gradient (written by the producing kernel next
+        # to the fp16 tensor): both operands of one tcgen05.mma must share a type, and gradients are bf16
+        self._shadow: Dict[int, List[torch.Tensor]] = {}
+
+        def shadow(ts):
+            self._shadow[id(ts)] = [torch.zeros_like(t, dtype=bf) for t in ts]
+
+        for ts in (self.x1, self.p2, self.x3, self.p4, self.x5, self.p6, self.x7):
+            shadow(ts)
         self.emb = [torch.zeros(batch, T, device=device) for _ in range(n_br)]
         # packed weights / gradients for cv2..cv8
         self.wf: Dict[str, List[torch.Tensor]] = {}
         self.wd: Dict[str, List[torch.Tensor]] = {}
         self.gp: Dict[str, List[torch.Tensor]] = {}
         for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
-            self.wf[name] = [torch.zeros(kh * kw, co, ci, dtype=bf, device=device) for _ in range(n_br)]
+            self.wf[name] = [torch.zeros(kh * kw, co, ci, dtype=fa, device=device) for _ in range(n_br)]
             self.wd[name] = [torch.zeros(kh * kw, ci, co, dtype=bf, device=device) for _ in range(n_br)]
         self._grad_ws_ready = False
         self.step_ctr = torch.zeros(1, dtype=torch.int32, device=device)  # dropout seed word / Adam step
         self._x_in: List[Optional[torch.Tensor]] = [None] * n_br
         self._x_stride = 0
         self._train = False
+        self._need_shadow = False
         self._p = 0.0
         # optional per-launch timing (bench.py): list of (tag, flops, start_event, end_event)
         self.timers: Optional[list] = None
@@ -156,38 +169,45 @@ class EncoderEngine:
             for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
                 w = params[br][f"pretrained.{name}.weight"]
                 L.check(lib.zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(self.wf[name][br]),
-                                             L.ptr(self.wd[name][br]) if (need_dgrad and name != "cv1") else None, st))
+                                             L.ptr(self.wd[name][br]) if (need_dgrad and name != "cv1") else None, 1, st))
 
     # -- forward -----------------------------------------------------------------------------------
     def _conv(self, name, H, ins, outs, params, relu, drop, layer_id):
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw, relu=relu, dropout_p=self._p if drop else 0.0,
-                        seed=self.seed, rng_stream=layer_id * 2, seed_dev=self.step_ctr if drop and self._p > 0 else None)
+                        seed=self.seed, rng_stream=layer_id * 2, seed_dev=self.step_ctr if drop and self._p > 0 else None,
+                        fmt=L.FMT_FORWARD_F16)
         bias = [params[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]
         with self._timed(_fwd_tag(co, H), self._conv_flops(name, H)):
+            sh = self._shadow.get(id(outs)) if self._need_shadow else None
             L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(ins), L.ptr_array(self.wf[name]),
-                                         L.ptr_array(bias), None, L.ptr_array(outs), L.current_stream()))
+                                         L.ptr_array(bias), None, L.ptr_array(outs), L.ptr_array(sh) if sh else None,
+                                         L.current_stream()))
 
     def _pool(self, H, Cc, pool, ys, outs, layer_id):
         lib, st = L.lib(), L.current_stream()
         for br in range(self.n_br):
+            sh = self._shadow[id(outs)][br] if self._need_shadow else None
             L.check(lib.zns_pool_fwd(L.ptr(ys[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, self._p, self.seed,
-                                     L.ptr(self.step_ctr) if self._p > 0 else None, layer_id * 2 + br, st))
+                                     L.ptr(self.step_ctr) if self._p > 0 else None, layer_id * 2 + br, 1, L.ptr(sh), st))
 
     def forward(self, xs: Sequence[torch.Tensor], x_clip_stride: int, params: Sequence[Dict[str, torch.Tensor]],
-                train: bool, dropout_p: float = 0.1, x_row_stride: Optional[int] = None) -> List[torch.Tensor]:
+                train: bool, dropout_p: float = 0.1, x_row_stride: Optional[int] = None,
+                need_grad: Optional[bool] = None) -> List[torch.Tensor]:
         """xs[br]: fp32 CUDA tensor; clip b / row h / frame w is read at
         ``data_ptr + b * x_clip_stride + h * x_row_stride + w`` (x_row_stride defaults to T).
         Returns [emb (B, T)] per branch."""
         lib, st = L.lib(), L.current_stream()
         self._train, self._p = train, (dropout_p if train else 0.0)
+        self._need_shadow = train if need_grad is None else bool(need_grad)   # bf16 copies only when a backward follows
         self._x_in, self._x_stride = list(xs), x_clip_stride
         self._x_row = self.T if x_row_stride is None else int(x_row_stride)
         for br in range(self.n_br):
             p = params[br]
             L.check(lib.zns_conv1_fwd(L.ptr(xs[br]), x_clip_stride, self._x_row, L.ptr(p["pretrained.cv1.weight"]),
                                       L.ptr(p["pretrained.cv1.bias"]), L.ptr(self.x1[br]), self.B, N_BINS, self.T,
-                                      self._p, self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, 100 + br, st))
+                                      self._p, self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, 100 + br, 1,
+                                      L.ptr(self._shadow[id(self.x1)][br]) if self._need_shadow else None, st))
         if getattr(self, "_pack_event", None) is not None:      # packs issued by pack_weights_async
             torch.cuda.current_stream().wait_event(self._pack_event)
             self._pack_event = None
@@ -204,7 +224,7 @@ class EncoderEngine:
         for br in range(self.n_br):
             p = params[br]
             L.check(lib.zns_head_fwd(L.ptr(self.x8[br]), L.ptr(p["fc1.weight"]), L.ptr(p["fc1.bias"]), L.ptr(self.emb[br]),
-                                     self.B, self.T, st))
+                                     self.B, self.T, 1, st))
         return self.emb
 
     # -- backward ----------------------------------------------------------------------------------
@@ -228,8 +248,9 @@ class EncoderEngine:
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
         lib, st = L.lib(), L.current_stream()
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw)
+        xb = self._shadow[id(xs)]                      # bf16 copy of the fp16 forward activation (same type as dy)
         with self._timed(f"conv_wgrad_umma<{min(co, 128)}>", self._conv_flops(name, H)):
-            L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xs), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
+            L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xb), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
         for br in range(self.n_br):
             L.check(lib.zns_bias_grad(L.ptr(dys[br]), self.B, H, self.T, co, L.ptr(grads[br][f"pretrained.{name}.bias"]), st))
             # packed [tap][c_out][c_in] -> state_dict layout, on the same (side) stream: overlaps later layers
@@ -242,18 +263,20 @@ class EncoderEngine:
         d = L.conv_desc(self.B, H, self.T, co, ci, kh, kw, relu=0, out_scale=scale)
         with self._timed(_fwd_tag(ci, H), self._conv_flops(name, H)):
             L.check(L.lib().zns_conv_fwd(C.byref(d), self.n_br, L.ptr_array(dys), L.ptr_array(self.wd[name]), None,
-                                         L.ptr_array(masks), L.ptr_array(outs), L.current_stream()))
+                                         L.ptr_array(masks), L.ptr_array(outs), None, L.current_stream()))
 
     def _unpool(self, H, Cc, pool, ys, dps, outs):
         lib, st = L.lib(), L.current_stream()
         for br in range(self.n_br):
-            L.check(lib.zns_pool_bwd(L.ptr(ys[br]), L.ptr(dps[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, st))
+            L.check(lib.zns_pool_bwd(L.ptr(ys[br]), L.ptr(dps[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, 1, st))
 
     def backward(self, d_embs: Sequence[torch.Tensor], params: Sequence[Dict[str, torch.Tensor]],
                  grads: Sequence[Dict[str, torch.Tensor]]) -> None:
         """Accumulate (+=) parameter gradients into ``grads[br][name]`` (fp32, state_dict layout;
         they must be zeroed by the caller).  ``d_embs[br]``: (B, T) fp32 gradient of the loss."""
         self._ensure_grad_ws()
+        if not self._need_shadow:
+            raise RuntimeError("backward() needs a forward(..., train=True) or forward(..., need_grad=True) before it")
         lib, st = L.lib(), L.current_stream()
         scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
         ga, gb = self.ga, self.gb
@@ -261,7 +284,7 @@ class EncoderEngine:
             self.gp_flat[br].zero_()
             p, g = params[br], grads[br]
             L.check(lib.zns_head_bwd(L.ptr(self.x8[br]), L.ptr(self.emb[br]), L.ptr(d_embs[br]), L.ptr(p["fc1.weight"]),
-                                     L.ptr(g["fc1.weight"]), L.ptr(g["fc1.bias"]), L.ptr(ga[br]), self.B, self.T, scale, st))
+                                     L.ptr(g["fc1.weight"]), L.ptr(g["fc1.bias"]), L.ptr(ga[br]), self.B, self.T, scale, 1, st))
         main = torch.cuda.current_stream()
 
         def join(ev):

@@ -108,16 +108,17 @@ class _EncoderFunction(torch.autograd.Function):
             eng = cache.get(FOLD_SLOTS, plan[0], n_br, xs[0].device)
         else:
             eng = cache.get(B, T, n_br, xs[0].device)
-        eng.pack_weights(params, need_dgrad=True)
+        need_grad = any(ctx.needs_input_grad[4 + n_br:])     # a backward may follow (train or eval mode)
+        eng.pack_weights(params, need_dgrad=need_grad)
         if train and dropout_p > 0:
             # the keep masks are hash(element, seed ^ step counter, layer): a new counter value per training forward
             # gives a fresh mask (reference: nn.Dropout draws from the global generator, models.py:30)
             L.check(L.lib().zns_counter_add(L.ptr(eng.step_ctr), 1, L.current_stream()))
         if plan is not None:
-            embs = eng.forward(xs, plan[1], params, train=train, dropout_p=dropout_p, x_row_stride=T)
+            embs = eng.forward(xs, plan[1], params, train=train, dropout_p=dropout_p, x_row_stride=T, need_grad=need_grad)
             out = tuple(_unfold(e, plan, T) for e in embs)
         else:
-            embs = eng.forward(xs, 96 * T, params, train=train, dropout_p=dropout_p)
+            embs = eng.forward(xs, 96 * T, params, train=train, dropout_p=dropout_p, need_grad=need_grad)
             out = tuple(e.clone() for e in embs)
         ctx.eng, ctx.params, ctx.n_br, ctx.n_names, ctx.plan = eng, params, n_br, len(names), plan
         ctx.version = getattr(eng, "_version", 0) + 1
@@ -174,9 +175,9 @@ class _CNN(nn.Module):
         params[0]["fc1.weight"], params[0]["fc1.bias"] = zero_fc
         eng = self._cache.get(B, T, 1, x.device)
         eng.pack_weights(params, need_dgrad=False)
-        eng.forward(xs, 96 * T, params, train=self.training, dropout_p=self.dp.p)
+        eng.forward(xs, 96 * T, params, train=self.training, dropout_p=self.dp.p, need_grad=False)
         out = torch.empty(B, 128, 1, T, device=x.device)
-        L.check(L.lib().zns_act_to_nchw(L.ptr(eng.x8[0]), L.ptr(out), B, 128, 1, T, L.current_stream()))
+        L.check(L.lib().zns_act_to_nchw(L.ptr(eng.x8[0]), L.ptr(out), B, 128, 1, T, 1, L.current_stream()))
         return torch.squeeze(out, dim=2)
 
 

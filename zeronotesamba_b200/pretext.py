@@ -456,3 +456,126 @@ def crop_batches(bank: torch.Tensor, batch_len: int, rng: Optional[random.Random
         starts = sample_crop_starts(batch_len, rng, n_frames=frames, crop=crop)
         st = torch.tensor(starts, dtype=torch.int32, device=bank.device)
         yield [crop_batch(bank[i], st, crop=crop)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# train_model: the epoch driver of pretext.py:175-415 on device-resident banks
+# ---------------------------------------------------------------------------------------------------
+def _rank_world() -> Tuple[int, int]:
+    if dist_utils.is_distributed():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def _mean_over_ranks(values: Sequence[float], device: torch.device) -> List[float]:
+    """Average per-rank epoch statistics (every rank saw an equal share of the clips)."""
+    if not dist_utils.is_distributed():
+        return [float(v) for v in values]
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t)
+    return (t / torch.distributed.get_world_size()).tolist()
+
+
+def train_model(ymldict: Dict, train_bank: torch.Tensor, val_bank: torch.Tensor, model_dir: str = "models",
+                chunks_per_epoch: int = 20, val_chunks: int = 10, seed: int = 0, model: Optional[torch.nn.Module] = None,
+                verbose: bool = True):
+    """Pretext training driver with the reference's epoch structure (pretext.py:175-415) and YAML keys (``batch_size``,
+    ``num_epochs``, ``temp``, ``pt_task``; ``lr`` is honoured), on banks that already live on the GPU.
+
+    ``train_bank`` / ``val_bank``: CUDA fp32 (n, 2, 96, F) log-VQT banks, channel 0 = anchor stems, 1 = drums
+    (``vqt_bank`` builds them from audio; the reference unpickles 28800 / 6400 clips of 626 frames, pretext.py:255-263).
+
+    Per epoch, as the reference does: shuffle the training clips, walk them in ``chunks_per_epoch`` chunks, draw
+    ``batch_size`` distinct crop starts per clip so that one batch is the shifts of one clip (pretext.py:308-321),
+    ``train_epoch`` per chunk, average; validation crops are drawn once at epoch 0 (pretext.py:271-279) and reused;
+    the ``state_dict`` is saved to ``{model_dir}/shift_pret_cnn_{batch_size}.pth`` (``clmr_pret_cnn_...`` for CLMR)
+    whenever the validation loss improves (pretext.py:409-412).
+
+    Data parallel (one process per GPU, torch.distributed initialised): every rank holds the same banks and takes the
+    clips ``rank::world`` of the epoch's permutation (drawn from a seed shared by all ranks), statistics are averaged
+    over ranks, and rank 0 alone writes the checkpoint.  Clips a chunk cannot deal evenly to the ranks are dropped for
+    that epoch (the fused step is collective).
+    Returns (model, history) with history = dict of per-epoch lists."""
+    epochs = int(float(ymldict.get("num_epochs", -1)))
+    batch_len = int(float(ymldict.get("batch_size", -1)))
+    pt_task = ymldict.get("pt_task")
+    if pt_task not in ("zerons", "clmr"):
+        raise ValueError("Which pretext task are we running?")
+    if train_bank.device.type != "cuda" or val_bank.device.type != "cuda":
+        raise RuntimeError("train_model needs the banks on a CUDA device (no CPU fallback)")
+    device = train_bank.device
+    built, criterion, optimizer = build_from_config(ymldict, device)
+    if model is None:
+        model = built
+    else:                                                   # caller-provided weights (resume): same optimizer family
+        optimizer = FusedAdam(model.parameters(), lr=optimizer.param_groups[0]["lr"])
+    model_name = ("shift_pret_cnn_{}.pth" if pt_task == "zerons" else "clmr_pret_cnn_{}.pth").format(batch_len)
+    rank, world = _rank_world()
+    crop = CROP_FRAMES if train_bank.shape[3] > CROP_FRAMES else train_bank.shape[3]
+    shared = random.Random(seed)                            # same stream on every rank: permutations
+    local = random.Random(seed * 7919 + 1 + rank)           # per rank: crop starts
+    history = dict(train_loss=[], train_an_pos=[], train_an_neg=[], val_loss=[], val_an_pos=[], val_an_neg=[], saved=[])
+    best_val = float("inf")
+    say = print if (verbose and rank == 0) else (lambda *a, **k: None)
+
+    def my_share(indices: List[int]) -> List[int]:
+        return [indices[k] for k in dist_utils.shard_clips(len(indices), rank, world)]
+
+    # validation crops: drawn once, kept as start indices (the reference materialises 6400 x batch_len crops)
+    val_ids = my_share(list(range(val_bank.shape[0])))
+    if crop == val_bank.shape[3]:
+        val_starts = {i: [0] * batch_len for i in val_ids}
+    else:
+        val_starts = {i: sample_crop_starts(batch_len, local, n_frames=val_bank.shape[3], crop=crop) for i in val_ids}
+
+    def batches(bank, ids, starts_of):
+        for i in ids:
+            st = torch.tensor(starts_of(i), dtype=torch.int32, device=device)
+            yield [crop_batch(bank[i], st, crop=crop)]
+
+    def draw_train(_i):
+        if crop == train_bank.shape[3]:
+            return [0] * batch_len
+        return sample_crop_starts(batch_len, local, n_frames=train_bank.shape[3], crop=crop)
+
+    for epoch in range(epochs):
+        say("\n--- Epoch {} ---\n".format(epoch))
+        order = list(range(train_bank.shape[0]))
+        shared.shuffle(order)
+        n_chunks = max(1, min(chunks_per_epoch, len(order) // max(world, 1)))
+        per_chunk = len(order) // n_chunks
+        sums = [0.0, 0.0, 0.0]
+        for jj in range(n_chunks):
+            ids = my_share(order[jj * per_chunk:(jj + 1) * per_chunk])
+            say("{} : Training...".format(jj))
+            model, t_loss, t_pos, t_neg = train_epoch(model, batches(train_bank, ids, draw_train), criterion, optimizer,
+                                                      pt_task=pt_task)
+            sums = [a + b for a, b in zip(sums, (t_loss, t_pos, t_neg))]
+        tr_stats = _mean_over_ranks([s / n_chunks for s in sums], device)
+        say("\n!!! Mean training batch loss is {:.3f}.".format(tr_stats[0]))
+        say("!!! Mean training anchor / positive similiarity is {:.3f}.".format(tr_stats[1]))
+        say("!!! Mean training anchor / negative similiarity is {:.3f}.".format(tr_stats[2]))
+        say("\n{} : Validating...".format(epoch))
+        n_vc = max(1, min(val_chunks, len(val_ids)))
+        per_vc = len(val_ids) // n_vc
+        vsums = [0.0, 0.0, 0.0]
+        for zz in range(n_vc):
+            ids = val_ids[zz * per_vc:(zz + 1) * per_vc]
+            v = val_epoch(model, batches(val_bank, ids, lambda i: val_starts[i]), criterion, optimizer, pt_task=pt_task)
+            vsums = [a + b for a, b in zip(vsums, v)]
+        va_stats = _mean_over_ranks([s / n_vc for s in vsums], device)
+        say("\n!!! Mean validation batch loss is {:.3f}.".format(va_stats[0]))
+        say("!!! Mean validation anchor / positive similiarity is {:.3f}.".format(va_stats[1]))
+        say("!!! Mean validation anchor / negative similiarity is {:.3f}.".format(va_stats[2]))
+        improved = va_stats[0] < best_val
+        if improved:
+            best_val = va_stats[0]
+            if rank == 0:                                   # replicas are identical: one writer
+                os.makedirs(model_dir, exist_ok=True)
+                path = os.path.join(model_dir, model_name)
+                torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
+                say("...Saved model to " + path)
+        for k, v in zip(("train_loss", "train_an_pos", "train_an_neg", "val_loss", "val_an_pos", "val_an_neg", "saved"),
+                        (*tr_stats, *va_stats, improved)):
+            history[k].append(v)
+    return model, history
