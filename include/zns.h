@@ -181,6 +181,40 @@ int zns_act_from_nchw(const float* x, void* act, int batch, int C, int H, int W,
 int zns_act_to_nchw(const void* act, float* x, int batch, int C, int H, int W, int act_f16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched variants: the anchor and the positive encoder (models.py:114-124) have identical geometry, so one launch
+ * serves both (`n_br` = 1 or 2, arrays of per-branch pointers; branch b draws its dropout mask from rng_stream + b), and
+ * one launch packs / unpacks every convolution weight of both encoders.  The single-tensor entry points above are the
+ * n_br = 1 / n = 1 cases of these.
+ * ---------------------------------------------------------------------------------------- */
+int zns_conv1_fwd_nbr(int n_br, const float* const* x, long long x_clip_stride, long long x_row_stride,
+                      const float* const* weight, const float* const* bias, void* const* out_act, int batch, int H, int W,
+                      float dropout_p, uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int out_f16,
+                      void* const* out_act_bf16, void* stream);
+int zns_conv1_wgrad_nbr(int n_br, const void* const* dy_act, const float* const* x, long long x_clip_stride,
+                        long long x_row_stride, float* const* dw, float* const* db, int batch, int H, int W, void* stream);
+int zns_pool_fwd_nbr(int n_br, const void* const* y_act, void* const* out_act, int batch, int H, int W, int C, int pool,
+                     float dropout_p, uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int act_f16,
+                     void* const* out_act_bf16, void* stream);
+int zns_pool_bwd_nbr(int n_br, const void* const* y_act, const void* const* dpool_act, void* const* dy_act, int batch, int H,
+                     int W, int C, int pool, int y_f16, void* stream);
+int zns_head_fwd_nbr(int n_br, const void* const* x_act, const float* const* w128, const float* const* bias1,
+                     float* const* emb, int batch, int T, int x_f16, void* stream);
+int zns_head_bwd_nbr(int n_br, const void* const* x_act, const float* const* emb, const float* const* d_emb,
+                     const float* const* w128, float* const* dw128, float* const* dbias1, void* const* dy_act, int batch, int T,
+                     float out_scale, int x_f16, void* stream);
+int zns_bias_grad_nbr(int n_br, const void* const* dy_act, int batch, int H, int W, int C, float* const* db, void* stream);
+/* n <= 16 weights: w[i] fp32 [c_out[i]][c_in[i]][kh[i]][kw[i]] -> wf[i] / wd[i] as zns_pack_weights (entries or whole
+ * arrays may be NULL). */
+int zns_pack_weights_multi(int n, const float* const* w, const int* c_out, const int* c_in, const int* kh, const int* kw,
+                           void* const* wf, void* const* wd, int wf_f16, void* stream);
+/* n <= 32 packed gradients -> state_dict layout as zns_unpack_grads; with zero_packed the packed accumulators are
+ * cleared behind the read, so the next step's atomics start from zero without a memset launch. */
+int zns_unpack_grads_multi(int n, float* const* gpk, const int* c_out, const int* c_in, const int* kh, const int* kw,
+                           float scale, int accumulate, int zero_packed, float* const* g, void* stream);
+/* cudaMemsetAsync(p, 0, bytes): a memset node in a captured graph instead of a fill kernel. */
+int zns_zero(void* p, long long bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * NT-Xent (loss_functions.py:24-55), forward and backward in one launch.
  * anchors/poss fp32 [n_rows][dim]; result[0..2] = loss, mean cos(a_i,p_i), mean_i mean_{j!=i}
  * cos(a_i,p_j), all divided by batch_len as the reference does (rows beyond n_rows count as zero

@@ -493,3 +493,108 @@ def test_conv_full_size_layers(B, H, W, ci, co, kh, kw, adt):
                                  L.ptr_array([dx]), None, st()))
     xg = torch.autograd.grad(F.conv2d(xr, bf16_round(w), None, padding=(kh // 2, kw // 2)), xr, bf16_round(dy))[0]
     assert rel_err(from_act(dx, B), xg * (xr.detach() > 0)) < 4e-3
+
+
+# --------------------------------------------------------------------------------------------
+# batched (two-branch) and multi-tensor launches == the single-tensor entry points
+# --------------------------------------------------------------------------------------------
+def test_two_branch_launches_equal_single_calls():
+    lib = L.lib()
+    B, H, W, G = 11, 12, 37, 2
+    g = torch.Generator().manual_seed(21)
+    r = lambda *s: torch.randn(*s, generator=g).to(DEV)
+    # cv1 forward (dropout on: branch b draws from rng_stream + b) and weight gradient
+    xs, ws, bs = [r(B, H, W) for _ in range(2)], [r(64, 1, 3, 11) * 0.2 for _ in range(2)], [r(64) * 0.1 for _ in range(2)]
+    ctr = torch.tensor([3], dtype=torch.int32, device=DEV)
+    one = [torch.empty(G, H, W, 8, 64, dtype=F16, device=DEV) for _ in range(2)]
+    one_b = [torch.empty(G, H, W, 8, 64, dtype=BF16, device=DEV) for _ in range(2)]
+    for b in range(2):
+        L.check(lib.zns_conv1_fwd(L.ptr(xs[b]), H * W, W, L.ptr(ws[b]), L.ptr(bs[b]), L.ptr(one[b]), B, H, W, 0.1, 5, L.ptr(ctr),
+                                  40 + b, 1, L.ptr(one_b[b]), st()))
+    two = [torch.empty_like(t) for t in one]
+    two_b = [torch.empty_like(t) for t in one_b]
+    L.check(lib.zns_conv1_fwd_nbr(2, L.ptr_array(xs), H * W, W, L.ptr_array(ws), L.ptr_array(bs), L.ptr_array(two), B, H, W, 0.1,
+                                  5, L.ptr(ctr), 40, 1, L.ptr_array(two_b), st()))
+    assert all(torch.equal(a, b) for a, b in zip(one + one_b, two + two_b))
+    assert not torch.equal(two[0] != 0, two[1] != 0)
+    dys = [to_act(r(B, 64, H, W)) for _ in range(2)]
+    dw1, db1 = [torch.zeros(64, 1, 3, 11, device=DEV) for _ in range(2)], [torch.zeros(64, device=DEV) for _ in range(2)]
+    dw2, db2 = [torch.zeros_like(t) for t in dw1], [torch.zeros_like(t) for t in db1]
+    for b in range(2):
+        L.check(lib.zns_conv1_wgrad(L.ptr(dys[b]), L.ptr(xs[b]), H * W, W, L.ptr(dw1[b]), L.ptr(db1[b]), B, H, W, st()))
+    L.check(lib.zns_conv1_wgrad_nbr(2, L.ptr_array(dys), L.ptr_array(xs), H * W, W, L.ptr_array(dw2), L.ptr_array(db2), B, H, W, st()))
+    for a, b in zip(dw1 + db1, dw2 + db2):
+        assert rel_err(b, a) < 1e-5          # fp32 atomics: order differs
+    # pool forward / backward
+    Cc, pool = 128, 4
+    ys = [to_act(r(B, Cc, H, W), F16) for _ in range(2)]
+    p1 = [torch.empty(G, H // pool, W, 8, Cc, dtype=F16, device=DEV) for _ in range(2)]
+    p2 = [torch.empty_like(t) for t in p1]
+    p2b = [torch.empty_like(t, dtype=BF16) for t in p1]
+    for b in range(2):
+        L.check(lib.zns_pool_fwd(L.ptr(ys[b]), L.ptr(p1[b]), B, H, W, Cc, pool, 0.1, 9, None, 6 + b, 1, None, st()))
+    L.check(lib.zns_pool_fwd_nbr(2, L.ptr_array(ys), L.ptr_array(p2), B, H, W, Cc, pool, 0.1, 9, None, 6, 1, L.ptr_array(p2b), st()))
+    assert all(torch.equal(a, b) for a, b in zip(p1, p2)) and all(torch.equal(a.float().to(BF16), b) for a, b in zip(p2, p2b))
+    dps = [to_act(r(B, Cc, H // pool, W)) for _ in range(2)]
+    d1 = [torch.empty(G, H, W, 8, Cc, dtype=BF16, device=DEV) for _ in range(2)]
+    d2 = [torch.empty_like(t) for t in d1]
+    for b in range(2):
+        L.check(lib.zns_pool_bwd(L.ptr(ys[b]), L.ptr(dps[b]), L.ptr(d1[b]), B, H, W, Cc, pool, 1, st()))
+    L.check(lib.zns_pool_bwd_nbr(2, L.ptr_array(ys), L.ptr_array(dps), L.ptr_array(d2), B, H, W, Cc, pool, 1, st()))
+    assert all(torch.equal(a, b) for a, b in zip(d1, d2))
+    # head forward / backward, bias gradient
+    T = 50
+    x8 = [to_act(F.relu(r(B, 128, 1, T)), F16) for _ in range(2)]
+    hw, hb = [r(1, 128, 1) * 0.1 for _ in range(2)], [r(1) * 0.1 for _ in range(2)]
+    e1, e2 = [torch.empty(B, T, device=DEV) for _ in range(2)], [torch.empty(B, T, device=DEV) for _ in range(2)]
+    for b in range(2):
+        L.check(lib.zns_head_fwd(L.ptr(x8[b]), L.ptr(hw[b]), L.ptr(hb[b]), L.ptr(e1[b]), B, T, 1, st()))
+    L.check(lib.zns_head_fwd_nbr(2, L.ptr_array(x8), L.ptr_array(hw), L.ptr_array(hb), L.ptr_array(e2), B, T, 1, st()))
+    assert all(torch.equal(a, b) for a, b in zip(e1, e2))
+    de = [r(B, T) for _ in range(2)]
+    gw1, gb1 = [torch.zeros(1, 128, 1, device=DEV) for _ in range(2)], [torch.zeros(1, device=DEV) for _ in range(2)]
+    gw2, gb2 = [torch.zeros_like(t) for t in gw1], [torch.zeros_like(t) for t in gb1]
+    y1 = [torch.empty(G, 1, T, 8, 128, dtype=BF16, device=DEV) for _ in range(2)]
+    y2 = [torch.empty_like(t) for t in y1]
+    for b in range(2):
+        L.check(lib.zns_head_bwd(L.ptr(x8[b]), L.ptr(e1[b]), L.ptr(de[b]), L.ptr(hw[b]), L.ptr(gw1[b]), L.ptr(gb1[b]), L.ptr(y1[b]),
+                                 B, T, 1.25, 1, st()))
+    L.check(lib.zns_head_bwd_nbr(2, L.ptr_array(x8), L.ptr_array(e2), L.ptr_array(de), L.ptr_array(hw), L.ptr_array(gw2),
+                                 L.ptr_array(gb2), L.ptr_array(y2), B, T, 1.25, 1, st()))
+    assert all(torch.equal(a, b) for a, b in zip(y1, y2))
+    for a, b in zip(gw1 + gb1, gw2 + gb2):
+        assert rel_err(b, a) < 1e-5
+    bg1, bg2 = [torch.zeros(64, device=DEV) for _ in range(2)], [torch.zeros(64, device=DEV) for _ in range(2)]
+    for b in range(2):
+        L.check(lib.zns_bias_grad(L.ptr(dys[b]), B, H, W, 64, L.ptr(bg1[b]), st()))
+    L.check(lib.zns_bias_grad_nbr(2, L.ptr_array(dys), B, H, W, 64, L.ptr_array(bg2), st()))
+    for a, b in zip(bg1, bg2):
+        assert rel_err(b, a) < 1e-5
+
+
+def test_multi_tensor_pack_and_unpack():
+    lib = L.lib()
+    geo = [(64, 64, 7, 13), (128, 64, 5, 15), (128, 128, 9, 17), (256, 128, 3, 19), (256, 256, 5, 21), (128, 256, 1, 23),
+           (128, 128, 1, 25)] * 2                                   # the fourteen conv weights of the two encoders
+    ws = [torch.randn(co, ci, kh, kw, device=DEV) for co, ci, kh, kw in geo]
+    wf = [torch.empty(kh * kw, co, ci, dtype=F16, device=DEV) for co, ci, kh, kw in geo]
+    wd = [torch.empty(kh * kw, ci, co, dtype=BF16, device=DEV) for co, ci, kh, kw in geo]
+    cols = [L.int_array([x[i] for x in geo]) for i in range(4)]
+    L.check(lib.zns_pack_weights_multi(len(geo), L.ptr_array(ws), *cols, L.ptr_array(wf), L.ptr_array(wd), 1, st()))
+    for w, f, d in zip(ws, wf, wd):
+        assert torch.equal(f, pack_wf(w, F16)) and torch.equal(d, pack_wd(w))
+    # forward packs only (inference): the flipped packs stay untouched
+    wd0 = [t.clone() for t in wd]
+    wf2 = [torch.zeros_like(t) for t in wf]
+    L.check(lib.zns_pack_weights_multi(len(geo), L.ptr_array(ws), *cols, L.ptr_array(wf2), L.ptr_array([None] * len(geo)), 1, st()))
+    assert all(torch.equal(a, b) for a, b in zip(wf, wf2)) and all(torch.equal(a, b) for a, b in zip(wd, wd0))
+    gp = [torch.randn(kh * kw, co, ci, device=DEV) for co, ci, kh, kw in geo]
+    gp0 = [t.clone() for t in gp]
+    gout = [torch.ones(co, ci, kh, kw, device=DEV) for co, ci, kh, kw in geo]
+    L.check(lib.zns_unpack_grads_multi(len(geo), L.ptr_array(gp), *cols, 0.5, 1, 1, L.ptr_array(gout), st()))
+    for (co, ci, kh, kw), a, b, c in zip(geo, gp0, gout, gp):
+        assert torch.allclose(b, 1.0 + 0.5 * a.view(kh, kw, co, ci).permute(2, 3, 0, 1))
+        assert float(c.abs().max()) == 0.0                          # packed accumulators cleared behind the read
+    z = torch.ones(1000, device=DEV)
+    L.check(lib.zns_zero(L.ptr(z), 4 * 1000, st()))
+    assert float(z.abs().max()) == 0.0

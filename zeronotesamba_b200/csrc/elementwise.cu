@@ -24,13 +24,22 @@ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 #define C1_TAPS 33
 #define C1_CO 64
 
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, long long clip_stride,
-                                                        long long row_stride, const float* __restrict__ weight,
-                                                        const float* __restrict__ bias, bf16* __restrict__ out,
+// Per-branch pointers of the kernels that run the anchor and the positive encoder in ONE launch (grid.z or grid.y carries
+// the branch): the reference's two DS_CNN branches (models.py:114-124) have identical geometry.
+struct C1FwdBr { const float* x; const float* weight; const float* bias; bf16* out; bf16* out2; };
+struct C1FwdArgs { C1FwdBr br[2]; int G; };
+
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const C1FwdArgs a, long long clip_stride, long long row_stride,
                                                         int B, int H, int W, float drop_p, uint32_t seed,
-                                                        const uint32_t* __restrict__ seed_dev, uint32_t stream_id, int f16,
-                                                        bf16* __restrict__ out2) {
+                                                        const uint32_t* __restrict__ seed_dev, uint32_t stream_id, int f16) {
   __shared__ __align__(16) float ws[C1_TAPS][C1_CO];
+  const int branch = blockIdx.z / a.G;
+  const float* __restrict__ x = a.br[branch].x;
+  const float* __restrict__ weight = a.br[branch].weight;
+  const float* __restrict__ bias = a.br[branch].bias;
+  bf16* __restrict__ out = a.br[branch].out;
+  bf16* __restrict__ out2 = a.br[branch].out2;
+  stream_id += branch;
   if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
   __shared__ float bs[C1_CO];
   for (int i = threadIdx.x; i < C1_TAPS * C1_CO; i += 256) {
@@ -40,7 +49,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   if (threadIdx.x < C1_CO) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int b8 = threadIdx.x & 7, wl = threadIdx.x >> 3;
-  const int g = blockIdx.z, h = blockIdx.y, w = blockIdx.x * 32 + wl;
+  const int g = blockIdx.z - branch * a.G, h = blockIdx.y, w = blockIdx.x * 32 + wl;
   if (w >= W) return;
   const int b = g * 8 + b8;
   uint4* dst = reinterpret_cast<uint4*>(out + zns_act_index(g, h, w, b8, 0, H, W, C1_CO));
@@ -90,17 +99,33 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   }
 }
 
+extern "C" int zns_conv1_fwd_nbr(int n_br, const float* const* x, long long clip_stride, long long row_stride,
+                                 const float* const* weight, const float* const* bias, void* const* out_act, int batch, int H,
+                                 int W, float drop_p, uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int out_f16,
+                                 void* const* out_act_bf16, void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  ZNS_REQUIRE(x && weight && bias && out_act, "NULL argument");
+  ZNS_REQUIRE(batch > 0 && H > 0 && W > 0 && drop_p >= 0.f && drop_p < 1.f, "bad conv1 geometry");
+  C1FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = zns_groups(batch);
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(x[b] && weight[b] && bias[b] && out_act[b], "NULL tensor for branch %d", b);
+    a.br[b] = C1FwdBr{x[b], weight[b], bias[b], (bf16*)out_act[b], out_act_bf16 ? (bf16*)out_act_bf16[b] : nullptr};
+  }
+  dim3 grid((W + 31) / 32, H, a.G * n_br);
+  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, clip_stride, row_stride, batch, H, W, drop_p, seed, seed_dev,
+                                                           rng_stream, out_f16);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
 extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long row_stride, const float* weight,
                              const float* bias, void* out_act, int batch, int H, int W, float drop_p, uint32_t seed,
                              const uint32_t* seed_dev, uint32_t rng_stream, int out_f16, void* out_act_bf16,
                              void* stream) {
-  ZNS_REQUIRE(x && weight && bias && out_act, "NULL argument");
-  ZNS_REQUIRE(batch > 0 && H > 0 && W > 0 && drop_p >= 0.f && drop_p < 1.f, "bad conv1 geometry");
-  dim3 grid((W + 31) / 32, H, zns_groups(batch));
-  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, clip_stride, row_stride, weight, bias, (bf16*)out_act, batch, H, W,
-                                                           drop_p, seed, seed_dev, rng_stream, out_f16, (bf16*)out_act_bf16);
-  ZNS_CHECK_LAUNCH();
-  return ZNS_OK;
+  return zns_conv1_fwd_nbr(1, &x, clip_stride, row_stride, &weight, &bias, &out_act, batch, H, W, drop_p, seed, seed_dev,
+                           rng_stream, out_f16, out_act_bf16 ? &out_act_bf16 : nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -111,12 +136,19 @@ extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long ro
 // shared-memory load of dy.
 #define C1W_TILES 5   // 32-frame tiles per block: fewer same-address atomics on the 64 x 33 gradient
 
-__global__ void __launch_bounds__(192) conv1_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
-                                                          long long clip_stride, long long row_stride, float* __restrict__ dw,
-                                                          float* __restrict__ db, int B, int H, int W) {
+struct C1WgBr { const bf16* dy; const float* x; float* dw; float* db; };
+struct C1WgArgs { C1WgBr br[2]; int G; };
+
+__global__ void __launch_bounds__(192) conv1_wgrad_kernel(const C1WgArgs a, long long clip_stride, long long row_stride,
+                                                          int B, int H, int W) {
   __shared__ float xs[C1_KH][8][32 + C1_KW - 1];
   __shared__ __align__(16) bf16 dys[32 * 8 * C1_CO];      // [frame][clip slot][64 channels], 32 KB
-  const int g = blockIdx.z, h = blockIdx.y;
+  const int branch = blockIdx.z / a.G;
+  const bf16* __restrict__ dy = a.br[branch].dy;
+  const float* __restrict__ x = a.br[branch].x;
+  float* __restrict__ dw = a.br[branch].dw;
+  float* __restrict__ db = a.br[branch].db;
+  const int g = blockIdx.z - branch * a.G, h = blockIdx.y;
   const int n = threadIdx.x & 63, r = threadIdx.x >> 6;   // r = 0..2
   float acc[C1_KW];
 #pragma unroll
@@ -170,14 +202,27 @@ __global__ void __launch_bounds__(192) conv1_wgrad_kernel(const bf16* __restrict
   if (r == 0) atomicAdd(db + n, accb);
 }
 
-extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long clip_stride, long long row_stride, float* dw,
-                               float* db, int batch, int H, int W, void* stream) {
+extern "C" int zns_conv1_wgrad_nbr(int n_br, const void* const* dy_act, const float* const* x, long long clip_stride,
+                                   long long row_stride, float* const* dw, float* const* db, int batch, int H, int W,
+                                   void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(dy_act && x && dw && db, "NULL argument");
-  dim3 grid((W + 32 * C1W_TILES - 1) / (32 * C1W_TILES), H, zns_groups(batch));
-  conv1_wgrad_kernel<<<grid, 192, 0, (cudaStream_t)stream>>>((const bf16*)dy_act, x, clip_stride, row_stride, dw, db, batch, H,
-                                                             W);
+  C1WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = zns_groups(batch);
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(dy_act[b] && x[b] && dw[b] && db[b], "NULL tensor for branch %d", b);
+    a.br[b] = C1WgBr{(const bf16*)dy_act[b], x[b], dw[b], db[b]};
+  }
+  dim3 grid((W + 32 * C1W_TILES - 1) / (32 * C1W_TILES), H, a.G * n_br);
+  conv1_wgrad_kernel<<<grid, 192, 0, (cudaStream_t)stream>>>(a, clip_stride, row_stride, batch, H, W);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
+}
+
+extern "C" int zns_conv1_wgrad(const void* dy_act, const float* x, long long clip_stride, long long row_stride, float* dw,
+                               float* db, int batch, int H, int W, void* stream) {
+  return zns_conv1_wgrad_nbr(1, &dy_act, &x, clip_stride, row_stride, &dw, &db, batch, H, W, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,9 +251,16 @@ __device__ __forceinline__ uint4 pack8(const float* f, bool f16 = false) {
   return make_uint4(pack_act2(f[0], f[1], f16), pack_act2(f[2], f[3], f16), pack_act2(f[4], f[5], f16), pack_act2(f[6], f[7], f16));
 }
 
-__global__ void pool_fwd_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, size_t n_vec, size_t row_vec,
+struct PoolBr { const uint4* y; uint4* out; uint4* out2; const uint4* dp; uint4* dy; };
+struct PoolArgs { PoolBr br[2]; };
+
+__global__ void pool_fwd_kernel(const PoolArgs a, size_t n_vec, size_t row_vec,
                                 int Hp, int pool, float drop_p, uint32_t seed, const uint32_t* __restrict__ seed_dev,
-                                uint32_t stream_id, int f16, uint4* __restrict__ out2) {
+                                uint32_t stream_id, int f16) {
+  const uint4* __restrict__ y = a.br[blockIdx.y].y;
+  uint4* __restrict__ out = a.br[blockIdx.y].out;
+  uint4* __restrict__ out2 = a.br[blockIdx.y].out2;
+  stream_id += blockIdx.y;
   if (seed_dev) seed ^= __ldg(seed_dev) * 0x9E3779B9u;
   // vec index = ((g*Hp + hp) * row_vec + r), row_vec = W*8*C/8
   const uint32_t thr = dropout_threshold(drop_p);
@@ -235,23 +287,40 @@ __global__ void pool_fwd_kernel(const uint4* __restrict__ y, uint4* __restrict__
   }
 }
 
-extern "C" int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, int W, int C, int pool, float drop_p,
-                            uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int act_f16, void* out_act_bf16,
-                            void* stream) {
+extern "C" int zns_pool_fwd_nbr(int n_br, const void* const* y_act, void* const* out_act, int batch, int H, int W, int C,
+                                int pool, float drop_p, uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int act_f16,
+                                void* const* out_act_bf16, void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(y_act && out_act, "NULL argument");
   ZNS_REQUIRE(pool >= 1 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
+  PoolArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(y_act[b] && out_act[b], "NULL tensor for branch %d", b);
+    a.br[b].y = (const uint4*)y_act[b]; a.br[b].out = (uint4*)out_act[b];
+    a.br[b].out2 = out_act_bf16 ? (uint4*)out_act_bf16[b] : nullptr;
+  }
   const int G = zns_groups(batch), Hp = H / pool;
   const size_t row_vec = (size_t)W * 8 * C / 8;
   const size_t n_vec = (size_t)G * Hp * row_vec;
   const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
-  pool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_act, (uint4*)out_act, n_vec, row_vec, Hp,
-                                                            pool, drop_p, seed, seed_dev, rng_stream, act_f16, (uint4*)out_act_bf16);
+  pool_fwd_kernel<<<dim3(blocks, n_br), 256, 0, (cudaStream_t)stream>>>(a, n_vec, row_vec, Hp, pool, drop_p, seed, seed_dev,
+                                                                        rng_stream, act_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
 
-__global__ void pool_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dp, uint4* __restrict__ dy,
-                                size_t n_vec, size_t row_vec, int Hp, int pool, int y_f16) {
+extern "C" int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, int W, int C, int pool, float drop_p,
+                            uint32_t seed, const uint32_t* seed_dev, uint32_t rng_stream, int act_f16, void* out_act_bf16,
+                            void* stream) {
+  return zns_pool_fwd_nbr(1, &y_act, &out_act, batch, H, W, C, pool, drop_p, seed, seed_dev, rng_stream, act_f16,
+                          out_act_bf16 ? &out_act_bf16 : nullptr, stream);
+}
+
+__global__ void pool_bwd_kernel(const PoolArgs a, size_t n_vec, size_t row_vec, int Hp, int pool, int y_f16) {
+  const uint4* __restrict__ y = a.br[blockIdx.y].y;
+  const uint4* __restrict__ dp = a.br[blockIdx.y].dp;
+  uint4* __restrict__ dy = a.br[blockIdx.y].dy;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
     const size_t ghp = i / row_vec, r = i - ghp * row_vec;
     const size_t g = ghp / Hp, hp = ghp - g * Hp;
@@ -276,18 +345,29 @@ __global__ void pool_bwd_kernel(const uint4* __restrict__ y, const uint4* __rest
   }
 }
 
-extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_act, int batch, int H, int W, int C,
-                            int pool, int y_f16, void* stream) {
+extern "C" int zns_pool_bwd_nbr(int n_br, const void* const* y_act, const void* const* dpool_act, void* const* dy_act, int batch,
+                                int H, int W, int C, int pool, int y_f16, void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(y_act && dpool_act && dy_act, "NULL argument");
   ZNS_REQUIRE(pool >= 1 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
+  PoolArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(y_act[b] && dpool_act[b] && dy_act[b], "NULL tensor for branch %d", b);
+    a.br[b].y = (const uint4*)y_act[b]; a.br[b].dp = (const uint4*)dpool_act[b]; a.br[b].dy = (uint4*)dy_act[b];
+  }
   const int G = zns_groups(batch), Hp = H / pool;
   const size_t row_vec = (size_t)W * 8 * C / 8;
   const size_t n_vec = (size_t)G * Hp * row_vec;
   const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
-  pool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_act, (const uint4*)dpool_act, (uint4*)dy_act,
-                                                            n_vec, row_vec, Hp, pool, y_f16);
+  pool_bwd_kernel<<<dim3(blocks, n_br), 256, 0, (cudaStream_t)stream>>>(a, n_vec, row_vec, Hp, pool, y_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
+}
+
+extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_act, int batch, int H, int W, int C,
+                            int pool, int y_f16, void* stream) {
+  return zns_pool_bwd_nbr(1, &y_act, &dpool_act, &dy_act, batch, H, W, C, pool, y_f16, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,9 +376,14 @@ extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_a
 // ---------------------------------------------------------------------------------------------
 #define HD_C 128
 
-__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ emb, int B,
-                                                       int T, int n_pos, int f16) {
+struct HeadBr { const bf16* x; const float* w; const float* bias; float* emb; const float* d_emb; float* dw; float* dbias; bf16* dy; };
+struct HeadArgs { HeadBr br[2]; };
+
+__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a, int B, int T, int n_pos, int f16) {
+  const bf16* __restrict__ x = a.br[blockIdx.y].x;
+  const float* __restrict__ w = a.br[blockIdx.y].w;
+  const float* __restrict__ bias = a.br[blockIdx.y].bias;
+  float* __restrict__ emb = a.br[blockIdx.y].emb;
   const int part = threadIdx.x & 7;
   const int pos = blockIdx.x * 32 + (threadIdx.x >> 3);
   float acc = 0.f;
@@ -324,20 +409,35 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ 
   }
 }
 
-extern "C" int zns_head_fwd(const void* x_act, const float* w128, const float* bias1, float* emb, int batch, int T,
-                            int x_f16, void* stream) {
+extern "C" int zns_head_fwd_nbr(int n_br, const void* const* x_act, const float* const* w128, const float* const* bias1,
+                                float* const* emb, int batch, int T, int x_f16, void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(x_act && w128 && bias1 && emb, "NULL argument");
+  HeadArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(x_act[b] && w128[b] && bias1[b] && emb[b], "NULL tensor for branch %d", b);
+    a.br[b].x = (const bf16*)x_act[b]; a.br[b].w = w128[b]; a.br[b].bias = bias1[b]; a.br[b].emb = emb[b];
+  }
   const int n_pos = zns_groups(batch) * T * 8;
-  head_fwd_kernel<<<(n_pos + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_act, w128, bias1, emb, batch, T,
-                                                                        n_pos, x_f16);
+  head_fwd_kernel<<<dim3((n_pos + 31) / 32, n_br), 256, 0, (cudaStream_t)stream>>>(a, batch, T, n_pos, x_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
 
-__global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ emb,
-                                                       const float* __restrict__ d_emb, const float* __restrict__ w,
-                                                       float* __restrict__ dw, float* __restrict__ dbias,
-                                                       bf16* __restrict__ dy, int B, int T, int n_pos, float out_scale, int x_f16) {
+extern "C" int zns_head_fwd(const void* x_act, const float* w128, const float* bias1, float* emb, int batch, int T,
+                            int x_f16, void* stream) {
+  return zns_head_fwd_nbr(1, &x_act, &w128, &bias1, &emb, batch, T, x_f16, stream);
+}
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a, int B, int T, int n_pos, float out_scale, int x_f16) {
+  const bf16* __restrict__ x = a.br[blockIdx.y].x;
+  const float* __restrict__ emb = a.br[blockIdx.y].emb;
+  const float* __restrict__ d_emb = a.br[blockIdx.y].d_emb;
+  const float* __restrict__ w = a.br[blockIdx.y].w;
+  float* __restrict__ dw = a.br[blockIdx.y].dw;
+  float* __restrict__ dbias = a.br[blockIdx.y].dbias;
+  bf16* __restrict__ dy = a.br[blockIdx.y].dy;
   __shared__ float sdw[HD_C];
   __shared__ float sdb;
   if (threadIdx.x < HD_C) sdw[threadIdx.x] = 0.f;
@@ -375,14 +475,27 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ 
   if (threadIdx.x == 0) atomicAdd(dbias, sdb);
 }
 
-extern "C" int zns_head_bwd(const void* x_act, const float* emb, const float* d_emb, const float* w128, float* dw128,
-                            float* dbias1, void* dy_act, int batch, int T, float out_scale, int x_f16, void* stream) {
+extern "C" int zns_head_bwd_nbr(int n_br, const void* const* x_act, const float* const* emb, const float* const* d_emb,
+                                const float* const* w128, float* const* dw128, float* const* dbias1, void* const* dy_act,
+                                int batch, int T, float out_scale, int x_f16, void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(x_act && emb && d_emb && w128 && dw128 && dbias1 && dy_act, "NULL argument");
+  HeadArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(x_act[b] && emb[b] && d_emb[b] && w128[b] && dw128[b] && dbias1[b] && dy_act[b], "NULL tensor for branch %d", b);
+    a.br[b].x = (const bf16*)x_act[b]; a.br[b].emb = const_cast<float*>(emb[b]); a.br[b].d_emb = d_emb[b]; a.br[b].w = w128[b];
+    a.br[b].dw = dw128[b]; a.br[b].dbias = dbias1[b]; a.br[b].dy = (bf16*)dy_act[b];
+  }
   const int n_pos = zns_groups(batch) * T * 8;
-  head_bwd_kernel<<<(n_pos + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)x_act, emb, d_emb, w128, dw128,
-                                                                        dbias1, (bf16*)dy_act, batch, T, n_pos, out_scale, x_f16);
+  head_bwd_kernel<<<dim3((n_pos + 31) / 32, n_br), 256, 0, (cudaStream_t)stream>>>(a, batch, T, n_pos, out_scale, x_f16);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
+}
+
+extern "C" int zns_head_bwd(const void* x_act, const float* emb, const float* d_emb, const float* w128, float* dw128,
+                            float* dbias1, void* dy_act, int batch, int T, float out_scale, int x_f16, void* stream) {
+  return zns_head_bwd_nbr(1, &x_act, &emb, &d_emb, &w128, &dw128, &dbias1, &dy_act, batch, T, out_scale, x_f16, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -453,10 +566,10 @@ extern "C" int zns_act_to_nchw(const void* act, float* x, int batch, int C, int 
 // weight packing: fp32 [co][ci][tap] -> bf16 wf [tap][co][ci] and wd [ntaps-1-tap][ci][co]
 // (each through a shared-memory tile so that both sides stay coalesced)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_wf_kernel(const float* __restrict__ w, bf16* __restrict__ wf, int c_out,
-                                                      int c_in, int ntaps, int f16) {
+__device__ __forceinline__ void pack_wf_block(int bx, int by, const float* __restrict__ w, bf16* __restrict__ wf, int c_out,
+                                              int c_in, int ntaps, int f16) {
   extern __shared__ float tile[];  // [64 ci][ntaps]
-  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  const int co = by, ci0 = bx * 64;
   const float* src = w + ((size_t)co * c_in + ci0) * ntaps;
   const int n = 64 * ntaps;
   for (int i = threadIdx.x; i < n; i += 256) tile[i] = __ldg(src + i);
@@ -468,10 +581,10 @@ __global__ void __launch_bounds__(256) pack_wf_kernel(const float* __restrict__ 
     else wf[o] = __float2bfloat16(tile[ci * ntaps + t]);
   }
 }
-__global__ void __launch_bounds__(256) pack_wd_kernel(const float* __restrict__ w, bf16* __restrict__ wd, int c_out,
-                                                      int c_in, int ntaps) {
+__device__ __forceinline__ void pack_wd_block(int bx, int by, const float* __restrict__ w, bf16* __restrict__ wd, int c_out,
+                                              int c_in, int ntaps) {
   extern __shared__ float tile[];  // [64 co][ntaps]
-  const int ci = blockIdx.y, co0 = blockIdx.x * 64;
+  const int ci = by, co0 = bx * 64;
   const int n = 64 * ntaps;
   for (int i = threadIdx.x; i < n; i += 256) {
     const int co = i / ntaps, t = i - co * ntaps;
@@ -484,56 +597,121 @@ __global__ void __launch_bounds__(256) pack_wd_kernel(const float* __restrict__ 
   }
 }
 
-extern "C" int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, int wf_f16,
-                                void* stream) {
-  ZNS_REQUIRE(w, "NULL weight");
-  ZNS_REQUIRE(c_out % 64 == 0 && c_in % 64 == 0, "channels must be multiples of 64 (got %d, %d)", c_out, c_in);
-  const int ntaps = kh * kw;
-  const size_t smem = (size_t)64 * ntaps * sizeof(float);
-  ZNS_REQUIRE(smem <= 48 * 1024, "filter with %d taps not supported", ntaps);
-  if (wf) {
-    pack_wf_kernel<<<dim3(c_in / 64, c_out), 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wf, c_out, c_in, ntaps, wf_f16);
-    ZNS_CHECK_LAUNCH();
-  }
-  if (wd) {
-    pack_wd_kernel<<<dim3(c_out / 64, c_in), 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wd, c_out, c_in, ntaps);
-    ZNS_CHECK_LAUNCH();
-  }
-  return ZNS_OK;
-}
-
-__global__ void __launch_bounds__(256) unpack_grads_kernel(const float* __restrict__ gpk, float* __restrict__ g,
-                                                           int c_out, int c_in, int ntaps, float scale, int accumulate) {
+__device__ __forceinline__ void unpack_grads_block(int bx, int by, float* __restrict__ gpk, float* __restrict__ g, int c_out,
+                                                   int c_in, int ntaps, float scale, int accumulate, int zero_src) {
   extern __shared__ float tile[];  // [64 ci][ntaps]
-  const int co = blockIdx.y, ci0 = blockIdx.x * 64;
+  const int co = by, ci0 = bx * 64;
   const int n = 64 * ntaps;
   for (int i = threadIdx.x; i < n; i += 256) {
     const int t = i / 64, ci = i - t * 64;
-    tile[ci * ntaps + t] = __ldg(gpk + ((size_t)t * c_out + co) * c_in + ci0 + ci);
+    float* src = gpk + ((size_t)t * c_out + co) * c_in + ci0 + ci;
+    tile[ci * ntaps + t] = *src;
+    if (zero_src) *src = 0.f;          // the packed accumulator is clean for the next step's atomics (no memset launch)
   }
   __syncthreads();
   float* dst = g + ((size_t)co * c_in + ci0) * ntaps;
   for (int i = threadIdx.x; i < n; i += 256) dst[i] = (accumulate ? dst[i] : 0.f) + scale * tile[i];
 }
 
+// Multi-tensor launches: one kernel packs (or unpacks) every convolution weight of both encoders.  A job is one
+// (tensor, direction); block b of the grid finds its job by scanning the (<= 32 entry) table in the kernel parameters.
+#define ZNS_MT_MAX_JOBS 32
+struct MtJob { const float* src; void* dst; int c_out, c_in, ntaps, kind, blk0, nbx; };   // kind 0 forward pack, 1 flipped pack, 2 unpack
+struct MtArgs { MtJob job[ZNS_MT_MAX_JOBS]; int n_jobs, f16, accumulate, zero_src; float scale; };
+
+__global__ void __launch_bounds__(256) multi_tensor_kernel(const MtArgs a) {
+  const int b = blockIdx.x;
+  int j = 0;
+  while (j + 1 < a.n_jobs && b >= a.job[j + 1].blk0) ++j;
+  const MtJob& J = a.job[j];
+  const int lb = b - J.blk0, bx = lb % J.nbx, by = lb / J.nbx;
+  if (J.kind == 0) pack_wf_block(bx, by, J.src, (bf16*)J.dst, J.c_out, J.c_in, J.ntaps, a.f16);
+  else if (J.kind == 1) pack_wd_block(bx, by, J.src, (bf16*)J.dst, J.c_out, J.c_in, J.ntaps);
+  else unpack_grads_block(bx, by, const_cast<float*>(J.src), (float*)J.dst, J.c_out, J.c_in, J.ntaps, a.scale, a.accumulate, a.zero_src);
+}
+
+static int launch_multi(MtArgs& a, int total_blocks, int max_taps, cudaStream_t st) {
+  const size_t smem = (size_t)64 * max_taps * sizeof(float);
+  ZNS_REQUIRE(smem <= 48 * 1024, "filter with %d taps not supported", max_taps);
+  if (total_blocks == 0) return ZNS_OK;
+  multi_tensor_kernel<<<total_blocks, 256, smem, st>>>(a);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
+extern "C" int zns_pack_weights_multi(int n, const float* const* w, const int* c_out, const int* c_in, const int* kh, const int* kw,
+                                      void* const* wf, void* const* wd, int wf_f16, void* stream) {
+  ZNS_REQUIRE(n >= 0 && 2 * n <= ZNS_MT_MAX_JOBS, "at most %d tensors per call", ZNS_MT_MAX_JOBS / 2);
+  ZNS_REQUIRE(n == 0 || (w && c_out && c_in && kh && kw), "NULL argument");
+  MtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.f16 = wf_f16;
+  int blk = 0, max_taps = 1;
+  for (int i = 0; i < n; ++i) {
+    ZNS_REQUIRE(w[i], "NULL weight %d", i);
+    ZNS_REQUIRE(c_out[i] % 64 == 0 && c_in[i] % 64 == 0, "channels must be multiples of 64 (got %d, %d)", c_out[i], c_in[i]);
+    const int ntaps = kh[i] * kw[i];
+    max_taps = std::max(max_taps, ntaps);
+    if (wf && wf[i]) {
+      a.job[a.n_jobs++] = MtJob{w[i], wf[i], c_out[i], c_in[i], ntaps, 0, blk, c_in[i] / 64};
+      blk += (c_in[i] / 64) * c_out[i];
+    }
+    if (wd && wd[i]) {
+      a.job[a.n_jobs++] = MtJob{w[i], wd[i], c_out[i], c_in[i], ntaps, 1, blk, c_out[i] / 64};
+      blk += (c_out[i] / 64) * c_in[i];
+    }
+  }
+  return launch_multi(a, blk, max_taps, (cudaStream_t)stream);
+}
+
+extern "C" int zns_pack_weights(const float* w, int c_out, int c_in, int kh, int kw, void* wf, void* wd, int wf_f16,
+                                void* stream) {
+  ZNS_REQUIRE(w, "NULL weight");
+  return zns_pack_weights_multi(1, &w, &c_out, &c_in, &kh, &kw, &wf, &wd, wf_f16, stream);
+}
+
+extern "C" int zns_unpack_grads_multi(int n, float* const* gpk, const int* c_out, const int* c_in, const int* kh, const int* kw,
+                                      float scale, int accumulate, int zero_packed, float* const* g, void* stream) {
+  ZNS_REQUIRE(n >= 0 && n <= ZNS_MT_MAX_JOBS, "at most %d tensors per call", ZNS_MT_MAX_JOBS);
+  ZNS_REQUIRE(n == 0 || (gpk && g && c_out && c_in && kh && kw), "NULL argument");
+  MtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = scale; a.accumulate = accumulate; a.zero_src = zero_packed;
+  int blk = 0, max_taps = 1;
+  for (int i = 0; i < n; ++i) {
+    ZNS_REQUIRE(gpk[i] && g[i], "NULL tensor %d", i);
+    ZNS_REQUIRE(c_out[i] >= 1 && c_in[i] % 64 == 0, "c_in must be a multiple of 64");
+    const int ntaps = kh[i] * kw[i];
+    max_taps = std::max(max_taps, ntaps);
+    a.job[a.n_jobs++] = MtJob{gpk[i], g[i], c_out[i], c_in[i], ntaps, 2, blk, c_in[i] / 64};
+    blk += (c_in[i] / 64) * c_out[i];
+  }
+  return launch_multi(a, blk, max_taps, (cudaStream_t)stream);
+}
+
 extern "C" int zns_unpack_grads(const float* gpk, int c_out, int c_in, int kh, int kw, float scale, int accumulate,
                                 float* g, void* stream) {
   ZNS_REQUIRE(gpk && g, "NULL argument");
-  ZNS_REQUIRE(c_out >= 1 && c_in % 64 == 0, "c_in must be a multiple of 64");
-  const int ntaps = kh * kw;
-  const size_t smem = (size_t)64 * ntaps * sizeof(float);
-  ZNS_REQUIRE(smem <= 48 * 1024, "filter with %d taps not supported", ntaps);
-  unpack_grads_kernel<<<dim3(c_in / 64, c_out), 256, smem, (cudaStream_t)stream>>>(gpk, g, c_out, c_in, ntaps, scale,
-                                                                                   accumulate);
-  ZNS_CHECK_LAUNCH();
+  float* src = const_cast<float*>(gpk);
+  return zns_unpack_grads_multi(1, &src, &c_out, &c_in, &kh, &kw, scale, accumulate, 0, &g, stream);
+}
+
+// Zero `bytes` bytes on the stream (cudaMemsetAsync: a memset node in a captured graph, not a kernel launch).
+extern "C" int zns_zero(void* p, long long bytes, void* stream) {
+  ZNS_REQUIRE(p && bytes >= 0, "bad argument");
+  ZNS_CHECK_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
   return ZNS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // bias gradient: db[c] += sum_p dy[p][c]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bias_grad_kernel(const uint4* __restrict__ dy, size_t n_pos, int C,
-                                                        float* __restrict__ db) {
+struct BiasBr { const uint4* dy; float* db; };
+struct BiasArgs { BiasBr br[2]; };
+
+__global__ void __launch_bounds__(256) bias_grad_kernel(const BiasArgs a, size_t n_pos, int C) {
+  const uint4* __restrict__ dy = a.br[blockIdx.y].dy;
+  float* __restrict__ db = a.br[blockIdx.y].db;
   // a thread owns 8 consecutive channels (one 16-byte load per position); C/8 threads span a position
   __shared__ float red[256 * 8];
   const int tpr = C / 8;                     // threads per position: 8, 16 or 32
@@ -560,15 +738,27 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const uint4* __restrict_
   }
 }
 
-extern "C" int zns_bias_grad(const void* dy_act, int batch, int H, int W, int C, float* db, void* stream) {
+extern "C" int zns_bias_grad_nbr(int n_br, const void* const* dy_act, int batch, int H, int W, int C, float* const* db,
+                                 void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(dy_act && db, "NULL argument");
   ZNS_REQUIRE(C == 64 || C == 128 || C == 256, "bias_grad supports C in {64,128,256}");
+  BiasArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(dy_act[b] && db[b], "NULL tensor for branch %d", b);
+    a.br[b].dy = (const uint4*)dy_act[b]; a.br[b].db = db[b];
+  }
   const size_t n_pos = (size_t)zns_groups(batch) * H * W * 8;
   const int rows_per_it = 256 / (C / 8);
   const int blocks = (int)std::min<size_t>((n_pos + (size_t)rows_per_it * 8 - 1) / ((size_t)rows_per_it * 8), 148 * 8);
-  bias_grad_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy_act, n_pos, C, db);
+  bias_grad_kernel<<<dim3(std::max(blocks, 1), n_br), 256, 0, (cudaStream_t)stream>>>(a, n_pos, C);
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
+}
+
+extern "C" int zns_bias_grad(const void* dy_act, int batch, int H, int W, int C, float* db, void* stream) {
+  return zns_bias_grad_nbr(1, &dy_act, batch, H, W, C, &db, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

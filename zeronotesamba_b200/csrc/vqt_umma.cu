@@ -351,6 +351,12 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* v) {
                : "memory");
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {       // MUFU.SQRT (2 ulp): the magnitude only feeds a log
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // 16-byte asynchronous global -> shared copy; bytes beyond src_bytes are zero filled
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -412,7 +418,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& c1, uint4& c2) {
 
 // Warp roles of the persistent level kernel: epilogue = warps 0..7, MMA issuers = warps 8..11 (one per scheduler
 // sub-partition), loaders = warps 12..19.
-#define VQT_EPI_WARPS 8
+#ifndef VQT_EPI_WARPS
+#define VQT_EPI_WARPS 8          // 16 measured slower (72 registers per thread -> spills): 0.88 vs 0.765 ms at cfg2
+#endif
+#define VQT_EPQ (VQT_EPI_WARPS / 4)      // epilogue warps per TMEM lane quadrant (2 or 4: must divide the twelve bins)
 #define VQT_LOAD_WARPS 8
 #define VQT_ISSUE_WARP0 VQT_EPI_WARPS
 #define VQT_LOAD_WARP0 (VQT_EPI_WARPS + ZNS_VQT_ISSUERS)
@@ -453,6 +462,57 @@ struct VqtLevelArgs {
 #define VQT_TIMING_ON false
 #define VQT_KO(bit) false
 #endif
+
+// Wait flavour of the level kernels (A/B at build time, -DZNS_VQT_WAIT=n): 0 parked (nanosleep back-off 20..80 ns),
+// 1 plain try_wait spin (the instruction itself suspends the thread for a while), 2 nanosleep fixed at 20 ns
+#ifndef ZNS_VQT_WAIT
+#define ZNS_VQT_WAIT 0
+#endif
+#ifndef ZNS_VQT_HINT
+#define ZNS_VQT_HINT 100000
+#endif
+#ifndef ZNS_VQT_SLEEP
+#define ZNS_VQT_SLEEP 200
+#endif
+__device__ __forceinline__ void vqt_wait(uint32_t bar, uint32_t parity) {
+#if ZNS_VQT_WAIT == 0
+  mbar_wait_parked(bar, parity);
+#elif ZNS_VQT_WAIT == 1
+#pragma unroll 1
+  for (int it = 0; it < 400000000; ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+#elif ZNS_VQT_WAIT == 2
+#pragma unroll 1
+  for (int it = 0; it < 100000000; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(20);
+  }
+  __trap();
+#elif ZNS_VQT_WAIT == 3
+  // try_wait with an explicit suspend-time hint: the hardware parks the thread until the phase completes or the hint expires
+#pragma unroll 1
+  for (int it = 0; it < 4000000; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ZNS_VQT_HINT)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+#else
+#pragma unroll 1
+  for (int it = 0; it < 100000000; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(ZNS_VQT_SLEEP);
+  }
+  __trap();
+#endif
+}
 
 template <bool SRC_F32>
 __global__ void __launch_bounds__(VQT_LEVEL_THREADS, 1)
@@ -513,7 +573,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           const int s_begin = L.seg_begin[isr][pos], s_end = L.seg_begin[isr][pos + 1];
           if (s_begin < s_end) {
             const long long t0 = VQT_CLOCK();
-            mbar_wait_parked(full0 + 8 * slot, full_par);
+            vqt_wait(full0 + 8 * slot, full_par);
             t_wait_full += VQT_CLOCK() - t0;
             tc_fence_after();
           }
@@ -530,7 +590,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             const uint32_t cb = tmem + stage * (uint32_t)L.ring_width[type];
             if (sg.flags & 1) {
               const long long t0 = VQT_CLOCK();
-              mbar_wait_parked(acce0 + 8 * bidx, ((inst >> sh) & 1) ^ 1);
+              vqt_wait(acce0 + 8 * bidx, ((inst >> sh) & 1) ^ 1);
               t_wait_acc += VQT_CLOCK() - t0;
               tc_fence_after();
               // clear this unit's columns: accumulate = 0 with the zero block as both operands
@@ -561,23 +621,33 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     __syncwarp();
   } else if (warp < VQT_EPI_WARPS) {
     // =================================== epilogue ===================================
-    const int quad = warp & 3, half = warp >> 2;
+    // VQT_EPQ warps per TMEM lane quadrant; warp `sub` of a quadrant takes every VQT_EPQ-th 16-column decimator block and
+    // its share of the filterbank bins / frames.  The roles run one dependent chain per warp (tcgen05.ld -> FP -> pack ->
+    // store), so throughput comes from the number of warps, not from the instruction count.
+    const int quad = warp & 3, sub = warp >> 2;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     long long t_wait_ep = 0;
     const long long t_begin_ep = VQT_CLOCK();
     int dst_shift = 3;                                      // log2(samples per row) of the next level
     while ((8 << (dst_shift - 3)) < 8 * A.dst_q) ++dst_shift;
+    constexpr int kBinsPerWarp = 12 / VQT_EPQ;              // fpr == 1: bins of this warp
     float isl[12];                                          // 1 / sqrt(L_k) / (coefficient scale) of this octave's bins
 #pragma unroll
     for (int k = 0; k < 12; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + k) * L.fb_scale;
+    float islw[kBinsPerWarp];
+#pragma unroll
+    for (int k = 0; k < kBinsPerWarp; ++k) islw[k] = __ldg(A.inv_sqrt_len + L.bin0 + kBinsPerWarp * sub + k) * L.fb_scale;
+    const float s_a = L.dec_scale, s_b = L.dec_scale * (1.f / 2048.f);
+    const int o_blk = A.dst_q == 1 ? 16 : 2048;             // 16 outputs further: two planes (tiled) / 16 samples
+    const int o_half = A.dst_q == 1 ? 8 : 1024;
+    int tau = (int)blockIdx.x, clip = tau / A.tiles_per_clip, tile_in_clip = tau - clip * A.tiles_per_clip;
+    const int clip_step = (int)gridDim.x / A.tiles_per_clip, tile_step = (int)gridDim.x - clip_step * A.tiles_per_clip;
 #pragma unroll 1
     for (int ts = 0; ts < n_my_tiles; ++ts) {
-      const int tau = (int)blockIdx.x + ts * (int)gridDim.x;
-      const int clip = tau / A.tiles_per_clip;
-      const long long row_first = (long long)(tau - clip * A.tiles_per_clip) * 128;
-      const long long g = row_first + quad * 32 + lane;   // global row
+      const int row_first = tile_in_clip * 128;
+      const int g = row_first + quad * 32 + lane;          // row of this thread inside the clip (< 2^24)
       // every decimator output of the tile lies inside the signal: no per-element masking (all but the last tile of a clip)
-      const bool tile_valid = (row_first + 128) * L.dec_w <= A.n_valid;
+      const bool tile_valid = (long long)(row_first + 128) * L.dec_w <= A.n_valid;
 #pragma unroll 1
       for (int jj = 0; jj < L.n_jobs; ++jj) {
         const int job = L.ep_job[jj];
@@ -587,7 +657,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const uint32_t stage = inst & (uint32_t)sh;
         {
           const long long t0 = VQT_CLOCK();
-          if (lane == 0) mbar_wait_parked(smem_u32(&bar_acc_full[type * 2 + stage]), (inst >> sh) & 1);
+          if (lane == 0) vqt_wait(smem_u32(&bar_acc_full[type * 2 + stage]), (inst >> sh) & 1);
           __syncwarp();
           t_wait_ep += VQT_CLOCK() - t0;
         }
@@ -600,16 +670,15 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           uint16_t* dh = A.dst_hi + (size_t)clip * A.dst_stride;
           uint16_t* dl = A.dst_lo + (size_t)clip * A.dst_stride;
           const int n_blk = (w + 15) / 16;
-          const long long t_row = g * L.dec_w + c0;                      // first output of this row in this pass
-          const long long o_row = level_index_pow2(t_row, A.dst_q, dst_shift);
-          const long long o_blk = A.dst_q == 1 ? 16 : 2048;               // 16 outputs further: two planes (tiled) / 16 samples
-          const float s_a = L.dec_scale, s_b = L.dec_scale * (1.f / 2048.f);
-          for (int kb = half; kb < n_blk; kb += 2) {
+          const int t_row = g * L.dec_w + c0;                            // first output of this row in this pass (< 2^31)
+          const long long o_row = level_index_pow2((long long)t_row, A.dst_q, dst_shift);
+#pragma unroll 1
+          for (int kb = sub; kb < n_blk; kb += VQT_EPQ) {
             uint32_t a[16], b[16];
             tmem_ld_32x16(acc + 16 * kb, a);
             tmem_ld_32x16(acc + L.dec_wp + 16 * kb, b);
             tmem_ld_wait();
-            const long long t0 = t_row + 16 * kb;
+            const int t0 = t_row + 16 * kb;
             float yv[16];
 #pragma unroll
             for (int o = 0; o < 16; ++o) yv[o] = fmaf(__uint_as_float(b[o]), s_b, __uint_as_float(a[o]) * s_a);
@@ -623,9 +692,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             if (t0 < A.dst_cap && !VQT_KO(16)) {
               const long long o = o_row + kb * o_blk;
               if (L.dec_w >= 16) {           // 16 outputs = two chunks of one row (tiled: 2 KB apart; linear: adjacent)
-                const long long o2 = A.dst_q == 1 ? o + 8 : o + 1024;
-                *reinterpret_cast<uint4*>(dh + o) = h1a; *reinterpret_cast<uint4*>(dh + o2) = h1b;
-                *reinterpret_cast<uint4*>(dl + o) = h2a; *reinterpret_cast<uint4*>(dl + o2) = h2b;
+                *reinterpret_cast<uint4*>(dh + o) = h1a; *reinterpret_cast<uint4*>(dh + o + o_half) = h1b;
+                *reinterpret_cast<uint4*>(dl + o) = h2a; *reinterpret_cast<uint4*>(dl + o + o_half) = h2b;
               } else {                       // dec_w == 4: four outputs per row
                 *reinterpret_cast<uint2*>(dh + o) = make_uint2(h1a.x, h1a.y);
                 *reinterpret_cast<uint2*>(dl + o) = make_uint2(h2a.x, h2a.y);
@@ -633,26 +701,35 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             }
           }
         } else if (L.fpr == 1) {
-          // one frame per row: the two warps of a lane quadrant take six bins each
-          const long long f = g;
-          uint32_t fa[12], fg[12], fb[12];
-          const int k0 = 6 * half;
-          tmem_ld_32x8(acc + 2 * k0, fa); tmem_ld_32x8(acc + 2 * k0 + 8, fa + 8);          // x1 . g1 (12 of the 16 loaded columns used)
-          tmem_ld_32x8(acc + 24 + 2 * k0, fg); tmem_ld_32x8(acc + 24 + 2 * k0 + 8, fg + 8); // x1 . g2
-          tmem_ld_32x8(acc + L.fb_n1 + 2 * k0, fb); tmem_ld_32x8(acc + L.fb_n1 + 2 * k0 + 8, fb + 8);   // x2 . g1
+          // one frame per row: the warps of a lane quadrant share the twelve bins
+          const int f = g;
+          constexpr int NC = 2 * kBinsPerWarp;             // accumulator columns of this warp's bins (re, im interleaved)
+          constexpr int NL = NC <= 8 ? 8 : 16;             // columns loaded (NC of them are used; the rest are allocated TMEM)
+          uint32_t fa[NL], fg[NL], fb[NL];
+          const int c0 = NC * sub;
+          if (NL == 8) {
+            tmem_ld_32x8(acc + c0, fa);                    // x1 . g1
+            tmem_ld_32x8(acc + 24 + c0, fg);               // x1 . g2
+            tmem_ld_32x8(acc + L.fb_n1 + c0, fb);          // x2 . g1
+          } else {
+            tmem_ld_32x16(acc + c0, fa);
+            tmem_ld_32x16(acc + 24 + c0, fg);
+            tmem_ld_32x16(acc + L.fb_n1 + c0, fb);
+          }
           tmem_ld_wait();
           if (f < A.n_frames && !VQT_KO(16)) {
-            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * A.n_frames + f;
+            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + kBinsPerWarp * sub) * A.n_frames + f;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < kBinsPerWarp; ++k) {
               const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
               const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-              op[(size_t)k * A.n_frames] = __logf(fmaf(__fsqrt_rn(fmaf(re, re, im * im)), half ? isl[6 + k] : isl[k], 1e-9f));
+              op[(size_t)k * A.n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), islw[k], 1e-9f));
             }
           }
         } else {
-          for (int j = half; j < L.fpr; j += 2) {
-            const long long f = g * L.fpr + j;
+#pragma unroll 1
+          for (int j = sub; j < L.fpr; j += VQT_EPQ) {
+            const int f = g * L.fpr + j;
             uint32_t fa[48], fb[24];
             tmem_ld_32x32(acc + 48 * j, fa);
             tmem_ld_32x16(acc + 48 * j + 32, fa + 32);
@@ -665,7 +742,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
               for (int k = 0; k < 12; ++k) {
                 const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fa[24 + 2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
                 const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fa[25 + 2 * k]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-                op[(size_t)k * A.n_frames] = __logf(fmaf(__fsqrt_rn(fmaf(re, re, im * im)), isl[k], 1e-9f));
+                op[(size_t)k * A.n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
               }
             }
           }
@@ -673,9 +750,12 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(smem_u32(&bar_acc_empty[type * 2 + stage]));
       }
+      // next tile of this CTA: tau += gridDim.x without a division
+      clip += clip_step; tile_in_clip += tile_step;
+      if (tile_in_clip >= A.tiles_per_clip) { tile_in_clip -= A.tiles_per_clip; ++clip; }
     }
     if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && (warp == 0 || warp == 4) && lane == 0) {
-      A.dbg[16 + 2 * half] = VQT_CLOCK() - t_begin_ep; A.dbg[17 + 2 * half] = t_wait_ep;
+      A.dbg[16 + 2 * sub] = VQT_CLOCK() - t_begin_ep; A.dbg[17 + 2 * sub] = t_wait_ep;
     }
   } else {
     // =================================== loaders: VQT_LOAD_WARPS / n_slots warps per ring slot ===================================
@@ -713,7 +793,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const long long base_s = (row0 - L.hb) * R + 8LL * plane0;     // sample of chunk (row 0, plane 0 of the group)
         {
           const long long t0 = VQT_CLOCK();
-          if (lane == 0) mbar_wait_parked(bempty, par);
+          if (lane == 0) vqt_wait(bempty, par);
           __syncwarp();
           t_wait_ld += VQT_CLOCK() - t0;
         }
@@ -752,56 +832,80 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           }
           continue;
         }
+#ifndef ZNS_VQT_NO_L2_PREFETCH
+        if (SRC_F32 && pos == 0 && sub == 0 && lane == 0 && ts + 1 < n_my_tiles) {
+          // pull the NEXT tile's samples (one contiguous span of the clip) into L2 while this tile is being processed: the
+          // ring holds a single tile, so its loads cannot be issued early -- but their DRAM latency can be taken now
+          const int tau_n = tau + (int)gridDim.x;
+          const int clip_n = tau_n / A.tiles_per_clip;
+          long long s_lo = ((long long)(tau_n - clip_n * A.tiles_per_clip) * 128 - L.hb) * R;
+          long long s_hi = s_lo + (long long)n_rows * R;
+          s_lo = max(s_lo, 0LL); s_hi = min(s_hi, (long long)A.n_sig);
+          const float* pn = A.y32 + (size_t)clip_n * A.src_stride + s_lo;
+          const uint32_t bytes = (uint32_t)((s_hi - s_lo) * 4) & ~15u;
+          if (s_hi > s_lo && bytes > 0 && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
+        }
+#endif
         if (vec_ok) {
-          // phase 1: asynchronous 16-byte copies, every chunk of the group in flight at once (one DRAM latency per group).
-          // The chunk's two 16-byte halves are parked where its x1 / x2 chunks will live.
+          // global -> registers -> two-term fp16 split -> shared memory, four chunks (128 bytes) per lane in flight: the
+          // shared-memory image is written once (a cp.async staging pass costs two more trips through shared memory, and
+          // the in-place conversion behind it was one dependent LDS -> convert -> STS chain per chunk)
           const long long tp0 = VQT_CLOCK();
           const bool interior = base_s >= 0 && base_s + (long long)(n_rows - 1) * R + 8 * L.pg <= (long long)A.n_sig;
-          if (interior) {
-            const float* src = yb + base_s + (long long)r_first * R + 8 * c_lane;
-            const long long src_step = (long long)r_step * R;
+          if (VQT_KO(1)) {
+          } else if (interior) {
+            const float4* src = reinterpret_cast<const float4*>(yb + base_s + (long long)r_first * R + 8 * c_lane);
+            const long long src_step = (long long)r_step * R / 4;      // in float4
             uint32_t d1 = s1 + off0, d2 = s2 + off0;
-#pragma unroll 4
-            for (int it = 0; it < n_it; ++it) {
-              cp_async16(d1, src, 16);
-              cp_async16(d2, src + 4, 16);
+            int it = 0;
+#pragma unroll 1
+            for (; it + 4 <= n_it; it += 4) {
+              float4 va[4], vb[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { va[u] = __ldg(src + u * src_step); vb[u] = __ldg(src + u * src_step + 1); }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                uint4 c1, c2;
+                split8(v, c1, c2);
+                sts128(d1 + u * off_step, c1);
+                sts128(d2 + u * off_step, c2);
+              }
+              src += 4 * src_step; d1 += 4 * off_step; d2 += 4 * off_step;
+            }
+#pragma unroll 1
+            for (; it < n_it; ++it) {
+              const float4 va = __ldg(src), vb = __ldg(src + 1);
+              const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+              uint4 c1, c2;
+              split8(v, c1, c2);
+              sts128(d1, c1);
+              sts128(d2, c2);
               src += src_step; d1 += off_step; d2 += off_step;
             }
           } else {
+            // first / last tile of a clip: chunks that stick out of the signal are zero filled
 #pragma unroll 1
             for (int it = 0; it < n_it; ++it) {
               const int r = r_first + it * r_step;
               const long long s0 = base_s + (long long)r * R + 8 * c_lane;
               const uint32_t off = off0 + (uint32_t)it * off_step;
-              const long long left = (long long)A.n_sig - s0;              // samples of this chunk inside the signal
-              const bool in = s0 >= 0 && left > 0;
-              const int n1 = in ? (int)min(4LL, left) * 4 : 0, n2 = in ? (int)max(0LL, min(4LL, left - 4)) * 4 : 0;
-              const float* src = yb + (in ? s0 : 0);
-              cp_async16(s1 + off, src, n1);
-              cp_async16(s2 + off, src + 4, n2);
-            }
-          }
-          const long long tp1 = VQT_CLOCK();
-          cp_async_wait_all();
-          const long long tp2 = VQT_CLOCK();
-          t_p1 += tp1 - tp0; t_cpw += tp2 - tp1;
-          if (!VQT_KO(1)) {
-            // phase 2: in place, every lane converts the chunks it fetched itself
-            uint32_t d1 = s1 + off0, d2 = s2 + off0;
-            const int n_cv = n_it;
-#pragma unroll 2
-            for (int it = 0; it < n_cv; ++it) {
-              const uint4 ra = lds128(d1), rb = lds128(d2);
-              const float v[8] = {__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z), __uint_as_float(ra.w),
-                                  __uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), __uint_as_float(rb.w)};
+              float v[8];
+              if (s0 >= 0 && s0 + 8 <= (long long)A.n_sig) {
+                const float4 va = __ldg(reinterpret_cast<const float4*>(yb + s0)), vb = __ldg(reinterpret_cast<const float4*>(yb + s0) + 1);
+                v[0] = va.x; v[1] = va.y; v[2] = va.z; v[3] = va.w; v[4] = vb.x; v[5] = vb.y; v[6] = vb.z; v[7] = vb.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (s0 + e >= 0 && s0 + e < (long long)A.n_sig) ? __ldg(yb + s0 + e) : 0.f;
+              }
               uint4 c1, c2;
               split8(v, c1, c2);
-              sts128(d1, c1);
-              sts128(d2, c2);
-              d1 += off_step; d2 += off_step;
+              sts128(s1 + off, c1);
+              sts128(s2 + off, c2);
             }
           }
-          t_p2 += VQT_CLOCK() - tp2;
+          t_p1 += VQT_CLOCK() - tp0;
         } else {
           // unaligned fp32 clips (n_samples not a multiple of 4): element-wise loads
           for (int it = 0; it < n_it; ++it) {

@@ -163,13 +163,19 @@ class EncoderEngine:
             self._pack_event.record(self._side)
 
     def pack_weights(self, params: Sequence[Dict[str, torch.Tensor]], need_dgrad: bool):
-        """fp32 state_dict-layout weights -> bf16 packs (forward, and flipped/transposed for dgrad)."""
-        lib, st = L.lib(), L.current_stream()
+        """fp32 state_dict-layout weights -> fp16 forward packs and bf16 flipped/transposed packs for the data gradient:
+        ONE multi-tensor launch for every layer of every branch."""
+        ws, wf, wd, geo = [], [], [], []
         for br in range(self.n_br):
             for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
-                w = params[br][f"pretrained.{name}.weight"]
-                L.check(lib.zns_pack_weights(L.ptr(w), co, ci, kh, kw, L.ptr(self.wf[name][br]),
-                                             L.ptr(self.wd[name][br]) if (need_dgrad and name != "cv1") else None, 1, st))
+                ws.append(params[br][f"pretrained.{name}.weight"])
+                wf.append(self.wf[name][br])
+                wd.append(self.wd[name][br] if need_dgrad else None)
+                geo.append((co, ci, kh, kw))
+        L.check(L.lib().zns_pack_weights_multi(len(ws), L.ptr_array(ws), L.int_array([g[0] for g in geo]),
+                                               L.int_array([g[1] for g in geo]), L.int_array([g[2] for g in geo]),
+                                               L.int_array([g[3] for g in geo]), L.ptr_array(wf), L.ptr_array(wd), 1,
+                                               L.current_stream()))
 
     # -- forward -----------------------------------------------------------------------------------
     def _conv(self, name, H, ins, outs, params, relu, drop, layer_id):
@@ -185,11 +191,10 @@ class EncoderEngine:
                                          L.current_stream()))
 
     def _pool(self, H, Cc, pool, ys, outs, layer_id):
-        lib, st = L.lib(), L.current_stream()
-        for br in range(self.n_br):
-            sh = self._shadow[id(outs)][br] if self._need_shadow else None
-            L.check(lib.zns_pool_fwd(L.ptr(ys[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, self._p, self.seed,
-                                     L.ptr(self.step_ctr) if self._p > 0 else None, layer_id * 2 + br, 1, L.ptr(sh), st))
+        sh = self._shadow[id(outs)] if self._need_shadow else None
+        L.check(L.lib().zns_pool_fwd_nbr(self.n_br, L.ptr_array(ys), L.ptr_array(outs), self.B, H, self.T, Cc, pool, self._p,
+                                         self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, layer_id * 2, 1,
+                                         L.ptr_array(sh) if sh else None, L.current_stream()))
 
     def forward(self, xs: Sequence[torch.Tensor], x_clip_stride: int, params: Sequence[Dict[str, torch.Tensor]],
                 train: bool, dropout_p: float = 0.1, x_row_stride: Optional[int] = None,
@@ -202,12 +207,13 @@ class EncoderEngine:
         self._need_shadow = train if need_grad is None else bool(need_grad)   # bf16 copies only when a backward follows
         self._x_in, self._x_stride = list(xs), x_clip_stride
         self._x_row = self.T if x_row_stride is None else int(x_row_stride)
-        for br in range(self.n_br):
-            p = params[br]
-            L.check(lib.zns_conv1_fwd(L.ptr(xs[br]), x_clip_stride, self._x_row, L.ptr(p["pretrained.cv1.weight"]),
-                                      L.ptr(p["pretrained.cv1.bias"]), L.ptr(self.x1[br]), self.B, N_BINS, self.T,
-                                      self._p, self.seed, L.ptr(self.step_ctr) if self._p > 0 else None, 100 + br, 1,
-                                      L.ptr(self._shadow[id(self.x1)][br]) if self._need_shadow else None, st))
+        sh1 = self._shadow[id(self.x1)] if self._need_shadow else None
+        L.check(lib.zns_conv1_fwd_nbr(self.n_br, L.ptr_array(xs), x_clip_stride, self._x_row,
+                                      L.ptr_array([p["pretrained.cv1.weight"] for p in params[:self.n_br]]),
+                                      L.ptr_array([p["pretrained.cv1.bias"] for p in params[:self.n_br]]), L.ptr_array(self.x1),
+                                      self.B, N_BINS, self.T, self._p, self.seed,
+                                      L.ptr(self.step_ctr) if self._p > 0 else None, 100, 1,
+                                      L.ptr_array(sh1) if sh1 else None, st))
         if getattr(self, "_pack_event", None) is not None:      # packs issued by pack_weights_async
             torch.cuda.current_stream().wait_event(self._pack_event)
             self._pack_event = None
@@ -221,9 +227,8 @@ class EncoderEngine:
         self._pool(8, 256, 8, self.y6, self.p6, 6)
         self._conv("cv7", 1, self.p6, self.x7, params, relu=1, drop=True, layer_id=7)
         self._conv("cv8", 1, self.x7, self.x8, params, relu=1, drop=True, layer_id=8)
-        for br in range(self.n_br):
-            p = params[br]
-            L.check(lib.zns_head_fwd(L.ptr(self.x8[br]), L.ptr(p["fc1.weight"]), L.ptr(p["fc1.bias"]), L.ptr(self.emb[br]),
+        L.check(lib.zns_head_fwd_nbr(self.n_br, L.ptr_array(self.x8), L.ptr_array([p["fc1.weight"] for p in params[:self.n_br]]),
+                                     L.ptr_array([p["fc1.bias"] for p in params[:self.n_br]]), L.ptr_array(self.emb),
                                      self.B, self.T, 1, st))
         return self.emb
 
@@ -251,11 +256,21 @@ class EncoderEngine:
         xb = self._shadow[id(xs)]                      # bf16 copy of the fp16 forward activation (same type as dy)
         with self._timed(f"conv_wgrad_umma<{min(co, 128)}>", self._conv_flops(name, H)):
             L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xb), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
+        L.check(lib.zns_bias_grad_nbr(self.n_br, L.ptr_array(dys), self.B, H, self.T, co,
+                                      L.ptr_array([grads[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]), st))
+
+    def _unpack_all(self, grads):
+        """Packed [tap][c_out][c_in] weight gradients of every layer and branch -> state_dict layout (+=), one launch; the
+        packed accumulators are cleared behind the read (next step's atomics start from zero: no fill kernel)."""
+        gp, g, geo = [], [], []
         for br in range(self.n_br):
-            L.check(lib.zns_bias_grad(L.ptr(dys[br]), self.B, H, self.T, co, L.ptr(grads[br][f"pretrained.{name}.bias"]), st))
-            # packed [tap][c_out][c_in] -> state_dict layout, on the same (side) stream: overlaps later layers
-            L.check(lib.zns_unpack_grads(L.ptr(self.gp[name][br]), co, ci, kh, kw, 1.0, 1,
-                                         L.ptr(grads[br][f"pretrained.{name}.weight"]), st))
+            for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
+                gp.append(self.gp[name][br])
+                g.append(grads[br][f"pretrained.{name}.weight"])
+                geo.append((co, ci, kh, kw))
+        L.check(L.lib().zns_unpack_grads_multi(len(gp), L.ptr_array(gp), L.int_array([x[0] for x in geo]),
+                                               L.int_array([x[1] for x in geo]), L.int_array([x[2] for x in geo]),
+                                               L.int_array([x[3] for x in geo]), 1.0, 1, 1, L.ptr_array(g), L.current_stream()))
 
     def _dgrad(self, name, H, dys, masks, outs):
         _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
@@ -266,9 +281,8 @@ class EncoderEngine:
                                          L.ptr_array(masks), L.ptr_array(outs), None, L.current_stream()))
 
     def _unpool(self, H, Cc, pool, ys, dps, outs):
-        lib, st = L.lib(), L.current_stream()
-        for br in range(self.n_br):
-            L.check(lib.zns_pool_bwd(L.ptr(ys[br]), L.ptr(dps[br]), L.ptr(outs[br]), self.B, H, self.T, Cc, pool, 1, st))
+        L.check(L.lib().zns_pool_bwd_nbr(self.n_br, L.ptr_array(ys), L.ptr_array(dps), L.ptr_array(outs), self.B, H, self.T, Cc,
+                                         pool, 1, L.current_stream()))
 
     def backward(self, d_embs: Sequence[torch.Tensor], params: Sequence[Dict[str, torch.Tensor]],
                  grads: Sequence[Dict[str, torch.Tensor]]) -> None:
@@ -280,11 +294,11 @@ class EncoderEngine:
         lib, st = L.lib(), L.current_stream()
         scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
         ga, gb = self.ga, self.gb
-        for br in range(self.n_br):
-            self.gp_flat[br].zero_()
-            p, g = params[br], grads[br]
-            L.check(lib.zns_head_bwd(L.ptr(self.x8[br]), L.ptr(self.emb[br]), L.ptr(d_embs[br]), L.ptr(p["fc1.weight"]),
-                                     L.ptr(g["fc1.weight"]), L.ptr(g["fc1.bias"]), L.ptr(ga[br]), self.B, self.T, scale, 1, st))
+        nb = self.n_br
+        L.check(lib.zns_head_bwd_nbr(nb, L.ptr_array(self.x8), L.ptr_array(self.emb), L.ptr_array(list(d_embs)[:nb]),
+                                     L.ptr_array([p["fc1.weight"] for p in params[:nb]]),
+                                     L.ptr_array([g["fc1.weight"] for g in grads[:nb]]),
+                                     L.ptr_array([g["fc1.bias"] for g in grads[:nb]]), L.ptr_array(ga), self.B, self.T, scale, 1, st))
         main = torch.cuda.current_stream()
 
         def join(ev):
@@ -317,8 +331,7 @@ class EncoderEngine:
         w2 = self._wgrad("cv2", 96, self.x1, gb, grads)
         self._dgrad("cv2", 96, gb, self.x1, ga)         # dy1
         join(w2)
-        for br in range(self.n_br):
-            g = grads[br]
-            L.check(lib.zns_conv1_wgrad(L.ptr(ga[br]), L.ptr(self._x_in[br]), self._x_stride, self._x_row,
-                                        L.ptr(g["pretrained.cv1.weight"]), L.ptr(g["pretrained.cv1.bias"]), self.B, N_BINS,
-                                        self.T, st))
+        L.check(lib.zns_conv1_wgrad_nbr(nb, L.ptr_array(ga), L.ptr_array(self._x_in), self._x_stride, self._x_row,
+                                        L.ptr_array([g["pretrained.cv1.weight"] for g in grads[:nb]]),
+                                        L.ptr_array([g["pretrained.cv1.bias"] for g in grads[:nb]]), self.B, N_BINS, self.T, st))
+        self._unpack_all(grads)

@@ -165,7 +165,7 @@ class PretextTrainer:
         eng = self.engine
         L.check(lib.zns_counter_add(L.ptr(eng.step_ctr), 1, st))
         eng.pack_weights_async(self.params, need_dgrad=True)      # side stream, joined before cv2
-        self.flat_g.zero_()
+        L.check(lib.zns_zero(L.ptr(self.flat_g), self.flat_g.numel() * 4, st))     # memset node, not a fill kernel
         eng.forward([self.batch_buf[:, 0], self.batch_buf[:, 1]], 2 * 96 * self.T, self.params, train=True,
                     dropout_p=self.dropout_p)
         L.check(lib.zns_ntxent_fwd_bwd(L.ptr(eng.emb[0]), L.ptr(eng.emb[1]), self.B, self.T, self.B, self.temperature,
