@@ -337,6 +337,11 @@ def run_ours(args) -> None:
             line.update(kernel_roofline(tr, dev_audio, starts_dev, peaks, args, ms / args.steps, clocks))
             # ---- cfg2: batched VQT of 256 x 30 s clips --------------------------------------------
             line.update(vqt_cfg2(dev, peaks))
+            # ---- cfg5: downstream inference + fine-tune on Ballroom-shaped clips -----------------------
+            try:
+                line.update(cfg5_downstream(dev, peaks))
+            except Exception as exc:      # the headline line must survive a failure of an auxiliary leg
+                line["cfg5_downstream"] = {"error": repr(exc)}
         # ---- CPU baseline on this box's host cores (bounded sample) -------------------------------
         if world == 1 and not args.no_cpu_baseline and not args.no_extras:
             line["cpu_baseline"] = cpu_baseline()
@@ -474,6 +479,59 @@ def vqt_cfg2(dev, peaks):
                                       "kernels": "8 tcgen05 level kernels (filterbank + 2:1 decimator per octave) + 1 edge-frame kernel",
                                       "note": "input 491 MB + output 184 MB > 126 MB L2; whole front-end (all launches) timed "
                                               "with CUDA events; traffic = sum of dram bytes of its launches (ncu)"}}}
+
+
+def cfg5_downstream(dev, peaks):
+    """BASELINE.json configs[4]: downstream beat tracking on Ballroom-shaped clips (30 s, T = 1876 frames): batched inference
+    through Down_CNN (the 10k-clip sweep is extrapolated from timed batches of 16 clips) and the batch-1 fine-tune step of
+    epochs.train_epoch (one file per step: time-folded encoders, fused BCE, FusedAdam)."""
+    import torch
+    from zeronotesamba_b200 import epochs
+    from zeronotesamba_b200.loader import load_models
+    from zeronotesamba_b200.models.checkpoint import he_normal_state_dict
+    T, B = 1876, 16
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    criterion, optimizer, model = load_models("pretrained", "finetune", 1e-5, state_dict=he_normal_state_dict(7))
+    pool = [(torch.rand(B, 2, 96, T, device=dev, generator=g) * 12 - 11) for _ in range(3)]     # > L2 per batch (92 MB each)
+    model.eval()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(3):
+            model(pool[i % 3][:, 0:1], pool[i % 3][:, 1:2])
+        torch.cuda.synchronize()
+        reps = 6
+        e0.record()
+        for i in range(reps):
+            out = model(pool[i % 3][:, 0:1], pool[i % 3][:, 1:2])
+        e1.record()
+        torch.cuda.synchronize()
+    ms_inf = e0.elapsed_time(e1) / reps
+    flops_inf = 2 * B * FWD_GFLOP_PER_SAMPLE_BRANCH * 1e9 * T / T_CROP
+    tf_inf = flops_inf / (ms_inf * 1e-3) / 1e12
+    # fine-tune: one file per step
+    files = {f"f{i}": (torch.rand(2, 96, T, device=dev, generator=g) * 12 - 11) for i in range(4)}
+    masks = {k: (torch.rand(T, device=dev, generator=g) < 0.07).float() for k in files}
+    idx = list(files)
+    epochs.train_epoch(model, criterion, optimizer, "pretrained", idx, {k: None for k in idx}, files, masks, False, False)
+    torch.cuda.synchronize()
+    n_ep = 3
+    e0.record()
+    for _ in range(n_ep):
+        res = epochs.train_epoch(model, criterion, optimizer, "pretrained", idx, {k: None for k in idx}, files, masks, False, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_ft = e0.elapsed_time(e1) / (n_ep * len(idx))
+    return {"cfg5_downstream": {
+        "workload": "Ballroom-shaped 30 s clips (2 stems x 96 x 1876 log-VQT): Down_CNN batched inference + batch-1 fine-tune step",
+        "inference": {"clips_per_sec": B / (ms_inf * 1e-3), "ms_per_batch": ms_inf, "batch": B,
+                      "seconds_for_10k_clips": 10000.0 / (B / (ms_inf * 1e-3)),
+                      "roofline": {"bound": "tensor", "achieved": tf_inf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                   "frac": tf_inf / peaks["bf16_tflops"],
+                                   "algorithmic": "2 branches x 129.59 GFLOP x 1876 / 313 per clip (forward convolutions)"}},
+        "finetune": {"files_per_sec": 1e3 / ms_ft, "ms_per_step": ms_ft, "loss_last_epoch": float(res[2]),
+                     "note": "epochs.train_epoch, one file per step (reference: epochs.py:45-63): time-folded encoders fwd+bwd, "
+                             "max merge, FusedBCELoss, FusedAdam; includes the loop's loss.item() host sync per file"}}}
 
 
 def _vqt_traffic():

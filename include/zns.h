@@ -202,6 +202,22 @@ int zns_head_fwd_nbr(int n_br, const void* const* x_act, const float* const* w12
 int zns_head_bwd_nbr(int n_br, const void* const* x_act, const float* const* emb, const float* const* d_emb,
                      const float* const* w128, float* const* dw128, float* const* dbias1, void* const* dy_act, int batch, int T,
                      float out_scale, int x_f16, void* stream);
+/* Convolution with the pooling block that follows it (models.py:41-44,50-53) fused into the epilogue:
+ * conv + bias -> MaxPool2d((pool, 1)) -> ReLU -> Dropout(d->dropout_p, d->rng_stream + branch).  d describes the convolution
+ * (d->relu must be 0: the reference applies ReLU after the pool); the pre-pool tensor is never written.
+ *   out_pooled[br]       act [G][H/pool][W][8][c_out] (fp16 / bf16 per d->fmt)
+ *   out_pooled_bf16      NULL, or per branch a bf16 copy (x operand of the next weight gradient)
+ *   argmax               NULL, or per branch uint8 [G][H/pool][W][8][c_out]: row (0..pool-1) of the first maximum of each
+ *                        window, the routing table zns_pool_bwd_arg_nbr consumes
+ * A tile holds whole pool windows in its TMEM accumulators: c_out = 64 (stacked kernel, pool 3 -> six rows, pool 4 / 8 ->
+ * four / eight rows), c_out = 128 (pool <= 4); other shapes return ZNS_ERR_INVALID (use zns_conv_fwd + zns_pool_fwd). */
+int zns_conv_pool_fwd(const zns_conv_desc* d, int pool, int n_br, const void* const* in, const void* const* wpk,
+                      const float* const* bias, void* const* out_pooled, void* const* out_pooled_bf16, void* const* argmax,
+                      void* stream);
+/* Backward of the fused pooling: dy act bf16 [G][H][W][8][C] = dpool routed to the arg-max row of each window, zeros
+ * elsewhere (dpool is already masked and scaled by the data-gradient epilogue of the layer above). */
+int zns_pool_bwd_arg_nbr(int n_br, const void* const* argmax, const void* const* dpool_act, void* const* dy_act, int batch,
+                         int H, int W, int C, int pool, void* stream);
 int zns_bias_grad_nbr(int n_br, const void* const* dy_act, int batch, int H, int W, int C, float* const* db, void* stream);
 /* n <= 16 weights: w[i] fp32 [c_out[i]][c_in[i]][kh[i]][kw[i]] -> wf[i] / wd[i] as zns_pack_weights (entries or whole
  * arrays may be NULL). */
@@ -222,6 +238,10 @@ int zns_zero(void* p, long long bytes, void* stream);
  * ---------------------------------------------------------------------------------------- */
 int zns_ntxent_fwd_bwd(const float* anchors, const float* poss, int n_rows, int dim, int batch_len,
                        float temperature, float* result3, float* d_anchors, float* d_poss, void* stream);
+
+/* torch.nn.BCELoss (mean reduction) of the downstream beat head (loader.py:20, epochs.py:52-54), forward and backward in one
+ * launch: out / target fp32 [n] in (0, 1) / {0, 1}; *loss = mean BCE with torch's clamps; d_out (NULL to skip) = d loss / d out. */
+int zns_bce_fwd_bwd(const float* out, const float* target, long long n, float* loss, float* d_out, void* stream);
 
 /* torch.optim.Adam defaults (pretext.py:202) over flat fp32 buffers; `step` counts from 1 and is
  * read from the device word step_dev when that is not NULL (CUDA-graph replays); gradients are

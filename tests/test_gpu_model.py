@@ -443,3 +443,28 @@ def test_train_model_epoch_driver(tmp_path):
     ref.load_state_dict(ckpt)                                    # the reference's loading call (sample_script.py:41-42)
     with pytest.raises(ValueError, match="Which pretext task are we running"):
         train_model(dict(yml, pt_task="other"), bank[:4], bank[4:], model_dir=str(tmp_path))
+
+
+def test_variable_length_clips_share_one_engine(sd):
+    """Downstream loops feed one file of its own length per step (epochs.py:45-63): the encoder workspaces are sized for the
+    longest clip and re-viewed for the others -- same results as fresh engines, no reallocation when T shrinks."""
+    from zeronotesamba_b200.models.models import Down_CNN
+    g = torch.Generator().manual_seed(12)
+    clips = [(torch.rand(1, 2, 96, T, generator=g) * 10 - 9).to(DEV) for T in (1876, 900, 1500, 1876, 640)]
+    clips[3] = clips[0]
+    model = Down_CNN().to(DEV)
+    model.pretext.load_state_dict(sd)
+    model.eval()
+    outs, engines = [], set()
+    with torch.no_grad():
+        for x in clips:
+            outs.append(model(x[:, 0:1], x[:, 1:2]).clone())
+            engines.add(id(next(iter(model.pretext._cache._engines.values()))))
+    assert len(engines) == 1 and len(model.pretext._cache._engines) == 1
+    assert torch.equal(outs[0], outs[3])                    # same clip again after shorter ones: identical
+    for x, o in zip(clips, outs):
+        fresh = Down_CNN().to(DEV)
+        fresh.pretext.load_state_dict(sd)
+        fresh.eval()
+        with torch.no_grad():
+            assert torch.equal(fresh(x[:, 0:1], x[:, 1:2]), o)

@@ -72,10 +72,13 @@ _PROTOS = {
     "zns_pack_weights_multi": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_void_p]),
     "zns_unpack_grads_multi": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), c_float, c_int, c_int, C.POINTER(c_void_p), c_void_p]),
     "zns_zero": (c_int, [c_void_p, c_ll, c_void_p]),
+    "zns_conv_pool_fwd": (c_int, [C.POINTER(ConvDesc), c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p]),
+    "zns_pool_bwd_arg_nbr": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "zns_act_from_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "zns_act_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "zns_ntxent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
+    "zns_bce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
     "zns_adam_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int,
                               c_void_p, c_float, c_void_p]),
     "zns_adam_p2p": (c_int, [c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p, c_void_p, c_ll, c_float, c_float,
@@ -100,9 +103,9 @@ KERNELS_PER_CALL = {
     "zns_vqt_forward": 9, "zns_vqt_forward_host": 9, "zns_crop_gather": 1, "zns_rms_gate": 1, "zns_conv1_fwd": 1, "zns_conv1_wgrad": 1,
     "zns_conv_fwd": 1, "zns_conv_wgrad": 1, "zns_bias_grad": 1, "zns_pack_weights": 1, "zns_unpack_grads": 1,
     "zns_conv1_fwd_nbr": 1, "zns_conv1_wgrad_nbr": 1, "zns_pool_fwd_nbr": 1, "zns_pool_bwd_nbr": 1, "zns_head_fwd_nbr": 1,
-    "zns_head_bwd_nbr": 1, "zns_bias_grad_nbr": 1, "zns_pack_weights_multi": 1, "zns_unpack_grads_multi": 1, "zns_zero": 0,
+    "zns_head_bwd_nbr": 1, "zns_bias_grad_nbr": 1, "zns_pack_weights_multi": 1, "zns_unpack_grads_multi": 1, "zns_zero": 0, "zns_conv_pool_fwd": 1, "zns_pool_bwd_arg_nbr": 1,
     "zns_pool_fwd": 1, "zns_pool_bwd": 1, "zns_head_fwd": 1, "zns_head_bwd": 1, "zns_merge": 1, "zns_act_from_nchw": 1,
-    "zns_act_to_nchw": 1, "zns_ntxent_fwd_bwd": 1, "zns_adam_flat": 1, "zns_adam_p2p": 1, "zns_counter_add": 1, "zns_dbg_conv_fwd_simt": 1,
+    "zns_act_to_nchw": 1, "zns_ntxent_fwd_bwd": 1, "zns_bce_fwd_bwd": 1, "zns_adam_flat": 1, "zns_adam_p2p": 1, "zns_counter_add": 1, "zns_dbg_conv_fwd_simt": 1,
     "zns_dbg_conv_wgrad_simt": 1, "zns_dbg_umma_probe": 1, "zns_dbg_umma_rate": 1, "zns_dbg_umma_raw": 1,
 }
 CALL_COUNTS: dict = {}

@@ -204,6 +204,13 @@ struct PlanDump {
   uint32_t items[256];
 };
 
+// Optional outputs / epilogue modes of the forward kernels beyond the plain act store.
+struct FwdExtra {
+  void* const* out2;   // per branch: bf16 copy of the output (NULL: none)
+  int pool;            // > 0: fused MaxPool2d((pool, 1)) -> ReLU -> Dropout; out / out2 are the pooled tensors
+  void* const* arg;    // per branch: first-arg-max row of every pooled element (NULL: not wanted)
+};
+
 // Launch with clusters of two CTAs: blocks (2i, 2i+1) form a pair -- same rows and branch, adjacent frame
 // tiles (callers check that the columns per branch are even, so a pair never straddles a row block or a branch).
 template <typename Kern, typename... Args>
@@ -237,6 +244,11 @@ struct FwdParams {
   bf16* out[2];
   bf16* out2[2];               // optional second copy of the output, always bf16 (x operand of the next weight gradient)
   int a_f16, b_f16, out_f16;   // element types: input activations / weights / output (0 = bf16, 1 = fp16)
+  // fused MaxPool2d((pool, 1)) -> ReLU -> Dropout epilogue (models.py:50-53): every tile holds exactly one pool window
+  // (`pool` accumulators = `pool` output rows); out / out2 are the POOLED tensors [G][H/pool][W][8][N], arg the row of the
+  // first maximum inside each window (one byte per pooled element, the routing table of the backward pass)
+  int pool;
+  uint8_t* arg[2];
 };
 
 struct FwdBarriers {
@@ -422,8 +434,62 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_co
     const double thr_d = (double)p.drop_p * 4294967296.0;
     const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
     const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    if (p.pool) {
+      // pooled epilogue: the warps of a quadrant take the 32-column blocks; a thread keeps a running maximum (and the row of
+      // the first maximum) over the window's accumulators, then bias -> ReLU -> dropout -> fp16 / bf16 stores of the POOLED
+      // tensor.  max and "+ bias" commute (the bias is per channel), rounding is monotone, so this is the unfused result.
+      const int hp = h0 / p.pool, Hp = p.H / p.pool;
+      const size_t e0 = zns_act_index(g, hp, valid ? w : 0, b8, 0, Hp, p.W, N);
+      uint8_t* argp = p.arg[br];
+#pragma unroll 1
+      for (int nb = half; nb < N / 32; nb += ZNS_EPI) {
+        uint32_t v[32];
+        float m[32];
+        uint32_t am[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // four 8-bit row indices per word
+        tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + nb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m[j] = __uint_as_float(v[j]);
+        for (int h = 1; h < p.pool; ++h) {
+          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + h * N + nb * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            if (x > m[j]) { m[j] = x; am[j >> 2] = (am[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)h << (8 * (j & 3))); }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = m[j];
+            if (bias) x += __ldg(bias + nb * 32 + j);
+            x = fmaxf(x, 0.f);
+            if (do_drop) x = (zns_hash32(e0 + nb * 32 + j, seed, p.stream_id + br) >= thr) ? x * keep : 0.f;
+            m[j] = x;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + e0 + nb * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_act2(m[q * 8], m[q * 8 + 1], p.out_f16), pack_act2(m[q * 8 + 2], m[q * 8 + 3], p.out_f16),
+                                pack_act2(m[q * 8 + 4], m[q * 8 + 5], p.out_f16), pack_act2(m[q * 8 + 6], m[q * 8 + 7], p.out_f16));
+          if (out2) {
+            uint4* dst2 = reinterpret_cast<uint4*>(out2 + e0 + nb * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              dst2[q] = make_uint4(pack_bf16x2(m[q * 8], m[q * 8 + 1]), pack_bf16x2(m[q * 8 + 2], m[q * 8 + 3]),
+                                   pack_bf16x2(m[q * 8 + 4], m[q * 8 + 5]), pack_bf16x2(m[q * 8 + 6], m[q * 8 + 7]));
+          }
+          if (argp) {
+            uint4* da = reinterpret_cast<uint4*>(argp + e0 + nb * 32);
+            da[0] = make_uint4(am[0], am[1], am[2], am[3]);
+            da[1] = make_uint4(am[4], am[5], am[6], am[7]);
+          }
+        }
+      }
+    }
     int nb = half;   // blocks of all rows are dealt round-robin: (h, nb) -> warp (h * N/32 + nb) % ZNS_EPI of the quadrant
-    for (int h = 0; h < ht_eff; ++h, nb -= N / 32) {
+    for (int h = 0; h < (p.pool ? 0 : ht_eff); ++h, nb -= N / 32) {
       const size_t e0 = zns_act_index(g, h0 + h, valid ? w : 0, b8, 0, p.H, p.W, N);
 #pragma unroll 1
       for (; nb < N / 32; nb += ZNS_EPI) {
@@ -513,6 +579,11 @@ struct FwdTParams {
   const bf16* mask[2];
   bf16* out[2];
   int a_f16, b_f16, out_f16;   // element types: input activations / weights / output (0 = bf16, 1 = fp16)
+  // stacked kernel only: fused MaxPool2d((pool, 1)) -> ReLU -> Dropout epilogue (models.py:41-44); a tile holds whole pool
+  // windows (2 * n_acc rows, a multiple of pool); out / out2 are the pooled tensors, arg the first-arg-max row per element
+  bf16* out2[2];
+  int pool;
+  uint8_t* arg[2];
 };
 
 struct FwdTBarriers {
@@ -921,8 +992,65 @@ conv_fwd_stack_umma_kernel(const __grid_constant__ CUtensorMap tm_in0, const __g
     const double thr_d = (double)p.drop_p * 4294967296.0;
     const uint32_t thr = thr_d >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr_d;
     const float keep = do_drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    if (p.pool) {
+      // pooled epilogue: work items = (pool window, 32-channel block); row r of the tile lives in accumulator r / 2, columns
+      // [0, 64) when r is odd (upper row of the stacked pair) and [64, 128) when it is even
+      const int n_win = 2 * acc_eff / p.pool, Hp = p.H / p.pool;
+      bf16* out2 = p.out2[br];
+      uint8_t* argp = p.arg[br];
+#pragma unroll 1
+      for (int item = half; item < 2 * n_win; item += ZNS_EPI) {
+        const int wi = item >> 1, c0 = (item & 1) * 32;
+        uint32_t v[32];
+        float mx[32];
+        uint32_t am[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < p.pool; ++k) {
+          const int r = wi * p.pool + k;
+          tmem_ld_32x32(tmem + ((uint32_t)(quad * 32) << 16) + (r >> 1) * 128 + ((r & 1) ? 0 : 64) + c0, v);
+          tmem_ld_wait();
+          if (k == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx[i] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = __uint_as_float(v[i]);
+              if (x > mx[i]) { mx[i] = x; am[i >> 2] = (am[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)k << (8 * (i & 3))); }
+            }
+          }
+        }
+        if (valid) {
+          const size_t e0 = zns_act_index(g, h0 / p.pool + wi, w, b8, c0, Hp, p.W, 64);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = mx[i];
+            if (bias) x += __ldg(bias + c0 + i);
+            x = fmaxf(x, 0.f);
+            if (do_drop) x = (zns_hash32(e0 + i, seed, p.stream_id + br) >= thr) ? x * keep : 0.f;
+            mx[i] = x;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + e0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_act2(mx[q * 8], mx[q * 8 + 1], p.out_f16), pack_act2(mx[q * 8 + 2], mx[q * 8 + 3], p.out_f16),
+                                pack_act2(mx[q * 8 + 4], mx[q * 8 + 5], p.out_f16), pack_act2(mx[q * 8 + 6], mx[q * 8 + 7], p.out_f16));
+          if (out2) {
+            uint4* dst2 = reinterpret_cast<uint4*>(out2 + e0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              dst2[q] = make_uint4(pack_bf16x2(mx[q * 8], mx[q * 8 + 1]), pack_bf16x2(mx[q * 8 + 2], mx[q * 8 + 3]),
+                                   pack_bf16x2(mx[q * 8 + 4], mx[q * 8 + 5]), pack_bf16x2(mx[q * 8 + 6], mx[q * 8 + 7]));
+          }
+          if (argp) {
+            uint4* da = reinterpret_cast<uint4*>(argp + e0);
+            da[0] = make_uint4(am[0], am[1], am[2], am[3]);
+            da[1] = make_uint4(am[4], am[5], am[6], am[7]);
+          }
+        }
+      }
+    }
     int nb = half;
-    for (int a = 0; a < acc_eff; ++a, nb -= 4) {
+    for (int a = 0; a < (p.pool ? 0 : acc_eff); ++a, nb -= 4) {
 #pragma unroll 1
       for (; nb < 4; nb += ZNS_EPI) {
         const int j = nb >> 1;                              // stacked block: 0 -> upper row, 1 -> lower row
@@ -995,14 +1123,28 @@ static bool fwd_stack_config(const zns_conv_desc* d, FwdTParams* p, int ctas) {
 template <int CTAS>
 static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, const void* const* in,
                             const void* const* wpk, const float* const* bias, const void* const* mask, void* const* out,
-                            cudaStream_t st, PlanDump* dry = nullptr) {
+                            const FwdExtra& ex, cudaStream_t st, PlanDump* dry = nullptr) {
   const int G = zns_groups(d->batch);
   FwdTParams p = cfg;
   p.G = G; p.H = d->H; p.W = d->W; p.batch = d->batch;
   p.kh = d->kh; p.kw = d->kw; p.ph = d->kh / 2; p.pw = d->kw / 2;
   p.n_chunks = d->c_in / 64;
   p.n_wtiles = (d->W + WT - 1) / WT;
-  {
+  if (ex.pool > 0) {
+    // whole pool windows per tile: the smallest number of stacked pairs whose rows are a multiple of the pool (3 pairs = 6
+    // rows = two windows of 3; 2 pairs = one window of 4)
+    int pairs = (ex.pool % 2 == 0) ? ex.pool / 2 : ex.pool;
+    ZNS_REQUIRE(pairs <= p.n_acc && d->H % (2 * pairs) == 0 && !mask && d->relu == 0,
+                "fused pooling: pool %d does not fit %d stacked accumulators / H %d", ex.pool, p.n_acc, d->H);
+    while (2 * pairs <= p.n_acc && d->H % (4 * pairs) == 0 && ex.pool % 2 == 0) pairs *= 2;
+    memset(&p.tiles, 0, sizeof(p.tiles));
+    p.tiles.n_cols = G * p.n_wtiles * n_br;
+    p.tiles.hb = pairs; p.tiles.nb = d->H / (2 * pairs); p.tiles.hs = pairs; p.tiles.ns = 0;
+    p.tiles.n_big = p.tiles.n_cols * p.tiles.nb; p.tiles.n_total = p.tiles.n_big;
+    p.n_acc = pairs;
+    p.n_slots = std::min(p.n_slots, std::min(MAX_RING, (p.n_acc - 1) * 2 + 3));
+    p.pool = ex.pool;
+  } else {
     const double pair_clk = (double)p.n_chunks * (d->kh + 1) * d->kw * 4.0 * 64.0;   // N = 128 MMAs per stacked pair
     p.tiles = plan_tiles(d->H / 2, G * p.n_wtiles * n_br, p.n_acc, 8000.0 / pair_clk, CTAS);
     p.n_acc = p.tiles.hb;
@@ -1027,6 +1169,8 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
     p.bias[b] = bias ? bias[s] : nullptr;
     p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
     p.out[b] = (bf16*)out[s];
+    p.out2[b] = ex.out2 ? (bf16*)ex.out2[s] : nullptr;
+    p.arg[b] = ex.arg ? (uint8_t*)ex.arg[s] : nullptr;
   }
   auto kern = conv_fwd_stack_umma_kernel<CTAS>;
   static bool attr_set = false;
@@ -1101,8 +1245,9 @@ static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, 
 
 template <int N, int HT, int CTAS = 1>
 static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                      const float* const* bias, const void* const* mask, void* const* out, void* const* out2,
+                      const float* const* bias, const void* const* mask, void* const* out, const FwdExtra& ex,
                       cudaStream_t st, PlanDump* dry = nullptr) {
+  void* const* out2 = ex.out2;
   const int G = zns_groups(d->batch);
   FwdParams p;
   memset(&p, 0, sizeof(p));
@@ -1118,7 +1263,16 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
   const uint32_t budget = ZNS_SMEM_LIMIT - 1024 - (uint32_t)sizeof(FwdBarriers) - 64;
   int u_max = std::min(HT, d->H);
   while (u_max > 1 && (uint64_t)(u_max + 1) * p.slot_bytes + 2ull * btile > budget) --u_max;
-  {
+  if (ex.pool > 0) {
+    // one pool window per tile: `pool` rows = `pool` accumulators, windows aligned to multiples of `pool`
+    ZNS_REQUIRE(ex.pool <= u_max && d->H % ex.pool == 0, "fused pooling needs pool %d <= %d accumulators and H %% pool == 0", ex.pool, u_max);
+    ZNS_REQUIRE(!mask && d->relu == 0, "fused pooling is a forward-pass epilogue (no mask, ReLU comes after the pool)");
+    memset(&p.tiles, 0, sizeof(p.tiles));
+    p.tiles.n_cols = G * p.n_wtiles * n_br;
+    p.tiles.hb = ex.pool; p.tiles.nb = d->H / ex.pool; p.tiles.hs = ex.pool; p.tiles.ns = 0;
+    p.tiles.n_big = p.tiles.n_cols * p.tiles.nb; p.tiles.n_total = p.tiles.n_big;
+    p.pool = ex.pool;
+  } else {
     const double row_clk = (double)p.n_chunks * d->kh * d->kw * 4.0 * (N / 2);
     p.tiles = plan_tiles(d->H, G * p.n_wtiles * n_br, u_max, 8000.0 / row_clk, CTAS);
   }
@@ -1150,6 +1304,7 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
     p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
     p.out[b] = (bf16*)out[s];
     p.out2[b] = out2 ? (bf16*)out2[s] : nullptr;
+    p.arg[b] = ex.arg ? (uint8_t*)ex.arg[s] : nullptr;
   }
   auto kern = conv_fwd_umma_kernel<N, HT, CTAS>;
   static bool attr_set = false;
@@ -1169,8 +1324,9 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
 
 // Kernel choice and launch of the forward / data-gradient convolution; with `dry` only the geometry is reported.
 static int conv_fwd_dispatch(const zns_conv_desc* d, int n_br, const void* const* in, const void* const* wpk,
-                             const float* const* bias, const void* const* mask, void* const* out, void* const* out2,
+                             const float* const* bias, const void* const* mask, void* const* out, const FwdExtra& ex,
                              cudaStream_t st, PlanDump* dry) {
+  void* const* out2 = ex.out2;
   ZNS_REQUIRE(d != nullptr, "NULL argument");
   ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   ZNS_REQUIRE(d->c_in % 64 == 0 && d->c_in >= 64, "c_in must be a multiple of 64 (got %d)", d->c_in);
@@ -1189,25 +1345,31 @@ static int conv_fwd_dispatch(const zns_conv_desc* d, int n_br, const void* const
     static const bool use_t = getenv("ZNS_CONV_TRANSPOSED") != nullptr;
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    if (use_t && !dry && d->fmt == 0 && !out2 && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
+    if (use_t && !dry && d->fmt == 0 && !out2 && !ex.pool && fwdT_config(d, &cfg)) return launch_fwdT(d, cfg, n_br, in, wpk, bias, mask, out, st);
   }
   {
     static const bool no_stack = getenv("ZNS_CONV_NO_STACK") != nullptr;   // A/B switch
     FwdTParams cfg;
     memset(&cfg, 0, sizeof(cfg));
-    // (a second bf16 output is written by the direct kernels only)
-    if (!no_stack && !out2 && use_pair && can_pair && fwd_stack_config(d, &cfg, 2))
-      return launch_fwd_stack<2>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
-    if (!no_stack && !out2 && fwd_stack_config(d, &cfg, 1)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, st, dry);
+    // (without pooling a second bf16 output is written by the direct kernels only)
+    const bool stack_ok = !no_stack && (!out2 || ex.pool > 0);
+    auto pool_fits = [&](const FwdTParams& c) {
+      if (ex.pool <= 0) return true;
+      const int pairs = (ex.pool % 2 == 0) ? ex.pool / 2 : ex.pool;
+      return pairs <= c.n_acc && d->H % (2 * pairs) == 0;
+    };
+    if (stack_ok && use_pair && can_pair && fwd_stack_config(d, &cfg, 2) && pool_fits(cfg))
+      return launch_fwd_stack<2>(d, cfg, n_br, in, wpk, bias, mask, out, ex, st, dry);
+    if (stack_ok && fwd_stack_config(d, &cfg, 1) && pool_fits(cfg)) return launch_fwd_stack<1>(d, cfg, n_br, in, wpk, bias, mask, out, ex, st, dry);
   }
   switch (d->c_out) {
-    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
+    case 64: return launch_fwd<64, 4>(d, n_br, in, wpk, bias, mask, out, ex, st, dry);
     case 128:
-      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
-      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
+      if (use_pair && can_pair) return launch_fwd<128, 4, 2>(d, n_br, in, wpk, bias, mask, out, ex, st, dry);
+      return launch_fwd<128, 4>(d, n_br, in, wpk, bias, mask, out, ex, st, dry);
     case 256:
-      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
-      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, out2, st, dry);
+      if (pair_mode >= 2 && can_pair) return launch_fwd<256, 2, 2>(d, n_br, in, wpk, bias, mask, out, ex, st, dry);
+      return launch_fwd<256, 2>(d, n_br, in, wpk, bias, mask, out, ex, st, dry);
     default: return zns_set_error(ZNS_ERR_INVALID, "c_out must be 64, 128 or 256 (got %d)", d->c_out);
   }
 }
@@ -1218,7 +1380,23 @@ extern "C" int zns_conv_fwd(const zns_conv_desc* d, int n_br, const void* const*
   ZNS_REQUIRE(d && in && wpk && out, "NULL argument");
   ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
   for (int b = 0; b < n_br; ++b) ZNS_REQUIRE(in[b] && wpk[b] && out[b] && (!out_bf16 || out_bf16[b]), "NULL tensor for branch %d", b);
-  return conv_fwd_dispatch(d, n_br, in, wpk, bias, mask, out, out_bf16, (cudaStream_t)stream, nullptr);
+  const FwdExtra ex = {out_bf16, 0, nullptr};
+  return conv_fwd_dispatch(d, n_br, in, wpk, bias, mask, out, ex, (cudaStream_t)stream, nullptr);
+}
+
+// Convolution with the pooling block of models.py:41-44,50-53 fused into its epilogue: conv + bias -> MaxPool2d((pool, 1))
+// -> ReLU -> Dropout(d->dropout_p), written as the pooled act tensor (+ optional bf16 copy + arg-max bytes).
+extern "C" int zns_conv_pool_fwd(const zns_conv_desc* d, int pool, int n_br, const void* const* in, const void* const* wpk,
+                                 const float* const* bias, void* const* out_pooled, void* const* out_pooled_bf16,
+                                 void* const* argmax, void* stream) {
+  ZNS_REQUIRE(d && in && wpk && out_pooled, "NULL argument");
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  ZNS_REQUIRE(pool >= 2, "pool must be >= 2");
+  for (int b = 0; b < n_br; ++b)
+    ZNS_REQUIRE(in[b] && wpk[b] && out_pooled[b] && (!out_pooled_bf16 || out_pooled_bf16[b]) && (!argmax || argmax[b]),
+                "NULL tensor for branch %d", b);
+  const FwdExtra ex = {out_pooled_bf16, pool, argmax};
+  return conv_fwd_dispatch(d, n_br, in, wpk, bias, nullptr, out_pooled, ex, (cudaStream_t)stream, nullptr);
 }
 
 // Host-only: the launch geometry zns_conv_fwd would use for this layer (no CUDA call is made).
@@ -1228,7 +1406,8 @@ extern "C" int zns_dbg_conv_fwd_plan(const zns_conv_desc* d, int n_br, int* out)
   ZNS_REQUIRE(d && out, "NULL argument");
   PlanDump pd;
   memset(&pd, 0, sizeof(pd));
-  int rc = conv_fwd_dispatch(d, n_br, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &pd);
+  const FwdExtra ex0 = {nullptr, 0, nullptr};
+  int rc = conv_fwd_dispatch(d, n_br, nullptr, nullptr, nullptr, nullptr, nullptr, ex0, nullptr, &pd);
   if (rc) return rc;
   const int vals[14] = {pd.kernel, pd.n, pd.ctas, pd.tiles.hb, pd.tiles.nb, pd.tiles.hs, pd.tiles.ns, pd.tiles.n_cols,
                         pd.tiles.n_total, pd.n_slots, pd.n_stages, pd.grid_x, (int)pd.smem, pd.kernel == 1 ? d->H / 2 : d->H};

@@ -29,7 +29,7 @@ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 struct C1FwdBr { const float* x; const float* weight; const float* bias; bf16* out; bf16* out2; };
 struct C1FwdArgs { C1FwdBr br[2]; int G; };
 
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(const C1FwdArgs a, long long clip_stride, long long row_stride,
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const __grid_constant__ C1FwdArgs a, long long clip_stride, long long row_stride,
                                                         int B, int H, int W, float drop_p, uint32_t seed,
                                                         const uint32_t* __restrict__ seed_dev, uint32_t stream_id, int f16) {
   __shared__ __align__(16) float ws[C1_TAPS][C1_CO];
@@ -56,6 +56,11 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const C1FwdArgs a, long 
   if (b >= B) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+    if (out2) {
+      uint4* dst2 = reinterpret_cast<uint4*>(out2 + zns_act_index(g, h, w, b8, 0, H, W, C1_CO));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst2[i] = make_uint4(0, 0, 0, 0);
+    }
     return;
   }
   float xin[C1_TAPS];
@@ -139,7 +144,7 @@ extern "C" int zns_conv1_fwd(const float* x, long long clip_stride, long long ro
 struct C1WgBr { const bf16* dy; const float* x; float* dw; float* db; };
 struct C1WgArgs { C1WgBr br[2]; int G; };
 
-__global__ void __launch_bounds__(192) conv1_wgrad_kernel(const C1WgArgs a, long long clip_stride, long long row_stride,
+__global__ void __launch_bounds__(192) conv1_wgrad_kernel(const __grid_constant__ C1WgArgs a, long long clip_stride, long long row_stride,
                                                           int B, int H, int W) {
   __shared__ float xs[C1_KH][8][32 + C1_KW - 1];
   __shared__ __align__(16) bf16 dys[32 * 8 * C1_CO];      // [frame][clip slot][64 channels], 32 KB
@@ -254,7 +259,7 @@ __device__ __forceinline__ uint4 pack8(const float* f, bool f16 = false) {
 struct PoolBr { const uint4* y; uint4* out; uint4* out2; const uint4* dp; uint4* dy; };
 struct PoolArgs { PoolBr br[2]; };
 
-__global__ void pool_fwd_kernel(const PoolArgs a, size_t n_vec, size_t row_vec,
+__global__ void pool_fwd_kernel(const __grid_constant__ PoolArgs a, size_t n_vec, size_t row_vec,
                                 int Hp, int pool, float drop_p, uint32_t seed, const uint32_t* __restrict__ seed_dev,
                                 uint32_t stream_id, int f16) {
   const uint4* __restrict__ y = a.br[blockIdx.y].y;
@@ -317,7 +322,7 @@ extern "C" int zns_pool_fwd(const void* y_act, void* out_act, int batch, int H, 
                           out_act_bf16 ? &out_act_bf16 : nullptr, stream);
 }
 
-__global__ void pool_bwd_kernel(const PoolArgs a, size_t n_vec, size_t row_vec, int Hp, int pool, int y_f16) {
+__global__ void pool_bwd_kernel(const __grid_constant__ PoolArgs a, size_t n_vec, size_t row_vec, int Hp, int pool, int y_f16) {
   const uint4* __restrict__ y = a.br[blockIdx.y].y;
   const uint4* __restrict__ dp = a.br[blockIdx.y].dp;
   uint4* __restrict__ dy = a.br[blockIdx.y].dy;
@@ -370,6 +375,54 @@ extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_a
   return zns_pool_bwd_nbr(1, &y_act, &dpool_act, &dy_act, batch, H, W, C, pool, y_f16, stream);
 }
 
+// Backward of the pooling fused into a convolution epilogue (zns_conv_pool_fwd): the forward pass kept one byte per pooled
+// element, the row of the first maximum inside its window; dy[row] = dp if row == arg else 0.  Reads dp (2 B) + arg (1 B) per
+// pooled element instead of the whole pre-pool activation.
+struct UnpoolBr { const uint4* dp; const uint2* arg; uint4* dy; };
+struct UnpoolArgs { UnpoolBr br[2]; };
+
+__global__ void pool_bwd_arg_kernel(const __grid_constant__ UnpoolArgs a, size_t n_vec, size_t row_vec, int Hp, int pool) {
+  const uint4* __restrict__ dp = a.br[blockIdx.y].dp;
+  const uint2* __restrict__ arg = a.br[blockIdx.y].arg;
+  uint4* __restrict__ dy = a.br[blockIdx.y].dy;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t ghp = i / row_vec, r = i - ghp * row_vec;
+    const size_t base = (ghp * pool) * row_vec + r;          // (g * Hp + hp) * pool rows of the unpooled tensor
+    const uint4 d = __ldg(dp + i);
+    const uint2 am = __ldg(arg + i);                          // eight row indices
+    const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+    for (int k = 0; k < pool; ++k) {
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t a0 = ((q < 2 ? am.x : am.y) >> (16 * (q & 1))) & 0xFFu, a1 = ((q < 2 ? am.x : am.y) >> (16 * (q & 1) + 8)) & 0xFFu;
+        o[q] = (a0 == (uint32_t)k ? (dw[q] & 0xFFFFu) : 0u) | (a1 == (uint32_t)k ? (dw[q] & 0xFFFF0000u) : 0u);
+      }
+      dy[base + (size_t)k * row_vec] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+extern "C" int zns_pool_bwd_arg_nbr(int n_br, const void* const* argmax, const void* const* dpool_act, void* const* dy_act,
+                                    int batch, int H, int W, int C, int pool, void* stream) {
+  ZNS_REQUIRE(n_br == 1 || n_br == 2, "n_br must be 1 or 2");
+  ZNS_REQUIRE(argmax && dpool_act && dy_act, "NULL argument");
+  ZNS_REQUIRE(pool >= 1 && pool <= 255 && H % pool == 0 && C % 8 == 0, "pool %d must divide H %d", pool, H);
+  UnpoolArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int b = 0; b < n_br; ++b) {
+    ZNS_REQUIRE(argmax[b] && dpool_act[b] && dy_act[b], "NULL tensor for branch %d", b);
+    a.br[b].dp = (const uint4*)dpool_act[b]; a.br[b].arg = (const uint2*)argmax[b]; a.br[b].dy = (uint4*)dy_act[b];
+  }
+  const int G = zns_groups(batch), Hp = H / pool;
+  const size_t row_vec = (size_t)W * 8 * C / 8;
+  const size_t n_vec = (size_t)G * Hp * row_vec;
+  const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+  pool_bwd_arg_kernel<<<dim3(blocks, n_br), 256, 0, (cudaStream_t)stream>>>(a, n_vec, row_vec, Hp, pool);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // head: Conv1d(128, 1, k=1) + Sigmoid + flatten, forward and backward
 // block = 256 threads = 32 positions x 8 lanes; a lane owns 16 channels
@@ -379,7 +432,7 @@ extern "C" int zns_pool_bwd(const void* y_act, const void* dpool_act, void* dy_a
 struct HeadBr { const bf16* x; const float* w; const float* bias; float* emb; const float* d_emb; float* dw; float* dbias; bf16* dy; };
 struct HeadArgs { HeadBr br[2]; };
 
-__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a, int B, int T, int n_pos, int f16) {
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __grid_constant__ HeadArgs a, int B, int T, int n_pos, int f16) {
   const bf16* __restrict__ x = a.br[blockIdx.y].x;
   const float* __restrict__ w = a.br[blockIdx.y].w;
   const float* __restrict__ bias = a.br[blockIdx.y].bias;
@@ -430,7 +483,7 @@ extern "C" int zns_head_fwd(const void* x_act, const float* w128, const float* b
   return zns_head_fwd_nbr(1, &x_act, &w128, &bias1, &emb, batch, T, x_f16, stream);
 }
 
-__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs a, int B, int T, int n_pos, float out_scale, int x_f16) {
+__global__ void __launch_bounds__(256) head_bwd_kernel(const __grid_constant__ HeadArgs a, int B, int T, int n_pos, float out_scale, int x_f16) {
   const bf16* __restrict__ x = a.br[blockIdx.y].x;
   const float* __restrict__ emb = a.br[blockIdx.y].emb;
   const float* __restrict__ d_emb = a.br[blockIdx.y].d_emb;
@@ -602,11 +655,19 @@ __device__ __forceinline__ void unpack_grads_block(int bx, int by, float* __rest
   extern __shared__ float tile[];  // [64 ci][ntaps]
   const int co = by, ci0 = bx * 64;
   const int n = 64 * ntaps;
+  // loads and the clearing stores in separate loops: a store to *src inside the load loop orders every later load behind
+  // it (same pointer), which leaves ONE load in flight per thread (measured: 1.15 ms instead of ~0.1 ms for all layers)
+#pragma unroll 4
   for (int i = threadIdx.x; i < n; i += 256) {
     const int t = i / 64, ci = i - t * 64;
-    float* src = gpk + ((size_t)t * c_out + co) * c_in + ci0 + ci;
-    tile[ci * ntaps + t] = *src;
-    if (zero_src) *src = 0.f;          // the packed accumulator is clean for the next step's atomics (no memset launch)
+    tile[ci * ntaps + t] = gpk[((size_t)t * c_out + co) * c_in + ci0 + ci];
+  }
+  if (zero_src) {                      // the packed accumulator is clean for the next step's atomics (no memset launch)
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int t = i / 64, ci = i - t * 64;
+      gpk[((size_t)t * c_out + co) * c_in + ci0 + ci] = 0.f;
+    }
   }
   __syncthreads();
   float* dst = g + ((size_t)co * c_in + ci0) * ntaps;
@@ -619,7 +680,9 @@ __device__ __forceinline__ void unpack_grads_block(int bx, int by, float* __rest
 struct MtJob { const float* src; void* dst; int c_out, c_in, ntaps, kind, blk0, nbx; };   // kind 0 forward pack, 1 flipped pack, 2 unpack
 struct MtArgs { MtJob job[ZNS_MT_MAX_JOBS]; int n_jobs, f16, accumulate, zero_src; float scale; };
 
-__global__ void __launch_bounds__(256) multi_tensor_kernel(const MtArgs a) {
+__global__ void __launch_bounds__(256) multi_tensor_kernel(const __grid_constant__ MtArgs a) {
+  // (the table stays in the constant bank: __grid_constant__ -- a by-value parameter indexed with a run-time subscript is
+  // copied to local memory by every thread, which made this kernel 60x slower than its work)
   const int b = blockIdx.x;
   int j = 0;
   while (j + 1 < a.n_jobs && b >= a.job[j + 1].blk0) ++j;
@@ -709,7 +772,7 @@ extern "C" int zns_zero(void* p, long long bytes, void* stream) {
 struct BiasBr { const uint4* dy; float* db; };
 struct BiasArgs { BiasBr br[2]; };
 
-__global__ void __launch_bounds__(256) bias_grad_kernel(const BiasArgs a, size_t n_pos, int C) {
+__global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasArgs a, size_t n_pos, int C) {
   const uint4* __restrict__ dy = a.br[blockIdx.y].dy;
   float* __restrict__ db = a.br[blockIdx.y].db;
   // a thread owns 8 consecutive channels (one 16-byte load per position); C/8 threads span a position

@@ -149,3 +149,37 @@ extern "C" int zns_ntxent_fwd_bwd(const float* anchors, const float* poss, int n
   ZNS_CHECK_LAUNCH();
   return ZNS_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Binary cross entropy of the downstream beat head (torch.nn.BCELoss, mean reduction; loader.py:20, epochs.py:52-54),
+// forward and backward in ONE launch: loss = -mean(t log o + (1 - t) log(1 - o)) with torch's clamps (log >= -100;
+// gradient denominator >= 1e-12), d_out = (o - t) / max(o (1 - o), 1e-12) / n.  One CTA: n is a clip's frame count.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ o, const float* __restrict__ t, long long n,
+                                                  float* __restrict__ loss, float* __restrict__ d_out) {
+  __shared__ float red[8];
+  const float inv_n = 1.f / (float)n;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const float x = o[i], y = t[i];
+    acc -= y * fmaxf(logf(x), -100.f) + (1.f - y) * fmaxf(log1pf(-x), -100.f);
+    if (d_out) d_out[i] = (x - y) / fmaxf(x * (1.f - x), 1e-12f) * inv_n;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    *loss = sum * inv_n;
+  }
+}
+
+extern "C" int zns_bce_fwd_bwd(const float* out, const float* target, long long n, float* loss, float* d_out, void* stream) {
+  ZNS_REQUIRE(out && target && loss && n > 0, "bad argument");
+  bce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out, target, n, loss, d_out);
+  ZNS_CHECK_LAUNCH();
+  return ZNS_OK;
+}

@@ -49,12 +49,29 @@ def _fwd_tag(c_out: int, H: int) -> str:
 
 
 class EncoderEngine:
-    """Workspaces + launch sequences for ``n_br`` encoders on a fixed (batch, T) geometry."""
+    """Workspaces + launch sequences for ``n_br`` encoders of ``batch`` clips with up to ``T`` frames.
+
+    The act layout [G][H][T][8][C] is compact for any frame count, so the buffers are flat storages sized for the
+    capacity ``T_cap`` and ``set_T`` re-views their prefix for a shorter clip: a dataset with variable lengths (the
+    downstream loops feed one file per step, epochs.py:45-63) keeps ONE engine instead of reallocating GBs per length."""
+
+    # (attribute, rows H, channels) of the forward activations; *_s = bf16 shadow wanted (x operand of a weight gradient)
+    _ACTS = (("x1", 96, 64, True),      # dropout(relu(cv1))
+             ("p2", 32, 64, True),      # dropout(relu(pool3(cv2))): the pool is fused into cv2's epilogue, the pre-pool tensor is never written
+             ("x3", 32, 128, True),
+             ("p4", 8, 128, True),      # dropout(relu(pool4(cv4))), fused likewise
+             ("x5", 8, 256, True),
+             ("y6", 8, 256, False),     # cv6 pre-pool (pool 8 > the two 256-column accumulators of a tile: separate pool kernel)
+             ("p6", 1, 256, True),
+             ("x7", 1, 128, True),
+             ("x8", 1, 128, False))
+    # row of the first maximum of every pool window (one byte per pooled element): the backward pass routes through it
+    _ARGS = (("arg2", 32, 64), ("arg4", 8, 128))
 
     def __init__(self, batch: int, T: int, n_br: int, device: torch.device, seed: int = 0):
         assert n_br in (1, 2)
         L.check(L.lib().zns_device_check())
-        self.B, self.T, self.n_br, self.device = batch, T, n_br, device
+        self.B, self.T_cap, self.n_br, self.device = batch, T, n_br, device
         self.G = (batch + 7) // 8
         self.seed = seed
         bf = torch.bfloat16
@@ -62,32 +79,22 @@ class EncoderEngine:
         # log-magnitude inputs in [-21, 2] and O(1..100) activations are far inside its range), gradients stay bf16
         fa = torch.float16
         G = self.G
-
-        def act(H, Cc):
-            return [torch.zeros(G, H, T, 8, Cc, dtype=fa, device=device) for _ in range(n_br)]
-
-        # forward activations (kept for backward)
-        self.x1 = act(96, 64)      # dropout(relu(cv1))
-        self.y2 = act(96, 64)      # cv2 pre-pool
-        self.p2 = act(32, 64)      # dropout(relu(pool3(y2)))
-        self.x3 = act(32, 128)
-        self.y4 = act(32, 128)
-        self.p4 = act(8, 128)
-        self.x5 = act(8, 256)
-        self.y6 = act(8, 256)
-        self.p6 = act(1, 256)
-        self.x7 = act(1, 128)
-        self.x8 = act(1, 128)
+        self._store: Dict[str, List[torch.Tensor]] = {}
         # bf16 shadows of the activations that are the x operand of a weight gradient (written by the producing kernel next
         # to the fp16 tensor): both operands of one tcgen05.mma must share a type, and gradients are bf16
         self._shadow: Dict[int, List[torch.Tensor]] = {}
-
-        def shadow(ts):
-            self._shadow[id(ts)] = [torch.zeros_like(t, dtype=bf) for t in ts]
-
-        for ts in (self.x1, self.p2, self.x3, self.p4, self.x5, self.p6, self.x7):
-            shadow(ts)
-        self.emb = [torch.zeros(batch, T, device=device) for _ in range(n_br)]
+        for name, H, Cc, shadowed in self._ACTS:
+            self._store[name] = [torch.zeros(G * H * T * 8 * Cc, dtype=fa, device=device) for _ in range(n_br)]
+            setattr(self, name, [None] * n_br)
+            if shadowed:
+                self._store[name + "_s"] = [torch.zeros(G * H * T * 8 * Cc, dtype=bf, device=device) for _ in range(n_br)]
+                self._shadow[id(getattr(self, name))] = [None] * n_br
+        for name, H, Cc in self._ARGS:
+            self._store[name] = [torch.zeros(G * H * T * 8 * Cc, dtype=torch.uint8, device=device) for _ in range(n_br)]
+            setattr(self, name, [None] * n_br)
+        self._store["emb"] = [torch.zeros(batch * T, device=device) for _ in range(n_br)]
+        self.emb: List[torch.Tensor] = [None] * n_br
+        self.set_T(T)
         # packed weights / gradients for cv2..cv8
         self.wf: Dict[str, List[torch.Tensor]] = {}
         self.wd: Dict[str, List[torch.Tensor]] = {}
@@ -109,6 +116,25 @@ class EncoderEngine:
         # the other (each kernel occupies an SM exclusively: ~200 KB of shared memory per CTA)
         self._side = torch.cuda.Stream(device=device)
         self.overlap_wgrad = True
+
+    def set_T(self, T: int) -> None:
+        """Work on clips of ``T <= T_cap`` frames: re-view the prefix of every workspace (no allocation, no copy)."""
+        if T > self.T_cap or T < 1:
+            raise ValueError(f"T = {T} outside this engine's capacity {self.T_cap}")
+        self.T = T
+        G = self.G
+        for name, H, Cc, shadowed in self._ACTS:
+            views = getattr(self, name)
+            for br in range(self.n_br):
+                views[br] = self._store[name][br][:G * H * T * 8 * Cc].view(G, H, T, 8, Cc)
+                if shadowed:
+                    self._shadow[id(views)][br] = self._store[name + "_s"][br][:G * H * T * 8 * Cc].view(G, H, T, 8, Cc)
+        for name, H, Cc in self._ARGS:
+            views = getattr(self, name)
+            for br in range(self.n_br):
+                views[br] = self._store[name][br][:G * H * T * 8 * Cc].view(G, H, T, 8, Cc)
+        for br in range(self.n_br):
+            self.emb[br] = self._store["emb"][br][:self.B * T].view(self.B, T)
 
     def _timed(self, tag: str, flops: float):
         eng = self
@@ -137,7 +163,7 @@ class EncoderEngine:
     def _ensure_grad_ws(self):
         if self._grad_ws_ready:
             return
-        bf, dev, G, T = torch.bfloat16, self.device, self.G, self.T
+        bf, dev, G, T = torch.bfloat16, self.device, self.G, self.T_cap
         n = G * 96 * T * 8 * 64
         self.ga = [torch.zeros(n, dtype=bf, device=dev) for _ in range(self.n_br)]
         self.gb = [torch.zeros(n, dtype=bf, device=dev) for _ in range(self.n_br)]
@@ -190,6 +216,18 @@ class EncoderEngine:
                                          L.ptr_array(bias), None, L.ptr_array(outs), L.ptr_array(sh) if sh else None,
                                          L.current_stream()))
 
+    def _conv_pool(self, name, H, pool, ins, outs, args, params, layer_id):
+        """conv + bias -> MaxPool((pool, 1)) -> ReLU -> Dropout in ONE launch (zns_conv_pool_fwd); outs are the pooled tensors."""
+        _, co, ci, kh, kw, _ = next(s for s in CONV_SPECS if s[0] == name)
+        d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw, relu=0, dropout_p=self._p, seed=self.seed, rng_stream=layer_id * 2,
+                        seed_dev=self.step_ctr if self._p > 0 else None, fmt=L.FMT_FORWARD_F16)
+        bias = [params[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]
+        sh = self._shadow[id(outs)] if self._need_shadow else None
+        with self._timed(_fwd_tag(co, H), self._conv_flops(name, H)):
+            L.check(L.lib().zns_conv_pool_fwd(C.byref(d), pool, self.n_br, L.ptr_array(ins), L.ptr_array(self.wf[name]),
+                                              L.ptr_array(bias), L.ptr_array(outs), L.ptr_array(sh) if sh else None,
+                                              L.ptr_array(args) if self._need_shadow else None, L.current_stream()))
+
     def _pool(self, H, Cc, pool, ys, outs, layer_id):
         sh = self._shadow[id(outs)] if self._need_shadow else None
         L.check(L.lib().zns_pool_fwd_nbr(self.n_br, L.ptr_array(ys), L.ptr_array(outs), self.B, H, self.T, Cc, pool, self._p,
@@ -217,11 +255,9 @@ class EncoderEngine:
         if getattr(self, "_pack_event", None) is not None:      # packs issued by pack_weights_async
             torch.cuda.current_stream().wait_event(self._pack_event)
             self._pack_event = None
-        self._conv("cv2", 96, self.x1, self.y2, params, relu=0, drop=False, layer_id=2)
-        self._pool(96, 64, 3, self.y2, self.p2, 2)
+        self._conv_pool("cv2", 96, 3, self.x1, self.p2, self.arg2, params, layer_id=2)
         self._conv("cv3", 32, self.p2, self.x3, params, relu=1, drop=True, layer_id=3)
-        self._conv("cv4", 32, self.x3, self.y4, params, relu=0, drop=False, layer_id=4)
-        self._pool(32, 128, 4, self.y4, self.p4, 4)
+        self._conv_pool("cv4", 32, 4, self.x3, self.p4, self.arg4, params, layer_id=4)
         self._conv("cv5", 8, self.p4, self.x5, params, relu=1, drop=True, layer_id=5)
         self._conv("cv6", 8, self.x5, self.y6, params, relu=0, drop=False, layer_id=6)
         self._pool(8, 256, 8, self.y6, self.p6, 6)
@@ -259,12 +295,14 @@ class EncoderEngine:
         L.check(lib.zns_bias_grad_nbr(self.n_br, L.ptr_array(dys), self.B, H, self.T, co,
                                       L.ptr_array([grads[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]), st))
 
-    def _unpack_all(self, grads):
-        """Packed [tap][c_out][c_in] weight gradients of every layer and branch -> state_dict layout (+=), one launch; the
-        packed accumulators are cleared behind the read (next step's atomics start from zero: no fill kernel)."""
+    def _unpack_all(self, grads, layers=None):
+        """Packed [tap][c_out][c_in] weight gradients of every (or the named) layer and branch -> state_dict layout (+=), one
+        launch; the packed accumulators are cleared behind the read (next step's atomics start from zero: no fill kernel)."""
         gp, g, geo = [], [], []
         for br in range(self.n_br):
             for name, co, ci, kh, kw, _ in CONV_SPECS[1:]:
+                if layers is not None and name not in layers:
+                    continue
                 gp.append(self.gp[name][br])
                 g.append(grads[br][f"pretrained.{name}.weight"])
                 geo.append((co, ci, kh, kw))
@@ -284,13 +322,43 @@ class EncoderEngine:
         L.check(L.lib().zns_pool_bwd_nbr(self.n_br, L.ptr_array(ys), L.ptr_array(dps), L.ptr_array(outs), self.B, H, self.T, Cc,
                                          pool, 1, L.current_stream()))
 
+    def _unpool_arg(self, H, Cc, pool, args, dps, outs):
+        L.check(L.lib().zns_pool_bwd_arg_nbr(self.n_br, L.ptr_array(args), L.ptr_array(dps), L.ptr_array(outs), self.B, H, self.T,
+                                             Cc, pool, L.current_stream()))
+
+    LATE_LAYERS = ("cv5", "cv6", "cv7", "cv8")     # their gradients are complete after phase "late" of backward()
+    EARLY_LAYERS = ("cv2", "cv3", "cv4")
+
     def backward(self, d_embs: Sequence[torch.Tensor], params: Sequence[Dict[str, torch.Tensor]],
-                 grads: Sequence[Dict[str, torch.Tensor]]) -> None:
+                 grads: Sequence[Dict[str, torch.Tensor]], phase: Optional[str] = None) -> None:
         """Accumulate (+=) parameter gradients into ``grads[br][name]`` (fp32, state_dict layout;
-        they must be zeroed by the caller).  ``d_embs[br]``: (B, T) fp32 gradient of the loss."""
+        they must be zeroed by the caller).  ``d_embs[br]``: (B, T) fp32 gradient of the loss.
+
+        ``phase`` splits the pass for data-parallel training: "late" runs the head and cv8..cv5 (80 % of the parameters:
+        their gradients, fc1 included, are final when it returns, so their exchange can overlap the rest), "early" runs
+        cv4..cv1 on the dp4 that "late" left in the workspace.  None runs both."""
         self._ensure_grad_ws()
         if not self._need_shadow:
             raise RuntimeError("backward() needs a forward(..., train=True) or forward(..., need_grad=True) before it")
+        lib, st = L.lib(), L.current_stream()
+        scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
+        ga, gb = self.ga, self.gb
+        nb = self.n_br
+        main = torch.cuda.current_stream()
+
+        def join(ev):
+            if ev is not None:
+                main.wait_event(ev)
+
+        if phase in (None, "late"):
+            self._backward_late(d_embs, params, grads, join)
+            if phase == "late":
+                self._unpack_all(grads, self.LATE_LAYERS)
+                return
+        self._backward_early(params, grads, join)
+        self._unpack_all(grads, None if phase is None else self.EARLY_LAYERS)
+
+    def _backward_late(self, d_embs, params, grads, join):
         lib, st = L.lib(), L.current_stream()
         scale = 1.0 / (1.0 - self._p) if self._p > 0 else 1.0
         ga, gb = self.ga, self.gb
@@ -299,12 +367,6 @@ class EncoderEngine:
                                      L.ptr_array([p["fc1.weight"] for p in params[:nb]]),
                                      L.ptr_array([g["fc1.weight"] for g in grads[:nb]]),
                                      L.ptr_array([g["fc1.bias"] for g in grads[:nb]]), L.ptr_array(ga), self.B, self.T, scale, 1, st))
-        main = torch.cuda.current_stream()
-
-        def join(ev):
-            if ev is not None:
-                main.wait_event(ev)
-
         # dY_L alternates between ga and gb; the wgrad of layer L (side stream) must have finished
         # reading its buffer before the dgrad of layer L-1 writes into it.
         w8 = self._wgrad("cv8", 1, self.x7, ga, grads)
@@ -320,18 +382,22 @@ class EncoderEngine:
         join(w6)
         self._dgrad("cv5", 8, ga, self.p4, gb)          # dp4
         join(w5)
-        self._unpool(32, 128, 4, self.y4, gb, ga)       # dy4
+
+    def _backward_early(self, params, grads, join):
+        lib, st = L.lib(), L.current_stream()
+        ga, gb = self.ga, self.gb
+        nb = self.n_br
+        self._unpool_arg(32, 128, 4, self.arg4, gb, ga)  # dy4
         w4 = self._wgrad("cv4", 32, self.x3, ga, grads)
         self._dgrad("cv4", 32, ga, self.x3, gb)         # dy3
         w3 = self._wgrad("cv3", 32, self.p2, gb, grads)
         join(w4)
         self._dgrad("cv3", 32, gb, self.p2, ga)         # dp2
         join(w3)
-        self._unpool(96, 64, 3, self.y2, ga, gb)        # dy2
+        self._unpool_arg(96, 64, 3, self.arg2, ga, gb)   # dy2
         w2 = self._wgrad("cv2", 96, self.x1, gb, grads)
         self._dgrad("cv2", 96, gb, self.x1, ga)         # dy1
         join(w2)
         L.check(lib.zns_conv1_wgrad_nbr(nb, L.ptr_array(ga), L.ptr_array(self._x_in), self._x_stride, self._x_row,
                                         L.ptr_array([g["pretrained.cv1.weight"] for g in grads[:nb]]),
                                         L.ptr_array([g["pretrained.cv1.bias"] for g in grads[:nb]]), self.B, N_BINS, self.T, st))
-        self._unpack_all(grads)

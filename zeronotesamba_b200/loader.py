@@ -4,7 +4,8 @@ Interface of /root/reference/zeroNoteSamba/loader.py::load_models (lines 8-69): 
 returns ``(criterion, optimizer, model)`` with the reference's status names and learning-rate rules.  Two additions:
 the checkpoint location is a parameter (the reference hard-codes ``models/saved/*_pret_cnn_16.pth``, blobs it does
 not ship) and a ``state_dict`` can be handed over directly; the optimizer is this package's ``FusedAdam`` (Adam
-defaults, one fused kernel per tensor) unless ``fused=False`` asks for ``torch.optim.Adam``.
+defaults, one fused kernel per tensor) and the loss ``FusedBCELoss`` (BCELoss forward + backward in one launch) unless
+``fused=False`` asks for ``torch.optim.Adam`` / ``torch.nn.BCELoss``.
 """
 from __future__ import annotations
 
@@ -47,7 +48,11 @@ def load_models(_status: str, _pre: str, _lr: float, checkpoint: Optional[str] =
     """
     recipe = _RECIPES.get(_status, _VANILLA)
     model = recipe.build().cuda()
-    criterion = torch.nn.BCELoss().cuda()
+    if fused:
+        from .models.loss_functions import FusedBCELoss
+        criterion = FusedBCELoss().cuda()
+    else:
+        criterion = torch.nn.BCELoss().cuda()
     if recipe.checkpoint is not None:
         weights = state_dict if state_dict is not None else torch.load(checkpoint or recipe.checkpoint,
                                                                         map_location=torch.device("cuda"))

@@ -67,3 +67,35 @@ class NTXent(nn.Module):
             host = res.tolist()
             return loss, host[1], host[2]
         return loss, res[1], res[2]
+
+
+
+class _BCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, target):
+        o = output.contiguous().float()
+        t = target.contiguous().float()
+        loss = torch.empty(1, device=o.device, dtype=torch.float32)
+        d_out = torch.empty_like(o)
+        L.check(L.lib().zns_bce_fwd_bwd(L.ptr(o), L.ptr(t), o.numel(), L.ptr(loss), L.ptr(d_out), L.current_stream()))
+        ctx.save_for_backward(d_out)
+        ctx.shape = output.shape
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (d_out,) = ctx.saved_tensors
+        return (d_out * g_loss).view(ctx.shape), None
+
+
+class FusedBCELoss(nn.Module):
+    """``torch.nn.BCELoss()`` (mean reduction) as the downstream loops use it (loader.py:20, epochs.py:52-54):
+    ``criterion(output, mask) -> 0-d loss`` with autograd; loss and d loss / d output come from one launch
+    (zns_bce_fwd_bwd) instead of the ~10 elementwise launches of the composed op."""
+
+    def forward(self, output: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if not output.is_cuda:
+            raise RuntimeError("zeronotesamba_b200.FusedBCELoss runs on the GPU only (no CPU fallback)")
+        if output.shape != target.shape:
+            raise ValueError(f"Using a target size ({tuple(target.shape)}) that is different to the input size ({tuple(output.shape)})")
+        return _BCEFunction.apply(output, target)

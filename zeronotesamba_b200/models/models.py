@@ -27,18 +27,24 @@ def _require_cuda(x: torch.Tensor) -> None:
 
 
 class _EngineCache:
-    """One EncoderEngine per (batch, T, n_br) geometry, kept on the owning module."""
+    """One EncoderEngine per (batch, n_br, device), kept on the owning module and shared by every clip length: the engine's
+    workspaces are sized for the longest clip seen so far (plus 25 % head room when they have to grow) and re-viewed for
+    shorter ones, so a dataset with variable T (one file per step, epochs.py:45-63) does not reallocate per length."""
 
     def __init__(self):
         self._engines: Dict[Tuple[int, int, int], EncoderEngine] = {}
 
     def get(self, batch: int, T: int, n_br: int, device) -> EncoderEngine:
-        key = (batch, T, n_br, device.index if device.index is not None else torch.cuda.current_device())
+        key = (batch, n_br, device.index if device.index is not None else torch.cuda.current_device())
         eng = self._engines.get(key)
-        if eng is None:
-            if len(self._engines) >= 4:   # bounded: variable-length inference would otherwise pile up workspaces
+        if eng is None or T > eng.T_cap:
+            cap = T if eng is None else max(T, int(1.25 * eng.T_cap))
+            if eng is None and len(self._engines) >= 4:   # bounded number of (batch, branches) geometries
                 self._engines.pop(next(iter(self._engines)))
-            eng = self._engines[key] = EncoderEngine(batch, T, n_br, device)
+            self._engines.pop(key, None)
+            del eng
+            eng = self._engines[key] = EncoderEngine(batch, cap, n_br, device)
+        eng.set_T(T)
         return eng
 
 

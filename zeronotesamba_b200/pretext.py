@@ -123,6 +123,16 @@ class PretextTrainer:
         self.flat_v = torch.zeros(total, device=dev)
         self.params: List[Dict[str, torch.Tensor]] = [{}, {}]
         self.grads: List[Dict[str, torch.Tensor]] = [{}, {}]
+        # data-parallel buckets (element ranges of the flat buffers): per branch, "late" = cv5.weight .. fc1.bias (final after
+        # the first phase of the backward pass, 80 % of the parameters), "early" = cv1.weight .. cv4.bias
+        n_per = len(names)
+        i5 = names.index("pretrained.cv5.weight")
+        self._bucket_late, self._bucket_early = [], []
+        for br in range(2):
+            lo, mid = offs[br * n_per], offs[br * n_per + i5]
+            hi = offs[(br + 1) * n_per] if br == 0 else total
+            self._bucket_early.append((lo, mid))
+            self._bucket_late.append((mid, hi))
         for i, p in enumerate(plist):
             seg = self.flat_p[offs[i]:offs[i] + p.numel()].view_as(p)
             seg.copy_(p.data)
@@ -141,6 +151,13 @@ class PretextTrainer:
         self.batch_buf = torch.zeros(self.B, 2, 96, self.T, device=dev)
         self.result = torch.zeros(3, device=dev)
         self.d_emb = [torch.zeros(self.B, self.T, device=dev) for _ in range(2)]
+        # overlapped exchange (N > 1, peer-memory optimizer): ZNS_DP_OVERLAP=0 selects the exchange after the whole backward
+        self.dp_overlap = self._symm is not None and os.environ.get("ZNS_DP_OVERLAP", "1") != "0"
+        self._graph_late: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_early: Optional[torch.cuda.CUDAGraph] = None
+        self._comm = torch.cuda.Stream(device=dev)
+        self._ev_late = torch.cuda.Event()
+        self._ev_comm = torch.cuda.Event()
         self._graph_fb: Optional[torch.cuda.CUDAGraph] = None
         self._graph_opt: Optional[torch.cuda.CUDAGraph] = None
         self._graph_eval: Optional[torch.cuda.CUDAGraph] = None
@@ -172,11 +189,65 @@ class PretextTrainer:
                                        L.ptr(self.result), L.ptr(self.d_emb[0]), L.ptr(self.d_emb[1]), st))
         eng.backward(self.d_emb, self.params, self.grads)
 
-    def _optimizer_p2p(self):
+    def _optimizer_p2p(self, ranges=None):
+        """Fused reduce-scatter + Adam + all-gather over peer memory for the whole flat buffer or for element ranges of it."""
+        import ctypes
         sm = self._symm
-        L.check(L.lib().zns_adam_p2p(sm.world, sm.rank, sm.g_ptrs, sm.p_ptrs, L.ptr(self.flat_m), L.ptr(self.flat_v),
-                                     self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0,
-                                     L.ptr(self.engine.step_ctr), L.current_stream()))
+        for lo, hi in (ranges if ranges is not None else [(0, self.flat_p.numel())]):
+            if hi <= lo:
+                continue
+            g_ptrs = (ctypes.c_void_p * sm.world)(*[int(a) + 4 * lo for a in sm.g_ptrs])
+            p_ptrs = (ctypes.c_void_p * sm.world)(*[int(a) + 4 * lo for a in sm.p_ptrs])
+            L.check(L.lib().zns_adam_p2p(sm.world, sm.rank, g_ptrs, p_ptrs, self.flat_m.data_ptr() + 4 * lo,
+                                         self.flat_v.data_ptr() + 4 * lo, hi - lo, self.lr, self.betas[0], self.betas[1],
+                                         self.eps, 0, L.ptr(self.engine.step_ctr), L.current_stream()))
+
+    # ---- overlapped data-parallel step: exchange of the late bucket under the early half of the backward pass -----------
+    def _fb_late(self):
+        lib, st = L.lib(), L.current_stream()
+        eng = self.engine
+        L.check(lib.zns_counter_add(L.ptr(eng.step_ctr), 1, st))
+        eng.pack_weights_async(self.params, need_dgrad=True)
+        L.check(lib.zns_zero(L.ptr(self.flat_g), self.flat_g.numel() * 4, st))
+        eng.forward([self.batch_buf[:, 0], self.batch_buf[:, 1]], 2 * 96 * self.T, self.params, train=True,
+                    dropout_p=self.dropout_p)
+        L.check(lib.zns_ntxent_fwd_bwd(L.ptr(eng.emb[0]), L.ptr(eng.emb[1]), self.B, self.T, self.B, self.temperature,
+                                       L.ptr(self.result), L.ptr(self.d_emb[0]), L.ptr(self.d_emb[1]), st))
+        eng.backward(self.d_emb, self.params, self.grads, phase="late")
+
+    def _fb_early(self):
+        self.engine.backward(self.d_emb, self.params, self.grads, phase="early")
+
+    def _step_overlapped(self):
+        """late phase -> [comm stream: barrier, exchange + Adam of the late bucket, barrier]  ||  early phase -> exchange of
+        the early bucket.  The backward pass reads the packed 16-bit weight copies, never the fp32 masters, so the late
+        bucket's parameters may be updated (by every peer) while the early phase still runs."""
+        main = torch.cuda.current_stream()
+        if self.use_graph:
+            if self._graph_late is None:
+                snap = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.engine.step_ctr.clone())
+                self._graph_late = self._capture(self._fb_late)
+                self._graph_early = self._capture(self._fb_early)
+                self.flat_p.copy_(snap[0]); self.flat_m.copy_(snap[1]); self.flat_v.copy_(snap[2])
+                self.engine.step_ctr.copy_(snap[3])
+            self._graph_late.replay()
+        else:
+            self._fb_late()
+        self._ev_late.record(main)
+        self._comm.wait_event(self._ev_late)
+        with torch.cuda.stream(self._comm):
+            self._symm.barrier(2)              # every rank's late-bucket gradients are complete
+            self._optimizer_p2p(self._bucket_late)
+            self._symm.barrier(3)              # every rank's stores into this rank's late-bucket parameters have landed
+            self._ev_comm.record(self._comm)
+        if self.use_graph:
+            self._graph_early.replay()
+        else:
+            self._fb_early()
+        self._symm.barrier(0)
+        self._optimizer_p2p(self._bucket_early)
+        self._symm.barrier(1)
+        main.wait_event(self._ev_comm)
 
     def _reduce_and_update(self):
         """Gradient exchange + optimizer of one step (eager calls between the captured graphs)."""
@@ -229,6 +300,9 @@ class PretextTrainer:
         [loss, mean cos(anchor,pos), mean cos(anchor,neg)] of this step (no host sync)."""
         if batch is not None:
             self.load_batch(batch)
+        if self.dp_overlap:
+            self._step_overlapped()
+            return self.result
         if self.use_graph:
             if self._graph_fb is None:
                 snap = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.engine.step_ctr.clone())
