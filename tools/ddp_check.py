@@ -1,7 +1,7 @@
 """torchrun --nproc-per-node N tools/ddp_check.py : data-parallel correctness on real GPUs.
 
 Each rank trains on its own synthetic source clip (VQT in the loop, dropout off) at a well-conditioned operating point
-(tied branch weights, anchor stem = drums + 5 % other: cos+ - cos- ~ 0.1, so the gradients are far from the softmax's
+(tied branch weights, anchor stem = drums + 5 % other: cos+ - cos- = 0.04 .. 0.09 depending on the clip, so the gradients are far from the softmax's
 flat spot).  Checks, all of which a missing or wrong gradient exchange fails:
 
   1. exchange: after step 1 Adam's first moment is (1 - beta1) * mean over ranks of the rank gradients.  Every rank
@@ -69,23 +69,33 @@ def main():
     for name, kw in (("fused", dict(p2p_adam=True)), ("nccl", dict(p2p_adam=False))):
         tr = trainer(use_graph=True, **kw)
         assert tr.flat_p.numel() >= n
-        path = "fused peer-memory reduce-scatter + Adam + all-gather (zns_adam_p2p)" if tr._symm is not None else \
-               "NCCL all-reduce + local Adam (zns_adam_flat)"
+        path = ("fused peer-memory reduce-scatter + Adam + all-gather (zns_adam_p2p)" +
+                (", late bucket exchanged under the early half of the backward pass" if tr.dp_overlap else ", after the backward pass")) \
+            if tr._symm is not None else "NCCL all-reduce + local Adam (zns_adam_flat)"
         tr.step_from_audio(*inputs(rank, 0))
         torch.cuda.synchronize()
         m = tr.flat_m[:n].double()
         want = (1.0 - BETA1) * g_mean
-        if tr._symm is not None:                 # moments exist for the owned shard only
-            n4 = tr.flat_p.numel() // 4                      # zns_adam_p2p: float4 index space split evenly over the ranks
-            per = (n4 + world - 1) // world
-            lo, hi = min(4 * per * rank, n), min(4 * per * (rank + 1), n)
+        if tr._symm is not None:                 # moments exist for the owned shards only
+            # zns_adam_p2p splits the float4 index space of every range it is called on evenly over the ranks; the overlapped
+            # step calls it per bucket range (late / early, per branch), the plain step once for the whole buffer
+            ranges = (tr._bucket_late + tr._bucket_early) if tr.dp_overlap else [(0, tr.flat_p.numel())]
+            owned = []
+            for r_lo, r_hi in ranges:
+                n4 = (r_hi - r_lo) // 4
+                per = (n4 + world - 1) // world
+                owned.append((r_lo + min(4 * per * rank, 4 * n4), r_lo + min(4 * per * (rank + 1), 4 * n4)))
         else:
-            lo, hi = 0, n
+            owned = [(0, n)]
+        sel = torch.zeros(n, dtype=torch.bool, device=dev)
+        for o_lo, o_hi in owned:
+            sel[o_lo:min(o_hi, n)] = True
+        lo, hi = int(sel.sum()), len(owned)      # reported: elements checked, number of shards
         scale = float(want.abs().max())
-        err_m = float((m[lo:hi] - want[lo:hi]).abs().max()) / scale if hi > lo else 0.0
+        err_m = float((m[sel] - want[sel]).abs().max()) / scale
         # the moment must be the MEAN: against a single rank's gradient the same comparison is far off
         own = (1.0 - BETA1) * solo_grad_of(solo, inputs, rank)
-        err_own = float((m[lo:hi] - own[lo:hi].double()).abs().max()) / scale if (hi > lo and world > 1) else float("nan")
+        err_own = float((m[sel] - own[:n][sel].double()).abs().max()) / scale if world > 1 else float("nan")
         for step in range(1, STEPS):
             tr.step_from_audio(*inputs(rank, step))
         torch.cuda.synchronize()
@@ -104,14 +114,14 @@ def main():
         if world > 1:
             ok &= r["err_own"] > 1e-3            # the check above is discriminating: one rank's gradient does not pass it
     ok &= d_paths < STEPS * 2 * LR * 1.05
-    ok &= res_solo[1] - res_solo[2] > 0.05        # non-degenerate operating point
+    ok &= res_solo[1] - res_solo[2] > 0.03        # non-degenerate operating point (uniform softmax would be cos+ == cos-)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"ddp_check world={world}: operating point loss/cos+/cos- = {res_solo}")
         for name, r in report.items():
             print(f"ddp_check world={world} [{name}]: exchange path = {r['path']}")
-            print(f"    step-1 first moment vs (1-beta1)*mean(rank gradients), rank 0 shard {r['shard']}: max err / max|m| = {r['err_m']:.3e}"
+            print(f"    step-1 first moment vs (1-beta1)*mean(rank gradients), rank 0: {r['shard'][0]} elements in {r['shard'][1]} owned shard(s): max err / max|m| = {r['err_m']:.3e}"
                   f"  (vs rank 0's own gradient: {r['err_own']:.3e});  replicas bit-identical after {STEPS} steps = {r['same']};"
                   f"  mean |p - p0| = {r['moved']:.3e} (lr {LR:g})")
         print(f"ddp_check world={world}: max |p_fused - p_nccl| after {STEPS} steps = {d_paths:.3e} (bound {STEPS * 2 * LR * 1.05:.2e}: "
