@@ -58,7 +58,7 @@ EXECUTED_FRACTION = {
     "conv_fwd_umma<256>": _family_fraction(["cv5", "cv6", "cv6", "cv7"]),                         # fwd cv5 cv6; dgrad cv6 cv7
     "conv_fwd_stack_umma(c_out=64, 2 rows on N)": _family_fraction(["cv2", "cv2", "cv3"]),         # fwd cv2; dgrad cv2 cv3
     "conv_wgrad_umma<128>": _family_fraction(["cv3", "cv4", "cv5", "cv6", "cv7", "cv8"]),
-    "conv_wgrad_umma<64>": _family_fraction(["cv2"]),
+    "conv_wgrad_umma<128> stacked dy (c_out=64)": _family_fraction(["cv2"]),
 }
 
 
@@ -426,13 +426,13 @@ def kernel_roofline(tr, dev_audio, starts_dev, peaks, args, ms_step, clocks=None
 
 def _ncu_traffic(tag: str):
     """DRAM bytes per launch (read + write) of the dominant kernel family from the committed ncu capture
-    (profiles/r01_ncu_conv_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over every
+    (profiles/r02_ncu_conv_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over every
     tensor-core launch of one step); None when the family is not in the capture."""
     names = {"conv_fwd_umma<128>": ("conv_fwd_umma_kernel", "128"), "conv_fwd_umma<256>": ("conv_fwd_umma_kernel", "256"),
              "conv_fwd_umma<64>": ("conv_fwd_umma_kernel", "64"), "conv_wgrad_umma<128>": ("conv_wgrad_umma_kernel", "128"),
-             "conv_wgrad_umma<64>": ("conv_wgrad_umma_kernel", "64"),
+             "conv_wgrad_umma<128> stacked dy (c_out=64)": ("conv_wgrad_umma_kernel", "128"),
              "conv_fwd_stack_umma(c_out=64, 2 rows on N)": ("conv_fwd_stack_umma_kernel", None)}
-    path = os.path.join(ROOT, "profiles", "r01_ncu_conv_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_conv_traffic.json")
     try:
         table = json.load(open(path))
         base, arg = names[tag]
@@ -444,7 +444,7 @@ def _ncu_traffic(tag: str):
         if not n:
             return None, None
         return (sum(r["dram_bytes_per_launch"] * r["launches"] for r in rows) / n,
-                "profiles/r01_ncu_conv_traffic.json (ncu, per launch)")
+                "profiles/r02_ncu_conv_traffic.json (ncu, per launch)")
     except Exception:
         return None, None
 

@@ -121,7 +121,8 @@ def test_weight_gradient_plans_of_the_reference_layers(ci, co, kh, kw, H):
     for B, W, n_br in [(16, 313, 2), (8, 48, 2), (1, 371, 1), (5, 37, 1)]:
         p = wgrad_plan(B, H, W, ci, co, kh, kw, n_br)
         check_wgrad(p, B, H, W, ci, co, kh, kw, n_br)
-        assert p["ctas"] == (1 if co == 64 else 2)      # c_out = 64 keeps the N = 64 single-CTA kernel by default
+        assert p["ctas"] == 2                           # CTA pairs everywhere; c_out = 64 runs with dy rows stacked on N = 128
+        assert p["stack_dy"] == (1 if co == 64 else 0) and p["NB"] == 128
 
 
 def test_weight_gradient_plans_random_shapes():
@@ -143,7 +144,7 @@ def test_plan_argument_errors():
     assert L.lib().zns_dbg_conv_fwd_plan(C.byref(L.conv_desc(16, 8, 40, 64, 64, 3, 5)), 3, out) != 0    # n_br
 
 
-@pytest.mark.parametrize("env", [{"ZNS_CONV_PAIR": "0"}, {"ZNS_CONV_PAIR": "1"}, {"ZNS_WGRAD_STACK": "1"},
+@pytest.mark.parametrize("env", [{"ZNS_CONV_PAIR": "0"}, {"ZNS_CONV_PAIR": "1"}, {"ZNS_WGRAD_STACK": "1"}, {"ZNS_WGRAD_STACK": "0"},
                                  {"ZNS_CONV_NO_STACK": "1"}])
 def test_plans_of_the_kernel_variants(env):
     """The A/B switches are read once per process, so the variants are checked in a child process."""
@@ -170,6 +171,8 @@ def test_plans_of_the_kernel_variants(env):
         assert (w_ctas, f_ctas) == (1, 1)
     if env.get("ZNS_CONV_PAIR") == "1":
         assert (w_ctas, f_ctas) == (1, 2)
-    if "ZNS_WGRAD_STACK" in env:
+    if env.get("ZNS_WGRAD_STACK") == "1":
         assert (stack_dy, w_ctas, nb) == (1, 2, 128)
+    if env.get("ZNS_WGRAD_STACK") == "0":
+        assert (stack_dy, nb) == (0, 64)
     assert kern == (0 if "ZNS_CONV_NO_STACK" in env else 1)

@@ -1806,8 +1806,9 @@ static int conv_wgrad_dispatch(const zns_conv_desc* d, int n_br, const void* con
   const int n_items = (d->kh + 1) * ((row_acc + 3) / 4) * (d->c_in == 64 ? 1 : d->c_in / 128);
   const bool pair_ok = pair_mode >= 3 && n_items + 2 <= WG_MAX_ITEMS && d->c_in / 128 <= 15;
   if (d->c_out == 64) {
-    // ZNS_WGRAD_STACK=1 (experimental, opt-in): dy rows (h, h + 1) stacked on N instead of the N = 64 kernel
-    static const bool stack = getenv("ZNS_WGRAD_STACK") != nullptr && atoi(getenv("ZNS_WGRAD_STACK")) != 0;
+    // dy rows (h, h + 1) stacked on N (N = 128 MMAs, CTA pairs) instead of the A-read-bound N = 64 kernel: +1.0 .. 1.5 % on the
+    // training step in an alternating A/B on one box (profiles/r02_wgrad_stack_ab.txt); ZNS_WGRAD_STACK=0 restores N = 64
+    static const bool stack = getenv("ZNS_WGRAD_STACK") == nullptr || atoi(getenv("ZNS_WGRAD_STACK")) != 0;
     if (stack && d->kh < 15)
       return pair_ok ? launch_wgrad<128, 2>(d, n_br, x, dy, dwpk, st, true, dry) : launch_wgrad<128, 1>(d, n_br, x, dy, dwpk, st, true, dry);
     return launch_wgrad<64>(d, n_br, x, dy, dwpk, st, false, dry);

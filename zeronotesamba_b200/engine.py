@@ -290,7 +290,8 @@ class EncoderEngine:
         lib, st = L.lib(), L.current_stream()
         d = L.conv_desc(self.B, H, self.T, ci, co, kh, kw)
         xb = self._shadow[id(xs)]                      # bf16 copy of the fp16 forward activation (same type as dy)
-        with self._timed(f"conv_wgrad_umma<{min(co, 128)}>", self._conv_flops(name, H)):
+        tag = "conv_wgrad_umma<128> stacked dy (c_out=64)" if co == 64 else "conv_wgrad_umma<128>"
+        with self._timed(tag, self._conv_flops(name, H)):
             L.check(lib.zns_conv_wgrad(C.byref(d), self.n_br, L.ptr_array(xb), L.ptr_array(dys), L.ptr_array(self.gp[name]), st))
         L.check(lib.zns_bias_grad_nbr(self.n_br, L.ptr_array(dys), self.B, H, self.T, co,
                                       L.ptr_array([grads[br][f"pretrained.{name}.bias"] for br in range(self.n_br)]), st))
