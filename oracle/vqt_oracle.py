@@ -53,6 +53,17 @@ KAISER_FAST_ZEROS = 16
 KAISER_FAST_PRECISION = 9
 
 
+# ---- alternative readings of the three points SURVEY.md Appendix A could not pin against the absent wheels -------------
+# Consulted by the functions below; the defaults are this oracle's reading.  tests/test_oracle_vqt.py perturbs each one and
+# bounds how far the output moves (a sensitivity test: none of them can reach the parity tolerance).
+#   tap_wings:        (left, right) tap counts of resampy's 2:1 loop -- (32, 31) reads table entries j = 0..-31 and +1..+31;
+#                     (32, 32) would also read entry 32 (j = +32), (31, 31) would drop j = -31
+#   c64_before_scale: constant_q filters cast to complex64 BEFORE the len / n_fft scaling (True) or after it (False)
+#   sparsify_ties:    among entries whose magnitude EQUALS the threshold, sparsify_rows keeps all of them ("ge": librosa's
+#                     `mags >= threshold`) or only the first ("first")
+VARIANT = {"tap_wings": (32, 31), "c64_before_scale": True, "sparsify_ties": "ge"}
+
+
 # ---- resampy "kaiser_fast" half window (resampy.filters.sinc_window) -------------------------
 @functools.lru_cache(maxsize=None)
 def kaiser_fast_half_window() -> np.ndarray:
@@ -90,9 +101,10 @@ def resample_2to1_f32(x: np.ndarray) -> np.ndarray:
     xz[32:32 + n_in] = x
     acc = np.zeros(n_out, dtype=np.float32)
     centre = 32 + 2 * np.arange(n_out)
-    for i in range(32):  # left wing: x[n - i]
+    n_left, n_right = VARIANT["tap_wings"]
+    for i in range(n_left):  # left wing: x[n - i]
         acc = (acc.astype(np.float64) + h[i] * xz[centre - i].astype(np.float64)).astype(np.float32)
-    for k in range(31):  # right wing: x[n + k + 1]
+    for k in range(n_right):  # right wing: x[n + k + 1]
         acc = (acc.astype(np.float64) + h[k + 1] * xz[centre + k + 1].astype(np.float64)).astype(np.float32)
     n_fix = int(np.ceil(n_in * 0.5))
     y = np.zeros(n_fix, dtype=np.float32)
@@ -140,6 +152,9 @@ def sparsify_rows(x: np.ndarray, quantile: float) -> np.ndarray:
     out = np.zeros_like(x)
     for i, j in enumerate(threshold_idx):
         keep = mags[i] >= mag_sort[i, j]
+        if VARIANT["sparsify_ties"] == "first":
+            ties = np.flatnonzero(mags[i] == mag_sort[i, j])
+            keep[ties[1:]] = False
         out[i, keep] = x[i, keep]
     return out
 
@@ -164,7 +179,7 @@ def octave_fft_basis(octave: int, sr: float, gamma: float, sparsity: float = 0.0
         filts.append(sig)
     n_fft = int(2.0 ** (np.ceil(np.log2(max(lengths)))))
     cdtype = np.complex64 if f32_faithful else np.complex128
-    basis = np.zeros((BINS_PER_OCTAVE, n_fft), dtype=cdtype)
+    basis = np.zeros((BINS_PER_OCTAVE, n_fft), dtype=cdtype if VARIANT["c64_before_scale"] else np.complex128)
     for k, filt in enumerate(filts):
         lpad = int((n_fft - len(filt)) // 2)  # util.pad_center
         basis[k, lpad:lpad + len(filt)] = filt

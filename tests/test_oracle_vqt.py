@@ -103,3 +103,41 @@ def test_resampler_f32_vs_f64():
     assert np.abs(a - b).max() < 5e-7
     odd = vo.resample_2to1_f32(y[:1001])
     assert odd.shape == (501,) and odd[-1] == 0.0  # fix_length zero-fills the last sample
+
+
+def test_sensitivity_to_the_unpinned_readings_of_appendix_a():
+    """SURVEY.md Appendix A lists three points of librosa 0.8.1 / resampy 0.4.2 that could not be checked against the
+    (absent) wheels.  Perturb each reading of the oracle and report how far the output moves in the metric of the parity
+    tests (helpers.vqt_check: relative on bins >= 1e-2 max, absolute over max).  Measured (4 s synthetic stem):
+      * resampy tap-loop bounds: reading table entry 32 (j = +32, weight -1.3e-5) moves bins by up to 4.3e-4 relative /
+        2.1e-5 of full scale; dropping j = -31 (weight -1.9e-5) by 8.9e-4 / 3.4e-5.  THIS reading therefore matters at the
+        parity tolerance (1e-4 relative): the oracle follows resampy's loop as SURVEY.md Appendix A derives it (left wing
+        i < 8193 // 256 = 32 from offset 0, right wing k < (8193 - 256) // 256 = 31 from offset 256), and the GPU kernels use the
+        same 63 taps; with the wheel absent this is the part of "parity unpinned" that could be visible.
+      * complex64 cast before / after the len / n_fft scaling: 1.4e-6 / 2.3e-7 -- irrelevant.
+      * sparsify_rows ties: no row of any octave has a second entry equal to its threshold, so the tie rule cannot matter."""
+    from helpers import vqt_check
+    from zeronotesamba_b200 import synth
+    y = synth.stem_pair(3, 4.0)[1]
+    base = vo.vqt_ref_f32(y)
+    moved = {}
+    for name, patch in [("right wing reads table entry 32 (j = +32)", {"tap_wings": (32, 32)}),
+                        ("left wing stops at j = -30", {"tap_wings": (31, 31)}),
+                        ("complex64 cast after the len / n_fft scaling", {"c64_before_scale": False}),
+                        ("sparsify_rows keeps only the first of tied entries", {"sparsify_ties": "first"})]:
+        saved = dict(vo.VARIANT)
+        try:
+            vo.VARIANT.update(patch)
+            moved[name] = vqt_check(vo.vqt_ref_f32(y), base)
+        finally:
+            vo.VARIANT.clear()
+            vo.VARIANT.update(saved)
+    assert vo.VARIANT == {"tap_wings": (32, 31), "c64_before_scale": True, "sparsify_ties": "ge"}
+    for name, (rel, ab) in moved.items():
+        print(f"{name}: max relative change {rel:.2e} (bins >= 1e-2 max), max |change| / max {ab:.2e}")
+    rel, ab = moved["right wing reads table entry 32 (j = +32)"]
+    assert 1e-5 < rel < 1e-3 and ab < 5e-5          # visible at the 1e-4 tolerance: the reading matters (docstring)
+    rel, ab = moved["left wing stops at j = -30"]
+    assert 1e-5 < rel < 2e-3 and ab < 1e-4
+    assert moved["complex64 cast after the len / n_fft scaling"][0] < 5e-6
+    assert moved["sparsify_rows keeps only the first of tied entries"] == (0.0, 0.0)
