@@ -328,7 +328,9 @@ int vqt_umma_build(zns_vqt_plan* p, double fmin, double gamma_in) {
       const size_t rows = std::max((f_max + L.fpr - 1) / L.fpr, (n + R - 1) / R);
       const size_t tiles = (rows + 127) / 128;
       p->sig_cap[i] = (long long)(tiles * 128 * R);
-      p->sig_stride[i] = (long long)((tiles + 2) * L.q * 1024);       // one zero pad tile before and after
+      // tiled: (tiles + 1) images of q planes x rtot rows x 8 samples (the extra one takes the "halo before" copy of the last
+      // tile's rows); linear (q == 1): the samples behind a 1024-sample zero pad, one pad tile of slack behind
+      p->sig_stride[i] = L.q == 1 ? (long long)((tiles + 2) * 1024) : (long long)((tiles + 1) * L.q * L.rtot * 8);
       const size_t bytes = (size_t)p->max_batch * p->sig_stride[i] * sizeof(uint16_t);
       ZNS_CHECK_CUDA(cudaMalloc(&p->d_hi[i], bytes));
       ZNS_CHECK_CUDA(cudaMalloc(&p->d_lo[i], bytes));
@@ -371,28 +373,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Global layout of a level signal (levels >= 1; written by the previous level's epilogue, read by this level's
-// loader as a handful of bulk copies per plane group).  q >= 4 ("tiled"): the 16-byte chunk c of row r of tile t lives at
-//   (((t + 1) q + c) 128 + r) chunks   -- i.e. per tile the shared-memory plane order; tile -1 and the tile after the
-// last one are zero padding, so halo rows never need a special case.  q == 1: linear, one 1024-sample zero pad in front.
-__host__ __device__ __forceinline__ long long level_index(long long p, int q) {
+// Global layout of a level signal (levels >= 1; written by the previous level's epilogue).  q >= 4 ("tiled"): the buffer holds,
+// tile after tile and plane group after plane group, exactly the shared-memory image the loader needs -- per tile t and plane c
+// `rtot` rows of 16 bytes: hb halo rows (the last rows of tile t - 1), the 128 rows of the tile, ha halo rows (the first rows of
+// tile t + 1), padding up to rtot.  A plane group of a tile is therefore ONE contiguous block per fp16 term and its load is one
+// bulk copy (the TMA unit's request rate, not bytes, bounded the earlier layout with ~48 small copies per group).  The
+// producer writes the (<= 3 of 128) halo rows twice.  Row rr of plane c of tile t: chunk index (t q + c) rtot + rr.
+// q == 1: linear, one 1024-sample zero pad in front.
+__host__ __device__ __forceinline__ long long level_index(long long p, int q, int rtot, int hb) {
   if (q == 1) return 1024 + p;
   const int R = 8 * q;
   const long long row = p / R;
   const int c = (int)(p - row * R) >> 3, e = (int)(p & 7);
   const long long t = row >> 7;
   const int r = (int)(row & 127);
-  return (((t + 1) * q + c) * 128 + r) * 8 + e;
-}
-
-// the same for a power-of-two row length 8 q = 1 << shift (device epilogue: no 64-bit division)
-__device__ __forceinline__ long long level_index_pow2(long long p, int q, int shift) {
-  if (q == 1) return 1024 + p;
-  const long long row = p >> shift;
-  const int c = (int)(p & ((1 << shift) - 1)) >> 3, e = (int)(p & 7);
-  const long long t = row >> 7;
-  const int r = (int)(row & 127);
-  return (((t + 1) * q + c) * 128 + r) * 8 + e;
+  return ((t * q + c) * rtot + hb + r) * 8 + e;
 }
 
 // bulk asynchronous copy global -> shared (TMA, no tensor map), completion counted on an mbarrier
@@ -442,6 +437,7 @@ struct VqtLevelArgs {
   int n_valid;
   long long dst_stride;
   int dst_q;                   // planes per row of the next level (1: linear layout)
+  int dst_rtot, dst_hb, dst_ha; // next level: rows per plane image, halo rows before / after (tiled layout, see level_index)
   long long dst_cap;           // samples the next level's buffer holds per clip
   int tiles_per_clip, n_tiles;
   long long* dbg;              // optional per-role cycle counters of CTA 0 (zns_dbg_vqt_timing), else NULL
@@ -457,7 +453,12 @@ struct VqtLevelArgs {
 // 2 epilogue skips everything but the handshakes, 4 issuers skip the MMAs, 8 loaders skip the copies, 16 epilogue skips
 // the global stores only
 #define VQT_KO(bit) ((A.mode & (bit)) != 0)
+// timeline of CTA 0 of the fp32-source (level 0) kernel, tiles 4..7: absolute clock64 stamps at dbg[320 + i]
+// (loaders: [tile][warp][wait end, arrive]; issuers: [tile][issuer][pos][operands ready, after commit]; epilogue warps 0 / 4:
+// [tile][half][job][accumulator ready, arrive])
+#define VQT_TL(cond, i) do { if (SRC_F32 && A.dbg && blockIdx.x == 0 && (cond)) A.dbg[320 + (i)] = clock64(); } while (0)
 #else
+#define VQT_TL(cond, i) do { } while (0)
 #define VQT_CLOCK() 0LL
 #define VQT_TIMING_ON false
 #define VQT_KO(bit) false
@@ -514,7 +515,9 @@ __device__ __forceinline__ void vqt_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
-template <bool SRC_F32>
+// FPR1: one frame per signal row (levels whose hop is >= 32 samples: the four big levels) -- a compile-time switch so that the
+// register needs of the multi-frame epilogue (72 accumulator columns per thread) do not spill the hot single-frame one.
+template <bool SRC_F32, bool FPR1>
 __global__ void __launch_bounds__(VQT_LEVEL_THREADS, 1)
 vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ VqtLevelArgs A) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -529,13 +532,14 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.n_slots; ++i) {
-      // VQT_LOAD_WARPS / n_slots loader warps fill a slot: all their lanes arrive (fp32 source) or one per warp (bulk copies)
-      mbar_init(smem_u32(&bar_full[i]), (SRC_F32 ? 32 : 1) * (VQT_LOAD_WARPS / L.n_slots));
+      // VQT_LOAD_WARPS / n_slots loader warps fill a slot; ONE lane per warp arrives (an mbarrier arrive is an atomic on one
+      // shared-memory word: 64 lane arrivals per group and 256 per accumulator hand-off serialised into ~10 K clocks per tile)
+      mbar_init(smem_u32(&bar_full[i]), VQT_LOAD_WARPS / L.n_slots);
       mbar_init(smem_u32(&bar_empty[i]), ZNS_VQT_ISSUERS);          // every issuer commits once per group
     }
     for (int t = 0; t < 4; ++t) {
       mbar_init(smem_u32(&bar_acc_full[t]), 2);                    // two accumulator units (parts) per job
-      mbar_init(smem_u32(&bar_acc_empty[t]), 32 * VQT_EPI_WARPS);
+      mbar_init(smem_u32(&bar_acc_empty[t]), VQT_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -571,12 +575,14 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
 #pragma unroll 1
         for (int pos = 0; pos < L.gpt; ++pos) {
           const int s_begin = L.seg_begin[isr][pos], s_end = L.seg_begin[isr][pos + 1];
+          VQT_TL(ts >= 4 && ts < 8 && isr == 0, 240 + ((ts - 4) * 4 + pos) * 2);     // issuer 0: before the operand wait
           if (s_begin < s_end) {
             const long long t0 = VQT_CLOCK();
             vqt_wait(full0 + 8 * slot, full_par);
             t_wait_full += VQT_CLOCK() - t0;
             tc_fence_after();
           }
+          VQT_TL(ts >= 4 && ts < 8, 64 + ((((ts - 4) * 4 + isr) * 4 + pos) * 2));
           const uint32_t a16 = ring16 + (uint32_t)slot * slot16;
 #pragma unroll 1
           for (int si = s_begin; si < s_end; ++si) {
@@ -593,6 +599,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
               vqt_wait(acce0 + 8 * bidx, ((inst >> sh) & 1) ^ 1);
               t_wait_acc += VQT_CLOCK() - t0;
               tc_fence_after();
+              VQT_TL(ts >= 4 && ts < 8 && isr == 0, 240 + ((ts - 4) * 4 + pos) * 2 + 1);   // issuer 0: accumulator stage granted (last one of the position)
               // clear this unit's columns: accumulate = 0 with the zero block as both operands
               const int w0 = type ? L.dec_wp : L.fb_n1, w1 = type ? L.dec_wp : L.fb_n2;
               const int c_lo = sg.part ? w0 : 0, c_hi = sg.part ? w0 + w1 : w0;
@@ -610,6 +617,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             if (sg.flags & 2) umma_commit(accf0 + 8 * bidx);
           }
           umma_commit(empty0 + 8 * slot);       // this issuer no longer reads the slot (immediate when it had no MMAs)
+          VQT_TL(ts >= 4 && ts < 8, 64 + ((((ts - 4) * 4 + isr) * 4 + pos) * 2) + 1);
           if (++slot == L.n_slots) { slot = 0; full_par ^= 1; }
         }
       }
@@ -626,20 +634,28 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     // store), so throughput comes from the number of warps, not from the instruction count.
     const int quad = warp & 3, sub = warp >> 2;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-    long long t_wait_ep = 0;
+    long long t_wait_ep = 0, t_ld = 0, t_math = 0, t_st = 0;
     const long long t_begin_ep = VQT_CLOCK();
     int dst_shift = 3;                                      // log2(samples per row) of the next level
     while ((8 << (dst_shift - 3)) < 8 * A.dst_q) ++dst_shift;
     constexpr int kBinsPerWarp = 12 / VQT_EPQ;              // fpr == 1: bins of this warp
-    float isl[12];                                          // 1 / sqrt(L_k) / (coefficient scale) of this octave's bins
+    constexpr int kIsl = FPR1 ? kBinsPerWarp : 12;
+    float isl[kIsl];                                        // 1 / sqrt(L_k) / (coefficient scale) of the bins this thread writes
 #pragma unroll
-    for (int k = 0; k < 12; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + k) * L.fb_scale;
-    float islw[kBinsPerWarp];
-#pragma unroll
-    for (int k = 0; k < kBinsPerWarp; ++k) islw[k] = __ldg(A.inv_sqrt_len + L.bin0 + kBinsPerWarp * sub + k) * L.fb_scale;
+    for (int k = 0; k < kIsl; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + (FPR1 ? kBinsPerWarp * sub : 0) + k) * L.fb_scale;
+    // everything the per-job code needs from the level description, read ONCE with compile-time subscripts (uniform loads):
+    // a run-time subscript into the kernel parameters is an indexed constant load of several hundred clocks, and the job loop
+    // used to issue a chain of them per job
+    const int n_jobs = L.n_jobs, n_pass = L.n_pass, dec_w = L.dec_w, dec_wp = L.dec_wp, fb_n1 = L.fb_n1, fpr = L.fpr;
+    const int job_of0 = L.ep_job[0], job_of1 = L.ep_job[1], job_of2 = L.ep_job[2];
+    const int rbase0 = L.ring_base[0], rbase1 = L.ring_base[1], rwid0 = L.ring_width[0], rwid1 = L.ring_width[1];
+    const uint32_t accf = smem_u32(&bar_acc_full[0]), acce = smem_u32(&bar_acc_empty[0]);
+    const int n_frames = A.n_frames, n_valid = A.n_valid;
+    const long long dst_cap = A.dst_cap;
     const float s_a = L.dec_scale, s_b = L.dec_scale * (1.f / 2048.f);
-    const int o_blk = A.dst_q == 1 ? 16 : 2048;             // 16 outputs further: two planes (tiled) / 16 samples
-    const int o_half = A.dst_q == 1 ? 8 : 1024;
+    const int dst_q = A.dst_q, dst_rtot = A.dst_rtot, dst_hb = A.dst_hb, dst_ha = A.dst_ha;
+    const int o_half = dst_q == 1 ? 8 : dst_rtot * 8;      // the next chunk of a row: next plane (tiled) / adjacent (linear)
+    const long long o_dup = (long long)(dst_q * dst_rtot - 128) * 8;   // a row's copy in the neighbouring tile's halo
     int tau = (int)blockIdx.x, clip = tau / A.tiles_per_clip, tile_in_clip = tau - clip * A.tiles_per_clip;
     const int clip_step = (int)gridDim.x / A.tiles_per_clip, tile_step = (int)gridDim.x - clip_step * A.tiles_per_clip;
 #pragma unroll 1
@@ -647,60 +663,85 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
       const int row_first = tile_in_clip * 128;
       const int g = row_first + quad * 32 + lane;          // row of this thread inside the clip (< 2^24)
       // every decimator output of the tile lies inside the signal: no per-element masking (all but the last tile of a clip)
-      const bool tile_valid = (long long)(row_first + 128) * L.dec_w <= A.n_valid;
-#pragma unroll 1
-      for (int jj = 0; jj < L.n_jobs; ++jj) {
-        const int job = L.ep_job[jj];
+      const bool tile_valid = (long long)(row_first + 128) * dec_w <= n_valid;
+#pragma unroll
+      for (int jj = 0; jj < ZNS_VQT_MAX_JOBS; ++jj) {
+        if (jj >= n_jobs) break;
+        const int job = jj == 0 ? job_of0 : (jj == 1 ? job_of1 : job_of2);
         const int type = job ? 1 : 0;
-        const uint32_t inst = type ? (uint32_t)(ts * L.n_pass + (job - 1)) : (uint32_t)ts;
+        const uint32_t inst = type ? (uint32_t)(ts * n_pass + (job - 1)) : (uint32_t)ts;
         const int sh = type ? sh1 : sh0;
         const uint32_t stage = inst & (uint32_t)sh;
+        const uint32_t bidx = (uint32_t)(type * 2) + stage;
         {
           const long long t0 = VQT_CLOCK();
-          if (lane == 0) vqt_wait(smem_u32(&bar_acc_full[type * 2 + stage]), (inst >> sh) & 1);
+          if (lane == 0) vqt_wait(accf + 8 * bidx, (inst >> sh) & 1);
           __syncwarp();
           t_wait_ep += VQT_CLOCK() - t0;
         }
         tc_fence_after();
-        const uint32_t acc = tl + (uint32_t)(L.ring_base[type] + (int)stage * L.ring_width[type]);
+        VQT_TL(ts >= 4 && ts < 8 && quad == 0 && lane == 0, 192 + ((((ts - 4) * 2 + sub) * 3 + jj) * 2));
+        const uint32_t acc = tl + (uint32_t)((type ? rbase1 : rbase0) + (int)stage * (type ? rwid1 : rwid0));
         if (VQT_KO(2)) {
         } else if (type == 1) {
           const int c0 = 64 * (job - 1);
-          const int w = min(64, L.dec_w - c0);
+          const int w = min(64, dec_w - c0);
           uint16_t* dh = A.dst_hi + (size_t)clip * A.dst_stride;
           uint16_t* dl = A.dst_lo + (size_t)clip * A.dst_stride;
           const int n_blk = (w + 15) / 16;
-          const int t_row = g * L.dec_w + c0;                            // first output of this row in this pass (< 2^31)
-          const long long o_row = level_index_pow2((long long)t_row, A.dst_q, dst_shift);
+          const int t_row = g * dec_w + c0;                            // first output of this row in this pass (< 2^31)
 #pragma unroll 1
           for (int kb = sub; kb < n_blk; kb += VQT_EPQ) {
             uint32_t a[16], b[16];
+            const long long c0_ = VQT_CLOCK();
             tmem_ld_32x16(acc + 16 * kb, a);
-            tmem_ld_32x16(acc + L.dec_wp + 16 * kb, b);
+            tmem_ld_32x16(acc + dec_wp + 16 * kb, b);
             tmem_ld_wait();
+            const long long c1_ = VQT_CLOCK();
+            t_ld += c1_ - c0_;
             const int t0 = t_row + 16 * kb;
             float yv[16];
 #pragma unroll
             for (int o = 0; o < 16; ++o) yv[o] = fmaf(__uint_as_float(b[o]), s_b, __uint_as_float(a[o]) * s_a);
             if (!tile_valid) {
 #pragma unroll
-              for (int o = 0; o < 16; ++o) if (t0 + o >= A.n_valid) yv[o] = 0.f;
+              for (int o = 0; o < 16; ++o) if (t0 + o >= n_valid) yv[o] = 0.f;
             }
             uint4 h1a, h2a, h1b, h2b;
             split8(yv, h1a, h2a);
             split8(yv + 8, h1b, h2b);
-            if (t0 < A.dst_cap && !VQT_KO(16)) {
-              const long long o = o_row + kb * o_blk;
-              if (L.dec_w >= 16) {           // 16 outputs = two chunks of one row (tiled: 2 KB apart; linear: adjacent)
+            const long long c2_ = VQT_CLOCK();
+            t_math += c2_ - c1_;
+            if (t0 < dst_cap && !VQT_KO(16)) {
+              if (dst_q == 1) {
+                const long long o = 1024 + (long long)t0;
+                if (dec_w >= 16) {         // 16 adjacent samples
+                  *reinterpret_cast<uint4*>(dh + o) = h1a; *reinterpret_cast<uint4*>(dh + o + 8) = h1b;
+                  *reinterpret_cast<uint4*>(dl + o) = h2a; *reinterpret_cast<uint4*>(dl + o + 8) = h2b;
+                } else {                   // dec_w == 4: four outputs per row
+                  *reinterpret_cast<uint2*>(dh + o) = make_uint2(h1a.x, h1a.y);
+                  *reinterpret_cast<uint2*>(dl + o) = make_uint2(h2a.x, h2a.y);
+                }
+              } else {
+                // 16 outputs = two chunks (adjacent planes) of one row of the next level's tile image
+                const int row2 = t0 >> dst_shift, c2 = (t0 & ((1 << dst_shift) - 1)) >> 3;
+                const int t2 = row2 >> 7, r2 = row2 & 127;
+                const long long o = (((long long)t2 * dst_q + c2) * dst_rtot + dst_hb + r2) * 8;
                 *reinterpret_cast<uint4*>(dh + o) = h1a; *reinterpret_cast<uint4*>(dh + o + o_half) = h1b;
                 *reinterpret_cast<uint4*>(dl + o) = h2a; *reinterpret_cast<uint4*>(dl + o + o_half) = h2b;
-              } else {                       // dec_w == 4: four outputs per row
-                *reinterpret_cast<uint2*>(dh + o) = make_uint2(h1a.x, h1a.y);
-                *reinterpret_cast<uint2*>(dl + o) = make_uint2(h2a.x, h2a.y);
+                if (r2 < dst_ha && t2 > 0) {            // also the "halo after" rows of the previous tile
+                  *reinterpret_cast<uint4*>(dh + o - o_dup) = h1a; *reinterpret_cast<uint4*>(dh + o - o_dup + o_half) = h1b;
+                  *reinterpret_cast<uint4*>(dl + o - o_dup) = h2a; *reinterpret_cast<uint4*>(dl + o - o_dup + o_half) = h2b;
+                }
+                if (r2 >= 128 - dst_hb) {               // and the "halo before" rows of the next tile
+                  *reinterpret_cast<uint4*>(dh + o + o_dup) = h1a; *reinterpret_cast<uint4*>(dh + o + o_dup + o_half) = h1b;
+                  *reinterpret_cast<uint4*>(dl + o + o_dup) = h2a; *reinterpret_cast<uint4*>(dl + o + o_dup + o_half) = h2b;
+                }
               }
             }
+            t_st += VQT_CLOCK() - c2_;
           }
-        } else if (L.fpr == 1) {
+        } else if (FPR1) {
           // one frame per row: the warps of a lane quadrant share the twelve bins
           const int f = g;
           constexpr int NC = 2 * kBinsPerWarp;             // accumulator columns of this warp's bins (re, im interleaved)
@@ -710,45 +751,47 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           if (NL == 8) {
             tmem_ld_32x8(acc + c0, fa);                    // x1 . g1
             tmem_ld_32x8(acc + 24 + c0, fg);               // x1 . g2
-            tmem_ld_32x8(acc + L.fb_n1 + c0, fb);          // x2 . g1
+            tmem_ld_32x8(acc + fb_n1 + c0, fb);          // x2 . g1
           } else {
             tmem_ld_32x16(acc + c0, fa);
             tmem_ld_32x16(acc + 24 + c0, fg);
-            tmem_ld_32x16(acc + L.fb_n1 + c0, fb);
+            tmem_ld_32x16(acc + fb_n1 + c0, fb);
           }
           tmem_ld_wait();
-          if (f < A.n_frames && !VQT_KO(16)) {
-            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + kBinsPerWarp * sub) * A.n_frames + f;
+          if (f < n_frames && !VQT_KO(16)) {
+            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + kBinsPerWarp * sub) * n_frames + f;
 #pragma unroll
             for (int k = 0; k < kBinsPerWarp; ++k) {
               const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
               const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-              op[(size_t)k * A.n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), islw[k], 1e-9f));
+              op[(size_t)k * n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
             }
           }
-        } else {
+        } else if (!FPR1) {
 #pragma unroll 1
-          for (int j = sub; j < L.fpr; j += VQT_EPQ) {
-            const int f = g * L.fpr + j;
+          for (int j = sub; j < fpr; j += VQT_EPQ) {
+            const int f = g * fpr + j;
             uint32_t fa[48], fb[24];
             tmem_ld_32x32(acc + 48 * j, fa);
             tmem_ld_32x16(acc + 48 * j + 32, fa + 32);
-            tmem_ld_32x16(acc + L.fb_n1 + 24 * j, fb);
-            tmem_ld_32x8(acc + L.fb_n1 + 24 * j + 16, fb + 16);
+            tmem_ld_32x16(acc + fb_n1 + 24 * j, fb);
+            tmem_ld_32x8(acc + fb_n1 + 24 * j + 16, fb + 16);
             tmem_ld_wait();
-            if (f < A.n_frames && !VQT_KO(16)) {
-              float* op = A.out + ((size_t)clip * A.n_bins + L.bin0) * A.n_frames + f;
+            if (f < n_frames && !VQT_KO(16)) {
+              float* op = A.out + ((size_t)clip * A.n_bins + L.bin0) * n_frames + f;
 #pragma unroll
               for (int k = 0; k < 12; ++k) {
                 const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fa[24 + 2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
                 const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fa[25 + 2 * k]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-                op[(size_t)k * A.n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
+                op[(size_t)k * n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[FPR1 ? 0 : k], 1e-9f));
               }
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&bar_acc_empty[type * 2 + stage]));
+        __syncwarp();                              // every lane has read its accumulator rows
+        if (lane == 0) mbar_arrive(acce + 8 * bidx);
+        VQT_TL(ts >= 4 && ts < 8 && quad == 0 && lane == 0, 192 + ((((ts - 4) * 2 + sub) * 3 + jj) * 2) + 1);
       }
       // next tile of this CTA: tau += gridDim.x without a division
       clip += clip_step; tile_in_clip += tile_step;
@@ -756,6 +799,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     }
     if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && (warp == 0 || warp == 4) && lane == 0) {
       A.dbg[16 + 2 * sub] = VQT_CLOCK() - t_begin_ep; A.dbg[17 + 2 * sub] = t_wait_ep;
+      if (sub == 0) { A.dbg[27] = t_ld; A.dbg[28] = t_math; A.dbg[29] = t_st; }
     }
   } else {
     // =================================== loaders: VQT_LOAD_WARPS / n_slots warps per ring slot ===================================
@@ -797,8 +841,9 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           __syncwarp();
           t_wait_ld += VQT_CLOCK() - t0;
         }
+        VQT_TL(ts >= 4 && ts < 8 && lane == 0, ((ts - 4) * 8 + lw) * 2);
         if (VQT_KO(8)) {
-          if (SRC_F32 || lane == 0) mbar_arrive(bfull);     // fp32 source: every lane arrives; bulk copies: one per warp
+          if (lane == 0) mbar_arrive(bfull);
           continue;
         }
         if (!SRC_F32) {
@@ -806,19 +851,13 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           // 128 tile rows plus two small ones for the halo rows out of the neighbouring tiles (zero pad tiles at the ends)
           const long long t = row0 >> 7;
           if (L.pg > 1) {
-            const int n_cp = 6 * L.pg;                    // (term, plane, part) copies of the group
-            uint32_t tx = 0;
-            for (int k = sub; k < n_cp; k += wps) { const int part = k % 3; tx += part == 1 ? 2048u : 16u * (part == 0 ? L.hb : L.ha); }
-            if (lane == 0) mbar_expect_tx(bfull, tx);
+            // the plane group of the tile is one contiguous image per term in global memory: two bulk copies per group
+            const uint32_t tb = (uint32_t)L.slot_term_bytes;
+            if (lane == 0) mbar_expect_tx(bfull, sub == 0 ? 2u * tb : 0u);
             __syncwarp();
-            for (int k = sub + wps * lane; k < n_cp; k += 32 * wps) {
-              const int term = k / (3 * L.pg), c = (k % (3 * L.pg)) / 3, part = k % 3;     // part: 0 halo before, 1 main, 2 halo after
-              const uint16_t* src = (term ? lsrc : hsrc);
-              const uint32_t dst = (term ? s2 : s1) + (uint32_t)(c * L.a_lbo);
-              const long long plane = (long long)(plane0 + c);
-              if (part == 1) bulk_g2s(dst + 16u * L.hb, src + (((t + 1) * q + plane) * 128) * 8, 2048u, bfull);
-              else if (part == 0) { if (L.hb > 0) bulk_g2s(dst, src + ((t * q + plane) * 128 + (128 - L.hb)) * 8, 16u * L.hb, bfull); }
-              else if (L.ha > 0) bulk_g2s(dst + 16u * (L.hb + 128), src + (((t + 2) * q + plane) * 128) * 8, 16u * L.ha, bfull);
+            if (sub == 0 && lane < 2) {
+              const uint16_t* src = (lane ? lsrc : hsrc) + ((t * q + plane0) * (long long)L.rtot) * 8;
+              bulk_g2s(lane ? s2 : s1, src, tb, bfull);
             }
           } else {                             // q == 1: rows are consecutive chunks of the linear signal; warp `sub` moves term `sub` (wps >= 2)
             const uint32_t bytes = (uint32_t)(n_rows * 16);
@@ -847,6 +886,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
         }
 #endif
+        __syncwarp();     // reconverge after the single-lane blocks above: without it lane 0 ran the whole fill loop on its own
+                          // and lanes 1..31 repeated it afterwards (measured with per-lane clock stamps), doubling the fill time
         if (vec_ok) {
           // global -> registers -> two-term fp16 split -> shared memory, four chunks (128 bytes) per lane in flight: the
           // shared-memory image is written once (a cp.async staging pass costs two more trips through shared memory, and
@@ -858,31 +899,30 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             const float4* src = reinterpret_cast<const float4*>(yb + base_s + (long long)r_first * R + 8 * c_lane);
             const long long src_step = (long long)r_step * R / 4;      // in float4
             uint32_t d1 = s1 + off0, d2 = s2 + off0;
-            int it = 0;
+            // warp-uniform trip count (lanes own 16 or 17 chunks): a lane-dependent bound splits the warp for the whole loop
+            // under independent thread scheduling -- measured: lanes 24..31 ran the loop AFTER lanes 0..23, doubling the fill
+            // time of every slot -- so the bound is the maximum and the chunks beyond a lane's share are predicated off
+            const int n_it_max = (n_chunks + 32 * wps - 1) / (32 * wps);
 #pragma unroll 1
-            for (; it + 4 <= n_it; it += 4) {
+            for (int it = 0; it < n_it_max; it += 4) {
               float4 va[4], vb[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) { va[u] = __ldg(src + u * src_step); vb[u] = __ldg(src + u * src_step + 1); }
+              for (int u = 0; u < 4; ++u) {
+                const bool on = it + u < n_it;
+                va[u] = on ? __ldg(src + u * src_step) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[u] = on ? __ldg(src + u * src_step + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
                 uint4 c1, c2;
                 split8(v, c1, c2);
-                sts128(d1 + u * off_step, c1);
-                sts128(d2 + u * off_step, c2);
+                if (it + u < n_it) {
+                  sts128(d1 + u * off_step, c1);
+                  sts128(d2 + u * off_step, c2);
+                }
               }
               src += 4 * src_step; d1 += 4 * off_step; d2 += 4 * off_step;
-            }
-#pragma unroll 1
-            for (; it < n_it; ++it) {
-              const float4 va = __ldg(src), vb = __ldg(src + 1);
-              const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-              uint4 c1, c2;
-              split8(v, c1, c2);
-              sts128(d1, c1);
-              sts128(d2, c2);
-              src += src_step; d1 += off_step; d2 += off_step;
             }
           } else {
             // first / last tile of a clip: chunks that stick out of the signal are zero filled
@@ -921,8 +961,14 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             sts128(s2 + off, c2);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bfull);
+        VQT_TL(ts == 5 && lw == 1, 384 + lane);                                         // every lane of loader warp 1, tile 5: work done
+        VQT_TL(ts >= 4 && ts < 8 && lane == 0, 280 + ((ts - 4) * 8 + lw) * 3);        // lane 0: work done
+        VQT_TL(ts >= 4 && ts < 8 && lane == 31, 280 + ((ts - 4) * 8 + lw) * 3 + 1);   // lane 31: work done
+        if (!VQT_KO(32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        VQT_TL(ts >= 4 && ts < 8 && lane == 0, 280 + ((ts - 4) * 8 + lw) * 3 + 2);    // lane 0: fenced
+        __syncwarp();                              // every lane's stores are fenced
+        if (lane == 0) mbar_arrive(bfull);
+        VQT_TL(ts >= 4 && ts < 8 && lane == 0, ((ts - 4) * 8 + lw) * 2 + 1);
       }
       if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && lw == 0 && lane == 0) { A.dbg[20] = VQT_CLOCK() - t_begin_ld; A.dbg[21] = t_wait_ld;
                                                               A.dbg[22] = t_p1; A.dbg[23] = t_cpw; A.dbg[24] = t_p2; }
@@ -940,7 +986,7 @@ struct VqtEdgeParams {
   int item0[ZNS_VQT_MAX_OCT + 1];          // first (frame, filter) item of each octave
   int n_left[ZNS_VQT_MAX_OCT], t_right[ZNS_VQT_MAX_OCT];
   long long stride[ZNS_VQT_MAX_OCT];
-  int q[ZNS_VQT_MAX_OCT];                  // layout of the level buffers (level_index)
+  int q[ZNS_VQT_MAX_OCT], rtot[ZNS_VQT_MAX_OCT], hb[ZNS_VQT_MAX_OCT];   // layout of the level buffers (level_index)
   const float* coef[ZNS_VQT_MAX_OCT];      // [n][2][bpo/2][2]
   const uint16_t* hi[ZNS_VQT_MAX_OCT];
   const uint16_t* lo[ZNS_VQT_MAX_OCT];
@@ -974,7 +1020,7 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
     float s;
     if (oct == 0) s = __ldg(y32 + (size_t)clip * y_stride + idx);
     else {
-      const size_t o = (size_t)clip * P.stride[oct] + (size_t)level_index(idx, P.q[oct]);
+      const size_t o = (size_t)clip * P.stride[oct] + (size_t)level_index(idx, P.q[oct], P.rtot[oct], P.hb[oct]);
       s = __half2float(__ushort_as_half(P.hi[oct][o])) + __half2float(__ushort_as_half(P.lo[oct][o])) * (1.f / 2048.f);
     }
     const float* cn = cf + (size_t)i * P.bpo * 2;
@@ -1010,8 +1056,10 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
   ZNS_CHECK_CUDA(cudaGetDevice(&dev));
   ZNS_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
   if (!attr_set[dev]) {
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ZNS_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -1049,6 +1097,7 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     a.n_valid = n_cur / 2;
     a.dst_stride = last ? 0 : p->sig_stride[i + 1];
     a.dst_q = last ? 1 : p->level[i + 1].q;
+    a.dst_rtot = last ? 0 : p->level[i + 1].rtot; a.dst_hb = last ? 0 : p->level[i + 1].hb; a.dst_ha = last ? 0 : p->level[i + 1].ha;
     a.dst_cap = last ? 0 : p->sig_cap[i + 1];
     a.tiles_per_clip = (rows + 127) / 128;
     a.n_tiles = a.tiles_per_clip * batch;
@@ -1058,14 +1107,16 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
 #endif
     const int grid = std::min(a.n_tiles, n_sm[dev]);
     const size_t smem = level_smem(L);
-    if (i == 0) vqt_level_kernel<true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
-    else vqt_level_kernel<false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
+    if (i == 0 && L.fpr == 1) vqt_level_kernel<true, true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
+    else if (i == 0) vqt_level_kernel<true, false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
+    else if (L.fpr == 1) vqt_level_kernel<false, true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
+    else vqt_level_kernel<false, false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
     ZNS_CHECK_LAUNCH();
     // edge frames: left t*hop < nf/2 ; right t*hop + nf/2 > n
     const int nl = std::min(n_frames, (L.n_fft / 2 + L.hop - 1) / L.hop);
     int tr = (n_cur >= L.n_fft / 2) ? (n_cur - L.n_fft / 2) / L.hop + 1 : 0;
     tr = std::max(tr, nl);
-    E.n_fft[i] = L.n_fft; E.hop[i] = L.hop; E.n_sig[i] = n_cur; E.stride[i] = p->sig_stride[i]; E.q[i] = L.q;
+    E.n_fft[i] = L.n_fft; E.hop[i] = L.hop; E.n_sig[i] = n_cur; E.stride[i] = p->sig_stride[i]; E.q[i] = L.q; E.rtot[i] = L.rtot; E.hb[i] = L.hb;
     E.coef[i] = p->d_coef[i]; E.hi[i] = p->d_hi[i]; E.lo[i] = p->d_lo[i];
     E.n_left[i] = nl; E.t_right[i] = tr;
     E.item0[i + 1] = E.item0[i] + (nl + std::max(0, n_frames - tr)) * p->bpo;
