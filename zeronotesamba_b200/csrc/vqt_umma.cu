@@ -532,14 +532,13 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.n_slots; ++i) {
-      // VQT_LOAD_WARPS / n_slots loader warps fill a slot; ONE lane per warp arrives (an mbarrier arrive is an atomic on one
-      // shared-memory word: 64 lane arrivals per group and 256 per accumulator hand-off serialised into ~10 K clocks per tile)
-      mbar_init(smem_u32(&bar_full[i]), VQT_LOAD_WARPS / L.n_slots);
+      // VQT_LOAD_WARPS / n_slots loader warps fill a slot: all their lanes arrive (fp32 source) or one per warp (bulk copies)
+      mbar_init(smem_u32(&bar_full[i]), (SRC_F32 ? 32 : 1) * (VQT_LOAD_WARPS / L.n_slots));
       mbar_init(smem_u32(&bar_empty[i]), ZNS_VQT_ISSUERS);          // every issuer commits once per group
     }
     for (int t = 0; t < 4; ++t) {
       mbar_init(smem_u32(&bar_acc_full[t]), 2);                    // two accumulator units (parts) per job
-      mbar_init(smem_u32(&bar_acc_empty[t]), VQT_EPI_WARPS);
+      mbar_init(smem_u32(&bar_acc_empty[t]), 32 * VQT_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -675,8 +674,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const uint32_t bidx = (uint32_t)(type * 2) + stage;
         {
           const long long t0 = VQT_CLOCK();
-          if (lane == 0) vqt_wait(accf + 8 * bidx, (inst >> sh) & 1);
-          __syncwarp();
+          vqt_wait(accf + 8 * bidx, (inst >> sh) & 1);     // every lane polls (see the loader: no single-lane code before the drain)
           t_wait_ep += VQT_CLOCK() - t0;
         }
         tc_fence_after();
@@ -789,8 +787,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        __syncwarp();                              // every lane has read its accumulator rows
-        if (lane == 0) mbar_arrive(acce + 8 * bidx);
+        mbar_arrive(acce + 8 * bidx);              // every lane, once it has read its accumulator rows
         VQT_TL(ts >= 4 && ts < 8 && quad == 0 && lane == 0, 192 + ((((ts - 4) * 2 + sub) * 3 + jj) * 2) + 1);
       }
       // next tile of this CTA: tau += gridDim.x without a division
@@ -837,13 +834,16 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const long long base_s = (row0 - L.hb) * R + 8LL * plane0;     // sample of chunk (row 0, plane 0 of the group)
         {
           const long long t0 = VQT_CLOCK();
-          if (lane == 0) vqt_wait(bempty, par);
-          __syncwarp();
+          // EVERY lane polls: `if (lane == 0) wait(); __syncwarp();` left lane 0 and lanes 1..31 as two convergence groups that
+          // ran the fill loop (and, in the epilogue, the whole drain) one after the other -- per-lane clock stamps showed
+          // lane 0 finishing a fill 6..10 K clocks apart from the rest (0.635 -> 0.540 ms at cfg2 once removed).  No single-lane
+          // code in front of heavy warp-wide work.
+          vqt_wait(bempty, par);
           t_wait_ld += VQT_CLOCK() - t0;
         }
         VQT_TL(ts >= 4 && ts < 8 && lane == 0, ((ts - 4) * 8 + lw) * 2);
         if (VQT_KO(8)) {
-          if (lane == 0) mbar_arrive(bfull);
+          if (SRC_F32 || lane == 0) mbar_arrive(bfull);
           continue;
         }
         if (!SRC_F32) {
@@ -871,23 +871,6 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           }
           continue;
         }
-#ifndef ZNS_VQT_NO_L2_PREFETCH
-        if (SRC_F32 && pos == 0 && sub == 0 && lane == 0 && ts + 1 < n_my_tiles) {
-          // pull the NEXT tile's samples (one contiguous span of the clip) into L2 while this tile is being processed: the
-          // ring holds a single tile, so its loads cannot be issued early -- but their DRAM latency can be taken now
-          const int tau_n = tau + (int)gridDim.x;
-          const int clip_n = tau_n / A.tiles_per_clip;
-          long long s_lo = ((long long)(tau_n - clip_n * A.tiles_per_clip) * 128 - L.hb) * R;
-          long long s_hi = s_lo + (long long)n_rows * R;
-          s_lo = max(s_lo, 0LL); s_hi = min(s_hi, (long long)A.n_sig);
-          const float* pn = A.y32 + (size_t)clip_n * A.src_stride + s_lo;
-          const uint32_t bytes = (uint32_t)((s_hi - s_lo) * 4) & ~15u;
-          if (s_hi > s_lo && bytes > 0 && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
-        }
-#endif
-        __syncwarp();     // reconverge after the single-lane blocks above: without it lane 0 ran the whole fill loop on its own
-                          // and lanes 1..31 repeated it afterwards (measured with per-lane clock stamps), doubling the fill time
         if (vec_ok) {
           // global -> registers -> two-term fp16 split -> shared memory, four chunks (128 bytes) per lane in flight: the
           // shared-memory image is written once (a cp.async staging pass costs two more trips through shared memory, and
@@ -966,8 +949,23 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         VQT_TL(ts >= 4 && ts < 8 && lane == 31, 280 + ((ts - 4) * 8 + lw) * 3 + 1);   // lane 31: work done
         if (!VQT_KO(32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         VQT_TL(ts >= 4 && ts < 8 && lane == 0, 280 + ((ts - 4) * 8 + lw) * 3 + 2);    // lane 0: fenced
-        __syncwarp();                              // every lane's stores are fenced
-        if (lane == 0) mbar_arrive(bfull);
+        mbar_arrive(bfull);                        // every lane (its own stores are fenced)
+#ifndef ZNS_VQT_NO_L2_PREFETCH
+        // (single-lane block: kept BEHIND the warp-wide fill, see above)
+        if (SRC_F32 && pos == 0 && sub == 0 && lane == 0 && ts + 1 < n_my_tiles) {
+          // pull the NEXT tile's samples (one contiguous span of the clip) into L2 while this tile is being processed: the
+          // ring holds a single tile, so its loads cannot be issued early -- but their DRAM latency can be taken now
+          const int tau_n = tau + (int)gridDim.x;
+          const int clip_n = tau_n / A.tiles_per_clip;
+          long long s_lo = ((long long)(tau_n - clip_n * A.tiles_per_clip) * 128 - L.hb) * R;
+          long long s_hi = s_lo + (long long)n_rows * R;
+          s_lo = max(s_lo, 0LL); s_hi = min(s_hi, (long long)A.n_sig);
+          const float* pn = A.y32 + (size_t)clip_n * A.src_stride + s_lo;
+          const uint32_t bytes = (uint32_t)((s_hi - s_lo) * 4) & ~15u;
+          if (s_hi > s_lo && bytes > 0 && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
+        }
+#endif
         VQT_TL(ts >= 4 && ts < 8 && lane == 0, ((ts - 4) * 8 + lw) * 2 + 1);
       }
       if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && lw == 0 && lane == 0) { A.dbg[20] = VQT_CLOCK() - t_begin_ld; A.dbg[21] = t_wait_ld;
