@@ -998,7 +998,9 @@ __device__ __forceinline__ int reflect_idx32(int qq, int n) {
   return qq < n ? qq : period - qq;
 }
 
-// one warp per (edge frame, filter): lanes stride over the taps
+// one warp per edge frame: every lane gathers up to four samples of the frame's window ONCE (reflect index + level layout are
+// the expensive part), applies all bins_per_octave filters to them, then the warp reduces the 2 x bpo partial sums
+#define VQT_EDGE_MAX_BPO 12
 __global__ void __launch_bounds__(256)
 vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict__ y32, long long y_stride,
                 const float* __restrict__ inv_sqrt_len, float* __restrict__ out) {
@@ -1007,12 +1009,12 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
   if (item >= P.item0[P.n_oct]) return;
   int oct = 0;
   while (item >= P.item0[oct + 1]) ++oct;
-  const int w = item - P.item0[oct];
-  const int e = w / P.bpo, k = w - e * P.bpo;
-  const int nf = P.n_fft[oct], hop = P.hop[oct], n = P.n_sig[oct], F = P.n_frames;
+  const int e = item - P.item0[oct];
+  const int nf = P.n_fft[oct], hop = P.hop[oct], n = P.n_sig[oct], F = P.n_frames, bpo = P.bpo;
   const int t = e < P.n_left[oct] ? e : P.t_right[oct] + (e - P.n_left[oct]);
-  float re = 0.f, im = 0.f;
-  const float* cf = P.coef[oct] + (size_t)k * 2;
+  float re[VQT_EDGE_MAX_BPO], im[VQT_EDGE_MAX_BPO];
+#pragma unroll
+  for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k) { re[k] = 0.f; im[k] = 0.f; }
   for (int i = lane; i < nf; i += 32) {
     const int idx = reflect_idx32(t * hop + i - nf / 2, n);
     float s;
@@ -1021,18 +1023,32 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
       const size_t o = (size_t)clip * P.stride[oct] + (size_t)level_index(idx, P.q[oct], P.rtot[oct], P.hb[oct]);
       s = __half2float(__ushort_as_half(P.hi[oct][o])) + __half2float(__ushort_as_half(P.lo[oct][o])) * (1.f / 2048.f);
     }
-    const float* cn = cf + (size_t)i * P.bpo * 2;
-    re = fmaf(__ldg(cn), s, re);
-    im = fmaf(__ldg(cn + 1), s, im);
+    const float2* cn = reinterpret_cast<const float2*>(P.coef[oct]) + (size_t)i * bpo;     // [tap][filter](re, im)
+#pragma unroll
+    for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k) {
+      if (k < bpo) {
+        const float2 c = __ldg(cn + k);
+        re[k] = fmaf(c.x, s, re[k]);
+        im[k] = fmaf(c.y, s, im[k]);
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    re += __shfl_xor_sync(0xffffffffu, re, o);
-    im += __shfl_xor_sync(0xffffffffu, im, o);
+  for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re[k] += __shfl_xor_sync(0xffffffffu, re[k], o);
+      im[k] += __shfl_xor_sync(0xffffffffu, im[k], o);
+    }
   }
-  if (lane == 0) {
-    const int bin = P.n_bins - P.bpo * (oct + 1) + k;
-    out[((size_t)clip * P.n_bins + bin) * F + t] = logf(sqrtf(re * re + im * im) * __ldg(inv_sqrt_len + bin) + 1e-9f);
+  // lane k writes bin k (static register indexing: select by predicate)
+  float r = 0.f, m = 0.f;
+#pragma unroll
+  for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k)
+    if (lane == k) { r = re[k]; m = im[k]; }
+  if (lane < bpo) {
+    const int bin = P.n_bins - bpo * (oct + 1) + lane;
+    out[((size_t)clip * P.n_bins + bin) * F + t] = logf(sqrtf(r * r + m * m) * __ldg(inv_sqrt_len + bin) + 1e-9f);
   }
 }
 
@@ -1117,7 +1133,7 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     E.n_fft[i] = L.n_fft; E.hop[i] = L.hop; E.n_sig[i] = n_cur; E.stride[i] = p->sig_stride[i]; E.q[i] = L.q; E.rtot[i] = L.rtot; E.hb[i] = L.hb;
     E.coef[i] = p->d_coef[i]; E.hi[i] = p->d_hi[i]; E.lo[i] = p->d_lo[i];
     E.n_left[i] = nl; E.t_right[i] = tr;
-    E.item0[i + 1] = E.item0[i] + (nl + std::max(0, n_frames - tr)) * p->bpo;
+    E.item0[i + 1] = E.item0[i] + (nl + std::max(0, n_frames - tr));          // one warp per edge frame
     n_cur = n_next;
   }
   const int n_items = E.item0[p->n_oct];
