@@ -418,6 +418,9 @@ __device__ __forceinline__ void split8(const float* v, uint4& c1, uint4& c2) {
 #endif
 #define VQT_EPQ (VQT_EPI_WARPS / 4)      // epilogue warps per TMEM lane quadrant (2 or 4: must divide the twelve bins)
 #define VQT_LOAD_WARPS 8
+#ifndef VQT_LD_U
+#define VQT_LD_U 6               // level-0 loader: 32-byte chunks per lane in flight
+#endif
 #define VQT_ISSUE_WARP0 VQT_EPI_WARPS
 #define VQT_LOAD_WARP0 (VQT_EPI_WARPS + ZNS_VQT_ISSUERS)
 #define VQT_LEVEL_THREADS (32 * (VQT_LOAD_WARP0 + VQT_LOAD_WARPS))
@@ -515,6 +518,9 @@ __device__ __forceinline__ void vqt_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // FPR1: one frame per signal row (levels whose hop is >= 32 samples: the four big levels) -- a compile-time switch so that the
 // register needs of the multi-frame epilogue (72 accumulator columns per thread) do not spill the hot single-frame one.
 template <bool SRC_F32, bool FPR1>
@@ -542,11 +548,17 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     }
     mbar_fence_init();
   }
+  // Programmatic dependent launch: the level kernels of a pass are launched back to back with the "programmatic stream
+  // serialization" attribute, so the CTAs of level i + 1 start on an SM as soon as level i's CTA has left it and run this
+  // prologue (barriers, TMEM, the constant coefficient image) under level i's tail; griddepcontrol.wait then holds them until
+  // level i has completed and its level signal is visible.  Both instructions are no-ops in a launch without the attribute.
+  pdl_launch_dependents();
   if (warp == VQT_ISSUE_WARP0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
   if (threadIdx.x < VQT_ZERO_BYTES / 4) reinterpret_cast<uint32_t*>(sZero)[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < L.b_bytes / 16; i += VQT_LEVEL_THREADS)
     reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(A.bimg) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -638,10 +650,9 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     int dst_shift = 3;                                      // log2(samples per row) of the next level
     while ((8 << (dst_shift - 3)) < 8 * A.dst_q) ++dst_shift;
     constexpr int kBinsPerWarp = 12 / VQT_EPQ;              // fpr == 1: bins of this warp
-    constexpr int kIsl = FPR1 ? kBinsPerWarp : 12;
-    float isl[kIsl];                                        // 1 / sqrt(L_k) / (coefficient scale) of the bins this thread writes
+    float isl[kBinsPerWarp];                                // 1 / sqrt(L_k) / (coefficient scale) of the bins this thread writes
 #pragma unroll
-    for (int k = 0; k < kIsl; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + (FPR1 ? kBinsPerWarp * sub : 0) + k) * L.fb_scale;
+    for (int k = 0; k < kBinsPerWarp; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + kBinsPerWarp * sub + k) * L.fb_scale;
     // everything the per-job code needs from the level description, read ONCE with compile-time subscripts (uniform loads):
     // a run-time subscript into the kernel parameters is an indexed constant load of several hundred clocks, and the job loop
     // used to issue a chain of them per job
@@ -766,22 +777,40 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             }
           }
         } else if (!FPR1) {
-#pragma unroll 1
-          for (int j = sub; j < fpr; j += VQT_EPQ) {
-            const int f = g * fpr + j;
-            uint32_t fa[48], fb[24];
-            tmem_ld_32x32(acc + 48 * j, fa);
-            tmem_ld_32x16(acc + 48 * j + 32, fa + 32);
-            tmem_ld_32x16(acc + fb_n1 + 24 * j, fb);
-            tmem_ld_32x8(acc + fb_n1 + 24 * j + 16, fb + 16);
-            tmem_ld_wait();
-            if (f < n_frames && !VQT_KO(16)) {
-              float* op = A.out + ((size_t)clip * A.n_bins + L.bin0) * n_frames + f;
+          // several frames per row (hop < 32 samples): a thread owns the fpr CONSECUTIVE frames of its row, so the warps of a
+          // quadrant split the BINS and a thread writes its frames of one bin as one 8 / 16-byte store -- consecutive lanes,
+          // consecutive addresses (one store per frame and bin was a 16-byte-strided scatter, 4 x the store instructions)
+          constexpr int KB = 12 / VQT_EPQ;                 // bins of this warp
+          const int k0 = KB * sub;
+          float res[4][KB];
 #pragma unroll
-              for (int k = 0; k < 12; ++k) {
-                const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fa[24 + 2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
-                const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fa[25 + 2 * k]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-                op[(size_t)k * n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[FPR1 ? 0 : k], 1e-9f));
+          for (int j = 0; j < 4; ++j) {
+            if (j < fpr) {
+              uint32_t fa[16], fg[16], fb[16];
+              tmem_ld_32x16(acc + 48 * j + 2 * k0, fa);            // x1 . g1 (2 KB of the 16 loaded columns are used)
+              tmem_ld_32x16(acc + 48 * j + 24 + 2 * k0, fg);       // x1 . g2
+              tmem_ld_32x16(acc + fb_n1 + 24 * j + 2 * k0, fb);    // x2 . g1
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < KB; ++k) {
+                const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
+                const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
+                res[j][k] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
+              }
+            }
+          }
+          const int f0 = g * fpr;
+          if (f0 < n_frames && !VQT_KO(16)) {
+            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * n_frames + f0;
+            const bool whole = f0 + fpr <= n_frames && (n_frames % fpr) == 0 && (reinterpret_cast<uintptr_t>(A.out) & 15) == 0;
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+              float* o = op + (size_t)k * n_frames;
+              if (whole && fpr == 4) *reinterpret_cast<float4*>(o) = make_float4(res[0][k], res[1][k], res[2][k], res[3][k]);
+              else if (whole && fpr == 2) *reinterpret_cast<float2*>(o) = make_float2(res[0][k], res[1][k]);
+              else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < fpr && f0 + j < n_frames) o[j] = res[j][k];
               }
             }
           }
@@ -872,31 +901,41 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           continue;
         }
         if (vec_ok) {
-          // global -> registers -> two-term fp16 split -> shared memory, four chunks (128 bytes) per lane in flight: the
+          // global -> registers -> two-term fp16 split -> shared memory, VQT_LD_U chunks of 32 bytes per lane in flight: the
           // shared-memory image is written once (a cp.async staging pass costs two more trips through shared memory, and
           // the in-place conversion behind it was one dependent LDS -> convert -> STS chain per chunk)
           const long long tp0 = VQT_CLOCK();
-          const bool interior = base_s >= 0 && base_s + (long long)(n_rows - 1) * R + 8 * L.pg <= (long long)A.n_sig;
           if (VQT_KO(1)) {
-          } else if (interior) {
-            const float4* src = reinterpret_cast<const float4*>(yb + base_s + (long long)r_first * R + 8 * c_lane);
-            const long long src_step = (long long)r_step * R / 4;      // in float4
+          } else {
+            // One path for interior tiles and for the first / last tile of a clip (2 of 15 tiles at cfg2: a scalar loop for them
+            // cost as much as five interior fills): a chunk that lies outside the signal is zero, a chunk that straddles its end
+            // (at most one per row) is read element by element.
+            // (sample indices fit 32 bits: a clip holds fewer than 2^31 samples)
+            int s_it = (int)base_s + r_first * R + 8 * c_lane;       // first sample of this lane's chunk of the current iteration
+            const int s_step = r_step * R;
             uint32_t d1 = s1 + off0, d2 = s2 + off0;
+            const int n_sig_i = A.n_sig;
             // warp-uniform trip count (lanes own 16 or 17 chunks): a lane-dependent bound splits the warp for the whole loop
             // under independent thread scheduling -- measured: lanes 24..31 ran the loop AFTER lanes 0..23, doubling the fill
             // time of every slot -- so the bound is the maximum and the chunks beyond a lane's share are predicated off
             const int n_it_max = (n_chunks + 32 * wps - 1) / (32 * wps);
+            // VQT_LD_U chunks (32 bytes each) per lane in flight: the loop is one load -> wait -> convert -> store chain per
+            // warp, so its rate is (bytes in flight) / (memory latency + convert time)
 #pragma unroll 1
-            for (int it = 0; it < n_it_max; it += 4) {
-              float4 va[4], vb[4];
+            for (int it = 0; it < n_it_max; it += VQT_LD_U) {
+              float4 va[VQT_LD_U], vb[VQT_LD_U];
+              uint32_t ragged = 0;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const bool on = it + u < n_it;
-                va[u] = on ? __ldg(src + u * src_step) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[u] = on ? __ldg(src + u * src_step + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int u = 0; u < VQT_LD_U; ++u) {
+                const int s0 = s_it + u * s_step;
+                const bool in = it + u < n_it && s0 >= 0 && s0 + 8 <= n_sig_i;
+                const float4* sp = reinterpret_cast<const float4*>(yb + s0);
+                va[u] = in ? __ldg(sp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[u] = in ? __ldg(sp + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!in && it + u < n_it && s0 < n_sig_i && s0 + 8 > 0) ragged |= 1u << u;
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < VQT_LD_U; ++u) {
                 const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
                 uint4 c1, c2;
                 split8(v, c1, c2);
@@ -905,27 +944,22 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
                   sts128(d2 + u * off_step, c2);
                 }
               }
-              src += 4 * src_step; d1 += 4 * off_step; d2 += 4 * off_step;
-            }
-          } else {
-            // first / last tile of a clip: chunks that stick out of the signal are zero filled
+              if (ragged) {                 // rare: overwrite the straddling chunks (stored as zeros above)
 #pragma unroll 1
-            for (int it = 0; it < n_it; ++it) {
-              const int r = r_first + it * r_step;
-              const long long s0 = base_s + (long long)r * R + 8 * c_lane;
-              const uint32_t off = off0 + (uint32_t)it * off_step;
-              float v[8];
-              if (s0 >= 0 && s0 + 8 <= (long long)A.n_sig) {
-                const float4 va = __ldg(reinterpret_cast<const float4*>(yb + s0)), vb = __ldg(reinterpret_cast<const float4*>(yb + s0) + 1);
-                v[0] = va.x; v[1] = va.y; v[2] = va.z; v[3] = va.w; v[4] = vb.x; v[5] = vb.y; v[6] = vb.z; v[7] = vb.w;
-              } else {
+                for (int u = 0; u < VQT_LD_U; ++u) {
+                  if (ragged & (1u << u)) {
+                    const int s0 = s_it + u * s_step;
+                    float e[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = (s0 + e >= 0 && s0 + e < (long long)A.n_sig) ? __ldg(yb + s0 + e) : 0.f;
+                    for (int k = 0; k < 8; ++k) e[k] = (s0 + k >= 0 && s0 + k < n_sig_i) ? __ldg(yb + s0 + k) : 0.f;
+                    uint4 c1, c2;
+                    split8(e, c1, c2);
+                    sts128(d1 + u * off_step, c1);
+                    sts128(d2 + u * off_step, c2);
+                  }
+                }
               }
-              uint4 c1, c2;
-              split8(v, c1, c2);
-              sts128(s1 + off, c1);
-              sts128(s2 + off, c2);
+              d1 += VQT_LD_U * off_step; d2 += VQT_LD_U * off_step; s_it += VQT_LD_U * s_step;
             }
           }
           t_p1 += VQT_CLOCK() - tp0;
@@ -1006,6 +1040,7 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
                 const float* __restrict__ inv_sqrt_len, float* __restrict__ out) {
   const int clip = blockIdx.z;
   const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  pdl_wait();                              // launched behind the last level kernel with programmatic serialization
   if (item >= P.item0[P.n_oct]) return;
   int oct = 0;
   while (item >= P.item0[oct + 1]) ++oct;
@@ -1086,6 +1121,10 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     }
   }
   p->umma_last_n = n_samples;
+  static const bool pdl = !(getenv("ZNS_VQT_PDL") && atoi(getenv("ZNS_VQT_PDL")) == 0);
+  cudaLaunchAttribute pdl_attr = {};
+  pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr.val.programmaticStreamSerializationAllowed = 1;
   VqtEdgeParams E;
   memset(&E, 0, sizeof(E));
   E.n_oct = p->n_oct; E.bpo = p->bpo; E.n_bins = p->n_bins; E.n_frames = n_frames;
@@ -1121,11 +1160,14 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
 #endif
     const int grid = std::min(a.n_tiles, n_sm[dev]);
     const size_t smem = level_smem(L);
-    if (i == 0 && L.fpr == 1) vqt_level_kernel<true, true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
-    else if (i == 0) vqt_level_kernel<true, false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
-    else if (L.fpr == 1) vqt_level_kernel<false, true><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
-    else vqt_level_kernel<false, false><<<grid, VQT_LEVEL_THREADS, smem, st>>>(L, a);
-    ZNS_CHECK_LAUNCH();
+    // levels >= 1 (and the edge-frame kernel) are programmatic dependents of the launch in front of them
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(VQT_LEVEL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = &pdl_attr; cfg.numAttrs = (pdl && i > 0) ? 1 : 0;
+    if (i == 0 && L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, true>, L, a));
+    else if (i == 0) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, false>, L, a));
+    else if (L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, true>, L, a));
+    else ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, false>, L, a));
     // edge frames: left t*hop < nf/2 ; right t*hop + nf/2 > n
     const int nl = std::min(n_frames, (L.n_fft / 2 + L.hop - 1) / L.hop);
     int tr = (n_cur >= L.n_fft / 2) ? (n_cur - L.n_fft / 2) / L.hop + 1 : 0;
@@ -1138,8 +1180,10 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
   }
   const int n_items = E.item0[p->n_oct];
   if (n_items > 0) {
-    vqt_edge_kernel<<<dim3((n_items + 7) / 8, 1, batch), 256, 0, st>>>(E, y, (long long)n_samples, p->d_inv_sqrt_len, out);
-    ZNS_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((n_items + 7) / 8, 1, batch); cfg.blockDim = dim3(256); cfg.stream = st;
+    cfg.attrs = &pdl_attr; cfg.numAttrs = pdl ? 1 : 0;
+    ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_edge_kernel, E, y, (long long)n_samples, (const float*)p->d_inv_sqrt_len, out));
   }
   return ZNS_OK;
 }
