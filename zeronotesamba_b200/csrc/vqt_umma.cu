@@ -411,19 +411,25 @@ __device__ __forceinline__ void split8(const float* v, uint4& c1, uint4& c2) {
   c2 = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
-// Warp roles of the persistent level kernel: epilogue = warps 0..7, MMA issuers = warps 8..11 (one per scheduler
-// sub-partition), loaders = warps 12..19.
-#ifndef VQT_EPI_WARPS
-#define VQT_EPI_WARPS 8          // 16 measured slower (72 registers per thread -> spills): 0.88 vs 0.765 ms at cfg2
-#endif
-#define VQT_EPQ (VQT_EPI_WARPS / 4)      // epilogue warps per TMEM lane quadrant (2 or 4: must divide the twelve bins)
+// Warp roles of the persistent level kernel (20 / 21 warps): epilogue = warps 0..7, MMA issuers = warps 8..11 (one per scheduler
+// sub-partition), warps 12..20 depend on the source:
+//   fp32 source (level 0): warps 12..19 load (global -> registers -> two-term split -> shared memory);
+//   levels >= 1: the source is already split and tile ordered, a group is two bulk copies -- warp 12 alone issues them and
+//   warps 13..20 are EIGHT MORE EPILOGUE warps (four per TMEM lane quadrant instead of two): the small levels are bound by the
+//   per-tile latency chain of the epilogue (tcgen05.ld -> FP -> store), which only more warps shorten.
+#define VQT_EPI_WARPS 8          // base epilogue warps (all kernels)
 #define VQT_LOAD_WARPS 8
+#ifndef VQT_PF_DIST
+#define VQT_PF_DIST 1            // level-0 loader: L2 prefetch distance in tiles (2: 0.495 ms, 3: 0.522 ms vs 0.461 at cfg2 -- L2 thrash)
+#endif
 #ifndef VQT_LD_U
 #define VQT_LD_U 6               // level-0 loader: 32-byte chunks per lane in flight
 #endif
 #define VQT_ISSUE_WARP0 VQT_EPI_WARPS
 #define VQT_LOAD_WARP0 (VQT_EPI_WARPS + ZNS_VQT_ISSUERS)
-#define VQT_LEVEL_THREADS (32 * (VQT_LOAD_WARP0 + VQT_LOAD_WARPS))
+#define VQT_EXTRA_WARP0 (VQT_LOAD_WARP0 + 1)      // levels >= 1: first of the eight extra epilogue warps
+// 20 warps at level 0, 21 behind it (a sixth warp on one scheduler sub-partition caps the kernel at 80 registers: level 0 needs 96)
+#define VQT_LEVEL_THREADS(src_f32) (32 * (VQT_LOAD_WARP0 + VQT_LOAD_WARPS + ((src_f32) ? 0 : 1)))
 
 struct VqtLevelArgs {
   const float* y32;            // level 0 source [batch][src_stride]
@@ -524,7 +530,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // FPR1: one frame per signal row (levels whose hop is >= 32 samples: the four big levels) -- a compile-time switch so that the
 // register needs of the multi-frame epilogue (72 accumulator columns per thread) do not spill the hot single-frame one.
 template <bool SRC_F32, bool FPR1>
-__global__ void __launch_bounds__(VQT_LEVEL_THREADS, 1)
+__global__ void __launch_bounds__(VQT_LEVEL_THREADS(SRC_F32), 1)
 vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ VqtLevelArgs A) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t bar_full[8], bar_empty[8], bar_acc_full[4], bar_acc_empty[4];   // acc barriers: [type * 2 + stage]
@@ -535,16 +541,18 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
   uint8_t* sB = sm + VQT_ZERO_BYTES;
   uint8_t* sRing = sB + ((L.b_bytes + 127) / 128) * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int EPQ = SRC_F32 ? 2 : 4;                   // epilogue warps per TMEM lane quadrant (must divide the twelve bins)
+  const bool is_epi = warp < VQT_EPI_WARPS || (!SRC_F32 && warp >= VQT_EXTRA_WARP0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < L.n_slots; ++i) {
-      // VQT_LOAD_WARPS / n_slots loader warps fill a slot: all their lanes arrive (fp32 source) or one per warp (bulk copies)
-      mbar_init(smem_u32(&bar_full[i]), (SRC_F32 ? 32 : 1) * (VQT_LOAD_WARPS / L.n_slots));
+      // fp32 source: VQT_LOAD_WARPS / n_slots loader warps fill a slot and all their lanes arrive; bulk copies: one arrive.expect_tx
+      mbar_init(smem_u32(&bar_full[i]), SRC_F32 ? 32 * (VQT_LOAD_WARPS / L.n_slots) : 1);
       mbar_init(smem_u32(&bar_empty[i]), ZNS_VQT_ISSUERS);          // every issuer commits once per group
     }
     for (int t = 0; t < 4; ++t) {
       mbar_init(smem_u32(&bar_acc_full[t]), 2);                    // two accumulator units (parts) per job
-      mbar_init(smem_u32(&bar_acc_empty[t]), 32 * VQT_EPI_WARPS);
+      mbar_init(smem_u32(&bar_acc_empty[t]), 32 * 4 * EPQ);
     }
     mbar_fence_init();
   }
@@ -555,7 +563,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
   pdl_launch_dependents();
   if (warp == VQT_ISSUE_WARP0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
   if (threadIdx.x < VQT_ZERO_BYTES / 4) reinterpret_cast<uint32_t*>(sZero)[threadIdx.x] = 0;
-  for (int i = threadIdx.x; i < L.b_bytes / 16; i += VQT_LEVEL_THREADS)
+  for (int i = threadIdx.x; i < L.b_bytes / 16; i += VQT_LEVEL_THREADS(SRC_F32))
     reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(A.bimg) + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   pdl_wait();
@@ -638,18 +646,19 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp < VQT_EPI_WARPS) {
+  } else if (is_epi) {
     // =================================== epilogue ===================================
-    // VQT_EPQ warps per TMEM lane quadrant; warp `sub` of a quadrant takes every VQT_EPQ-th 16-column decimator block and
+    // EPQ warps per TMEM lane quadrant; warp `sub` of a quadrant takes every EPQ-th 16-column decimator block and
     // its share of the filterbank bins / frames.  The roles run one dependent chain per warp (tcgen05.ld -> FP -> pack ->
     // store), so throughput comes from the number of warps, not from the instruction count.
-    const int quad = warp & 3, sub = warp >> 2;
+    // (a warp reads the TMEM lanes of quadrant warp % 4: the extra warps 13..20 are quadrants 1, 2, 3, 0, 1, 2, 3, 0)
+    const int quad = warp & 3, sub = warp < VQT_EPI_WARPS ? warp >> 2 : 2 + ((warp - VQT_EXTRA_WARP0) >> 2);
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     long long t_wait_ep = 0, t_ld = 0, t_math = 0, t_st = 0;
     const long long t_begin_ep = VQT_CLOCK();
     int dst_shift = 3;                                      // log2(samples per row) of the next level
     while ((8 << (dst_shift - 3)) < 8 * A.dst_q) ++dst_shift;
-    constexpr int kBinsPerWarp = 12 / VQT_EPQ;              // fpr == 1: bins of this warp
+    constexpr int kBinsPerWarp = 12 / EPQ;              // fpr == 1: bins of this warp
     float isl[kBinsPerWarp];                                // 1 / sqrt(L_k) / (coefficient scale) of the bins this thread writes
 #pragma unroll
     for (int k = 0; k < kBinsPerWarp; ++k) isl[k] = __ldg(A.inv_sqrt_len + L.bin0 + kBinsPerWarp * sub + k) * L.fb_scale;
@@ -700,7 +709,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           const int n_blk = (w + 15) / 16;
           const int t_row = g * dec_w + c0;                            // first output of this row in this pass (< 2^31)
 #pragma unroll 1
-          for (int kb = sub; kb < n_blk; kb += VQT_EPQ) {
+          for (int kb = sub; kb < n_blk; kb += EPQ) {
             uint32_t a[16], b[16];
             const long long c0_ = VQT_CLOCK();
             tmem_ld_32x16(acc + 16 * kb, a);
@@ -780,16 +789,23 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           // several frames per row (hop < 32 samples): a thread owns the fpr CONSECUTIVE frames of its row, so the warps of a
           // quadrant split the BINS and a thread writes its frames of one bin as one 8 / 16-byte store -- consecutive lanes,
           // consecutive addresses (one store per frame and bin was a 16-byte-strided scatter, 4 x the store instructions)
-          constexpr int KB = 12 / VQT_EPQ;                 // bins of this warp
+          constexpr int KB = 12 / EPQ;                     // bins of this warp
           const int k0 = KB * sub;
           float res[4][KB];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j < fpr) {
-              uint32_t fa[16], fg[16], fb[16];
-              tmem_ld_32x16(acc + 48 * j + 2 * k0, fa);            // x1 . g1 (2 KB of the 16 loaded columns are used)
-              tmem_ld_32x16(acc + 48 * j + 24 + 2 * k0, fg);       // x1 . g2
-              tmem_ld_32x16(acc + fb_n1 + 24 * j + 2 * k0, fb);    // x2 . g1
+              constexpr int NL = 2 * KB <= 8 ? 8 : 16;             // columns loaded (2 KB of them are used)
+              uint32_t fa[NL], fg[NL], fb[NL];
+              if (NL == 8) {
+                tmem_ld_32x8(acc + 48 * j + 2 * k0, fa);           // x1 . g1
+                tmem_ld_32x8(acc + 48 * j + 24 + 2 * k0, fg);      // x1 . g2
+                tmem_ld_32x8(acc + fb_n1 + 24 * j + 2 * k0, fb);   // x2 . g1
+              } else {
+                tmem_ld_32x16(acc + 48 * j + 2 * k0, fa);
+                tmem_ld_32x16(acc + 48 * j + 24 + 2 * k0, fg);
+                tmem_ld_32x16(acc + fb_n1 + 24 * j + 2 * k0, fb);
+              }
               tmem_ld_wait();
 #pragma unroll
               for (int k = 0; k < KB; ++k) {
@@ -827,8 +843,48 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
       A.dbg[16 + 2 * sub] = VQT_CLOCK() - t_begin_ep; A.dbg[17 + 2 * sub] = t_wait_ep;
       if (sub == 0) { A.dbg[27] = t_ld; A.dbg[28] = t_math; A.dbg[29] = t_st; }
     }
-  } else {
-    // =================================== loaders: VQT_LOAD_WARPS / n_slots warps per ring slot ===================================
+  } else if (!SRC_F32) {
+    // =================================== loader of the levels >= 1: one warp, two bulk copies per plane group ===================================
+    // The source is stored tile by tile in plane order (see level_index): a plane group of a tile is ONE contiguous image per
+    // fp16 term (q == 1: the rows are consecutive chunks of the linear signal), so a slot fill is two bulk copies.
+    if (warp == VQT_LOAD_WARP0) {
+      const int n_rows = 128 + L.hb + L.ha;
+      const int n_groups = n_my_tiles * L.gpt;
+      const uint32_t tb = L.pg > 1 ? (uint32_t)L.slot_term_bytes : (uint32_t)(n_rows * 16);
+      int slot = 0, pos = 0, tau = (int)blockIdx.x;
+      uint32_t par = 1;                           // first use of a slot passes immediately
+      long long t_wait_ld = 0;
+      const long long t_begin_ld = VQT_CLOCK();
+#pragma unroll 1
+      for (int gi = 0; gi < n_groups; ++gi) {
+        const int clip = tau / A.tiles_per_clip;
+        const long long t = tau - clip * A.tiles_per_clip;                 // tile inside the clip
+        const uint32_t s1 = smem_u32(sRing) + (uint32_t)slot * slot_bytes;
+        const uint32_t bfull = smem_u32(&bar_full[slot]);
+        {
+          const long long t0 = VQT_CLOCK();
+          vqt_wait(smem_u32(&bar_empty[slot]), par);                       // every lane polls
+          t_wait_ld += VQT_CLOCK() - t0;
+        }
+        if (VQT_KO(8)) {
+          if (lane == 0) mbar_arrive(bfull);
+        } else {
+          if (lane == 0) mbar_expect_tx(bfull, 2u * tb);
+          __syncwarp();
+          if (lane < 2) {
+            const uint16_t* base = (lane ? A.src_lo : A.src_hi) + (size_t)clip * A.src_stride;
+            const uint16_t* src = L.pg > 1 ? base + ((t * q + L.g_order[pos] * L.pg) * (long long)L.rtot) * 8
+                                           : base + 1024 + (t * 128 - L.hb) * 8;
+            bulk_g2s(s1 + (lane ? (uint32_t)L.slot_term_bytes : 0u), src, tb, bfull);
+          }
+        }
+        if (++slot == L.n_slots) { slot = 0; par ^= 1; }
+        if (++pos == L.gpt) { pos = 0; tau += (int)gridDim.x; }
+      }
+      if (VQT_TIMING_ON && A.dbg && blockIdx.x == 0 && lane == 0) { A.dbg[20] = VQT_CLOCK() - t_begin_ld; A.dbg[21] = t_wait_ld; }
+    }
+  } else if (warp < VQT_LOAD_WARP0 + VQT_LOAD_WARPS) {
+    // =================================== loaders of level 0: VQT_LOAD_WARPS / n_slots warps per ring slot ===================================
     const int lw = warp - VQT_LOAD_WARP0;
     const int wps = VQT_LOAD_WARPS / L.n_slots;              // warps per slot
     const int my_slot = lw % L.n_slots, sub = lw / L.n_slots; // this warp takes every wps-th block of 32 chunks of its slot's groups
@@ -855,10 +911,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         const int tau = (int)blockIdx.x + ts * (int)gridDim.x;
         const int clip = tau / A.tiles_per_clip;
         const long long row0 = (long long)(tau - clip * A.tiles_per_clip) * 128;
-        const float* yb = SRC_F32 ? A.y32 + (size_t)clip * A.src_stride : nullptr;
-        const uint16_t* hsrc = SRC_F32 ? nullptr : A.src_hi + (size_t)clip * A.src_stride;
-        const uint16_t* lsrc = SRC_F32 ? nullptr : A.src_lo + (size_t)clip * A.src_stride;
-        const bool vec_ok = SRC_F32 && ((reinterpret_cast<uintptr_t>(yb) & 15) == 0);
+        const float* yb = A.y32 + (size_t)clip * A.src_stride;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(yb) & 15) == 0;
         const int plane0 = L.g_order[pos] * L.pg;
         const long long base_s = (row0 - L.hb) * R + 8LL * plane0;     // sample of chunk (row 0, plane 0 of the group)
         {
@@ -872,32 +926,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         }
         VQT_TL(ts >= 4 && ts < 8 && lane == 0, ((ts - 4) * 8 + lw) * 2);
         if (VQT_KO(8)) {
-          if (SRC_F32 || lane == 0) mbar_arrive(bfull);
-          continue;
-        }
-        if (!SRC_F32) {
-          // levels >= 1: the source is stored tile by tile in plane order: per plane and term one 2 KB bulk copy for the
-          // 128 tile rows plus two small ones for the halo rows out of the neighbouring tiles (zero pad tiles at the ends)
-          const long long t = row0 >> 7;
-          if (L.pg > 1) {
-            // the plane group of the tile is one contiguous image per term in global memory: two bulk copies per group
-            const uint32_t tb = (uint32_t)L.slot_term_bytes;
-            if (lane == 0) mbar_expect_tx(bfull, sub == 0 ? 2u * tb : 0u);
-            __syncwarp();
-            if (sub == 0 && lane < 2) {
-              const uint16_t* src = (lane ? lsrc : hsrc) + ((t * q + plane0) * (long long)L.rtot) * 8;
-              bulk_g2s(lane ? s2 : s1, src, tb, bfull);
-            }
-          } else {                             // q == 1: rows are consecutive chunks of the linear signal; warp `sub` moves term `sub` (wps >= 2)
-            const uint32_t bytes = (uint32_t)(n_rows * 16);
-            const int n_mine = (wps >= 2) ? (sub < 2 ? 1 : 0) : 2;
-            if (lane == 0) mbar_expect_tx(bfull, bytes * (uint32_t)n_mine);
-            __syncwarp();
-            if (lane < 2 && (wps < 2 || lane == 0) && n_mine > 0) {
-              const int term = (wps >= 2) ? sub : lane;
-              bulk_g2s(term ? s2 : s1, (term ? lsrc : hsrc) + 1024 + (row0 - L.hb) * 8, bytes, bfull);
-            }
-          }
+          mbar_arrive(bfull);
           continue;
         }
         if (vec_ok) {
@@ -986,18 +1015,23 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
         mbar_arrive(bfull);                        // every lane (its own stores are fenced)
 #ifndef ZNS_VQT_NO_L2_PREFETCH
         // (single-lane block: kept BEHIND the warp-wide fill, see above)
-        if (SRC_F32 && pos == 0 && sub == 0 && lane == 0 && ts + 1 < n_my_tiles) {
-          // pull the NEXT tile's samples (one contiguous span of the clip) into L2 while this tile is being processed: the
-          // ring holds a single tile, so its loads cannot be issued early -- but their DRAM latency can be taken now
-          const int tau_n = tau + (int)gridDim.x;
-          const int clip_n = tau_n / A.tiles_per_clip;
-          long long s_lo = ((long long)(tau_n - clip_n * A.tiles_per_clip) * 128 - L.hb) * R;
-          long long s_hi = s_lo + (long long)n_rows * R;
-          s_lo = max(s_lo, 0LL); s_hi = min(s_hi, (long long)A.n_sig);
-          const float* pn = A.y32 + (size_t)clip_n * A.src_stride + s_lo;
-          const uint32_t bytes = (uint32_t)((s_hi - s_lo) * 4) & ~15u;
-          if (s_hi > s_lo && bytes > 0 && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
+        if (SRC_F32 && pos == 0 && sub == 0 && lane == 0) {
+          // pull the samples of the tile VQT_PF_DIST tiles ahead (one contiguous span of the clip) into L2: the ring holds a
+          // single tile, so its loads cannot be issued early -- but their DRAM latency can be taken now.  A distance of one
+          // tile leaves the demand loads barely behind the prefetch (28 % L2 hits), yet two or three tiles measured SLOWER.
+#pragma unroll 1
+          for (int d = (ts == 0 ? 1 : VQT_PF_DIST); d <= VQT_PF_DIST; ++d) {
+            if (ts + d >= n_my_tiles) break;
+            const int tau_n = tau + d * (int)gridDim.x;
+            const int clip_n = tau_n / A.tiles_per_clip;
+            long long s_lo = ((long long)(tau_n - clip_n * A.tiles_per_clip) * 128 - L.hb) * R;
+            long long s_hi = s_lo + (long long)n_rows * R;
+            s_lo = max(s_lo, 0LL); s_hi = min(s_hi, (long long)A.n_sig);
+            const float* pn = A.y32 + (size_t)clip_n * A.src_stride + s_lo;
+            const uint32_t bytes = (uint32_t)((s_hi - s_lo) * 4) & ~15u;
+            if (s_hi > s_lo && bytes > 0 && (reinterpret_cast<uintptr_t>(pn) & 15) == 0)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
+          }
         }
 #endif
         VQT_TL(ts >= 4 && ts < 8 && lane == 0, ((ts - 4) * 8 + lw) * 2 + 1);
@@ -1162,7 +1196,7 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     const size_t smem = level_smem(L);
     // levels >= 1 (and the edge-frame kernel) are programmatic dependents of the launch in front of them
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(VQT_LEVEL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(VQT_LEVEL_THREADS(i == 0)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cfg.attrs = &pdl_attr; cfg.numAttrs = (pdl && i > 0) ? 1 : 0;
     if (i == 0 && L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, true>, L, a));
     else if (i == 0) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, false>, L, a));
