@@ -353,6 +353,11 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* v) {
                : "memory");
 }
 
+__device__ __forceinline__ float log_approx(float x) {        // MUFU.LG2 * ln 2 for x >= 1e-9 (no denormal pre-scaling as in __logf)
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.69314718055994530942f;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {       // MUFU.SQRT (2 ulp): the magnitude only feeds a log
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -670,6 +675,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     const int rbase0 = L.ring_base[0], rbase1 = L.ring_base[1], rwid0 = L.ring_width[0], rwid1 = L.ring_width[1];
     const uint32_t accf = smem_u32(&bar_acc_full[0]), acce = smem_u32(&bar_acc_empty[0]);
     const int n_frames = A.n_frames, n_valid = A.n_valid;
+    const bool out_vec = (n_frames % L.fpr) == 0 && (reinterpret_cast<uintptr_t>(A.out) & 15) == 0;   // rows of `out` keep vector alignment
     const long long dst_cap = A.dst_cap;
     const float s_a = L.dec_scale, s_b = L.dec_scale * (1.f / 2048.f);
     const int dst_q = A.dst_q, dst_rtot = A.dst_rtot, dst_hb = A.dst_hb, dst_ha = A.dst_ha;
@@ -782,7 +788,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
             for (int k = 0; k < kBinsPerWarp; ++k) {
               const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
               const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-              op[(size_t)k * n_frames] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
+              op[(size_t)k * n_frames] = log_approx(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
             }
           }
         } else if (!FPR1) {
@@ -811,14 +817,14 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
               for (int k = 0; k < KB; ++k) {
                 const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
                 const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-                res[j][k] = __logf(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
+                res[j][k] = log_approx(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
               }
             }
           }
           const int f0 = g * fpr;
           if (f0 < n_frames && !VQT_KO(16)) {
             float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * n_frames + f0;
-            const bool whole = f0 + fpr <= n_frames && (n_frames % fpr) == 0 && (reinterpret_cast<uintptr_t>(A.out) & 15) == 0;
+            const bool whole = f0 + fpr <= n_frames && out_vec;
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
               float* o = op + (size_t)k * n_frames;
