@@ -31,6 +31,17 @@ int zns_set_error(int code, const char* fmt, ...);
 
 #define ZNS_CHECK_LAUNCH() ZNS_CHECK_CUDA(cudaGetLastError())
 
+// One-time per-DEVICE initialisation guard (function attributes and constant memory are per device, the library may
+// serve several GPUs from one process): true the first time it is called on the current device for this mask.
+static inline bool zns_first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Activation layout: bf16 [G][H][W][8][C]  (G = ceil(B / 8) groups of eight clips).
 // The eight clips of a group are the eight rows of one 128-byte-swizzle atom once a

@@ -1173,10 +1173,9 @@ static int launch_fwd_stack(const zns_conv_desc* d, const FwdTParams& cfg, int n
     p.arg[b] = ex.arg ? (uint8_t*)ex.arg[s] : nullptr;
   }
   auto kern = conv_fwd_stack_umma_kernel<CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
-    attr_set = true;
   }
   dim3 grid(p.tiles.n_total, 1, 1);
   if (CTAS == 2) {
@@ -1232,10 +1231,9 @@ static int launch_fwdT(const zns_conv_desc* d, const FwdTParams& cfg, int n_br, 
     p.mask[b] = mask ? (const bf16*)mask[s] : nullptr;
     p.out[b] = (bf16*)out[s];
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(conv_fwdT_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
-    attr_set = true;
   }
   dim3 grid(p.n_wtiles * p.n_htiles * G, 1, n_br);
   conv_fwdT_umma_kernel<<<grid, 192, smem, st>>>(tm_in[0], tm_in[1], tm_w[0], tm_w[1], p);
@@ -1307,10 +1305,9 @@ static int launch_fwd(const zns_conv_desc* d, int n_br, const void* const* in, c
     p.arg[b] = ex.arg ? (uint8_t*)ex.arg[s] : nullptr;
   }
   auto kern = conv_fwd_umma_kernel<N, HT, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
-    attr_set = true;
   }
   dim3 grid(p.tiles.n_total, 1, 1);
   if (CTAS == 2) {
@@ -1775,10 +1772,9 @@ static int launch_wgrad(const zns_conv_desc* d, int n_br, const void* const* x, 
     p.dw[b] = dwpk[s];
   }
   auto kern = conv_wgrad_umma_kernel<NB, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ZNS_SMEM_LIMIT));
-    attr_set = true;
   }
   dim3 grid(items * p.n_slices, 1, n_br);
   if (CTAS == 2) {
@@ -1931,10 +1927,9 @@ extern "C" int zns_dbg_umma_probe(int variant, const void* a, const void* b, flo
   ZNS_REQUIRE((variant == 0 || variant == 1) && n % 64 == 0 && n >= 64 && n <= 256 && k % 64 == 0 && k >= 64 && k <= 256,
               "probe supports n,k in multiples of 64 up to 256");
   const size_t smem = 1024 + (size_t)(128 + n) * k * 2 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(variant, (const bf16*)a, (const bf16*)b, d, n, k);
   ZNS_CHECK_LAUNCH();
@@ -2015,10 +2010,9 @@ umma_rate_kernel(int n, int iters, int per_group, int mode, long long* __restric
 
 extern "C" int zns_dbg_umma_rate(int n, int iters, int per_group, int mode, int n_ctas, long long* cycles, void* stream) {
   ZNS_REQUIRE(cycles && n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && per_group > 0 && n_ctas > 0, "bad arguments");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   umma_rate_kernel<<<n_ctas, 128, 170 * 1024, (cudaStream_t)stream>>>(n, iters, per_group, mode, cycles);
   ZNS_CHECK_LAUNCH();

@@ -139,10 +139,9 @@ extern "C" int zns_ntxent_fwd_bwd(const float* anchors, const float* poss, int n
   ZNS_REQUIRE(temperature > 0.f, "temperature must be positive");
   const size_t smem = ((size_t)4 * n_rows * dim + (size_t)n_rows * n_rows + 5 * n_rows) * sizeof(float);
   ZNS_REQUIRE(smem <= 200 * 1024, "NT-Xent problem %d x %d does not fit shared memory", n_rows, dim);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(ntxent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   ntxent_kernel<<<1, NT_THREADS, smem, (cudaStream_t)stream>>>(anchors, poss, n_rows, dim, batch_len, temperature,
                                                                result3, d_anchors, d_poss);

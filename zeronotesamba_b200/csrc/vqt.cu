@@ -200,7 +200,7 @@ extern "C" int zns_vqt_basis_host(int sr, int n_bins, int bpo, double fmin, doub
 #include "vqt_plan.h"
 
 __constant__ float c_dec_taps[32];
-static bool g_taps_uploaded = false;
+static unsigned long long g_taps_devs = 0;      // devices whose constant-memory decimator taps are uploaded
 
 extern "C" int zns_vqt_num_frames(int n_samples, int hop) { return 1 + n_samples / hop; }
 
@@ -253,13 +253,12 @@ extern "C" int zns_vqt_plan_create(int sr, int hop, int n_bins, int bpo, double 
 static int vqt_plan_fill(zns_vqt_plan* p, int sr, int n_bins, int bpo, double fmin, double gamma_in, double gamma,
                          int n_oct, int max_batch, int max_samples) {
   int rc = ZNS_OK;
-  if (!g_taps_uploaded) {
+  if (zns_first_use_on_device(&g_taps_devs)) {
     double t64[32];
     float t32[32];
     zns_vqt_decimator_taps_host(t64);
     for (int i = 0; i < 32; ++i) t32[i] = (float)t64[i];
     ZNS_CHECK_CUDA(cudaMemcpyToSymbol(c_dec_taps, t32, sizeof(t32)));
-    g_taps_uploaded = true;
   }
 
   std::vector<float> re(bpo * 1024), im(bpo * 1024), coef;
@@ -803,10 +802,9 @@ static int fbu_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, l
                         int n_frames, float* out, cudaStream_t st) {
   constexpr int KB = (NFFT + 63) / 64;
   const size_t smem = 1024 + (size_t)KB * (2 * 128 * 128 + 48 * 128);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_filterbank_umma_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   dim3 grid((n_frames + 128 * FBU_TILES - 1) / (128 * FBU_TILES), 1, batch);
   vqt_filterbank_umma_kernel<NFFT><<<grid, 256, smem, st>>>(sig, n_sig, stride, p->d_coef_umma[oct], p->coef_inv_scale[oct], hop_i,
@@ -820,11 +818,10 @@ template <int NFFT, int FBT_FRAMES>
 static int fbt_launch_t(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long long stride, int hop_i, int batch,
                         int n_frames, float* out, cudaStream_t st) {
   const size_t smem = (size_t)(2 * FBT_FRAMES + 2 * FBT_COLS) * ((NFFT + 8) / 2) * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+  if (zns_first_use_on_device(&attr_devs)) {
     ZNS_CHECK_CUDA(cudaFuncSetAttribute((vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES>),
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   dim3 grid((n_frames + FBT_FRAMES * FBT_TILES - 1) / (FBT_FRAMES * FBT_TILES), 1, batch);
   vqt_filterbank_mma_kernel<NFFT, FBT_FRAMES><<<grid, FBT_FRAMES * 2, smem, st>>>(sig, n_sig, stride, p->d_coef_bf[oct], p->coef_inv_scale[oct], hop_i,
@@ -866,11 +863,10 @@ static int fb_launch(zns_vqt_plan* p, int oct, const float* sig, int n_sig, long
   dim3 grid((n_frames + FB_FRAMES - 1) / FB_FRAMES, 1, batch);
   const int bin0 = p->n_bins - p->bpo * (oct + 1);
   if (hb == 6) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;          // one bit per device ordinal: function attributes are per device
+    if (zns_first_use_on_device(&attr_devs)) {
       ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_filterbank_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           200 * 1024));
-      attr_set = true;
     }
     ZNS_REQUIRE(smem <= 200 * 1024, "filterbank tile does not fit shared memory (n_fft %d)", nf);
     vqt_filterbank_kernel<6><<<grid, FB_THREADS, smem, st>>>(sig, n_sig, stride, p->d_coef[oct], nf, hop_i,

@@ -366,6 +366,12 @@ class PretextTrainer:
             self._ev_ready.record(torch.cuda.current_stream())
             return
         self._side.wait_event(self._ev_consumed)       # the staging batch of the previous prefetch has been taken
+        cuda_inputs = [t for t in (anchor_audio, positive_audio, starts) if t.is_cuda]
+        if cuda_inputs:
+            # device inputs may still be in flight on the caller's stream, and the caller may free them right after this call
+            self._side.wait_stream(torch.cuda.current_stream())
+            for t in cuda_inputs:
+                t.record_stream(self._side)
         with torch.cuda.stream(self._side):
             self._run_front(anchor_audio, positive_audio, starts)
             self._ev_ready.record(self._side)
