@@ -1072,14 +1072,19 @@ __device__ __forceinline__ int reflect_idx32(int qq, int n) {
   return qq < n ? qq : period - qq;
 }
 
-// one warp per edge frame: every lane gathers up to four samples of the frame's window ONCE (reflect index + level layout are
-// the expensive part), applies all bins_per_octave filters to them, then the warp reduces the 2 x bpo partial sums
+// one warp per edge frame: the lanes gather the frame's window ONCE into shared memory (reflect index + level layout are the
+// expensive part), then lane j < 2 bpo accumulates output component j (filter j / 2, re / im) over the taps -- coefficient
+// reads are coalesced ([tap][filter](re, im)), the sample is a shared-memory broadcast, no cross-lane reduction (the first
+// version reduced 24 partial sums with 120 shuffles and needed 62 registers: three waves of blocks at cfg2)
 #define VQT_EDGE_MAX_BPO 12
+#define VQT_EDGE_MAX_NFFT 128
 __global__ void __launch_bounds__(256)
 vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict__ y32, long long y_stride,
                 const float* __restrict__ inv_sqrt_len, float* __restrict__ out) {
+  __shared__ float win[8][VQT_EDGE_MAX_NFFT];
   const int clip = blockIdx.z;
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 8 + wib;
   pdl_wait();                              // launched behind the last level kernel with programmatic serialization
   if (item >= P.item0[P.n_oct]) return;
   int oct = 0;
@@ -1087,9 +1092,6 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
   const int e = item - P.item0[oct];
   const int nf = P.n_fft[oct], hop = P.hop[oct], n = P.n_sig[oct], F = P.n_frames, bpo = P.bpo;
   const int t = e < P.n_left[oct] ? e : P.t_right[oct] + (e - P.n_left[oct]);
-  float re[VQT_EDGE_MAX_BPO], im[VQT_EDGE_MAX_BPO];
-#pragma unroll
-  for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k) { re[k] = 0.f; im[k] = 0.f; }
   for (int i = lane; i < nf; i += 32) {
     const int idx = reflect_idx32(t * hop + i - nf / 2, n);
     float s;
@@ -1098,32 +1100,20 @@ vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict
       const size_t o = (size_t)clip * P.stride[oct] + (size_t)level_index(idx, P.q[oct], P.rtot[oct], P.hb[oct]);
       s = __half2float(__ushort_as_half(P.hi[oct][o])) + __half2float(__ushort_as_half(P.lo[oct][o])) * (1.f / 2048.f);
     }
-    const float2* cn = reinterpret_cast<const float2*>(P.coef[oct]) + (size_t)i * bpo;     // [tap][filter](re, im)
-#pragma unroll
-    for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k) {
-      if (k < bpo) {
-        const float2 c = __ldg(cn + k);
-        re[k] = fmaf(c.x, s, re[k]);
-        im[k] = fmaf(c.y, s, im[k]);
-      }
-    }
+    win[wib][i] = s;
   }
-#pragma unroll
-  for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      re[k] += __shfl_xor_sync(0xffffffffu, re[k], o);
-      im[k] += __shfl_xor_sync(0xffffffffu, im[k], o);
-    }
+  __syncwarp();
+  const int nc = 2 * bpo;                  // output components of a frame
+  float acc = 0.f;
+  if (lane < nc) {
+    const float* cj = P.coef[oct] + lane;  // [tap][filter](re, im)
+#pragma unroll 8
+    for (int i = 0; i < nf; ++i) acc = fmaf(__ldg(cj + (size_t)i * nc), win[wib][i], acc);
   }
-  // lane k writes bin k (static register indexing: select by predicate)
-  float r = 0.f, m = 0.f;
-#pragma unroll
-  for (int k = 0; k < VQT_EDGE_MAX_BPO; ++k)
-    if (lane == k) { r = re[k]; m = im[k]; }
-  if (lane < bpo) {
-    const int bin = P.n_bins - bpo * (oct + 1) + lane;
-    out[((size_t)clip * P.n_bins + bin) * F + t] = logf(sqrtf(r * r + m * m) * __ldg(inv_sqrt_len + bin) + 1e-9f);
+  const float other = __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (lane < nc && !(lane & 1)) {
+    const int bin = P.n_bins - bpo * (oct + 1) + (lane >> 1);
+    out[((size_t)clip * P.n_bins + bin) * F + t] = logf(sqrtf(acc * acc + other * other) * __ldg(inv_sqrt_len + bin) + 1e-9f);
   }
 }
 
