@@ -303,6 +303,29 @@ def test_batched_inference_long_clips(sd):
     assert float((out[1:2] - one).abs().max()) < 2e-3
 
 
+def test_val_epoch_length_buckets(sd):
+    """Row f1: validation with equal-length files sharing a forward pass (epochs.length_buckets) gives the per-file
+    results of the one-file-per-step loop (epochs.py:127-160); a file of another length stays single."""
+    from zeronotesamba_b200 import epochs
+    from zeronotesamba_b200.loader import load_models
+    criterion, _opt, model = load_models("pretrained", "finetune", 1e-5, state_dict=sd)
+    g = torch.Generator().manual_seed(21)
+    lens = {"a": 400, "b": 400, "c": 520, "d": 400, "e": 400}
+    inputs = {k: torch.rand(2, 96, T, generator=g) * 10 - 9 + 2 * torch.randn(2, 96, T, generator=g) for k, T in lens.items()}
+    masks = {k: (torch.rand(T, generator=g) < 0.1).float() for k, T in lens.items()}
+    idx = list(lens)
+    assert epochs.length_buckets(idx, inputs, 3) == [["a", "b", "d"], ["e"], ["c"]]
+    one = epochs.val_epoch(model, criterion, "pretrained", idx, {k: None for k in idx}, inputs, masks, False, False)
+    bat = epochs.val_epoch(model, criterion, "pretrained", idx, {k: None for k in idx}, inputs, masks, False, False,
+                           batch_files=16)
+    assert abs(one[0] - bat[0]) <= 2e-3 * abs(one[0])
+    outs = epochs.batched_inference(model, "pretrained", idx, inputs, 16)
+    with torch.no_grad():
+        for k in idx:
+            ref = model(inputs[k][0].reshape(1, 1, 96, -1).to(DEV), inputs[k][1].reshape(1, 1, 96, -1).to(DEV))
+            assert outs[k].shape == (lens[k],) and float((outs[k] - ref[0]).abs().max()) < 2e-3, k
+
+
 def test_rms_stem_gate_vs_oracle():
     """Row f3: check_CL_clips (stem_check.py:21-51) on the GPU against the librosa.feature.rms restatement."""
     from oracle import vqt_oracle as vo
