@@ -29,6 +29,10 @@ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 struct C1FwdBr { const float* x; const float* weight; const float* bias; bf16* out; bf16* out2; };
 struct C1FwdArgs { C1FwdBr br[2]; int G; };
 
+// Two adjacent frames per thread: a weight vector read from shared memory feeds both (the first version, one frame per
+// thread, ran at 87 % of the L1 / shared-memory pipe with 35 % occupancy: profiles/r02_ncu_cv1_summary.txt) and their 3 x 12
+// input patch overlaps in 10 of 11 columns.
+#define C1_NPOS 2
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const __grid_constant__ C1FwdArgs a, long long clip_stride, long long row_stride,
                                                         int B, int H, int W, float drop_p, uint32_t seed,
                                                         const uint32_t* __restrict__ seed_dev, uint32_t stream_id, int f16) {
@@ -49,58 +53,76 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const __grid_constant__ 
   if (threadIdx.x < C1_CO) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int b8 = threadIdx.x & 7, wl = threadIdx.x >> 3;
-  const int g = blockIdx.z - branch * a.G, h = blockIdx.y, w = blockIdx.x * 32 + wl;
+  const int g = blockIdx.z - branch * a.G, h = blockIdx.y, w = blockIdx.x * (32 * C1_NPOS) + C1_NPOS * wl;
   if (w >= W) return;
+  const int n_pos = min(C1_NPOS, W - w);
   const int b = g * 8 + b8;
-  uint4* dst = reinterpret_cast<uint4*>(out + zns_act_index(g, h, w, b8, 0, H, W, C1_CO));
+  const size_t e0 = zns_act_index(g, h, w, b8, 0, H, W, C1_CO);        // frame w; frame w + 1 is 8 * 64 elements further
+  const size_t e_step = 8 * C1_CO;
   if (b >= B) {
+    for (int p = 0; p < n_pos; ++p) {
+      uint4* dst = reinterpret_cast<uint4*>(out + e0 + p * e_step);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
-    if (out2) {
-      uint4* dst2 = reinterpret_cast<uint4*>(out2 + zns_act_index(g, h, w, b8, 0, H, W, C1_CO));
+      for (int i = 0; i < 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+      if (out2) {
+        uint4* dst2 = reinterpret_cast<uint4*>(out2 + e0 + p * e_step);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dst2[i] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 8; ++i) dst2[i] = make_uint4(0, 0, 0, 0);
+      }
     }
     return;
   }
-  float xin[C1_TAPS];
+  float xin[C1_KH][C1_KW + C1_NPOS - 1];
   const float* xb = x + (size_t)b * clip_stride;
 #pragma unroll
   for (int r = 0; r < C1_KH; ++r)
 #pragma unroll
-    for (int s = 0; s < C1_KW; ++s) {
+    for (int s = 0; s < C1_KW + C1_NPOS - 1; ++s) {
       int hh = h + r - 1, ww = w + s - 5;
-      xin[r * C1_KW + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * row_stride + ww) : 0.f;
+      xin[r][s] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + (size_t)hh * row_stride + ww) : 0.f;
     }
   const uint32_t thr = dropout_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const size_t e0 = zns_act_index(g, h, w, b8, 0, H, W, C1_CO);
+#pragma unroll 1
+  for (int c0 = 0; c0 < C1_CO; c0 += 8) {
+    float acc[C1_NPOS][8];
 #pragma unroll
-  for (int cb = 0; cb < C1_CO; cb += 8) {
-    float acc[8];
+    for (int p = 0; p < C1_NPOS; ++p)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = bs[cb + i];
+      for (int i = 0; i < 8; ++i) acc[p][i] = bs[c0 + i];
 #pragma unroll
-    for (int t = 0; t < C1_TAPS; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&ws[t][cb]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&ws[t][cb + 4]);
-      const float v = xin[t];
-      acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
-      acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
-      acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
-      acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+    for (int r = 0; r < C1_KH; ++r)
+#pragma unroll
+      for (int sx = 0; sx < C1_KW; ++sx) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * C1_KW + sx][c0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * C1_KW + sx][c0 + 4]);
+#pragma unroll
+        for (int p = 0; p < C1_NPOS; ++p) {
+          const float v = xin[r][sx + p];
+          acc[p][0] = fmaf(w0.x, v, acc[p][0]); acc[p][1] = fmaf(w0.y, v, acc[p][1]);
+          acc[p][2] = fmaf(w0.z, v, acc[p][2]); acc[p][3] = fmaf(w0.w, v, acc[p][3]);
+          acc[p][4] = fmaf(w1.x, v, acc[p][4]); acc[p][5] = fmaf(w1.y, v, acc[p][5]);
+          acc[p][6] = fmaf(w1.z, v, acc[p][6]); acc[p][7] = fmaf(w1.w, v, acc[p][7]);
+        }
+      }
+#pragma unroll
+    for (int p = 0; p < C1_NPOS; ++p) {
+      if (p < n_pos) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = fmaxf(acc[p][i], 0.f);
+          if (drop_p > 0.f) v = (zns_hash32(e0 + p * e_step + c0 + i, seed, stream_id) >= thr) ? v * keep_scale : 0.f;
+          acc[p][i] = v;
+        }
+        *reinterpret_cast<uint4*>(out + e0 + p * e_step + c0) =
+            make_uint4(pack_act2(acc[p][0], acc[p][1], f16), pack_act2(acc[p][2], acc[p][3], f16),
+                       pack_act2(acc[p][4], acc[p][5], f16), pack_act2(acc[p][6], acc[p][7], f16));
+        if (out2)   // bf16 copy: the x operand of cv2's weight gradient
+          *reinterpret_cast<uint4*>(out2 + e0 + p * e_step + c0) =
+              make_uint4(pack_bf16x2(acc[p][0], acc[p][1]), pack_bf16x2(acc[p][2], acc[p][3]),
+                         pack_bf16x2(acc[p][4], acc[p][5]), pack_bf16x2(acc[p][6], acc[p][7]));
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = fmaxf(acc[i], 0.f);
-      if (drop_p > 0.f) v = (zns_hash32(e0 + cb + i, seed, stream_id) >= thr) ? v * keep_scale : 0.f;
-      acc[i] = v;
-    }
-    dst[cb / 8] = make_uint4(pack_act2(acc[0], acc[1], f16), pack_act2(acc[2], acc[3], f16), pack_act2(acc[4], acc[5], f16),
-                             pack_act2(acc[6], acc[7], f16));
-    if (out2)   // bf16 copy: the x operand of cv2's weight gradient
-      reinterpret_cast<uint4*>(out2 + e0)[cb / 8] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                                               pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
   }
 }
 
@@ -118,7 +140,7 @@ extern "C" int zns_conv1_fwd_nbr(int n_br, const float* const* x, long long clip
     ZNS_REQUIRE(x[b] && weight[b] && bias[b] && out_act[b], "NULL tensor for branch %d", b);
     a.br[b] = C1FwdBr{x[b], weight[b], bias[b], (bf16*)out_act[b], out_act_bf16 ? (bf16*)out_act_bf16[b] : nullptr};
   }
-  dim3 grid((W + 31) / 32, H, a.G * n_br);
+  dim3 grid((W + 32 * C1_NPOS - 1) / (32 * C1_NPOS), H, a.G * n_br);
   conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, clip_stride, row_stride, batch, H, W, drop_p, seed, seed_dev,
                                                            rng_stream, out_f16);
   ZNS_CHECK_LAUNCH();
