@@ -534,7 +534,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // FPR1: one frame per signal row (levels whose hop is >= 32 samples: the four big levels) -- a compile-time switch so that the
 // register needs of the multi-frame epilogue (72 accumulator columns per thread) do not spill the hot single-frame one.
-template <bool SRC_F32, bool FPR1>
+// GROUPED (levels >= 1 whose accumulator rings have two stages): the sixteen epilogue warps form two groups of eight and
+// group g drains accumulator stage g, i.e. every other tile -- a tile's drain is one latency chain (barrier -> tcgen05.ld ->
+// FP -> store -> barrier, ~3 K clocks whether eight or sixteen warps share it), so two tiles in flight double the rate.
+template <bool SRC_F32, bool FPR1, bool GROUPED>
 __global__ void __launch_bounds__(VQT_LEVEL_THREADS(SRC_F32), 1)
 vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ VqtLevelArgs A) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -546,7 +549,8 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
   uint8_t* sB = sm + VQT_ZERO_BYTES;
   uint8_t* sRing = sB + ((L.b_bytes + 127) / 128) * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int EPQ = SRC_F32 ? 2 : 4;                   // epilogue warps per TMEM lane quadrant (must divide the twelve bins)
+  static_assert(!(SRC_F32 && GROUPED), "level 0 has eight epilogue warps");
+  constexpr int EPQ = (SRC_F32 || GROUPED) ? 2 : 4;      // epilogue warps per TMEM lane quadrant that share a tile (must divide the twelve bins)
   const bool is_epi = warp < VQT_EPI_WARPS || (!SRC_F32 && warp >= VQT_EXTRA_WARP0);
 
   if (threadIdx.x == 0) {
@@ -657,7 +661,9 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     // its share of the filterbank bins / frames.  The roles run one dependent chain per warp (tcgen05.ld -> FP -> pack ->
     // store), so throughput comes from the number of warps, not from the instruction count.
     // (a warp reads the TMEM lanes of quadrant warp % 4: the extra warps 13..20 are quadrants 1, 2, 3, 0, 1, 2, 3, 0)
-    const int quad = warp & 3, sub = warp < VQT_EPI_WARPS ? warp >> 2 : 2 + ((warp - VQT_EXTRA_WARP0) >> 2);
+    const int quad = warp & 3, sub_all = warp < VQT_EPI_WARPS ? warp >> 2 : 2 + ((warp - VQT_EXTRA_WARP0) >> 2);
+    const int sub = GROUPED ? (sub_all & 1) : sub_all;     // index among the warps of the quadrant that share a tile
+    const int group = GROUPED ? (sub_all >> 1) : 0;        // GROUPED: warps 0..7 drain the even tiles (stage 0), warps 13..20 the odd ones
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     long long t_wait_ep = 0, t_ld = 0, t_math = 0, t_st = 0;
     const long long t_begin_ep = VQT_CLOCK();
@@ -685,6 +691,11 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     const int clip_step = (int)gridDim.x / A.tiles_per_clip, tile_step = (int)gridDim.x - clip_step * A.tiles_per_clip;
 #pragma unroll 1
     for (int ts = 0; ts < n_my_tiles; ++ts) {
+      if (GROUPED && (ts & 1) != group) {                  // the other group's tile
+        clip += clip_step; tile_in_clip += tile_step;
+        if (tile_in_clip >= A.tiles_per_clip) { tile_in_clip -= A.tiles_per_clip; ++clip; }
+        continue;
+      }
       const int row_first = tile_in_clip * 128;
       const int g = row_first + quad * 32 + lane;          // row of this thread inside the clip (< 2^24)
       // every decimator output of the tile lies inside the signal: no per-element masking (all but the last tile of a clip)
@@ -795,44 +806,41 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
           // several frames per row (hop < 32 samples): a thread owns the fpr CONSECUTIVE frames of its row, so the warps of a
           // quadrant split the BINS and a thread writes its frames of one bin as one 8 / 16-byte store -- consecutive lanes,
           // consecutive addresses (one store per frame and bin was a 16-byte-strided scatter, 4 x the store instructions)
+          // Three bins (six accumulator columns, one 32x8 load per product term) at a time: 36 live registers instead of 72.
           constexpr int KB = 12 / EPQ;                     // bins of this warp
-          const int k0 = KB * sub;
-          float res[4][KB];
+          const int f0 = g * fpr;
+          const bool whole = f0 + fpr <= n_frames && out_vec;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < fpr) {
-              constexpr int NL = 2 * KB <= 8 ? 8 : 16;             // columns loaded (2 KB of them are used)
-              uint32_t fa[NL], fg[NL], fb[NL];
-              if (NL == 8) {
+          for (int kh = 0; kh < KB; kh += 3) {
+            const int k0 = KB * sub + kh;
+            float res[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < fpr) {
+                uint32_t fa[8], fg[8], fb[8];
                 tmem_ld_32x8(acc + 48 * j + 2 * k0, fa);           // x1 . g1
                 tmem_ld_32x8(acc + 48 * j + 24 + 2 * k0, fg);      // x1 . g2
                 tmem_ld_32x8(acc + fb_n1 + 24 * j + 2 * k0, fb);   // x2 . g1
-              } else {
-                tmem_ld_32x16(acc + 48 * j + 2 * k0, fa);
-                tmem_ld_32x16(acc + 48 * j + 24 + 2 * k0, fg);
-                tmem_ld_32x16(acc + fb_n1 + 24 * j + 2 * k0, fb);
-              }
-              tmem_ld_wait();
+                tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < KB; ++k) {
-                const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
-                const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
-                res[j][k] = log_approx(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[k], 1e-9f));
+                for (int k = 0; k < 3; ++k) {
+                  const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
+                  const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
+                  res[j][k] = log_approx(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[kh + k], 1e-9f));
+                }
               }
             }
-          }
-          const int f0 = g * fpr;
-          if (f0 < n_frames && !VQT_KO(16)) {
-            float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * n_frames + f0;
-            const bool whole = f0 + fpr <= n_frames && out_vec;
+            if (f0 < n_frames && !VQT_KO(16)) {
+              float* op = A.out + ((size_t)clip * A.n_bins + L.bin0 + k0) * n_frames + f0;
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-              float* o = op + (size_t)k * n_frames;
-              if (whole && fpr == 4) *reinterpret_cast<float4*>(o) = make_float4(res[0][k], res[1][k], res[2][k], res[3][k]);
-              else if (whole && fpr == 2) *reinterpret_cast<float2*>(o) = make_float2(res[0][k], res[1][k]);
-              else {
+              for (int k = 0; k < 3; ++k) {
+                float* o = op + (size_t)k * n_frames;
+                if (whole && fpr == 4) *reinterpret_cast<float4*>(o) = make_float4(res[0][k], res[1][k], res[2][k], res[3][k]);
+                else if (whole && fpr == 2) *reinterpret_cast<float2*>(o) = make_float2(res[0][k], res[1][k]);
+                else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (j < fpr && f0 + j < n_frames) o[j] = res[j][k];
+                  for (int j = 0; j < 4; ++j) if (j < fpr && f0 + j < n_frames) o[j] = res[j][k];
+                }
               }
             }
           }
@@ -1135,10 +1143,12 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
   ZNS_CHECK_CUDA(cudaGetDevice(&dev));
   ZNS_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
   if (!attr_set[dev]) {
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ZNS_CHECK_CUDA(cudaFuncSetAttribute(vqt_level_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     ZNS_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -1194,10 +1204,18 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(VQT_LEVEL_THREADS(i == 0)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cfg.attrs = &pdl_attr; cfg.numAttrs = (pdl && i > 0) ? 1 : 0;
-    if (i == 0 && L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, true>, L, a));
-    else if (i == 0) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, false>, L, a));
-    else if (L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, true>, L, a));
-    else ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, false>, L, a));
+    // two epilogue groups need two stages in every accumulator ring in use and one decimator pass per tile (stage == tile parity)
+    // (measured at cfg2, profiles/r02_vqt_epilogue_groups_ab.txt: multi-frame levels 0.440 -> 0.434 ms, one-frame levels -- which are
+    // bound by their MMAs -- 0.440 -> 0.441: only the former by default)
+    static const int grp_mask = getenv("ZNS_VQT_GROUPS") ? atoi(getenv("ZNS_VQT_GROUPS")) : 2;   // bit 0: one-frame levels, bit 1: multi-frame levels
+    const bool can_group = i > 0 && L.ring_stages[0] == 2 && (L.n_jobs == 1 || (L.ring_stages[1] == 2 && L.n_pass == 1));
+    const bool grouped = can_group && (grp_mask & (L.fpr == 1 ? 1 : 2));
+    if (i == 0 && L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, true, false>, L, a));
+    else if (i == 0) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, false, false>, L, a));
+    else if (L.fpr == 1 && grouped) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, true, true>, L, a));
+    else if (L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, true, false>, L, a));
+    else if (grouped) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, false, true>, L, a));
+    else ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, false, false>, L, a));
     // edge frames: left t*hop < nf/2 ; right t*hop + nf/2 > n
     const int nl = std::min(n_frames, (L.n_fft / 2 + L.hop - 1) / L.hop);
     int tr = (n_cur >= L.n_fft / 2) ? (n_cur - L.n_fft / 2) / L.hop + 1 : 0;
