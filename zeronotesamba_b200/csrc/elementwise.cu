@@ -806,7 +806,23 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (size_t p = (size_t)blockIdx.x * rows_per_it + lane_row; p < n_pos; p += (size_t)gridDim.x * rows_per_it) {
+  // four independent 16-byte loads per thread in flight (one per trip left the kernel latency bound: 19.7 us per launch on
+  // average for 374 MB per step over seven launches)
+  const size_t p_step = (size_t)gridDim.x * rows_per_it;
+  size_t p = (size_t)blockIdx.x * rows_per_it + lane_row;
+  for (; p + 3 * p_step < n_pos; p += 4 * p_step) {
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(dy + (p + u * p_step) * tpr + cg);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(q[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+  for (; p < n_pos; p += p_step) {
     float v[8];
     unpack8(__ldg(dy + p * tpr + cg), v);
 #pragma unroll
