@@ -222,6 +222,11 @@ def test_cfg2_bench_batch_against_oracle():
     out = plan.forward(y)
     torch.cuda.synchronize()
     assert out.shape == (256, 96, 1876) and bool(torch.isfinite(out).all())
+    # the only configuration with many tiles per persistent CTA (ring slots and accumulator stages are reused ~13 times on the
+    # small levels): repeated passes must be bit-identical -- a hand-off race shows up here first
+    for _ in range(2):
+        again = plan.forward(y, out=torch.empty_like(out))
+        assert torch.equal(again, out)
     worst = (0.0, 0.0)
     for i in range(0, 256, 16):
         ref = vo.vqt_ref_f32(y[i].cpu().numpy())

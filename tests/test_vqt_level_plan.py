@@ -120,7 +120,10 @@ def replay(lv, bimg, sig, row0):
                 if sg.flags & 2:
                     finished.add(unit)
     assert covered == set(range(lv.n_mma))
-    assert started == finished == {(j, p) for j in range(lv.n_jobs) for p in (0, 1)}   # two commits per job
+    units = {(j, p) for j in range(lv.n_jobs) for p in (0, 1)}                         # two commits per job ...
+    if lv.fb_n2 == 0:
+        units.discard((0, 1))                    # ... but one for a merged filterbank accumulator (several frames per row)
+    assert started == finished == units
     assert sorted(lv.ep_job[: lv.n_jobs]) == list(range(lv.n_jobs))
     return D
 
@@ -157,9 +160,14 @@ def test_level_plan_replay_matches_oracle(level):
     assert n_fft == lv.n_fft
     for j in range(lv.fpr):
         fb0 = acc_base(lv, 0)
-        a = D[:, fb0 + 48 * j: fb0 + 48 * j + 48]
-        b = D[:, fb0 + lv.fb_n1 + 24 * j: fb0 + lv.fb_n1 + 24 * j + 24]
-        c = (a[:, :24] + (a[:, 24:48] + b) / 2048.0) * lv.fb_scale
+        if lv.fb_n2 == 0:         # merged: [g1 of every frame | g2 of every frame], x2 . g1 accumulated onto the g2 columns
+            main = D[:, fb0 + 24 * j: fb0 + 24 * j + 24]
+            small = D[:, fb0 + 24 * lv.fpr + 24 * j: fb0 + 24 * lv.fpr + 24 * j + 24]
+            c = (main + small / 2048.0) * lv.fb_scale
+        else:
+            a = D[:, fb0 + 48 * j: fb0 + 48 * j + 48]
+            b = D[:, fb0 + lv.fb_n1 + 24 * j: fb0 + lv.fb_n1 + 24 * j + 24]
+            c = (a[:, :24] + (a[:, 24:48] + b) / 2048.0) * lv.fb_scale
         got = c[:, 0::2] + 1j * c[:, 1::2]                        # [128 rows][12 bins]
         f = (row0 + np.arange(128)) * lv.fpr + j
         start = f * lv.hop - n_fft // 2

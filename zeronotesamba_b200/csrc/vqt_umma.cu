@@ -123,7 +123,13 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   };
 
   // ---- TMEM rings: [0] filterbank, [1] decimator ----
-  const int n1 = fpr * 48, n2 = std::max(32, fpr * 24);
+  // Filterbank accumulator of a stage.  One frame per row: [x1.g1 | x1.g2] (48 columns) and x2.g1 in 24 (padded to 32) columns
+  // of its own, two accumulator units issued by different threads.  Several frames per row ("merged"): columns
+  // [g1 of frame 0 .. fpr-1 | g2 of frame 0 .. fpr-1]; x1 . [g1; g2] is one MMA over all 48 fpr columns, x2 . g1 a second one
+  // that ACCUMULATES ONTO the g2 columns (both carry the 1/2048 scale) and reads the first 24 fpr rows of the same coefficient
+  // tile -- 48 fpr instead of 72 fpr columns per stage, so the four-frame levels get two stages too.
+  const bool merged = fpr >= 2;
+  const int n1 = fpr * 48, n2 = merged ? 0 : std::max(32, fpr * 24);
   L.fb_n1 = n1; L.fb_n2 = n2;
   L.ring_width[0] = n1 + n2;
   L.ring_width[1] = 2 * L.dec_wp;
@@ -154,9 +160,14 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
           const float v = ((col & 1) ? im[(size_t)bin * nf + n] : re[(size_t)bin * nf + n]) * gs;
           uint16_t h1, h2;
           split_half(v, &h1, &h2);
-          (*img)[tile_idx(t1, n1, j * 48 + col, k)] = h1;
-          (*img)[tile_idx(t1, n1, j * 48 + 24 + col, k)] = h2;
-          (*img)[tile_idx(t2, n2, j * 24 + col, k)] = h1;
+          if (merged) {
+            (*img)[tile_idx(t1, n1, j * 24 + col, k)] = h1;
+            (*img)[tile_idx(t1, n1, fpr * 24 + j * 24 + col, k)] = h2;
+          } else {
+            (*img)[tile_idx(t1, n1, j * 48 + col, k)] = h1;
+            (*img)[tile_idx(t1, n1, j * 48 + 24 + col, k)] = h2;
+            (*img)[tile_idx(t2, n2, j * 24 + col, k)] = h1;
+          }
         }
   }
   if (!last) {
@@ -186,7 +197,8 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   for (size_t s = 0; s < fb_x0.size(); ++s) {
     const size_t t1 = s * (fb_tile1 + fb_tile2), t2 = t1 + fb_tile1;
     push(fb_x0[s], t1, n1, 0, 0, n1, 0, 0);
-    push(fb_x0[s], t2, n2, n1, 1, n2, 0, 1);
+    if (merged) push(fb_x0[s], t1, fpr * 24, fpr * 24, 1, n1, 0, 0);     // same unit: issued behind the x1 MMA by the same thread
+    else push(fb_x0[s], t2, n2, n1, 1, n2, 0, 1);
   }
   for (int pass = 0; pass < L.n_pass; ++pass) {
     const int c0 = 64 * pass, c1 = std::min(L.dec_w, c0 + 64);   // output columns of this pass
@@ -265,7 +277,10 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   L.n_mma = m;
   L.n_seg = n_seg;
   for (int u = 0; u < n_units; ++u) {
-    if (last_seg[u] < 0) return 1;            // every unit must appear: the "full" barriers expect two commits per job
+    if (last_seg[u] < 0) {
+      if (merged && u == 1) continue;         // merged filterbank: one unit, its "full" barrier expects one commit
+      return 1;                               // every other unit must appear: the "full" barriers expect two commits per job
+    }
     L.seg[last_seg[u]].flags |= 2;
   }
   // epilogue order = completion order (ties: filterbank first)
@@ -557,10 +572,15 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
     for (int i = 0; i < L.n_slots; ++i) {
       // fp32 source: VQT_LOAD_WARPS / n_slots loader warps fill a slot and all their lanes arrive; bulk copies: one arrive.expect_tx
       mbar_init(smem_u32(&bar_full[i]), SRC_F32 ? 32 * (VQT_LOAD_WARPS / L.n_slots) : 1);
-      mbar_init(smem_u32(&bar_empty[i]), ZNS_VQT_ISSUERS);          // every issuer commits once per group
+      // every issuer that owns accumulator units commits once per group.  An issuer WITHOUT units must stay out of the
+      // count: nothing throttles it (it never waits for operands), so it would run through all its tiles at once and its
+      // arrivals of later ring turns would complete a slot's "empty" phase before the working issuers have left the slot.
+      int n_active = 0;
+      for (int k = 0; k < ZNS_VQT_ISSUERS; ++k) n_active += L.seg_begin[k][L.gpt] > L.seg_begin[k][0] ? 1 : 0;
+      mbar_init(smem_u32(&bar_empty[i]), n_active);
     }
     for (int t = 0; t < 4; ++t) {
-      mbar_init(smem_u32(&bar_acc_full[t]), 2);                    // two accumulator units (parts) per job
+      mbar_init(smem_u32(&bar_acc_full[t]), (t < 2 && L.fb_n2 == 0) ? 1 : 2);   // accumulator units (parts) per job
       mbar_init(smem_u32(&bar_acc_empty[t]), 32 * 4 * EPQ);
     }
     mbar_fence_init();
@@ -586,7 +606,7 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
   if (warp >= VQT_ISSUE_WARP0 && warp < VQT_LOAD_WARP0) {
     // =================================== MMA issuers: one elected thread each, O(1) bookkeeping ===================================
     const int isr = warp - VQT_ISSUE_WARP0;
-    if (elect_one()) {
+    if (L.seg_begin[isr][L.gpt] > L.seg_begin[isr][0] && elect_one()) {     // issuers without accumulator units sit the level out
       const uint32_t ring16 = smem_u32(sRing) >> 4, b16 = smem_u32(sB) >> 4, z16 = smem_u32(sZero) >> 4;
       const uint32_t slot16 = slot_bytes >> 4;
       const uint64_t hi_norm = (uint64_t)((128u >> 4) | (1u << 14)) << 32, hi_zero = (uint64_t)(1u << 14) << 32;
@@ -817,15 +837,14 @@ vqt_level_kernel(const __grid_constant__ VqtLevelDev L, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j < fpr) {
-                uint32_t fa[8], fg[8], fb[8];
-                tmem_ld_32x8(acc + 48 * j + 2 * k0, fa);           // x1 . g1
-                tmem_ld_32x8(acc + 48 * j + 24 + 2 * k0, fg);      // x1 . g2
-                tmem_ld_32x8(acc + fb_n1 + 24 * j + 2 * k0, fb);   // x2 . g1
+                uint32_t fa[8], fg[8];
+                tmem_ld_32x8(acc + 24 * j + 2 * k0, fa);                // x1 . g1
+                tmem_ld_32x8(acc + 24 * fpr + 24 * j + 2 * k0, fg);     // x1 . g2 + x2 . g1 (merged columns, see build_level)
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                  const float re = __uint_as_float(fa[2 * k]) + (__uint_as_float(fg[2 * k]) + __uint_as_float(fb[2 * k])) * (1.f / 2048.f);
-                  const float im = __uint_as_float(fa[2 * k + 1]) + (__uint_as_float(fg[2 * k + 1]) + __uint_as_float(fb[2 * k + 1])) * (1.f / 2048.f);
+                  const float re = fmaf(__uint_as_float(fg[2 * k]), 1.f / 2048.f, __uint_as_float(fa[2 * k]));
+                  const float im = fmaf(__uint_as_float(fg[2 * k + 1]), 1.f / 2048.f, __uint_as_float(fa[2 * k + 1]));
                   res[j][k] = log_approx(fmaf(sqrt_approx(fmaf(re, re, im * im)), isl[kh + k], 1e-9f));
                 }
               }
@@ -1207,9 +1226,9 @@ int vqt_umma_forward(zns_vqt_plan* p, const float* y, int batch, int n_samples, 
     // two epilogue groups need two stages in every accumulator ring in use and one decimator pass per tile (stage == tile parity)
     // (measured at cfg2, profiles/r02_vqt_epilogue_groups_ab.txt: multi-frame levels 0.440 -> 0.434 ms, one-frame levels -- which are
     // bound by their MMAs -- 0.440 -> 0.441: only the former by default)
-    static const int grp_mask = getenv("ZNS_VQT_GROUPS") ? atoi(getenv("ZNS_VQT_GROUPS")) : 2;   // bit 0: one-frame levels, bit 1: multi-frame levels
+    static const int grp_mask = getenv("ZNS_VQT_GROUPS") ? atoi(getenv("ZNS_VQT_GROUPS")) : 6;   // bit 0: one-frame levels, bit 1 / 2: two- / four-frame levels
     const bool can_group = i > 0 && L.ring_stages[0] == 2 && (L.n_jobs == 1 || (L.ring_stages[1] == 2 && L.n_pass == 1));
-    const bool grouped = can_group && (grp_mask & (L.fpr == 1 ? 1 : 2));
+    const bool grouped = can_group && (grp_mask & (L.fpr == 1 ? 1 : (L.fpr == 2 ? 2 : 4)));
     if (i == 0 && L.fpr == 1) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, true, false>, L, a));
     else if (i == 0) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<true, false, false>, L, a));
     else if (L.fpr == 1 && grouped) ZNS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, vqt_level_kernel<false, true, true>, L, a));
