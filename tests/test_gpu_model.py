@@ -176,7 +176,7 @@ def test_dropout_train_mode_statistics(sd):
     model.train()
     with torch.no_grad():
         a1, _ = model(x[:, 0:1], x[:, 1:2])
-        eng = next(iter(model._cache._engines.values()))
+        eng = next(iter(model._cache._engines.values()))[0]
         x3 = eng.x3[0].float()
         zero_frac_train = float((x3 == 0).float().mean())
         model.eval()
@@ -468,6 +468,46 @@ def test_train_model_epoch_driver(tmp_path):
         train_model(dict(yml, pt_task="other"), bank[:4], bank[4:], model_dir=str(tmp_path))
 
 
+def test_two_forwards_before_backward(sd):
+    """The reference's CLMR loop calls ONE DS_CNN twice and then backward (pretext.py:503-507): each outstanding forward
+    keeps its own workspaces (engine pool), the shared parameters receive the sum of both contributions -- the same
+    gradients as forward_pair -- and a fourth outstanding forward recycles the oldest, whose backward then raises."""
+    from zeronotesamba_b200.models.models import DS_CNN, _EngineCache
+    branch_sd = {k[len("anchor."):]: v for k, v in sd.items() if k.startswith("anchor.")}
+    g = torch.Generator().manual_seed(31)
+    a = (torch.rand(4, 1, 96, 64, generator=g) * 10 - 9).to(DEV)
+    p = (torch.rand(4, 1, 96, 64, generator=g) * 10 - 9).to(DEV)
+    wa = torch.randn(4, 64, generator=g).to(DEV)
+    wp = torch.randn(4, 64, generator=g).to(DEV)
+
+    def grads(two_calls: bool):
+        m = DS_CNN().to(DEV)
+        m.load_state_dict(branch_sd)
+        m.train()
+        m.pretrained.dp.p = 0.0
+        if two_calls:
+            ea = m(a)
+            ep = m(p)                                       # second forward while the first still awaits its backward
+        else:
+            ea, ep = m.forward_pair(a, p)
+        ((ea * wa).sum() + (ep * wp).sum()).backward()
+        return m, {k: v.grad.clone() for k, v in m.named_parameters()}, (ea.detach(), ep.detach())
+
+    m2, g2, e2 = grads(True)
+    _m1, g1, e1 = grads(False)
+    assert len(next(iter(m2._cache._engines.values()))) == 2
+    for x, y in zip(e1, e2):
+        assert float((x - y).abs().max()) < 2e-3
+    for k in g1:
+        num = float((g1[k] - g2[k]).double().norm())
+        assert num <= 2e-2 * float(g1[k].double().norm()) + 1e-7, (k, num)
+    # more outstanding forwards than the pool holds: the oldest is recycled and says so at backward
+    outs = [m2(a) for _ in range(_EngineCache.MAX_PENDING + 1)]
+    with pytest.raises(RuntimeError, match="outstanding"):
+        outs[0].sum().backward()
+    outs[-1].sum().backward()
+
+
 def test_variable_length_clips_share_one_engine(sd):
     """Downstream loops feed one file of its own length per step (epochs.py:45-63): the encoder workspaces are sized for the
     longest clip and re-viewed for the others -- same results as fresh engines, no reallocation when T shrinks."""
@@ -482,7 +522,9 @@ def test_variable_length_clips_share_one_engine(sd):
     with torch.no_grad():
         for x in clips:
             outs.append(model(x[:, 0:1], x[:, 1:2]).clone())
-            engines.add(id(next(iter(model.pretext._cache._engines.values()))))
+            pool = next(iter(model.pretext._cache._engines.values()))
+            assert len(pool) == 1                            # inference never reserves an engine: no second one is built
+            engines.add(id(pool[0]))
     assert len(engines) == 1 and len(model.pretext._cache._engines) == 1
     assert torch.equal(outs[0], outs[3])                    # same clip again after shorter ones: identical
     for x, o in zip(clips, outs):

@@ -27,23 +27,44 @@ def _require_cuda(x: torch.Tensor) -> None:
 
 
 class _EngineCache:
-    """One EncoderEngine per (batch, n_br, device), kept on the owning module and shared by every clip length: the engine's
+    """EncoderEngines per (batch, n_br, device), kept on the owning module and shared by every clip length: an engine's
     workspaces are sized for the longest clip seen so far (plus 25 % head room when they have to grow) and re-viewed for
-    shorter ones, so a dataset with variable T (one file per step, epochs.py:45-63) does not reallocate per length."""
+    shorter ones, so a dataset with variable T (one file per step, epochs.py:45-63) does not reallocate per length.
+
+    Activations live in the engine's workspaces, not in autograd-saved tensors, so an engine whose forward still awaits its
+    backward (``_pending``) must not run another forward.  A key therefore holds a small POOL: ``anc = model(a); pos =
+    model(p); loss.backward()`` on one module (the reference's CLMR loop, pretext.py:503-507) takes two engines.  At most
+    ``MAX_PENDING`` forwards of a geometry may be outstanding; one more recycles the oldest, whose backward then raises.
+    Engines of a pool draw different dropout masks (seed = pool index)."""
+
+    MAX_PENDING = 3
 
     def __init__(self):
-        self._engines: Dict[Tuple[int, int, int], EncoderEngine] = {}
+        self._engines: Dict[Tuple[int, int, int], List[EncoderEngine]] = {}
 
     def get(self, batch: int, T: int, n_br: int, device) -> EncoderEngine:
         key = (batch, n_br, device.index if device.index is not None else torch.cuda.current_device())
-        eng = self._engines.get(key)
+        pool = self._engines.get(key)
+        if pool is None:
+            if len(self._engines) >= 4:                   # bounded number of (batch, branches) geometries
+                self._engines.pop(next(iter(self._engines)))
+            pool = self._engines[key] = []
+        slot = next((i for i, e in enumerate(pool) if not getattr(e, "_pending", False)), None)
+        if slot is None:
+            if len(pool) < self.MAX_PENDING:
+                slot = len(pool)
+                pool.append(None)
+            else:                                         # recycle the engine of the oldest outstanding forward
+                slot = min(range(len(pool)), key=lambda i: getattr(pool[i], "_version", 0))
+        eng = pool[slot]
         if eng is None or T > eng.T_cap:
             cap = T if eng is None else max(T, int(1.25 * eng.T_cap))
-            if eng is None and len(self._engines) >= 4:   # bounded number of (batch, branches) geometries
-                self._engines.pop(next(iter(self._engines)))
-            self._engines.pop(key, None)
+            version = getattr(eng, "_version", 0)
+            pool[slot] = None
             del eng
-            eng = self._engines[key] = EncoderEngine(batch, cap, n_br, device)
+            eng = pool[slot] = EncoderEngine(batch, cap, n_br, device, seed=0x9E3779B1 * slot & 0x7FFFFFFF)
+            eng._version = version
+        eng._pending = False
         eng.set_T(T)
         return eng
 
@@ -101,9 +122,10 @@ def _check_input(x: torch.Tensor) -> Tuple[int, int]:
 
 class _EncoderFunction(torch.autograd.Function):
     """n_br DS_CNN branches: (x_0 [, x_1], *params) -> emb_0 [, emb_1].  No gradient w.r.t. inputs."""
+    _clock = 0
 
     @staticmethod
-    def forward(ctx, cache: _EngineCache, n_br: int, train: bool, dropout_p: float, *tensors):
+    def forward(ctx, cache: _EngineCache, n_br: int, train: bool, dropout_p: float, grad_on: bool, *tensors):
         xs = [t.contiguous().float() for t in tensors[:n_br]]
         flat = tensors[n_br:]
         names = branch_param_names()
@@ -114,7 +136,9 @@ class _EncoderFunction(torch.autograd.Function):
             eng = cache.get(FOLD_SLOTS, plan[0], n_br, xs[0].device)
         else:
             eng = cache.get(B, T, n_br, xs[0].device)
-        need_grad = any(ctx.needs_input_grad[4 + n_br:])     # a backward may follow (train or eval mode)
+        # a backward may follow (train or eval mode).  grad_on = the caller's torch.is_grad_enabled(): inside forward() grad mode is
+        # always off, and under no_grad the parameters still "need" gradients although no backward will ever release the engine
+        need_grad = bool(grad_on) and any(ctx.needs_input_grad[5 + n_br:])
         eng.pack_weights(params, need_dgrad=need_grad)
         if train and dropout_p > 0:
             # the keep masks are hash(element, seed ^ step counter, layer): a new counter value per training forward
@@ -127,16 +151,17 @@ class _EncoderFunction(torch.autograd.Function):
             embs = eng.forward(xs, 96 * T, params, train=train, dropout_p=dropout_p, need_grad=need_grad)
             out = tuple(e.clone() for e in embs)
         ctx.eng, ctx.params, ctx.n_br, ctx.n_names, ctx.plan = eng, params, n_br, len(names), plan
-        ctx.version = getattr(eng, "_version", 0) + 1
-        eng._version = ctx.version
+        _EncoderFunction._clock += 1                           # process-wide order of forwards (oldest-first recycling)
+        ctx.version = eng._version = _EncoderFunction._clock
+        eng._pending = bool(need_grad)                         # the workspaces are reserved until this forward's backward
         return out if n_br > 1 else out[0]
 
     @staticmethod
     def backward(ctx, *d_embs):
         eng: EncoderEngine = ctx.eng
         if eng._version != ctx.version:
-            raise RuntimeError("encoder workspaces were overwritten by a later forward of the same geometry; "
-                               "call backward before the next forward")
+            raise RuntimeError("encoder workspaces were overwritten by a later forward of the same geometry (more than "
+                               f"{_EngineCache.MAX_PENDING} forwards outstanding); call backward before further forwards")
         names = branch_param_names()
         grads = [{n: torch.zeros_like(ctx.params[br][n]) for n in names} for br in range(ctx.n_br)]
         if ctx.plan is not None:
@@ -144,8 +169,9 @@ class _EncoderFunction(torch.autograd.Function):
         else:
             d = [(g if g is not None else torch.zeros_like(eng.emb[i])).contiguous().float() for i, g in enumerate(d_embs)]
         eng.backward(d, ctx.params, grads)
+        eng._pending = False
         flat = [grads[br][n] for br in range(ctx.n_br) for n in names]
-        return (None, None, None, None) + (None,) * ctx.n_br + tuple(flat)
+        return (None, None, None, None, None) + (None,) * ctx.n_br + tuple(flat)
 
 
 class _CNN(nn.Module):
@@ -211,7 +237,8 @@ class DS_CNN(nn.Module):
         -- x: input (vqt)
         """
         _check_input(x)
-        return _EncoderFunction.apply(self._cache, 1, self.training, self.pretrained.dp.p, x, *self._flat_params())
+        return _EncoderFunction.apply(self._cache, 1, self.training, self.pretrained.dp.p, torch.is_grad_enabled(), x,
+                                      *self._flat_params())
 
     def forward_pair(self, a: torch.Tensor, p: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """``(self(a), self(p))`` in one pass with SHARED weights -- the CLMR baseline applies one DS_CNN
@@ -222,7 +249,8 @@ class DS_CNN(nn.Module):
         if (ba, ta) != (bp, tp):
             raise ValueError("forward_pair needs two inputs of the same shape")
         params = self._flat_params()
-        return _EncoderFunction.apply(self._pair_cache, 2, self.training, self.pretrained.dp.p, a, p, *params, *params)
+        return _EncoderFunction.apply(self._pair_cache, 2, self.training, self.pretrained.dp.p, torch.is_grad_enabled(), a, p,
+                                      *params, *params)
 
 
 class Pretext_CNN(nn.Module):
@@ -245,7 +273,7 @@ class Pretext_CNN(nn.Module):
         if (ba, ta) != (bp, tp):
             return self.anchor(anc), self.postve(pos)
         train = self.anchor.training
-        anc_emb, pos_emb = _EncoderFunction.apply(self._cache, 2, train, self.anchor.pretrained.dp.p, anc, pos,
+        anc_emb, pos_emb = _EncoderFunction.apply(self._cache, 2, train, self.anchor.pretrained.dp.p, torch.is_grad_enabled(), anc, pos,
                                                   *self.anchor._flat_params(), *self.postve._flat_params())
         return anc_emb, pos_emb
 
