@@ -116,6 +116,40 @@ def _check_step(gold, sd, model, res, lr=1e-6):
     #                                                  tests/test_gpu_configs.py::test_conditioned_step_* for the tight check
 
 
+def test_fused_adam_lr_change_and_moment_carry_over(gold, sd):
+    """train_epoch with FusedAdam: a learning rate changed in param_groups (a scheduler) takes effect on the next epoch, and
+    the Adam moments and the step count survive the trainer rebuild that a new crop length forces."""
+    from zeronotesamba_b200.models.loss_functions import NTXent
+    from zeronotesamba_b200.models.models import Pretext_CNN
+    from zeronotesamba_b200.pretext import FusedAdam, train_epoch
+    batch = torch.from_numpy(gold["step_batch"])
+    B = batch.shape[0]
+    model = Pretext_CNN().to(DEV)
+    model.load_state_dict(sd)
+    crit = NTXent(batch_len=B, temperature=0.25)
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    train_epoch(model, [[batch]], crit, opt)
+    tr = opt._trainer
+    p0 = tr.flat_p.clone()
+    train_epoch(model, [[batch]], crit, opt)
+    big = float((tr.flat_p - p0).abs().max())
+    assert opt._trainer is tr and 2e-5 < big < 3e-4                 # second step at lr 1e-4
+    opt.param_groups[0]["lr"] = 1e-6
+    p0 = tr.flat_p.clone()
+    train_epoch(model, [[batch]], crit, opt)
+    small = float((tr.flat_p - p0).abs().max())
+    assert opt._trainer is tr and tr.lr == 1e-6 and 2e-7 < small < 3e-6, small
+    steps = int(tr.engine.step_ctr.item())
+    m_norm = float(tr.flat_m.double().norm())
+    assert steps == 3 and m_norm > 0
+    longer = torch.cat([batch, batch[..., :16]], dim=-1)            # another crop length: the trainer is rebuilt
+    train_epoch(model, [[longer]], crit, opt)
+    tr2 = opt._trainer
+    assert tr2 is not tr and tr2.T == longer.shape[-1] and int(tr2.engine.step_ctr.item()) == steps + 1
+    # one more step moved the first moment by at most (1 - beta1) of a gradient: it was carried over, not reset
+    assert float(tr2.flat_m.double().norm()) > 0.5 * m_norm
+
+
 def test_trainer_step_golden(gold, sd):
     from zeronotesamba_b200.models.models import Pretext_CNN
     from zeronotesamba_b200.pretext import PretextTrainer

@@ -263,6 +263,13 @@ class PretextTrainer:
             else:
                 self._optimizer()
 
+    def set_lr(self, lr: float) -> None:
+        """Change the learning rate of the following steps (the captured optimizer graph bakes it in: dropped, the optimizer then
+        runs as an eager launch behind the forward/backward graph)."""
+        if float(lr) != self.lr:
+            self.lr = float(lr)
+            self._graph_opt = None
+
     def _optimizer(self):
         L.check(L.lib().zns_adam_flat(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
                                       self.flat_p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0,
@@ -398,12 +405,21 @@ class PretextTrainer:
 # reference-signature epoch functions
 # ---------------------------------------------------------------------------------------------------
 def _trainer_for(model: Pretext_CNN, criterion: NTXent, optimizer: FusedAdam, T: int) -> PretextTrainer:
+    """The graph-captured trainer behind ``train_epoch(..., FusedAdam)``.  It is rebuilt when the batch geometry changes; the
+    Adam moments and the step count then move over to the new trainer (same model), and a learning rate changed in
+    ``optimizer.param_groups`` (a scheduler) is picked up before every epoch."""
     tr = optimizer._trainer
+    g = optimizer.param_groups[0]
     if tr is None or tr.model is not model or tr.T != T or tr.B != criterion.batch_len:
-        g = optimizer.param_groups[0]
+        old = tr
         tr = PretextTrainer(model, batch_len=criterion.batch_len, temperature=criterion.temperature, lr=g["lr"],
                             betas=g["betas"], eps=g["eps"], crop_frames=T)
+        if old is not None and old.model is model and old.flat_m.numel() == tr.flat_m.numel():
+            tr.flat_m.copy_(old.flat_m)
+            tr.flat_v.copy_(old.flat_v)
+            tr.engine.step_ctr.copy_(old.engine.step_ctr)
         optimizer._trainer = tr
+    tr.set_lr(g["lr"])
     return tr
 
 
