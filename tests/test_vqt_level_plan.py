@@ -137,9 +137,10 @@ def dec_outputs(lv, D):
     return np.concatenate(cols, axis=1)
 
 
+@pytest.mark.parametrize("mode", ["vqt", "cqt"])
 @pytest.mark.parametrize("level", range(8))
-def test_level_plan_replay_matches_oracle(level):
-    lv, bimg = level_plan(level)
+def test_level_plan_replay_matches_oracle(level, mode):
+    lv, bimg = level_plan(level, mode)
     R = 8 * lv.q
     rng = np.random.default_rng(level)
     n_sig = R * 128 * 3 + 37
@@ -156,7 +157,7 @@ def test_level_plan_replay_matches_oracle(level):
     else:
         assert level == 7
     # ---- filterbank ----
-    g, n_fft = vo.octave_time_kernels(level, 16000.0, vo.default_gamma())
+    g, n_fft = vo.octave_time_kernels(level, 16000.0, vo.default_gamma() if mode == "vqt" else 0.0)
     assert n_fft == lv.n_fft
     for j in range(lv.fpr):
         fb0 = acc_base(lv, 0)
@@ -200,8 +201,19 @@ def test_level_geometry_table():
         assert lv.n_slots * 2 * lv.slot_term_bytes + lv.b_bytes + 256 < 220 * 1024
 
 
-def test_cqt_geometry_falls_back():
-    """gamma = 0 (CQT) needs n_fft = 256 at every octave: not covered by the level kernels (the plan then keeps the
-    round-1 kernels); the host hook reports it instead of building a wrong plan."""
+def test_cqt_geometry_is_covered():
+    """gamma = 0 (CQT) needs n_fft = 256 at every octave: twice the filterbank k-steps and wider halos (up to 17 rows at the
+    8-sample levels), still inside the level kernels' limits -- CQT runs on the tcgen05 pyramid like VQT."""
+    for level in range(8):
+        lv, _ = level_plan(level, "cqt")
+        assert lv.n_fft == 256 and lv.n_mma <= MAX_MMA and lv.n_seg <= 64
+        assert lv.n_slots * 2 * lv.slot_term_bytes + lv.b_bytes + 256 < 220 * 1024
+        assert lv.ring_base[0] + lv.ring_stages[0] * lv.ring_width[0] <= 512
+
+
+def test_unsupported_geometry_is_reported():
+    """A hop whose top-level row would not fit the plane layout is refused by the host hook (the plan then keeps the round-1
+    kernels) instead of building a wrong plan."""
+    lv = VqtLevel()
     with pytest.raises(L.ZnsError, match="not supported"):
-        level_plan(0, "cqt")
+        L.check(L.lib().zns_dbg_vqt_level_plan(16000, 1024, 96, 12, vo.FMIN_C0, -1.0, 0, C.byref(lv), C.sizeof(lv), None, 0))

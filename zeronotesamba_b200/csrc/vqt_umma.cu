@@ -76,7 +76,7 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   memset(&L, 0, sizeof(L));
   const int hop = p->hop >> lvl;
   const int nf = p->n_fft[lvl];
-  if (hop < 2 || nf > 128 || nf < 16 || p->bpo != 12) return 1;
+  if (hop < 2 || nf > 256 || nf < 16 || p->bpo != 12) return 1;
   const int R = hop >= 32 ? hop : (hop >= 8 ? 32 : 8);
   const int q = R / 8, fpr = R / hop;
   if (!(q == 1 || q == 4 || q == 8 || q == 16 || q == 32) || fpr > 4) return 1;
@@ -1104,7 +1104,7 @@ __device__ __forceinline__ int reflect_idx32(int qq, int n) {
 // reads are coalesced ([tap][filter](re, im)), the sample is a shared-memory broadcast, no cross-lane reduction (the first
 // version reduced 24 partial sums with 120 shuffles and needed 62 registers: three waves of blocks at cfg2)
 #define VQT_EDGE_MAX_BPO 12
-#define VQT_EDGE_MAX_NFFT 128
+#define VQT_EDGE_MAX_NFFT 256
 __global__ void __launch_bounds__(256)
 vqt_edge_kernel(const __grid_constant__ VqtEdgeParams P, const float* __restrict__ y32, long long y_stride,
                 const float* __restrict__ inv_sqrt_len, float* __restrict__ out) {
