@@ -191,6 +191,16 @@ def test_level_plan_edges_zero_extension():
     assert np.abs(got[ok] - want[t[ok]]).max() <= 2e-6 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("mode", ["vqt", "cqt"])
+def test_issuers_work_at_every_position_or_not_at_all(mode):
+    """Slot hand-off invariant (see build_level): no issuer idles at one position of a tile and works at another."""
+    for level in range(8):
+        lv, _ = level_plan(level, mode)
+        for isr in range(N_ISSUERS):
+            per_pos = [lv.seg_begin[isr][p + 1] - lv.seg_begin[isr][p] for p in range(lv.gpt)]
+            assert all(per_pos) or not any(per_pos), (mode, level, isr, per_pos)
+
+
 def test_level_geometry_table():
     rows = {0: (32, 1), 1: (16, 1), 2: (8, 1), 3: (4, 1), 4: (4, 2), 5: (4, 4), 6: (1, 2), 7: (1, 4)}
     for level, (q, fpr) in rows.items():

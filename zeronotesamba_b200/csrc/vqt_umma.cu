@@ -276,6 +276,14 @@ static int build_level(zns_vqt_plan* p, int lvl, double fmin, double gamma_in, c
   }
   L.n_mma = m;
   L.n_seg = n_seg;
+  // Hand-off invariant of the slot barriers: an issuer that works at all must have MMAs at EVERY position of a tile.  One that
+  // idles at position p but works at a later one skips ahead inside the tile, and with a one-tile ring its next-tile arrival
+  // on slot p could complete the slot's "empty" phase before the others have read it (issuers without any unit are not counted).
+  for (int isr = 0; isr < ZNS_VQT_ISSUERS; ++isr) {
+    if (L.seg_begin[isr][L.gpt] == L.seg_begin[isr][0]) continue;
+    for (int pos = 0; pos < L.gpt; ++pos)
+      if (L.seg_begin[isr][pos + 1] == L.seg_begin[isr][pos]) return 1;
+  }
   for (int u = 0; u < n_units; ++u) {
     if (last_seg[u] < 0) {
       if (merged && u == 1) continue;         // merged filterbank: one unit, its "full" barrier expects one commit
